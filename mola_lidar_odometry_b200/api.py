@@ -1,0 +1,270 @@
+"""Python host layer over the C ABI (libmlo_b200.so).  Names follow the reference's domain:
+mola::HashedVoxelPointCloud / mola::NDT (local map), mp2p_icp_filters::FilterDecimateVoxels,
+mp2p_icp::ICP::align.  Everything here calls the CUDA library; nothing computes on the CPU.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Sequence
+
+import numpy as np
+
+from . import capi
+from .capi import (DecimateParams, Filter1Params, IcpParams, IcpResult, MapParams, Profile)
+
+
+class MloError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"mlo error {code}: {msg}")
+        self.code = code
+
+
+def _pts(a) -> np.ndarray:
+    a = np.ascontiguousarray(a, dtype=np.float32)
+    if a.ndim != 2 or a.shape[1] not in (3, 4):
+        raise ValueError("point cloud must be [n,3] or [n,4] float32")
+    return a
+
+
+def _pose(p) -> np.ndarray:
+    return np.ascontiguousarray(np.asarray(p, dtype=np.float64)[..., :3, :4])
+
+
+class Context:
+    """One CUDA device + one stream + one caller thread (mirrors one LidarOdometry worker, LidarOdometry.h:546-549)."""
+
+    def __init__(self, device: int = 0):
+        self.lib = capi.load()
+        h = C.c_void_p()
+        rc = self.lib.mlo_create(device, C.byref(h))
+        if rc != 0:
+            raise MloError(rc, "mlo_create failed (no sm_100 device?) — there is no CPU fallback")
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.mlo_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def check(self, rc: int):
+        if rc != 0:
+            raise MloError(rc, self.lib.mlo_last_error(self.h).decode())
+
+    @property
+    def stream(self) -> int:
+        return int(self.lib.mlo_stream(self.h) or 0)
+
+    @property
+    def launch_count(self) -> int:
+        return int(self.lib.mlo_launch_count(self.h))
+
+    def device_info(self):
+        name = C.create_string_buffer(128)
+        sm, ma, mi = C.c_int(), C.c_int(), C.c_int()
+        self.check(self.lib.mlo_device_info(self.h, name, 128, C.byref(sm), C.byref(ma), C.byref(mi)))
+        return name.value.decode(), sm.value, (ma.value, mi.value)
+
+    def profile_enable(self, on: bool = True):
+        self.check(self.lib.mlo_profile_enable(self.h, int(on)))
+
+    def profile_get(self, reset: bool = True) -> Profile:
+        p = Profile()
+        self.check(self.lib.mlo_profile_get(self.h, C.byref(p), int(reset)))
+        return p
+
+    # ---- filters
+    def voxel_decimate_first(self, pts, params: DecimateParams) -> np.ndarray:
+        pts = _pts(pts)
+        idx = np.empty(max(len(pts), 1), np.uint32)
+        n = C.c_uint64()
+        self.check(self.lib.mlo_voxel_decimate_first(self.h, pts.ctypes.data, pts.shape[1], len(pts), C.byref(params),
+                                                     idx.ctypes.data, C.byref(n)))
+        return idx[:n.value].copy()
+
+    def filter_1st_pass(self, pts, fp: Filter1Params):
+        pts = _pts(pts)
+        a = np.empty((max(len(pts), 1), 3), np.float32)
+        b = np.empty((max(len(pts), 1), 3), np.float32)
+        na, nb = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.mlo_filter_1st_pass(self.h, pts.ctypes.data, pts.shape[1], len(pts), C.byref(fp),
+                                                a.ctypes.data, C.byref(na), b.ctypes.data, C.byref(nb)))
+        return a[:na.value].copy(), b[:nb.value].copy()
+
+    # ---- ICP
+    def icp_align(self, local, lmap: "LocalMap", init_pose, params: IcpParams) -> IcpResult:
+        local, init_pose = _pts(local), _pose(init_pose)
+        res = IcpResult()
+        self.check(self.lib.mlo_icp_align(self.h, local.ctypes.data, local.shape[1], len(local), lmap.h,
+                                          init_pose.ctypes.data, C.byref(params), C.byref(res)))
+        return res
+
+    def icp_align_soa(self, x, y, z, lmap: "LocalMap", init_pose, params: IcpParams) -> IcpResult:
+        x, y, z = (np.ascontiguousarray(v, np.float32) for v in (x, y, z))
+        init_pose = _pose(init_pose)
+        res = IcpResult()
+        self.check(self.lib.mlo_icp_align_soa(self.h, x.ctypes.data, y.ctypes.data, z.ctypes.data, len(x), lmap.h,
+                                              init_pose.ctypes.data, C.byref(params), C.byref(res)))
+        return res
+
+    @staticmethod
+    def _concat(clouds: Sequence[np.ndarray]):
+        clouds = [_pts(c) for c in clouds]
+        stride = clouds[0].shape[1]
+        assert all(c.shape[1] == stride for c in clouds)
+        offs = np.zeros(len(clouds) + 1, np.uint64)
+        offs[1:] = np.cumsum([len(c) for c in clouds])
+        return np.ascontiguousarray(np.concatenate(clouds, 0)), offs, stride
+
+    @staticmethod
+    def _params_array(params: Sequence[IcpParams]):
+        arr = (IcpParams * len(params))()
+        for i, p in enumerate(params):
+            C.memmove(C.byref(arr, i * C.sizeof(IcpParams)), C.byref(p), C.sizeof(IcpParams))
+        return arr
+
+    def icp_align_batch(self, locals_: Sequence[np.ndarray], lmap: "LocalMap", init_poses, params: Sequence[IcpParams]):
+        flat, offs, stride = self._concat(locals_)
+        B = len(locals_)
+        init_poses = _pose(init_poses).reshape(B, 12)
+        parr = self._params_array(params)
+        out = (IcpResult * B)()
+        self.check(self.lib.mlo_icp_align_batch(self.h, B, flat.ctypes.data, stride, offs.ctypes.data, lmap.h,
+                                                init_poses.ctypes.data, parr, out))
+        return list(out)
+
+    def scan_register(self, lmap: "LocalMap", raw, fp: Filter1Params, init_pose, params: IcpParams, insert: bool = False,
+                      cull_dist: float = 0.0) -> IcpResult:
+        raw, init_pose = _pts(raw), _pose(init_pose)
+        res = IcpResult()
+        self.check(self.lib.mlo_scan_register(self.h, lmap.h, raw.ctypes.data, raw.shape[1], len(raw), C.byref(fp),
+                                              init_pose.ctypes.data, C.byref(params), int(insert), cull_dist,
+                                              C.byref(res)))
+        return res
+
+    def scan_register_batch(self, lmap: "LocalMap", raws: Sequence[np.ndarray], fps: Sequence[Filter1Params], init_poses,
+                            params: Sequence[IcpParams]):
+        flat, offs, stride = self._concat(raws)
+        return self.scan_register_batch_flat(lmap, flat, offs, stride, fps, init_poses, params)
+
+    def scan_register_batch_flat(self, lmap, flat, offs, stride, fps, init_poses, params):
+        B = len(offs) - 1
+        init_poses = _pose(init_poses).reshape(B, 12)
+        farr = (Filter1Params * B)(*fps)
+        parr = self._params_array(params)
+        out = (IcpResult * B)()
+        self.check(self.lib.mlo_scan_register_batch(self.h, lmap.h, B, flat.ctypes.data, stride, offs.ctypes.data, farr,
+                                                    init_poses.ctypes.data, parr, out))
+        return list(out)
+
+    def upload_batch(self, clouds: Sequence[np.ndarray]) -> "DeviceClouds":
+        flat, offs, stride = self._concat(clouds)
+        h = C.c_void_p()
+        self.check(self.lib.mlo_dcloud_upload_batch(self.h, flat.ctypes.data, stride, len(clouds), offs.ctypes.data,
+                                                    C.byref(h)))
+        return DeviceClouds(self, h, len(clouds))
+
+    def scan_register_batch_resident(self, lmap, dclouds: "DeviceClouds", fps, init_poses, params):
+        B = dclouds.n_clouds
+        init_poses = _pose(init_poses).reshape(B, 12)
+        farr = (Filter1Params * B)(*fps)
+        parr = self._params_array(params)
+        out = (IcpResult * B)()
+        self.check(self.lib.mlo_scan_register_batch_resident(self.h, lmap.h, dclouds.h, farr, init_poses.ctypes.data,
+                                                             parr, out))
+        return list(out)
+
+    def icp_align_batch_resident(self, dclouds: "DeviceClouds", lmap, init_poses, params):
+        B = dclouds.n_clouds
+        init_poses = _pose(init_poses).reshape(B, 12)
+        parr = self._params_array(params)
+        out = (IcpResult * B)()
+        self.check(self.lib.mlo_icp_align_batch_resident(self.h, dclouds.h, lmap.h, init_poses.ctypes.data, parr, out))
+        return list(out)
+
+
+class DeviceClouds:
+    def __init__(self, ctx: Context, h, n_clouds: int):
+        self.ctx, self.h, self.n_clouds = ctx, h, n_clouds
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.mlo_dcloud_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class LocalMap:
+    """Hash-voxel local map in HBM: mola::HashedVoxelPointCloud (kind 0) or mola::NDT (kind 1)."""
+
+    def __init__(self, ctx: Context, voxel_size: float = 1.0, max_points_per_voxel: int = 20,
+                 min_distance_between_points: float = 0.0, capacity_voxels: int = 1 << 18, kind: int = capi.MAP_POINTS,
+                 max_eigen_ratio_for_planes: float = 0.05, min_points_for_plane: int = 5):
+        self.ctx = ctx
+        p = MapParams(kind, voxel_size, max_points_per_voxel, min_distance_between_points, max_eigen_ratio_for_planes,
+                      min_points_for_plane, capacity_voxels)
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mlo_map_create(ctx.h, C.byref(p), C.byref(h)))
+        self.h = h
+        self.params = p
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.mlo_map_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def clear(self):
+        self.ctx.check(self.ctx.lib.mlo_map_clear(self.h))
+
+    def insert(self, pts, pose):
+        pts, pose = _pts(pts), _pose(pose)
+        self.ctx.check(self.ctx.lib.mlo_map_insert(self.h, pts.ctypes.data, pts.shape[1], len(pts), pose.ctypes.data))
+
+    def insert_soa(self, x, y, z, pose):
+        x, y, z = (np.ascontiguousarray(v, np.float32) for v in (x, y, z))
+        pose = _pose(pose)
+        self.ctx.check(self.ctx.lib.mlo_map_insert_soa(self.h, x.ctypes.data, y.ctypes.data, z.ctypes.data, len(x),
+                                                       pose.ctypes.data))
+
+    def cull(self, sensor_xyz, dist: float):
+        s = np.ascontiguousarray(sensor_xyz, dtype=np.float64)
+        self.ctx.check(self.ctx.lib.mlo_map_cull(self.h, s.ctypes.data, dist))
+
+    def stats(self):
+        a, b = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.mlo_map_stats(self.h, C.byref(a), C.byref(b)))
+        return a.value, b.value
+
+    def nn_single(self, q):
+        q = _pts(q)
+        n = len(q)
+        xyz, d2, f = np.empty((max(n, 1), 3), np.float32), np.empty(max(n, 1), np.float32), np.empty(max(n, 1), np.uint8)
+        self.ctx.check(self.ctx.lib.mlo_map_nn_single(self.h, q.ctypes.data, q.shape[1], n, xyz.ctypes.data,
+                                                      d2.ctypes.data, f.ctypes.data))
+        return xyz[:n], d2[:n], f[:n].astype(bool)
+
+    def export(self):
+        nv, npts = C.c_uint64(), C.c_uint64()
+        self.ctx.check(self.ctx.lib.mlo_map_export(self.h, None, None, None, 0, 0, C.byref(nv), C.byref(npts)))
+        keys, cnt = np.empty((max(nv.value, 1), 3), np.int32), np.empty(max(nv.value, 1), np.uint32)
+        xyz = np.empty((max(npts.value, 1), 3), np.float32)
+        self.ctx.check(self.ctx.lib.mlo_map_export(self.h, keys.ctypes.data, cnt.ctypes.data, xyz.ctypes.data, nv.value,
+                                                   npts.value, C.byref(nv), C.byref(npts)))
+        return keys[:nv.value], cnt[:nv.value], xyz[:npts.value]

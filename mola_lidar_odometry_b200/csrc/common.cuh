@@ -1,0 +1,74 @@
+// common.cuh — shared device/host helpers of libmlo_b200 (sm_100a).
+//
+// Bit-exactness rules (DESIGN.md "Numerics"): the translation unit is compiled with --fmad=false so
+// every float/double expression below rounds exactly as written, in the same operation order as the
+// CPU statement of the algorithm; voxel indices, NN argmin and threshold tests are therefore
+// bit-identical to the reference arithmetic, while the double-precision normal-equation sums differ
+// only by summation order.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "mlo_b200.h"
+
+#define MLO_HD __host__ __device__ __forceinline__
+#define MLO_D __device__ __forceinline__
+
+namespace mlo {
+
+constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
+constexpr int32_t KEY_BIAS = 1 << 20;  // 21 bits per axis
+constexpr uint32_t HARD_LIMIT_PTS = 32; // upstream HARDLIMIT_MAX_POINTS_PER_VOXEL
+enum : uint32_t { ERR_CAPACITY = 1u, ERR_KEY_RANGE = 2u };  // device-side error bits
+
+// mola::HashedVoxelPointCloud::coordToGlobalIdx (pipelines/lidar3d-default.yaml:233 voxel_size):
+// static_cast<int32_t>(coord * voxel_size_inv), truncation toward zero.
+MLO_HD int32_t voxel_index_map(float coord, float inv_voxel) { return static_cast<int32_t>(coord * inv_voxel); }
+// mp2p_icp_filters::FilterDecimateVoxels grid index (default.yaml:289,316): static_cast<int32_t>(coord / resolution)
+MLO_HD int32_t voxel_index_filter(float coord, float resolution) { return static_cast<int32_t>(coord / resolution); }
+
+MLO_HD bool key_in_range(int32_t k) { return k > -KEY_BIAS && k < KEY_BIAS - 1; }
+MLO_HD uint64_t pack_key(int32_t kx, int32_t ky, int32_t kz) {
+  return (uint64_t(uint32_t(kx + KEY_BIAS) & 0x1FFFFFu) << 42) | (uint64_t(uint32_t(ky + KEY_BIAS) & 0x1FFFFFu) << 21) |
+         uint64_t(uint32_t(kz + KEY_BIAS) & 0x1FFFFFu);
+}
+MLO_HD void unpack_key(uint64_t k, int32_t& kx, int32_t& ky, int32_t& kz) {
+  kx = int32_t((k >> 42) & 0x1FFFFFu) - KEY_BIAS;
+  ky = int32_t((k >> 21) & 0x1FFFFFu) - KEY_BIAS;
+  kz = int32_t(k & 0x1FFFFFu) - KEY_BIAS;
+}
+// 64-bit finaliser (splitmix / murmur3 style): spreads neighbouring cells over the table.
+MLO_HD uint64_t hash_key(uint64_t k) {
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return k;
+}
+
+// Row-major 3x4 pose in double.
+struct Pose34 {
+  double m[12];
+};
+
+// CPose3D::composePoint evaluated in double and stored as float, operation order
+// R0*x + R1*y + R2*z + t (left to right), matching the CPU statement bit for bit.
+MLO_HD void compose_point_f(const double* T, float lx, float ly, float lz, float& gx, float& gy, float& gz) {
+  const double x = lx, y = ly, z = lz;
+  gx = static_cast<float>(T[0] * x + T[1] * y + T[2] * z + T[3]);
+  gy = static_cast<float>(T[4] * x + T[5] * y + T[6] * z + T[7]);
+  gz = static_cast<float>(T[8] * x + T[9] * y + T[10] * z + T[11]);
+}
+
+MLO_HD float sqr_dist(float ax, float ay, float az, float bx, float by, float bz) {
+  const float dx = ax - bx, dy = ay - by, dz = az - bz;
+  return dx * dx + dy * dy + dz * dz;
+}
+
+}  // namespace mlo

@@ -1,0 +1,1048 @@
+// mlo_b200.cu — C ABI (include/mlo_b200.h) over the sm_100a kernels in map.cuh / filter.cuh / icp.cuh.
+// Host side only orchestrates: it owns device memory, the context stream and the launch sequence.
+// There is no CPU implementation of any compute entry point in this library.
+#include <algorithm>
+#include <map>
+#include <mutex>
+#include <vector>
+
+#include "filter.cuh"
+#include "icp.cuh"
+#include "map.cuh"
+#include "se3.cuh"
+
+using namespace mlo;
+
+// ------------------------------------------------------------------ small host utilities
+struct DBuf {  // grow-only device buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, size_t(1) << 16);
+    want = (want + 255) & ~size_t(255);
+    cudaError_t e = cudaMalloc(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFree(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+struct HBuf {  // grow-only pinned host buffer
+  void* p = nullptr;
+  size_t cap = 0;
+  cudaError_t ensure(size_t bytes) {
+    if (bytes <= cap) return cudaSuccess;
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+    size_t want = std::max(bytes, size_t(1) << 12);
+    cudaError_t e = cudaMallocHost(&p, want);
+    if (e == cudaSuccess) cap = want;
+    return e;
+  }
+  void release() {
+    if (p) cudaFreeHost(p);
+    p = nullptr;
+    cap = 0;
+  }
+  template <class T>
+  T* as() const {
+    return static_cast<T*>(p);
+  }
+};
+
+struct mlo_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  std::string err;
+  uint64_t launches = 0;
+  int sm_count = 0, cc_major = 0, cc_minor = 0;
+  std::string dev_name;
+  // scratch
+  DBuf d_in, d_local, d_pairA, d_pairB, d_partials, d_partcnt, d_probs, d_states, d_tables, d_init, d_misc;
+  DBuf d_f_tab, d_f_pslot, d_f_flags, d_f_blk, d_f_jobs, d_f_cnt, d_f_stage1, d_f_map, d_f_icp;
+  DBuf d_ins_g, d_ins_slot, d_ins_next;
+  HBuf h_misc, h_states, h_stage;
+  // profiling
+  bool prof_on = false;
+  mlo_profile prof{};
+  std::vector<cudaEvent_t> ev_pool;
+  size_t ev_used = 0;
+  struct Span {
+    int bucket;
+    size_t e0, e1;
+  };
+  std::vector<Span> spans;
+};
+
+struct mlo_map {
+  mlo_ctx* ctx = nullptr;
+  mlo_map_params prm{};
+  MapDev dev{};
+  MapDev alt{};  // second buffer set for filtered rebuilds (allocated on first cull)
+  bool alt_ready = false;
+  uint64_t table_size = 0;
+  int32_t* head = nullptr;  // per-slot scratch list heads for insert
+};
+
+struct mlo_dcloud {
+  mlo_ctx* ctx = nullptr;
+  float4* pts = nullptr;
+  uint64_t n = 0;
+  std::vector<uint64_t> offsets;  // n_clouds + 1
+};
+
+namespace {
+
+int fail(mlo_ctx* c, int code, const std::string& msg) {
+  if (c) c->err = msg;
+  return code;
+}
+#define CU(ctx, call)                                                                                          \
+  do {                                                                                                         \
+    cudaError_t e__ = (call);                                                                                  \
+    if (e__ != cudaSuccess)                                                                                    \
+      return fail(ctx, MLO_ERR_CUDA, std::string(#call) + ": " + cudaGetErrorString(e__) + " @" + std::to_string(__LINE__)); \
+  } while (0)
+#define LAUNCH(ctx, kern, grid, block, ...)            \
+  do {                                                 \
+    kern<<<grid, block, 0, (ctx)->stream>>>(__VA_ARGS__); \
+    (ctx)->launches++;                                 \
+  } while (0)
+
+struct DeviceGuard {
+  int prev = 0;
+  explicit DeviceGuard(int d) {
+    cudaGetDevice(&prev);
+    if (prev != d) cudaSetDevice(d);
+    cur = d;
+  }
+  ~DeviceGuard() {
+    if (prev != cur) cudaSetDevice(prev);
+  }
+  int cur;
+};
+
+uint64_t next_pow2(uint64_t v) {
+  uint64_t p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+size_t prof_begin(mlo_ctx* c) {
+  if (!c->prof_on) return 0;
+  if (c->ev_used >= c->ev_pool.size()) {
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    c->ev_pool.push_back(e);
+  }
+  cudaEventRecord(c->ev_pool[c->ev_used], c->stream);
+  return c->ev_used++;
+}
+void prof_end(mlo_ctx* c, int bucket, size_t e0) {
+  if (!c->prof_on) return;
+  const size_t e1 = prof_begin(c);
+  c->spans.push_back({bucket, e0, e1});
+}
+void prof_collect(mlo_ctx* c) {  // call after a stream synchronize
+  if (!c->prof_on) return;
+  for (auto& s : c->spans) {
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, c->ev_pool[s.e0], c->ev_pool[s.e1]);
+    switch (s.bucket) {
+      case 0: c->prof.filter_1st_ms += ms; break;
+      case 1: c->prof.run_icp_ms += ms; break;
+      case 2: c->prof.update_local_map_ms += ms; break;
+      case 3: c->prof.nn_kernel_ms += ms; c->prof.nn_kernel_launches++; break;
+    }
+  }
+  c->spans.clear();
+  c->ev_used = 0;
+}
+
+int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, MapDev& d) {
+  uint32_t cap = p.max_points_per_voxel;
+  if (cap == 0 || cap > HARD_LIMIT_PTS) cap = HARD_LIMIT_PTS;
+  d.cap = cap;
+  d.capacity_voxels = uint32_t(p.capacity_voxels);
+  d.inv_voxel = 1.0f / p.voxel_size;
+  d.min_dist2 = p.min_distance_between_points * p.min_distance_between_points;
+  d.eig_ratio = p.max_eigen_ratio_for_planes;
+  d.min_pts_plane = p.min_points_for_plane ? p.min_points_for_plane : 5;
+  d.kind = p.kind;
+  d.mask = table_size - 1;
+  CU(c, cudaMalloc(&d.slots, table_size * sizeof(uint4)));
+  CU(c, cudaMalloc(&d.pts, size_t(p.capacity_voxels) * cap * sizeof(float4)));
+  CU(c, cudaMalloc(&d.counters, 4 * sizeof(uint32_t)));
+  d.mean = d.normal = nullptr;
+  if (p.kind == MLO_MAP_NDT) {
+    CU(c, cudaMalloc(&d.mean, size_t(p.capacity_voxels) * sizeof(float4)));
+    CU(c, cudaMalloc(&d.normal, size_t(p.capacity_voxels) * sizeof(float4)));
+  }
+  return MLO_OK;
+}
+int clear_map_buffers(mlo_ctx* c, MapDev& d, uint64_t table_size) {
+  CU(c, cudaMemsetAsync(d.slots, 0xFF, table_size * sizeof(uint4), c->stream));
+  CU(c, cudaMemsetAsync(d.counters, 0, 4 * sizeof(uint32_t), c->stream));
+  return MLO_OK;
+}
+void free_map_buffers(MapDev& d) {
+  if (d.slots) cudaFree(d.slots);
+  if (d.pts) cudaFree(d.pts);
+  if (d.counters) cudaFree(d.counters);
+  if (d.mean) cudaFree(d.mean);
+  if (d.normal) cudaFree(d.normal);
+  d = MapDev{};
+}
+
+int check_map_errors(mlo_map* m) {
+  mlo_ctx* c = m->ctx;
+  CU(c, c->h_misc.ensure(64));
+  uint32_t* h = c->h_misc.as<uint32_t>();
+  CU(c, cudaMemcpyAsync(h, m->dev.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h[2] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  if ((h[2] & ERR_CAPACITY) || h[0] > m->dev.capacity_voxels)
+    return fail(c, MLO_ERR_CAPACITY, "map voxel capacity exhausted (" + std::to_string(h[0]) + " > " +
+                                         std::to_string(m->dev.capacity_voxels) + ")");
+  return MLO_OK;
+}
+
+// device-side insert of n points already on the device (float array with stride)
+int map_insert_device(mlo_map* m, const float* d_pts, uint32_t stride, uint64_t n, const double pose[12]) {
+  mlo_ctx* c = m->ctx;
+  if (n == 0) return MLO_OK;
+  CU(c, c->d_ins_g.ensure(n * sizeof(float4)));
+  CU(c, c->d_ins_slot.ensure(n * sizeof(uint32_t)));
+  CU(c, c->d_ins_next.ensure(n * sizeof(int32_t)));
+  Pose34 T;
+  std::memcpy(T.m, pose, sizeof(T.m));
+  const uint32_t nb = uint32_t((n + 255) / 256);
+  LAUNCH(c, k_insert_link, nb, 256, m->dev, d_pts, stride, uint32_t(n), T, c->d_ins_g.as<float4>(),
+         c->d_ins_slot.as<uint32_t>(), m->head, c->d_ins_next.as<int32_t>());
+  LAUNCH(c, k_insert_commit, nb, 256, m->dev, uint32_t(n), c->d_ins_g.as<float4>(), c->d_ins_slot.as<uint32_t>(),
+         m->head, c->d_ins_next.as<int32_t>());
+  CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+
+int map_rebuild(mlo_map* m, bool use_filter, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
+  mlo_ctx* c = m->ctx;
+  if (!m->alt_ready) {
+    int rc = alloc_map_buffers(c, m->prm, m->table_size, m->alt);
+    if (rc != MLO_OK) return rc;
+    m->alt_ready = true;
+  }
+  int rc = clear_map_buffers(c, m->alt, m->table_size);
+  if (rc != MLO_OK) return rc;
+  const uint64_t threads = m->table_size * 32;
+  LAUNCH(c, k_rebuild, uint32_t((threads + 255) / 256), 256, m->dev, m->alt, m->table_size, sx, sy, sz, d,
+         use_filter ? 1 : 0);
+  CU(c, cudaGetLastError());
+  std::swap(m->dev, m->alt);
+  return MLO_OK;
+}
+
+void fill_decim(DecimJob& j, const mlo_decimate_params& p, bool with_predicates) {
+  j.resolution = p.voxel_filter_resolution;
+  j.min_pts = p.minimum_input_points_to_filter;
+  j.use_range = with_predicates && p.use_range;
+  j.rmin2 = p.range_min * p.range_min;
+  j.rmax2 = p.range_max * p.range_max;
+  j.use_bbox = with_predicates && p.use_bbox_outside;
+  for (int k = 0; k < 3; k++) {
+    j.bmin[k] = p.bbox_min[k];
+    j.bmax[k] = p.bbox_max[k];
+  }
+}
+
+// Device filter pipeline over a batch of raw clouds resident on the device.
+//   stage 1: decimate(raw, for_map.resolution)                  -> s1 (float4)
+//   stage 2: range/bbox predicates -> map layer ; decimate(.., for_icp.resolution) -> icp layer
+// Outputs per cloud b live at [out_off[b], ...) of d_f_map / d_f_icp with device counts in d_f_cnt
+// (layout per cloud: [n_s1, n_map, n_icp, npred1, npred2, err]).
+struct FilterBatch {
+  uint32_t n_clouds = 0;
+  std::vector<uint64_t> out_off;  // per-cloud output offset (== raw offset: outputs never exceed inputs)
+  uint32_t max_n = 0;
+};
+constexpr uint32_t CNT_STRIDE = 8;
+
+int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n_clouds, const uint64_t* offsets,
+                     const mlo_filter1_params* fps, bool single_decimate_idx, uint32_t* d_idx_out, FilterBatch& fb) {
+  fb.n_clouds = n_clouds;
+  fb.out_off.assign(offsets, offsets + n_clouds + 1);
+  const uint64_t total = offsets[n_clouds];
+  uint32_t max_n = 0;
+  for (uint32_t b = 0; b < n_clouds; b++) max_n = std::max<uint32_t>(max_n, uint32_t(offsets[b + 1] - offsets[b]));
+  fb.max_n = max_n;
+  if (total == 0 || max_n == 0) return MLO_OK;
+  // scratch hash tables: one per cloud per stage, sized 2x the cloud (power of two)
+  std::vector<uint64_t> tab_off(n_clouds + 1, 0);
+  for (uint32_t b = 0; b < n_clouds; b++)
+    tab_off[b + 1] = tab_off[b] + next_pow2(std::max<uint64_t>(2 * (offsets[b + 1] - offsets[b]), 1024));
+  const uint64_t tab_total = tab_off[n_clouds];
+  const uint32_t nblk_max = (max_n + DECIM_BLOCK - 1) / DECIM_BLOCK;
+  std::vector<uint64_t> blk_off(n_clouds + 1, 0);
+  for (uint32_t b = 0; b < n_clouds; b++)
+    blk_off[b + 1] = blk_off[b] + (offsets[b + 1] - offsets[b] + DECIM_BLOCK - 1) / DECIM_BLOCK;
+  const uint64_t blk_total = blk_off[n_clouds];
+
+  CU(c, c->d_f_tab.ensure(2 * tab_total * (sizeof(uint64_t) + sizeof(uint32_t))));
+  CU(c, c->d_f_pslot.ensure(2 * total * sizeof(uint32_t)));
+  CU(c, c->d_f_flags.ensure(2 * total));
+  CU(c, c->d_f_blk.ensure(2 * blk_total * 4 * sizeof(uint32_t)));
+  CU(c, c->d_f_cnt.ensure(size_t(n_clouds) * CNT_STRIDE * sizeof(uint32_t)));
+  CU(c, c->d_f_stage1.ensure(total * sizeof(float4)));
+  CU(c, c->d_f_map.ensure(total * sizeof(float4)));
+  CU(c, c->d_f_icp.ensure(total * sizeof(float4)));
+  CU(c, c->d_f_jobs.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
+  CU(c, c->h_stage.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
+
+  uint64_t* keys = c->d_f_tab.as<uint64_t>();
+  uint32_t* firsts = reinterpret_cast<uint32_t*>(keys + 2 * tab_total);
+  uint32_t* cnt = c->d_f_cnt.as<uint32_t>();
+  DecimJob* hj = c->h_stage.as<DecimJob>();
+  for (uint32_t b = 0; b < n_clouds; b++) {
+    const uint32_t n = uint32_t(offsets[b + 1] - offsets[b]);
+    for (int s = 0; s < 2; s++) {
+      DecimJob& j = hj[s * n_clouds + b];
+      std::memset(&j, 0, sizeof(j));
+      const uint64_t t0 = s * tab_total + tab_off[b];
+      j.tab_keys = keys + t0;
+      j.tab_first = firsts + t0;
+      j.tab_mask = uint32_t(tab_off[b + 1] - tab_off[b]) - 1;
+      j.pslot = c->d_f_pslot.as<uint32_t>() + s * total + offsets[b];
+      j.flags = c->d_f_flags.as<uint8_t>() + s * total + offsets[b];
+      j.blockcnt = c->d_f_blk.as<uint32_t>() + (s * blk_total + blk_off[b]) * 2;
+      j.blockoff = c->d_f_blk.as<uint32_t>() + 2 * blk_total * 2 + (s * blk_total + blk_off[b]) * 2;
+      j.err = cnt + b * CNT_STRIDE + 5;
+    }
+    DecimJob& j1 = hj[b];
+    j1.in = d_raw + offsets[b] * stride;
+    j1.in_stride = stride;
+    j1.n_in_static = n;
+    fill_decim(j1, fps[b].for_map, single_decimate_idx);
+    j1.npred = cnt + b * CNT_STRIDE + 3;
+    j1.outB = c->d_f_stage1.as<float4>() + offsets[b];
+    j1.nB = cnt + b * CNT_STRIDE + 0;
+    j1.outB_idx = single_decimate_idx ? d_idx_out + offsets[b] : nullptr;
+    DecimJob& j2 = hj[n_clouds + b];
+    j2.in = reinterpret_cast<const float*>(c->d_f_stage1.as<float4>() + offsets[b]);
+    j2.in_stride = 4;
+    j2.n_in_dev = cnt + b * CNT_STRIDE + 0;
+    fill_decim(j2, fps[b].for_icp, true);
+    j2.npred = cnt + b * CNT_STRIDE + 4;
+    j2.outA = c->d_f_map.as<float4>() + offsets[b];
+    j2.nA = cnt + b * CNT_STRIDE + 1;
+    j2.outB = c->d_f_icp.as<float4>() + offsets[b];
+    j2.nB = cnt + b * CNT_STRIDE + 2;
+  }
+  const int n_stages = single_decimate_idx ? 1 : 2;
+  CU(c, cudaMemcpyAsync(c->d_f_jobs.p, hj, 2 * size_t(n_clouds) * sizeof(DecimJob), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemsetAsync(c->d_f_tab.p, 0xFF, 2 * tab_total * (sizeof(uint64_t) + sizeof(uint32_t)), c->stream));
+  CU(c, cudaMemsetAsync(cnt, 0, size_t(n_clouds) * CNT_STRIDE * sizeof(uint32_t), c->stream));
+  const dim3 grid(nblk_max, n_clouds);
+  for (int s = 0; s < n_stages; s++) {
+    const DecimJob* dj = c->d_f_jobs.as<DecimJob>() + s * n_clouds;
+    LAUNCH(c, k_decim_hash, grid, DECIM_BLOCK, dj);
+    LAUNCH(c, k_decim_flag, grid, DECIM_BLOCK, dj);
+    LAUNCH(c, k_decim_scan, n_clouds, 512, dj);
+    LAUNCH(c, k_decim_scatter, grid, DECIM_BLOCK, dj);
+  }
+  CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+
+__global__ void k_to_float4(const float* __restrict__ src, uint32_t stride, uint64_t n, float4* __restrict__ dst) {
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = src + i * stride;
+  dst[i] = make_float4(p[0], p[1], p[2], 0.f);
+}
+__global__ void k_soa_to_float4(const float* __restrict__ x, const float* __restrict__ y, const float* __restrict__ z, uint64_t n,
+                                float4* __restrict__ dst) {
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  dst[i] = make_float4(x[i], y[i], z[i], 0.f);
+}
+
+int upload_strided(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t n, DBuf& dst) {
+  if (stride != 3 && stride != 4) return fail(c, MLO_ERR_INVALID_ARG, "stride_floats must be 3 or 4");
+  CU(c, dst.ensure(std::max<size_t>(n * stride * sizeof(float), 16)));
+  if (n) CU(c, cudaMemcpyAsync(dst.p, pts, n * stride * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+  return MLO_OK;
+}
+
+// The batched align driver over device-resident float4 local points.
+int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64_t* offsets, const mlo_map* map,
+                       const double* init_poses, const mlo_icp_params* params, mlo_icp_result* out) {
+  if (B == 0) return MLO_OK;
+  // ---- problems + tables
+  std::vector<IcpProblem> probs(B);
+  std::vector<double> tables;
+  std::map<const double*, size_t> seen;
+  auto put = [&](const double* t, uint32_t len) -> size_t {
+    if (!t || len == 0) return size_t(-1);
+    auto it = seen.find(t);
+    if (it != seen.end()) return it->second;
+    const size_t off = tables.size();
+    tables.insert(tables.end(), t, t + len);
+    seen[t] = off;
+    return off;
+  };
+  std::vector<size_t> toff(3 * size_t(B));
+  uint32_t part_total = 0, max_blocks = 0, max_it = 0, max_inner = 1;
+  for (uint32_t b = 0; b < B; b++) {
+    const mlo_icp_params& p = params[b];
+    IcpProblem& P = probs[b];
+    std::memset(&P, 0, sizeof(P));
+    if ((p.matcher_mask & MLO_MATCHER_PT2PL) && map->prm.kind != MLO_MAP_NDT)
+      return fail(c, MLO_ERR_UNSUPPORTED, "Matcher_Point2Plane needs an NDT map");
+    if (p.solver == MLO_SOLVER_HORN && (p.matcher_mask & MLO_MATCHER_PT2PL))
+      return fail(c, MLO_ERR_UNSUPPORTED, "Solver_Horn handles point-to-point pairings only");
+    if (p.table_len == 0 || !p.pt2pt_threshold_by_iter || !p.kernel_param_by_iter)
+      if (p.matcher_mask & MLO_MATCHER_PT2PT) return fail(c, MLO_ERR_INVALID_ARG, "missing per-iteration tables");
+    P.q_begin = offsets[b];
+    P.n_q = uint32_t(offsets[b + 1] - offsets[b]);
+    P.max_iterations = p.max_iterations;
+    P.min_abs_step_trans = p.min_abs_step_trans;
+    P.min_abs_step_rot = p.min_abs_step_rot;
+    P.solver = p.solver;
+    P.gn_max_iterations = std::max<uint32_t>(1, p.gn_max_iterations);
+    P.gn_min_delta = p.gn_min_delta;
+    P.robust_kernel = p.robust_kernel;
+    P.matcher_mask = p.matcher_mask;
+    P.table_len = p.table_len;
+    toff[3 * b] = put(p.pt2pt_threshold_by_iter, p.table_len);
+    toff[3 * b + 1] = put(p.pt2pl_threshold_by_iter, p.table_len);
+    toff[3 * b + 2] = put(p.kernel_param_by_iter, p.table_len);
+    const double ang = p.threshold_angular_deg * M_PI / 180.0;
+    P.ang2 = float(ang * ang);
+    P.w_pt2pt = p.pt2pt_weight;
+    P.w_pt2pl = p.pt2pl_weight;
+    P.has_prior = p.has_prior;
+    std::memcpy(P.prior_pose, p.prior_pose_3x4, sizeof(P.prior_pose));
+    std::memcpy(P.prior_info, p.prior_info_6x6, sizeof(P.prior_info));
+    P.hook_enabled = p.hook_enabled;
+    P.hook_min_trans = p.hook_min_trans;
+    P.hook_min_rot = p.hook_min_rot_rad;
+    std::memcpy(P.hook_checkpoint, p.hook_checkpoint_pose_3x4, sizeof(P.hook_checkpoint));
+    P.n_blocks = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
+    P.part_begin = part_total;
+    part_total += P.n_blocks;
+    max_blocks = std::max(max_blocks, P.n_blocks);
+    max_it = std::max(max_it, P.max_iterations);
+    if (P.solver == MLO_SOLVER_GAUSS_NEWTON) max_inner = std::max(max_inner, P.gn_max_iterations);
+  }
+  CU(c, c->d_tables.ensure(std::max<size_t>(tables.size(), 1) * sizeof(double)));
+  if (!tables.empty())
+    CU(c, cudaMemcpyAsync(c->d_tables.p, tables.data(), tables.size() * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  for (uint32_t b = 0; b < B; b++) {
+    const double* base = c->d_tables.as<double>();
+    probs[b].thr_pt2pt = toff[3 * b] == size_t(-1) ? nullptr : base + toff[3 * b];
+    probs[b].thr_pt2pl = toff[3 * b + 1] == size_t(-1) ? nullptr : base + toff[3 * b + 1];
+    probs[b].kparam = toff[3 * b + 2] == size_t(-1) ? nullptr : base + toff[3 * b + 2];
+  }
+  const uint64_t total_q = offsets[B];
+  CU(c, c->d_probs.ensure(B * sizeof(IcpProblem)));
+  CU(c, c->d_states.ensure(B * sizeof(IcpState)));
+  CU(c, c->d_init.ensure(B * 12 * sizeof(double)));
+  CU(c, c->d_pairA.ensure(std::max<size_t>(total_q, 1) * sizeof(float4)));
+  CU(c, c->d_pairB.ensure(std::max<size_t>(total_q, 1) * sizeof(float4)));
+  CU(c, c->d_partials.ensure(std::max<size_t>(part_total, 1) * NACC * sizeof(double)));
+  CU(c, c->d_partcnt.ensure(std::max<size_t>(part_total, 1) * 2 * sizeof(uint32_t)));
+  CU(c, c->d_misc.ensure(256));
+  CU(c, c->h_misc.ensure(256));
+  CU(c, c->h_states.ensure(B * sizeof(IcpState)));
+  CU(c, cudaMemcpyAsync(c->d_probs.p, probs.data(), B * sizeof(IcpProblem), cudaMemcpyHostToDevice, c->stream));
+  CU(c, cudaMemcpyAsync(c->d_init.p, init_poses, B * 12 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+  uint32_t* d_active = c->d_misc.as<uint32_t>();
+  uint32_t* h_active = c->h_misc.as<uint32_t>() + 8;
+  CU(c, cudaMemsetAsync(d_active, 0, sizeof(uint32_t), c->stream));
+  const IcpProblem* dP = c->d_probs.as<IcpProblem>();
+  IcpState* dS = c->d_states.as<IcpState>();
+  LAUNCH(c, k_init_states, (B + 127) / 128, 128, dP, dS, c->d_init.as<double>(), B, d_active);
+
+  const size_t e_icp = prof_begin(c);
+  const dim3 grid(std::max(max_blocks, 1u), B);
+  const uint32_t check_every = 4;
+  for (uint32_t it = 0; it < max_it; it++) {
+    const size_t e_nn = prof_begin(c);
+    LAUNCH(c, k_match_accumulate, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+           c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+    prof_end(c, 3, e_nn);
+    LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
+    for (uint32_t inner = 1; inner < max_inner; inner++) {
+      LAUNCH(c, k_accumulate, grid, ICP_BLOCK, dP, dS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
+             c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+      LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active);
+    }
+    if ((it % check_every) == check_every - 1 || it + 1 == max_it) {
+      CU(c, cudaMemcpyAsync(h_active, d_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      if (*h_active == 0) break;
+    }
+  }
+  prof_end(c, 1, e_icp);
+  CU(c, cudaMemcpyAsync(c->h_states.p, dS, B * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  const IcpState* hs = c->h_states.as<IcpState>();
+  for (uint32_t b = 0; b < B; b++) {
+    const IcpState& S = hs[b];
+    mlo_icp_result& r = out[b];
+    std::memset(&r, 0, sizeof(r));
+    std::memcpy(r.pose_3x4, S.T, sizeof(r.pose_3x4));
+    if (S.have_H) spd6_inverse(S.H, r.cov_6x6);
+    r.n_iterations = S.it;
+    r.termination = S.term;
+    r.n_pairings = S.n_pairs;
+    r.n_potential_pairings = S.n_potential;
+    r.quality = S.n_potential ? double(S.n_pairs) / double(S.n_potential) : 0.0;
+    r.n_query_iterations = S.n_query_it;
+    r.n_candidate_points = S.n_cand;
+    if (c->prof_on) {
+      c->prof.nn_query_iterations += S.n_query_it;
+      c->prof.nn_candidate_points += S.n_cand;
+      c->prof.nn_blocks += uint64_t(probs[b].n_blocks) * (S.n_query_it / std::max<uint32_t>(1, probs[b].n_q));
+    }
+  }
+  prof_collect(c);
+  return MLO_OK;
+}
+
+}  // namespace
+
+// =================================================================== C ABI
+extern "C" {
+
+int mlo_abi_version(void) { return MLO_ABI_VERSION; }
+
+int mlo_create(int cuda_device, mlo_ctx** out) {
+  if (!out) return MLO_ERR_INVALID_ARG;
+  *out = nullptr;
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0 || cuda_device < 0 || cuda_device >= n) return MLO_ERR_NO_DEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cuda_device) != cudaSuccess) return MLO_ERR_CUDA;
+  if (prop.major != 10) return MLO_ERR_NO_DEVICE;  // sm_100a cubin only: no other architecture, no CPU path
+  auto* c = new mlo_ctx;
+  c->device = cuda_device;
+  c->sm_count = prop.multiProcessorCount;
+  c->cc_major = prop.major;
+  c->cc_minor = prop.minor;
+  c->dev_name = prop.name;
+  cudaSetDevice(cuda_device);
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete c;
+    return MLO_ERR_CUDA;
+  }
+  *out = c;
+  return MLO_OK;
+}
+
+void mlo_destroy(mlo_ctx* c) {
+  if (!c) return;
+  DeviceGuard g(c->device);
+  cudaStreamSynchronize(c->stream);
+  for (DBuf* b : {&c->d_in, &c->d_local, &c->d_pairA, &c->d_pairB, &c->d_partials, &c->d_partcnt, &c->d_probs, &c->d_states,
+                  &c->d_tables, &c->d_init, &c->d_misc, &c->d_f_tab, &c->d_f_pslot, &c->d_f_flags, &c->d_f_blk, &c->d_f_jobs,
+                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next})
+    b->release();
+  c->h_misc.release();
+  c->h_states.release();
+  c->h_stage.release();
+  for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaStreamDestroy(c->stream);
+  delete c;
+}
+
+const char* mlo_last_error(const mlo_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int mlo_device_info(const mlo_ctx* c, char* name, uint32_t name_len, int* sm_count, int* cc_major, int* cc_minor) {
+  if (!c) return MLO_ERR_INVALID_ARG;
+  if (name && name_len) {
+    std::strncpy(name, c->dev_name.c_str(), name_len - 1);
+    name[name_len - 1] = 0;
+  }
+  if (sm_count) *sm_count = c->sm_count;
+  if (cc_major) *cc_major = c->cc_major;
+  if (cc_minor) *cc_minor = c->cc_minor;
+  return MLO_OK;
+}
+void* mlo_stream(const mlo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+uint64_t mlo_launch_count(const mlo_ctx* c) { return c ? c->launches : 0; }
+
+int32_t mlo_voxel_index(float coord, float voxel_size) { return voxel_index_map(coord, 1.0f / voxel_size); }
+
+// ------------------------------------------------------------------ map
+int mlo_map_create(mlo_ctx* c, const mlo_map_params* p, mlo_map** out) {
+  if (!c || !p || !out) return MLO_ERR_INVALID_ARG;
+  *out = nullptr;
+  if (!(p->voxel_size > 0.f) || p->capacity_voxels == 0 || p->capacity_voxels > (1ull << 27))
+    return fail(c, MLO_ERR_INVALID_ARG, "voxel_size must be > 0 and capacity_voxels in [1, 2^27]");
+  if (p->kind != MLO_MAP_HASHED_VOXEL_POINTS && p->kind != MLO_MAP_NDT) return fail(c, MLO_ERR_INVALID_ARG, "bad map kind");
+  DeviceGuard g(c->device);
+  auto* m = new mlo_map;
+  m->ctx = c;
+  m->prm = *p;
+  m->table_size = next_pow2(std::max<uint64_t>(4 * p->capacity_voxels, 1024));
+  int rc = alloc_map_buffers(c, *p, m->table_size, m->dev);
+  if (rc == MLO_OK) rc = clear_map_buffers(c, m->dev, m->table_size);
+  if (rc == MLO_OK) {
+    if (cudaMalloc(&m->head, m->table_size * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemsetAsync(m->head, 0xFF, m->table_size * sizeof(int32_t), c->stream) != cudaSuccess)
+      rc = fail(c, MLO_ERR_CUDA, "cudaMalloc(head) failed");
+  }
+  if (rc != MLO_OK) {
+    free_map_buffers(m->dev);
+    delete m;
+    return rc;
+  }
+  *out = m;
+  return MLO_OK;
+}
+
+void mlo_map_destroy(mlo_map* m) {
+  if (!m) return;
+  DeviceGuard g(m->ctx->device);
+  cudaStreamSynchronize(m->ctx->stream);
+  free_map_buffers(m->dev);
+  if (m->alt_ready) free_map_buffers(m->alt);
+  if (m->head) cudaFree(m->head);
+  delete m;
+}
+
+int mlo_map_clear(mlo_map* m) {
+  if (!m) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(m->ctx->device);
+  return clear_map_buffers(m->ctx, m->dev, m->table_size);
+}
+
+int mlo_map_insert(mlo_map* m, const float* pts, uint32_t stride, uint64_t n, const double pose[12]) {
+  if (!m || (!pts && n) || !pose) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = m->ctx;
+  DeviceGuard g(c->device);
+  const size_t e0 = prof_begin(c);
+  int rc = upload_strided(c, pts, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  rc = map_insert_device(m, c->d_in.as<float>(), stride, n, pose);
+  prof_end(c, 2, e0);
+  if (rc != MLO_OK) return rc;
+  rc = check_map_errors(m);
+  prof_collect(c);
+  return rc;
+}
+
+int mlo_map_insert_soa(mlo_map* m, const float* x, const float* y, const float* z, uint64_t n, const double pose[12]) {
+  if (!m || !pose || (n && (!x || !y || !z))) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = m->ctx;
+  DeviceGuard g(c->device);
+  CU(c, c->d_in.ensure(std::max<size_t>(3 * n * sizeof(float), 16)));
+  CU(c, c->d_local.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  float* d = c->d_in.as<float>();
+  if (n) {
+    CU(c, cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + 2 * n, z, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_soa_to_float4, uint32_t((n + 255) / 256), 256, d, d + n, d + 2 * n, n, c->d_local.as<float4>());
+  }
+  int rc = map_insert_device(m, c->d_local.as<float>(), 4, n, pose);
+  if (rc != MLO_OK) return rc;
+  return check_map_errors(m);
+}
+
+int mlo_map_cull(mlo_map* m, const double sensor[3], float dist) {
+  if (!m || !sensor) return MLO_ERR_INVALID_ARG;
+  if (!(dist > 0.f)) return MLO_OK;
+  mlo_ctx* c = m->ctx;
+  DeviceGuard g(c->device);
+  const float inv = m->dev.inv_voxel;
+  const int32_t sx = voxel_index_map(float(sensor[0]), inv), sy = voxel_index_map(float(sensor[1]), inv),
+                sz = voxel_index_map(float(sensor[2]), inv);
+  const int32_t d = int32_t(std::ceil(dist * inv));
+  const size_t e0 = prof_begin(c);
+  int rc = map_rebuild(m, true, sx, sy, sz, d);
+  prof_end(c, 2, e0);
+  if (rc != MLO_OK) return rc;
+  rc = check_map_errors(m);
+  prof_collect(c);
+  return rc;
+}
+
+int mlo_map_nn_single(const mlo_map* m, const float* q, uint32_t stride, uint64_t n, float* out_xyz, float* out_d2,
+                      uint8_t* out_found) {
+  if (!m || (n && (!q || !out_xyz || !out_d2 || !out_found))) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = m->ctx;
+  DeviceGuard g(c->device);
+  if (n == 0) return MLO_OK;
+  int rc = upload_strided(c, q, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  CU(c, c->d_local.ensure(n * (3 * sizeof(float) + sizeof(float) + 1) + 64));
+  float* dxyz = c->d_local.as<float>();
+  float* dd2 = dxyz + 3 * n;
+  uint8_t* df = reinterpret_cast<uint8_t*>(dd2 + n);
+  LAUNCH(c, k_nn_single, uint32_t((n + 127) / 128), 128, m->dev, c->d_in.as<float>(), stride, uint32_t(n), dxyz, dd2, df);
+  CU(c, cudaMemcpyAsync(out_xyz, dxyz, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_d2, dd2, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_found, df, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+
+int mlo_map_stats(const mlo_map* m, uint64_t* n_voxels, uint64_t* n_points) {
+  if (!m) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = m->ctx;
+  DeviceGuard g(c->device);
+  uint32_t h[4];
+  CU(c, cudaMemcpyAsync(h, m->dev.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (n_voxels) *n_voxels = std::min<uint32_t>(h[0], m->dev.capacity_voxels);
+  if (n_points) *n_points = h[1];
+  return MLO_OK;
+}
+
+int mlo_map_export(const mlo_map* m, int32_t* keys, uint32_t* counts, float* xyz, uint64_t max_voxels, uint64_t max_points,
+                   uint64_t* n_voxels, uint64_t* n_points) {
+  if (!m || !n_voxels || !n_points) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = m->ctx;
+  DeviceGuard g(c->device);
+  uint64_t nv = 0, np = 0;
+  int rc = mlo_map_stats(m, &nv, &np);
+  if (rc != MLO_OK) return rc;
+  *n_voxels = nv;
+  *n_points = np;
+  if (!keys || !counts || !xyz) return MLO_OK;
+  if (nv > max_voxels || np > max_points) return fail(c, MLO_ERR_INVALID_ARG, "export buffers too small");
+  if (nv == 0) return MLO_OK;
+  CU(c, c->d_local.ensure(nv * (sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 64));
+  uint64_t* dk = c->d_local.as<uint64_t>();
+  uint32_t* dc = reinterpret_cast<uint32_t*>(dk + nv);
+  uint32_t* dv = dc + nv;
+  uint32_t* cursor = c->d_misc.p ? c->d_misc.as<uint32_t>() + 16 : nullptr;
+  if (!cursor) {
+    CU(c, c->d_misc.ensure(256));
+    cursor = c->d_misc.as<uint32_t>() + 16;
+  }
+  CU(c, cudaMemsetAsync(cursor, 0, sizeof(uint32_t), c->stream));
+  LAUNCH(c, k_export_list, uint32_t((m->table_size + 255) / 256), 256, m->dev, m->table_size, cursor, dk, dc, dv);
+  std::vector<uint64_t> hk(nv);
+  std::vector<uint32_t> hc(nv), hv(nv);
+  CU(c, cudaMemcpyAsync(hk.data(), dk, nv * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hc.data(), dc, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(hv.data(), dv, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  std::vector<float4> hp(size_t(nv) * m->dev.cap);
+  CU(c, cudaStreamSynchronize(c->stream));
+  // payload of the allocated voxels (ids are dense in [0, nv) right after a rebuild, sparse otherwise)
+  uint32_t max_vid = 0;
+  for (auto v : hv) max_vid = std::max(max_vid, v);
+  hp.resize(size_t(max_vid + 1) * m->dev.cap);
+  CU(c, cudaMemcpyAsync(hp.data(), m->dev.pts, hp.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint32_t> order(nv);
+  for (uint32_t i = 0; i < nv; i++) order[i] = i;
+  std::vector<int32_t> k3(3 * nv);
+  for (uint32_t i = 0; i < nv; i++) unpack_key(hk[i], k3[3 * i], k3[3 * i + 1], k3[3 * i + 2]);
+  std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
+    for (int k = 0; k < 3; k++)
+      if (k3[3 * a + k] != k3[3 * b + k]) return k3[3 * a + k] < k3[3 * b + k];
+    return false;
+  });
+  uint64_t o = 0;
+  for (uint32_t i = 0; i < nv; i++) {
+    const uint32_t s = order[i];
+    for (int k = 0; k < 3; k++) keys[3 * i + k] = k3[3 * s + k];
+    counts[i] = hc[s];
+    for (uint32_t j = 0; j < hc[s]; j++) {
+      if (o >= max_points) return fail(c, MLO_ERR_INVALID_ARG, "export buffers too small");
+      const float4 p = hp[size_t(hv[s]) * m->dev.cap + j];
+      xyz[3 * o] = p.x;
+      xyz[3 * o + 1] = p.y;
+      xyz[3 * o + 2] = p.z;
+      o++;
+    }
+  }
+  *n_points = o;
+  return MLO_OK;
+}
+
+// ------------------------------------------------------------------ filters
+int mlo_voxel_decimate_first(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t n, const mlo_decimate_params* p,
+                             uint32_t* out_idx, uint64_t* out_n) {
+  if (!c || !p || !out_n || (n && (!pts || !out_idx))) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(c->device);
+  *out_n = 0;
+  if (n == 0) return MLO_OK;
+  if (!(p->voxel_filter_resolution > 0.f)) return fail(c, MLO_ERR_INVALID_ARG, "voxel_filter_resolution must be > 0");
+  int rc = upload_strided(c, pts, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  CU(c, c->d_local.ensure(n * sizeof(uint32_t)));
+  mlo_filter1_params fp;
+  std::memset(&fp, 0, sizeof(fp));
+  fp.for_map = *p;
+  fp.for_icp = *p;
+  const uint64_t offs[2] = {0, n};
+  FilterBatch fb;
+  const size_t e0 = prof_begin(c);
+  rc = run_filter_batch(c, c->d_in.as<float>(), stride, 1, offs, &fp, true, c->d_local.as<uint32_t>(), fb);
+  prof_end(c, 0, e0);
+  if (rc != MLO_OK) return rc;
+  uint32_t h[CNT_STRIDE];
+  CU(c, cudaMemcpyAsync(h, c->d_f_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h[5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  *out_n = h[0];
+  CU(c, cudaMemcpyAsync(out_idx, c->d_local.p, size_t(h[0]) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  prof_collect(c);
+  return MLO_OK;
+}
+
+static int download_xyz(mlo_ctx* c, const float4* d, uint64_t n, float* out) {
+  if (n == 0) return MLO_OK;
+  std::vector<float4> tmp(n);
+  CU(c, cudaMemcpyAsync(tmp.data(), d, n * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  for (uint64_t i = 0; i < n; i++) {
+    out[3 * i] = tmp[i].x;
+    out[3 * i + 1] = tmp[i].y;
+    out[3 * i + 2] = tmp[i].z;
+  }
+  return MLO_OK;
+}
+
+int mlo_filter_1st_pass(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t n, const mlo_filter1_params* p,
+                        float* out_map_xyz, uint64_t* out_map_n, float* out_icp_xyz, uint64_t* out_icp_n) {
+  if (!c || !p || !out_map_n || !out_icp_n || (n && !pts)) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(c->device);
+  *out_map_n = *out_icp_n = 0;
+  if (n == 0) return MLO_OK;
+  int rc = upload_strided(c, pts, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  const uint64_t offs[2] = {0, n};
+  FilterBatch fb;
+  const size_t e0 = prof_begin(c);
+  rc = run_filter_batch(c, c->d_in.as<float>(), stride, 1, offs, p, false, nullptr, fb);
+  prof_end(c, 0, e0);
+  if (rc != MLO_OK) return rc;
+  uint32_t h[CNT_STRIDE];
+  CU(c, cudaMemcpyAsync(h, c->d_f_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h[5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  *out_map_n = h[1];
+  *out_icp_n = h[2];
+  if (out_map_xyz) {
+    rc = download_xyz(c, c->d_f_map.as<float4>(), h[1], out_map_xyz);
+    if (rc != MLO_OK) return rc;
+  }
+  if (out_icp_xyz) {
+    rc = download_xyz(c, c->d_f_icp.as<float4>(), h[2], out_icp_xyz);
+    if (rc != MLO_OK) return rc;
+  }
+  prof_collect(c);
+  return MLO_OK;
+}
+
+// ------------------------------------------------------------------ ICP
+void mlo_icp_params_default(mlo_icp_params* p) {
+  if (!p) return;
+  std::memset(p, 0, sizeof(*p));
+  p->max_iterations = 300;       // default.yaml:173
+  p->min_abs_step_trans = 1e-4;  // :174
+  p->min_abs_step_rot = 5e-5;    // :175
+  p->solver = MLO_SOLVER_GAUSS_NEWTON;
+  p->gn_max_iterations = 2;  // :187
+  p->gn_min_delta = 1e-7;
+  p->robust_kernel = MLO_KERNEL_GEMAN_MCCLURE;  // :188
+  p->matcher_mask = MLO_MATCHER_PT2PT;          // :196
+  p->pt2pt_weight = p->pt2pl_weight = 1.0;
+  p->prior_pose_3x4[0] = p->prior_pose_3x4[5] = p->prior_pose_3x4[10] = 1.0;
+  p->hook_checkpoint_pose_3x4[0] = p->hook_checkpoint_pose_3x4[5] = p->hook_checkpoint_pose_3x4[10] = 1.0;
+}
+
+int mlo_icp_align_batch(mlo_ctx* c, uint32_t B, const float* local, uint32_t stride, const uint64_t* offsets,
+                        const mlo_map* map, const double* init_poses, const mlo_icp_params* params, mlo_icp_result* out) {
+  if (!c || !map || !offsets || !init_poses || !params || !out) return MLO_ERR_INVALID_ARG;
+  if (map->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "map belongs to another context");
+  DeviceGuard g(c->device);
+  const uint64_t total = offsets[B];
+  int rc = upload_strided(c, local, stride, total, c->d_in);
+  if (rc != MLO_OK) return rc;
+  CU(c, c->d_local.ensure(std::max<size_t>(total, 1) * sizeof(float4)));
+  if (total) LAUNCH(c, k_to_float4, uint32_t((total + 255) / 256), 256, c->d_in.as<float>(), stride, total, c->d_local.as<float4>());
+  return align_batch_device(c, B, c->d_local.as<float4>(), offsets, map, init_poses, params, out);
+}
+
+int mlo_icp_align(mlo_ctx* c, const float* local, uint32_t stride, uint64_t n, const mlo_map* map, const double init[12],
+                  const mlo_icp_params* p, mlo_icp_result* out) {
+  const uint64_t offs[2] = {0, n};
+  return mlo_icp_align_batch(c, 1, local, stride, offs, map, init, p, out);
+}
+
+int mlo_icp_align_soa(mlo_ctx* c, const float* x, const float* y, const float* z, uint64_t n, const mlo_map* map,
+                      const double init[12], const mlo_icp_params* p, mlo_icp_result* out) {
+  if (!c || !map || !init || !p || !out || (n && (!x || !y || !z))) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(c->device);
+  CU(c, c->d_in.ensure(std::max<size_t>(3 * n * sizeof(float), 16)));
+  CU(c, c->d_local.ensure(std::max<size_t>(n, 1) * sizeof(float4)));
+  float* d = c->d_in.as<float>();
+  if (n) {
+    CU(c, cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    CU(c, cudaMemcpyAsync(d + 2 * n, z, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    LAUNCH(c, k_soa_to_float4, uint32_t((n + 255) / 256), 256, d, d + n, d + 2 * n, n, c->d_local.as<float4>());
+  }
+  const uint64_t offs[2] = {0, n};
+  return align_batch_device(c, 1, c->d_local.as<float4>(), offs, map, init, p, out);
+}
+
+// ------------------------------------------------------------------ device-resident clouds
+int mlo_dcloud_upload_batch(mlo_ctx* c, const float* pts, uint32_t stride, uint32_t n_clouds, const uint64_t* offsets,
+                            mlo_dcloud** out) {
+  if (!c || !out || !offsets || n_clouds == 0) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(c->device);
+  *out = nullptr;
+  const uint64_t total = offsets[n_clouds];
+  int rc = upload_strided(c, pts, stride, total, c->d_in);
+  if (rc != MLO_OK) return rc;
+  auto* dc = new mlo_dcloud;
+  dc->ctx = c;
+  dc->n = total;
+  dc->offsets.assign(offsets, offsets + n_clouds + 1);
+  if (cudaMalloc(&dc->pts, std::max<size_t>(total, 1) * sizeof(float4)) != cudaSuccess) {
+    delete dc;
+    return fail(c, MLO_ERR_CUDA, "cudaMalloc(dcloud) failed");
+  }
+  if (total) LAUNCH(c, k_to_float4, uint32_t((total + 255) / 256), 256, c->d_in.as<float>(), stride, total, dc->pts);
+  CU(c, cudaStreamSynchronize(c->stream));
+  *out = dc;
+  return MLO_OK;
+}
+int mlo_dcloud_upload(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t n, mlo_dcloud** out) {
+  const uint64_t offs[2] = {0, n};
+  return mlo_dcloud_upload_batch(c, pts, stride, 1, offs, out);
+}
+void mlo_dcloud_destroy(mlo_dcloud* d) {
+  if (!d) return;
+  DeviceGuard g(d->ctx->device);
+  cudaStreamSynchronize(d->ctx->stream);
+  if (d->pts) cudaFree(d->pts);
+  delete d;
+}
+uint64_t mlo_dcloud_size(const mlo_dcloud* d) { return d ? d->n : 0; }
+
+int mlo_icp_align_batch_resident(mlo_ctx* c, const mlo_dcloud* local, const mlo_map* map, const double* init_poses,
+                                 const mlo_icp_params* params, mlo_icp_result* out) {
+  if (!c || !local || !map || !init_poses || !params || !out) return MLO_ERR_INVALID_ARG;
+  if (map->ctx != c || local->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "handle belongs to another context");
+  DeviceGuard g(c->device);
+  return align_batch_device(c, uint32_t(local->offsets.size() - 1), local->pts, local->offsets.data(), map, init_poses, params, out);
+}
+
+// filter -> align over device-resident raw clouds (float pointer + stride)
+static int scan_register_device(mlo_ctx* c, const mlo_map* map, uint32_t B, const float* d_raw, uint32_t stride,
+                                const uint64_t* offsets, const mlo_filter1_params* fps, const double* init_poses,
+                                const mlo_icp_params* ips, mlo_icp_result* out, std::vector<uint64_t>* map_layer_n) {
+  FilterBatch fb;
+  const size_t e0 = prof_begin(c);
+  int rc = run_filter_batch(c, d_raw, stride, B, offsets, fps, false, nullptr, fb);
+  prof_end(c, 0, e0);
+  if (rc != MLO_OK) return rc;
+  // the ICP grid depends on the decimated sizes: one small D2H of the device counters
+  std::vector<uint32_t> h(size_t(B) * CNT_STRIDE);
+  CU(c, cudaMemcpyAsync(h.data(), c->d_f_cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  // compact the per-cloud ICP layers into one contiguous problem array (offsets of the align batch)
+  std::vector<uint64_t> qoff(B + 1, 0);
+  for (uint32_t b = 0; b < B; b++) {
+    if (h[b * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+    qoff[b + 1] = qoff[b] + h[b * CNT_STRIDE + 2];
+    if (map_layer_n) (*map_layer_n)[b] = h[b * CNT_STRIDE + 1];
+  }
+  CU(c, c->d_local.ensure(std::max<uint64_t>(qoff[B], 1) * sizeof(float4)));
+  for (uint32_t b = 0; b < B; b++) {
+    const uint64_t nb = qoff[b + 1] - qoff[b];
+    if (nb)
+      CU(c, cudaMemcpyAsync(c->d_local.as<float4>() + qoff[b], c->d_f_icp.as<float4>() + offsets[b], nb * sizeof(float4),
+                            cudaMemcpyDeviceToDevice, c->stream));
+  }
+  return align_batch_device(c, B, c->d_local.as<float4>(), qoff.data(), map, init_poses, ips, out);
+}
+
+int mlo_scan_register_batch_resident(mlo_ctx* c, const mlo_map* map, const mlo_dcloud* raw, const mlo_filter1_params* fps,
+                                     const double* init_poses, const mlo_icp_params* ips, mlo_icp_result* out) {
+  if (!c || !map || !raw || !fps || !init_poses || !ips || !out) return MLO_ERR_INVALID_ARG;
+  if (map->ctx != c || raw->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "handle belongs to another context");
+  DeviceGuard g(c->device);
+  return scan_register_device(c, map, uint32_t(raw->offsets.size() - 1), reinterpret_cast<const float*>(raw->pts), 4,
+                              raw->offsets.data(), fps, init_poses, ips, out, nullptr);
+}
+
+int mlo_scan_register_batch(mlo_ctx* c, const mlo_map* map, uint32_t B, const float* raw, uint32_t stride,
+                            const uint64_t* offsets, const mlo_filter1_params* fps, const double* init_poses,
+                            const mlo_icp_params* ips, mlo_icp_result* out) {
+  if (!c || !map || !raw || !offsets || !fps || !init_poses || !ips || !out || B == 0) return MLO_ERR_INVALID_ARG;
+  if (map->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "map belongs to another context");
+  DeviceGuard g(c->device);
+  int rc = upload_strided(c, raw, stride, offsets[B], c->d_in);
+  if (rc != MLO_OK) return rc;
+  return scan_register_device(c, map, B, c->d_in.as<float>(), stride, offsets, fps, init_poses, ips, out, nullptr);
+}
+
+int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t stride, uint64_t n, const mlo_filter1_params* fp,
+                      const double init[12], const mlo_icp_params* ip, int insert_into_map, float cull_farther_than,
+                      mlo_icp_result* out) {
+  if (!c || !map || !raw || !fp || !init || !ip || !out) return MLO_ERR_INVALID_ARG;
+  if (map->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "map belongs to another context");
+  DeviceGuard g(c->device);
+  int rc = upload_strided(c, raw, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  const uint64_t offs[2] = {0, n};
+  std::vector<uint64_t> nmap(1, 0);
+  rc = scan_register_device(c, map, 1, c->d_in.as<float>(), stride, offs, fp, init, ip, out, &nmap);
+  if (rc != MLO_OK) return rc;
+  if (insert_into_map) {
+    const size_t e0 = prof_begin(c);
+    rc = map_insert_device(map, reinterpret_cast<const float*>(c->d_f_map.as<float4>()), 4, nmap[0], out->pose_3x4);
+    if (rc != MLO_OK) return rc;
+    if (cull_farther_than > 0.f) {
+      const double s[3] = {out->pose_3x4[3], out->pose_3x4[7], out->pose_3x4[11]};
+      const float inv = map->dev.inv_voxel;
+      rc = map_rebuild(map, true, voxel_index_map(float(s[0]), inv), voxel_index_map(float(s[1]), inv),
+                       voxel_index_map(float(s[2]), inv), int32_t(std::ceil(cull_farther_than * inv)));
+      if (rc != MLO_OK) return rc;
+    }
+    prof_end(c, 2, e0);
+    rc = check_map_errors(map);
+    prof_collect(c);
+  }
+  return rc;
+}
+
+// ------------------------------------------------------------------ profiling
+int mlo_profile_enable(mlo_ctx* c, int enabled) {
+  if (!c) return MLO_ERR_INVALID_ARG;
+  c->prof_on = enabled != 0;
+  return MLO_OK;
+}
+int mlo_profile_get(mlo_ctx* c, mlo_profile* out, int reset) {
+  if (!c || !out) return MLO_ERR_INVALID_ARG;
+  *out = c->prof;
+  if (reset) c->prof = mlo_profile{};
+  return MLO_OK;
+}
+
+}  // extern "C"
