@@ -43,8 +43,9 @@ struct IcpProblem {
   int32_t hook_enabled;
   double hook_min_trans, hook_min_rot;
   double hook_checkpoint[12];
-  uint32_t part_begin;  // first partial block of this problem
-  uint32_t n_blocks;
+  uint32_t part_begin;    // first partial block of this problem
+  uint32_t n_blocks;      // blocks of k_match_accumulate (4 warps x qpw queries each)
+  uint32_t n_blocks_acc;  // blocks of k_accumulate (ICP_BLOCK queries each)
 };
 
 struct IcpState {
@@ -177,10 +178,15 @@ MLO_D void block_reduce_store(double* a, uint32_t npairs, uint32_t ncand, double
 }
 
 // pair record: A = (gx, gy, gz | cx, cy, cz, kind) with kind 0 none, 1 pt2pt, 2 pt2pl; B = plane normal.
+//
+// Work decomposition: a warp owns `qpw` consecutive queries (qpw = 32 for throughput, smaller for
+// latency-bound small batches).  Lane t holds query t: its local point, its transformed point and, after
+// the warp-cooperative NN of that query (map.cuh: probe prefetched one query ahead), its pairing.  The
+// normal-equation terms are then computed once per query by the owning lane and butterfly-reduced.
 __global__ void __launch_bounds__(ICP_BLOCK)
     k_match_accumulate(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
                        const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
-                       double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+                       double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
   const IcpProblem& P = probs[blockIdx.y];
   if (blockIdx.x >= P.n_blocks) return;
   const IcpState& S = states[blockIdx.y];
@@ -188,52 +194,98 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   __shared__ double sT[12];
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
   __syncthreads();
+  const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t it = S.it;
   const double thr = table_at(P.thr_pt2pt, P.table_len, it);
   const float thr2 = float(thr * thr);
   const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
   const double kc = table_at(P.kparam, P.table_len, it);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
+  const uint32_t qbase = (blockIdx.x * (ICP_BLOCK / 32) + warp) * qpw;  // first query of this warp
+  const uint32_t nq_warp = qbase < P.n_q ? min(qpw, P.n_q - qbase) : 0u;
+  const bool mine = lane < nq_warp;
+  float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (mine) {
+    l = __ldg(&local[P.q_begin + qbase + lane]);
+    compose_point_f(sT, l.x, l.y, l.z, gx, gy, gz);
+  }
+  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t ncand = 0;
+  bool paired = false;
+  if ((P.matcher_mask & MLO_MATCHER_PT2PL) && mine) {
+    const PlaneHit h = nn_plane_thread(map, gx, gy, gz);
+    ncand += h.ncand;
+    if (h.found && h.dist < thr_pl) {
+      paired = true;
+      pa = make_float4(h.cx, h.cy, h.cz, 2.f);
+      pb = make_float4(h.nx, h.ny, h.nz, 0.f);
+    }
+  }
+  if (P.matcher_mask & MLO_MATCHER_PT2PT) {
+    // Matcher base rule: local points already paired by an earlier matcher are skipped
+    uint32_t todo = __ballot_sync(FULL, mine && !paired);
+    WarpProbe cur;
+    float cx = 0.f, cy = 0.f, cz = 0.f;
+    int t = -1;
+    if (todo) {
+      t = __ffs(todo) - 1;
+      todo &= todo - 1;
+      cx = __shfl_sync(FULL, gx, t);
+      cy = __shfl_sync(FULL, gy, t);
+      cz = __shfl_sync(FULL, gz, t);
+      cur = warp_probe_issue(map, cx, cy, cz);
+    }
+    while (t >= 0) {
+      // prefetch the probe of the next query before consuming this one
+      int tn = -1;
+      float nx = 0.f, ny = 0.f, nz = 0.f;
+      WarpProbe nxt;
+      if (todo) {
+        tn = __ffs(todo) - 1;
+        todo &= todo - 1;
+        nx = __shfl_sync(FULL, gx, tn);
+        ny = __shfl_sync(FULL, gy, tn);
+        nz = __shfl_sync(FULL, gz, tn);
+        nxt = warp_probe_issue(map, nx, ny, nz);
+      }
+      const NNHit h = warp_nn_finish(map, cur, cx, cy, cz);
+      if (int(lane) == t) {
+        ncand += h.ncand;
+        const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
+        if (h.found && h.d2 < lim) pa = make_float4(h.x, h.y, h.z, 1.f);
+      }
+      t = tn;
+      if (tn >= 0) {
+        cur = nxt;
+        cx = nx;
+        cy = ny;
+        cz = nz;
+      }
+    }
+  }
   double a[NACC];
 #pragma unroll
   for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
-  uint32_t npairs = 0, ncand = 0;
-  const uint32_t q = blockIdx.x * ICP_BLOCK + threadIdx.x;
-  if (q < P.n_q) {
-    const float4 l = __ldg(&local[P.q_begin + q]);
-    float gx, gy, gz;
-    compose_point_f(sT, l.x, l.y, l.z, gx, gy, gz);
-    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool paired = false;
-    if (P.matcher_mask & MLO_MATCHER_PT2PL) {
-      const PlaneHit h = nn_plane_thread(map, gx, gy, gz);
-      ncand += h.ncand;
-      if (h.found && h.dist < thr_pl) {
-        paired = true;
-        pa = make_float4(h.cx, h.cy, h.cz, 2.f);
-        pairB[P.q_begin + q] = make_float4(h.nx, h.ny, h.nz, 0.f);
-        if (P.solver == MLO_SOLVER_GAUSS_NEWTON)
-          contrib_pt2pl(sT, l.x, l.y, l.z, h.cx, h.cy, h.cz, h.nx, h.ny, h.nz, P.w_pt2pl, P.robust_kernel, kc, a);
-        npairs++;
-      }
+  uint32_t npairs = 0;
+  if (mine) {
+    if (pa.w == 1.f) {
+      if (P.solver == MLO_SOLVER_GAUSS_NEWTON)
+        contrib_pt2pt(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
+      else
+        contrib_horn(l.x, l.y, l.z, pa.x, pa.y, pa.z, a);
+      npairs = 1;
+    } else if (pa.w == 2.f) {
+      contrib_pt2pl(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+      npairs = 1;
+      pairB[P.q_begin + qbase + lane] = pb;
     }
-    if ((P.matcher_mask & MLO_MATCHER_PT2PT) && !paired) {
-      const NNHit h = nn_single_thread(map, gx, gy, gz);
-      ncand += h.ncand;
-      const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
-      if (h.found && h.d2 < lim) {
-        pa = make_float4(h.x, h.y, h.z, 1.f);
-        if (P.solver == MLO_SOLVER_GAUSS_NEWTON)
-          contrib_pt2pt(sT, l.x, l.y, l.z, h.x, h.y, h.z, P.w_pt2pt, P.robust_kernel, kc, a);
-        else
-          contrib_horn(l.x, l.y, l.z, h.x, h.y, h.z, a);
-        npairs++;
-      }
-    }
-    pairA[P.q_begin + q] = pa;
+    pairA[P.q_begin + qbase + lane] = pa;
   }
-  const uint32_t pb = P.part_begin + blockIdx.x;
-  block_reduce_store(a, npairs, ncand, partials + size_t(pb) * NACC, part_cnt + 2 * size_t(pb));
+  const uint32_t pbi = P.part_begin + blockIdx.x;
+  block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
 __global__ void __launch_bounds__(ICP_BLOCK)
@@ -241,7 +293,7 @@ __global__ void __launch_bounds__(ICP_BLOCK)
                  const float4* __restrict__ pairA, const float4* __restrict__ pairB, double* __restrict__ partials,
                  uint32_t* __restrict__ part_cnt) {
   const IcpProblem& P = probs[blockIdx.y];
-  if (blockIdx.x >= P.n_blocks) return;
+  if (blockIdx.x >= P.n_blocks_acc) return;
   const IcpState& S = states[blockIdx.y];
   if (S.done || !S.inner_pending) return;
   __shared__ double sT[12];
@@ -382,10 +434,11 @@ __global__ void __launch_bounds__(32)
   // ordered sum over this problem's block partials: lane k owns element k
   double acc = 0.0;
   uint32_t cnt = 0;
+  const uint32_t nblk = after_match ? P.n_blocks : P.n_blocks_acc;
   if (lane < NACC) {
-    for (uint32_t b = 0; b < P.n_blocks; b++) acc += partials[size_t(P.part_begin + b) * NACC + lane];
+    for (uint32_t b = 0; b < nblk; b++) acc += partials[size_t(P.part_begin + b) * NACC + lane];
   } else if (lane < NACC + 2) {
-    for (uint32_t b = 0; b < P.n_blocks; b++) cnt += part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)];
+    for (uint32_t b = 0; b < nblk; b++) cnt += part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)];
   }
   double a[NACC];
 #pragma unroll

@@ -1,22 +1,39 @@
 // map.cuh — hash-voxel local map resident in HBM (replaces mola::HashedVoxelPointCloud and the
 // per-voxel statistics of mola::NDT; pipelines/lidar3d-default.yaml:228-242, lidar3d-ndt.yaml:234-254).
 //
-// Layout in HBM
-//   slots[table_size]  uint4 {key_lo, key_hi, voxel_id, count}: open addressing, linear probing,
-//                      packed 3x21-bit key; one 16-byte probe yields key, payload id and fill count.
-//   pts[capacity*cap]  float4 (x, y, z, 0): the <= cap points of voxel v at [v*cap, v*cap+count).
+// Layout in HBM (designed around the 32-byte DRAM sector and the 3x3x3 neighbourhood query)
+//   buckets[n_buckets]  32-byte records {u64 key(kx, ky, kz>>2); u32 cell[4]; u64 pad}.  One bucket is a
+//                       z-column of 4 consecutive voxels; cell[kz&3] = (voxel_id << 6) | count, or ABSENT.
+//                       Open addressing with linear probing over buckets.  The 27 cells around a query
+//                       live in 9 columns x (1 or 2) buckets = 13.5 sector reads on average (not 27), and
+//                       each read returns key, payload ids and fill counts at once.
+//   pts[capacity*cap]   float4 (x, y, z, 0): the <= cap points of voxel v at [v*cap, v*cap+count),
+//                       64-byte aligned rows, read as one coalesced warp load per cell.
 //   mean/normal[capacity] float4, NDT only: (mean xyz, is_plane) and (unit normal xyz, 0).
-// table_size = next power of two >= 4 * capacity_voxels (load factor <= 0.25, so a probe for an
-// absent neighbour cell terminates after ~1.2 slots on average).
-// There are no tombstones: culling is a filtered rebuild into a second set of buffers.
+// n_buckets = next power of two >= 2 * capacity_voxels.  No tombstones: culling is a filtered rebuild
+// into a second set of buffers.
 #pragma once
 #include "common.cuh"
 
 namespace mlo {
 
+struct __align__(32) Bucket {
+  unsigned long long key;
+  uint32_t cell[4];
+  unsigned long long pad;
+};
+static_assert(sizeof(Bucket) == 32, "bucket must be one DRAM sector");
+
+constexpr uint32_t CELL_ABSENT = 0xFFFFFFFFu;
+constexpr uint32_t CELL_PENDING = 0xFFFFFFFEu;
+MLO_HD uint32_t cell_vid(uint32_t w) { return w >> 6; }
+MLO_HD uint32_t cell_cnt(uint32_t w) { return w & 63u; }
+MLO_HD uint32_t cell_make(uint32_t vid, uint32_t cnt) { return (vid << 6) | cnt; }
+MLO_HD uint64_t column_key(int32_t kx, int32_t ky, int32_t kz) { return pack_key(kx, ky, kz >> 2); }
+
 struct MapDev {
-  uint4* slots;
-  uint64_t mask;
+  Bucket* buckets;
+  uint64_t mask;  // n_buckets - 1
   float4* pts;
   float4* mean;
   float4* normal;
@@ -24,53 +41,78 @@ struct MapDev {
   uint32_t cap;
   uint32_t capacity_voxels;
   float inv_voxel;
+  float voxel_size;
   float min_dist2;
   float eig_ratio;
   uint32_t min_pts_plane;
   int32_t kind;
 };
 
+// Read-only bucket fetch: two 16-byte loads of one sector (ld.global.nc).
+struct BucketRO {
+  uint64_t key;
+  uint32_t cell[4];
+};
+MLO_D BucketRO load_bucket(const MapDev& m, uint64_t b) {
+  const uint4* p = reinterpret_cast<const uint4*>(&m.buckets[b]);
+  const uint4 a = __ldg(p);
+  const uint4 c = __ldg(p + 1);
+  BucketRO r;
+  r.key = (uint64_t(a.y) << 32) | uint64_t(a.x);
+  r.cell[0] = a.z;
+  r.cell[1] = a.w;
+  r.cell[2] = c.x;
+  r.cell[3] = c.y;
+  return r;
+}
 
-MLO_D uint64_t slot_key(const uint4& s) { return (uint64_t(s.y) << 32) | uint64_t(s.x); }
-
-// Look up one cell. Returns true and (vid,count) if present. Read-only path (ld.global.nc).
-MLO_D bool map_find(const MapDev& m, uint64_t key, uint32_t& vid, uint32_t& cnt) {
+// Find the bucket of a column key; returns false if the column does not exist.
+MLO_D bool find_column(const MapDev& m, uint64_t key, BucketRO& out) {
   uint64_t h = hash_key(key) & m.mask;
   for (;;) {
-    const uint4 s = __ldg(&m.slots[h]);
-    const uint64_t k = slot_key(s);
-    if (k == key) {
-      vid = s.z;
-      cnt = s.w;
-      return true;
-    }
-    if (k == KEY_EMPTY) return false;
+    out = load_bucket(m, h);
+    if (out.key == key) return true;
+    if (out.key == KEY_EMPTY) return false;
     h = (h + 1) & m.mask;
   }
 }
 
-// Find-or-claim the slot of `key` (writers). Returns the slot index, or ~0 on table exhaustion.
-MLO_D uint64_t map_find_or_insert(const MapDev& m, uint64_t key) {
+// Look up one cell: (vid, cnt) packed word or CELL_ABSENT.
+MLO_D uint32_t map_find_cell(const MapDev& m, int32_t kx, int32_t ky, int32_t kz) {
+  BucketRO b;
+  if (!find_column(m, column_key(kx, ky, kz), b)) return CELL_ABSENT;
+  return b.cell[kz & 3];
+}
+
+// Writers: find-or-claim the bucket of `key`. Returns the bucket index or ~0 on table exhaustion.
+MLO_D uint64_t find_or_insert_column(const MapDev& m, uint64_t key) {
   uint64_t h = hash_key(key) & m.mask;
   for (uint64_t probes = 0; probes <= m.mask; probes++) {
-    unsigned long long* kp = reinterpret_cast<unsigned long long*>(&m.slots[h]);
+    unsigned long long* kp = &m.buckets[h].key;
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-    if (cur == KEY_EMPTY) {
-      cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-      if (cur == KEY_EMPTY) {
-        // we created the voxel: allocate its payload id, count starts at 0
-        const uint32_t v = atomicAdd(&m.counters[0], 1u);
-        if (v >= m.capacity_voxels) atomicOr(&m.counters[2], ERR_CAPACITY);
-        m.slots[h].z = v;
-        m.slots[h].w = 0u;
-        return h;
-      }
-    }
-    if (cur == key) return h;
+    if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+    if (cur == KEY_EMPTY || cur == key) return h;
     h = (h + 1) & m.mask;
   }
   atomicOr(&m.counters[2], ERR_CAPACITY);
   return ~0ull;
+}
+
+// Writers: make sure cell (bucket, sub) exists; the creator allocates the payload id. Returns the
+// flat cell index bucket*4+sub (used for the per-voxel pending lists), or ~0 on error.
+MLO_D uint64_t find_or_insert_cell(const MapDev& m, int32_t kx, int32_t ky, int32_t kz) {
+  const uint64_t b = find_or_insert_column(m, column_key(kx, ky, kz));
+  if (b == ~0ull) return ~0ull;
+  const uint32_t sub = uint32_t(kz & 3);
+  uint32_t* cp = &m.buckets[b].cell[sub];
+  if (*reinterpret_cast<volatile uint32_t*>(cp) == CELL_ABSENT) {
+    if (atomicCAS(cp, CELL_ABSENT, CELL_PENDING) == CELL_ABSENT) {
+      const uint32_t v = atomicAdd(&m.counters[0], 1u);
+      if (v >= m.capacity_voxels) atomicOr(&m.counters[2], ERR_CAPACITY);
+      atomicExch(cp, cell_make(v, 0u));
+    }
+  }
+  return b * 4 + sub;
 }
 
 // ------------------------------------------------------------------ NDT voxel statistics
@@ -152,9 +194,11 @@ MLO_D void voxel_stats(const MapDev& m, uint32_t vid, uint32_t n) {
 // ------------------------------------------------------------------ insert
 // Deterministic parallel form of the sequential insertPoint loop (FilterMerge -> map insert,
 // default.yaml:362-368): the points that land in one voxel are appended in ascending input index.
-//   pass 1 (thread per point): g = pose*p, key, find-or-claim slot, push the point on the slot's list.
+//   pass 1 (thread per point): g = pose*p, key, find-or-claim cell, push the point on the cell's list.
 //   pass 2 (thread per point): the thread holding the smallest index of a list owns that voxel and
 //           appends the pending points in index order (cap and min-distance tests as upstream).
+constexpr uint32_t PSLOT_NONE = 0xFFFFFFFFu;
+
 __global__ void k_insert_link(MapDev m, const float* __restrict__ src, uint32_t stride, uint32_t n, Pose34 T,
                               float4* __restrict__ g_out, uint32_t* __restrict__ pslot, int32_t* head,
                               int32_t* __restrict__ next) {
@@ -168,38 +212,38 @@ __global__ void k_insert_link(MapDev m, const float* __restrict__ src, uint32_t 
   g_out[i] = make_float4(gx, gy, gz, 0.f);
   if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) {
     atomicOr(&m.counters[2], ERR_KEY_RANGE);
-    pslot[i] = 0xFFFFFFFFu;
+    pslot[i] = PSLOT_NONE;
     return;
   }
-  const uint64_t h = map_find_or_insert(m, pack_key(kx, ky, kz));
-  if (h == ~0ull) {
-    pslot[i] = 0xFFFFFFFFu;
+  const uint64_t c = find_or_insert_cell(m, kx, ky, kz);
+  if (c == ~0ull) {
+    pslot[i] = PSLOT_NONE;
     return;
   }
-  pslot[i] = uint32_t(h);
-  next[i] = atomicExch(&head[h], int32_t(i));
+  pslot[i] = uint32_t(c);
+  next[i] = atomicExch(&head[c], int32_t(i));
 }
 
 __global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__ g, const uint32_t* __restrict__ pslot,
                                 int32_t* head, const int32_t* __restrict__ next) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  const uint32_t h = pslot[i];
-  if (h == 0xFFFFFFFFu) return;
+  const uint32_t c = pslot[i];
+  if (c == PSLOT_NONE) return;
   // owner = smallest index on the list
-  const int32_t first = *reinterpret_cast<volatile int32_t*>(&head[h]);
+  const int32_t first = *reinterpret_cast<volatile int32_t*>(&head[c]);
   for (int32_t j = first; j >= 0; j = next[j])
     if (uint32_t(j) < i) return;
-  uint4 s = m.slots[h];
-  const uint32_t vid = s.z;
-  uint32_t c = s.w;
+  uint32_t* cp = &m.buckets[c >> 2].cell[c & 3u];
+  const uint32_t w = *cp;
+  const uint32_t vid = cell_vid(w);
+  uint32_t cnt = cell_cnt(w);
   if (vid >= m.capacity_voxels) return;  // capacity error already flagged
   float4* vp = m.pts + size_t(vid) * m.cap;
-  const uint32_t c0 = c;
+  const uint32_t c0 = cnt;
   int32_t last = -1;
-  while (c < m.cap) {
-    // next pending index in ascending order
-    int32_t best = 0x7FFFFFFF;
+  while (cnt < m.cap) {
+    int32_t best = 0x7FFFFFFF;  // next pending index in ascending order
     for (int32_t j = first; j >= 0; j = next[j])
       if (j > last && j < best) best = j;
     if (best == 0x7FFFFFFF) break;
@@ -207,7 +251,7 @@ __global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__
     const float4 q = g[best];
     bool ok = true;
     if (m.min_dist2 > 0.f) {
-      for (uint32_t k = 0; k < c; k++) {
+      for (uint32_t k = 0; k < cnt; k++) {
         const float4 e = vp[k];
         if (sqr_dist(e.x, e.y, e.z, q.x, q.y, q.z) < m.min_dist2) {
           ok = false;
@@ -215,51 +259,58 @@ __global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__
         }
       }
     }
-    if (ok) vp[c++] = q;
+    if (ok) vp[cnt++] = q;
   }
-  if (c != c0) {
-    m.slots[h].w = c;
-    atomicAdd(&m.counters[1], c - c0);
-    if (m.kind == MLO_MAP_NDT) voxel_stats(m, vid, c);
+  if (cnt != c0) {
+    *cp = cell_make(vid, cnt);
+    atomicAdd(&m.counters[1], cnt - c0);
+    if (m.kind == MLO_MAP_NDT) voxel_stats(m, vid, cnt);
   }
-  head[h] = -1;  // leave the scratch list heads clean for the next insert
+  head[c] = -1;  // leave the scratch list heads clean for the next insert
 }
 
 // ------------------------------------------------------------------ cull (filtered rebuild)
 // insertOpts.remove_voxels_farther_than (default.yaml:238): keep voxels whose per-axis cell distance
 // to the sensor's cell is <= ceil(dist * voxel_size_inv); survivors are re-hashed into `dst`.
-__global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_slots, int32_t sx, int32_t sy, int32_t sz, int32_t d,
+// One warp per source bucket; lanes cooperate on the payload copies.
+__global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_buckets, int32_t sx, int32_t sy, int32_t sz, int32_t d,
                           int32_t use_filter) {
-  // one warp per slot group: lanes cooperate on the payload copy
   const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
   const uint32_t lane = threadIdx.x & 31u;
-  if (warp >= n_slots) return;
-  const uint4 s = src.slots[warp];
-  const uint64_t key = slot_key(s);
-  if (key == KEY_EMPTY) return;
-  if (use_filter) {
-    int32_t kx, ky, kz;
-    unpack_key(key, kx, ky, kz);
-    if (abs(kx - sx) > d || abs(ky - sy) > d || abs(kz - sz) > d) return;
-  }
-  uint32_t nv = 0;
-  uint64_t h = 0;
-  if (lane == 0) {
-    h = map_find_or_insert(dst, key);
-    nv = dst.slots[h].z;
-    dst.slots[h].w = s.w;
-    atomicAdd(&dst.counters[1], s.w);
-  }
-  nv = __shfl_sync(0xFFFFFFFFu, nv, 0);
-  if (nv >= dst.capacity_voxels) return;
-  if (lane < s.w) dst.pts[size_t(nv) * dst.cap + lane] = src.pts[size_t(s.z) * src.cap + lane];
-  if (src.kind == MLO_MAP_NDT && lane == 0) {
-    dst.mean[nv] = src.mean[s.z];
-    dst.normal[nv] = src.normal[s.z];
+  if (warp >= n_buckets) return;
+  const Bucket b = src.buckets[warp];
+  if (b.key == KEY_EMPTY) return;
+  int32_t kx, ky, kzq;
+  unpack_key(b.key, kx, ky, kzq);
+  for (int sub = 0; sub < 4; sub++) {
+    const uint32_t w = b.cell[sub];
+    if (w == CELL_ABSENT || w == CELL_PENDING) continue;
+    const int32_t kz = kzq * 4 + sub;
+    if (use_filter && (abs(kx - sx) > d || abs(ky - sy) > d || abs(kz - sz) > d)) continue;
+    const uint32_t cnt = cell_cnt(w), ov = cell_vid(w);
+    uint32_t nv = 0xFFFFFFFFu;
+    if (lane == 0) {
+      const uint64_t c = find_or_insert_cell(dst, kx, ky, kz);
+      if (c != ~0ull) {
+        uint32_t* cp = &dst.buckets[c >> 2].cell[c & 3u];
+        nv = cell_vid(*reinterpret_cast<volatile uint32_t*>(cp));
+        if (nv < dst.capacity_voxels) {
+          *cp = cell_make(nv, cnt);
+          atomicAdd(&dst.counters[1], cnt);
+        }
+      }
+    }
+    nv = __shfl_sync(0xFFFFFFFFu, nv, 0);
+    if (nv >= dst.capacity_voxels) continue;
+    if (lane < cnt) dst.pts[size_t(nv) * dst.cap + lane] = src.pts[size_t(ov) * src.cap + lane];
+    if (src.kind == MLO_MAP_NDT && lane == 0) {
+      dst.mean[nv] = src.mean[ov];
+      dst.normal[nv] = src.normal[ov];
+    }
   }
 }
 
-// ------------------------------------------------------------------ nearest neighbour, thread per query
+// ------------------------------------------------------------------ nearest neighbour
 // NearestNeighborsCapable::nn_single_search over the 27 cells key(q)+{-1,0,1}^3, visited in cx, cy, cz
 // nested order, stored slot order inside a cell, strict '<' so the first minimum wins.
 struct NNHit {
@@ -268,6 +319,7 @@ struct NNHit {
   uint32_t ncand;
 };
 
+// Thread-per-query form (used by the plain query API and the NDT plane matcher).
 MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
   NNHit r;
   r.x = r.y = r.z = 0.f;
@@ -281,21 +333,25 @@ MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
   for (int dx = -1; dx <= 1; dx++) {
 #pragma unroll 1
     for (int dy = -1; dy <= 1; dy++) {
-      uint32_t vid[3], cnt[3];
+      // the column's three cells live in one or two buckets
+      uint32_t w[3] = {CELL_ABSENT, CELL_ABSENT, CELL_ABSENT};
+      BucketRO b;
+      const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
+      if (find_column(m, pack_key(kx + dx, ky + dy, zq0), b)) {
 #pragma unroll
-      for (int dz = -1; dz <= 1; dz++) {
-        cnt[dz + 1] = 0;
-        vid[dz + 1] = 0;
-        uint32_t v, c;
-        if (map_find(m, pack_key(kx + dx, ky + dy, kz + dz), v, c)) {
-          vid[dz + 1] = v;
-          cnt[dz + 1] = c;
-        }
+        for (int t = 0; t < 3; t++)
+          if (((kz - 1 + t) >> 2) == zq0) w[t] = b.cell[(kz - 1 + t) & 3];
+      }
+      if (zq1 != zq0 && find_column(m, pack_key(kx + dx, ky + dy, zq1), b)) {
+#pragma unroll
+        for (int t = 0; t < 3; t++)
+          if (((kz - 1 + t) >> 2) == zq1) w[t] = b.cell[(kz - 1 + t) & 3];
       }
 #pragma unroll
       for (int t = 0; t < 3; t++) {
-        const float4* vp = m.pts + size_t(vid[t]) * m.cap;
-        const uint32_t c = cnt[t];
+        if (w[t] == CELL_ABSENT || w[t] == CELL_PENDING) continue;
+        const float4* vp = m.pts + size_t(cell_vid(w[t])) * m.cap;
+        const uint32_t c = cell_cnt(w[t]);
         r.ncand += c;
         for (uint32_t j = 0; j < c; j++) {
           const float4 p = __ldg(&vp[j]);
@@ -311,6 +367,184 @@ MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
       }
     }
   }
+  return r;
+}
+
+// ---- warp-per-query form: the hot loop of the fused ICP kernel.
+// Phase 1 (probe): lane = column*2 + half, 18 lanes fetch the one or two buckets of each of the 9
+//   (dx,dy) columns: one 32-byte sector per lane, all in flight at once.
+// Phase 2 (gather): the 27 packed cell words are redistributed so lane e owns cell e in canonical
+//   order; occupied cells are streamed four at a time, each as ONE coalesced warp load of <= cap float4
+//   (lane j reads slot j).  Per-lane running minima see candidates in canonical order; the final warp
+//   arg-min breaks ties by (cell, slot) order, reproducing the sequential first-minimum rule bit for bit.
+struct WarpProbe {
+  BucketRO b;       // this lane's bucket (valid for lanes < 18 that probe)
+  uint64_t key;     // the column key this lane looks for
+  uint64_t h;       // current bucket index
+  int32_t kz;       // query cell z
+  bool active;      // lane takes part in the probe
+  bool in_range;
+};
+
+MLO_D WarpProbe warp_probe_issue(const MapDev& m, float qx, float qy, float qz) {
+  const uint32_t lane = threadIdx.x & 31u;
+  WarpProbe p;
+  const int32_t kx = voxel_index_map(qx, m.inv_voxel), ky = voxel_index_map(qy, m.inv_voxel),
+                kz = voxel_index_map(qz, m.inv_voxel);
+  p.kz = kz;
+  p.in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
+  const uint32_t col = lane >> 1, half = lane & 1u;
+  const int32_t dx = int32_t(col / 3) - 1, dy = int32_t(col % 3) - 1;
+  const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
+  p.active = p.in_range && lane < 18 && (half == 0 || zq1 != zq0);
+  p.key = pack_key(kx + dx, ky + dy, half ? zq1 : zq0);
+  p.h = hash_key(p.key) & m.mask;
+  p.b.key = KEY_EMPTY;
+  p.b.cell[0] = p.b.cell[1] = p.b.cell[2] = p.b.cell[3] = CELL_ABSENT;
+  if (p.active) p.b = load_bucket(m, p.h);
+  return p;
+}
+
+MLO_D NNHit warp_nn_finish(const MapDev& m, WarpProbe& p, float qx, float qy, float qz) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t FULL = 0xFFFFFFFFu;
+  // resolve hash collisions (linear probing), warp-uniform loop
+  bool pending = p.active && p.b.key != p.key && p.b.key != KEY_EMPTY;
+  while (__any_sync(FULL, pending)) {
+    if (pending) {
+      p.h = (p.h + 1) & m.mask;
+      p.b = load_bucket(m, p.h);
+      pending = p.b.key != p.key && p.b.key != KEY_EMPTY;
+    }
+  }
+  const bool have = p.active && p.b.key == p.key;
+  // per probing lane: the packed words of the column's cells dz = -1, 0, +1 that live in ITS bucket
+  uint32_t w3[3];
+  const int32_t myzq = (lane & 1u) ? ((p.kz + 1) >> 2) : ((p.kz - 1) >> 2);
+#pragma unroll
+  for (int t = 0; t < 3; t++) {
+    const int32_t z = p.kz - 1 + t;
+    uint32_t w = CELL_ABSENT;
+    if (have && (z >> 2) == myzq) {
+      const uint32_t s = uint32_t(z & 3);
+      w = s == 0 ? p.b.cell[0] : s == 1 ? p.b.cell[1] : s == 2 ? p.b.cell[2] : p.b.cell[3];
+    }
+    w3[t] = w;
+  }
+  // lane e (< 27) owns cell e = col*3 + t in canonical (dx, dy, dz) order
+  const uint32_t e_col = lane / 3, e_t = lane % 3;
+  const int32_t ez = p.kz - 1 + int32_t(e_t);
+  const uint32_t src = (lane < 27) ? (e_col * 2 + (((ez >> 2) != ((p.kz - 1) >> 2)) ? 1u : 0u)) : 0u;
+  const uint32_t v0 = __shfl_sync(FULL, w3[0], src), v1 = __shfl_sync(FULL, w3[1], src), v2 = __shfl_sync(FULL, w3[2], src);
+  uint32_t mine = e_t == 0 ? v0 : e_t == 1 ? v1 : v2;
+  if (lane >= 27 || mine == CELL_PENDING) mine = CELL_ABSENT;
+  const uint32_t my_cnt = (mine == CELL_ABSENT) ? 0u : cell_cnt(mine);
+  // algorithmic candidate count = all points of the 27 cells (what a plain scan would visit)
+  uint32_t ncand = my_cnt;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) ncand += __shfl_xor_sync(FULL, ncand, o);
+
+  float best = __int_as_float(0x7f800000);
+  float bx = 0.f, by = 0.f, bz = 0.f;
+  uint32_t border = 0xFFFFFFFFu;  // canonical order of this lane's best = cell*32 + slot
+
+  // Exact pruning: scan the query's own cell first (e = 13); a neighbour cell is then read only if
+  // the distance from q to its box can still be <= that best.  The cell boxes follow the
+  // truncation-toward-zero index (cell 0 spans (-vs, vs)); bounds are shrunk by a few ulps so that a
+  // point that rounds across a face is never missed.  Result (incl. tie order) equals the full scan.
+  const uint32_t w_home = __shfl_sync(FULL, mine, 13);
+  float bound = __int_as_float(0x7f800000);
+  if (w_home != CELL_ABSENT) {
+    const uint32_t c = cell_cnt(w_home);
+    if (lane < c) {
+      const float4 q = __ldg(m.pts + size_t(cell_vid(w_home)) * m.cap + lane);
+      best = sqr_dist(q.x, q.y, q.z, qx, qy, qz);
+      bx = q.x;
+      by = q.y;
+      bz = q.z;
+      border = 13u * 32u + lane;
+    }
+    bound = best;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound = fminf(bound, __shfl_xor_sync(FULL, bound, o));
+  }
+  bool visit = my_cnt > 0 && lane != 13;
+  if (visit && bound < __int_as_float(0x7f800000)) {
+    const float vs = m.voxel_size;
+    const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel), p.kz};
+    const float qv[3] = {qx, qy, qz};
+    const int32_t dd[3] = {int32_t(lane / 9) - 1, int32_t((lane / 3) % 3) - 1, int32_t(lane % 3) - 1};
+    float lb2 = 0.f;
+#pragma unroll
+    for (int a = 0; a < 3; a++) {
+      if (dd[a] == 0) continue;
+      const int32_t cc = kq[a] + dd[a];
+      float edge, gap;
+      if (dd[a] > 0) {  // lower face of cell cc
+        edge = cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs);
+        gap = edge - qv[a];
+      } else {          // upper face of cell cc
+        edge = cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs);
+        gap = qv[a] - edge;
+      }
+      gap -= 4e-6f * (fabsf(edge) + vs);
+      if (gap > 0.f) lb2 += gap * gap;
+    }
+    visit = lb2 * 0.99999f <= bound;
+  }
+  uint32_t occ = __ballot_sync(FULL, visit);
+  while (occ) {
+    // up to four cells per round: loads issued together, consumed in canonical order
+    uint32_t e[4], c[4];
+    float4 q[4];
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (occ) {
+        e[k] = __ffs(occ) - 1;
+        occ &= occ - 1;
+        const uint32_t w = __shfl_sync(FULL, mine, e[k]);
+        c[k] = cell_cnt(w);
+        if (lane < c[k]) q[k] = __ldg(m.pts + size_t(cell_vid(w)) * m.cap + lane);
+      } else {
+        c[k] = 0;
+        e[k] = 0;
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; k++) {
+      if (lane < c[k]) {
+        const float d2 = sqr_dist(q[k].x, q[k].y, q[k].z, qx, qy, qz);
+        if (d2 < best) {
+          best = d2;
+          bx = q[k].x;
+          by = q[k].y;
+          bz = q[k].z;
+          border = e[k] * 32u + lane;
+        }
+      }
+    }
+  }
+  // warp arg-min on (d2, canonical order)
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float od = __shfl_xor_sync(FULL, best, o);
+    const uint32_t oo = __shfl_xor_sync(FULL, border, o);
+    const float ox = __shfl_xor_sync(FULL, bx, o), oy = __shfl_xor_sync(FULL, by, o), oz = __shfl_xor_sync(FULL, bz, o);
+    if (od < best || (od == best && oo < border)) {
+      best = od;
+      border = oo;
+      bx = ox;
+      by = oy;
+      bz = oz;
+    }
+  }
+  NNHit r;
+  r.x = bx;
+  r.y = by;
+  r.z = bz;
+  r.d2 = best;
+  r.found = border != 0xFFFFFFFFu;
+  r.ncand = ncand;  // identical on every lane (counts are warp-uniform)
   return r;
 }
 
@@ -334,10 +568,11 @@ MLO_D PlaneHit nn_plane_thread(const MapDev& m, float qx, float qy, float qz) {
   for (int dx = -1; dx <= 1; dx++)
 #pragma unroll 1
     for (int dy = -1; dy <= 1; dy++)
-#pragma unroll
+#pragma unroll 1
       for (int dz = -1; dz <= 1; dz++) {
-        uint32_t v, c;
-        if (!map_find(m, pack_key(kx + dx, ky + dy, kz + dz), v, c)) continue;
+        const uint32_t w = map_find_cell(m, kx + dx, ky + dy, kz + dz);
+        if (w == CELL_ABSENT || w == CELL_PENDING) continue;
+        const uint32_t v = cell_vid(w);
         r.ncand += 2;
         const float4 mu = __ldg(&m.mean[v]);
         if (mu.w == 0.f) continue;
@@ -354,37 +589,42 @@ MLO_D PlaneHit nn_plane_thread(const MapDev& m, float qx, float qy, float qz) {
   return r;
 }
 
+// Plain query API: one warp per query through the same probe/gather path as the ICP kernel.
 __global__ void k_nn_single(MapDev m, const float* __restrict__ q, uint32_t stride, uint32_t n, float* __restrict__ out_xyz,
                             float* __restrict__ out_d2, uint8_t* __restrict__ out_found) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (i >= n) return;
   const float* p = q + size_t(i) * stride;
-  const NNHit r = nn_single_thread(m, p[0], p[1], p[2]);
-  out_xyz[3 * size_t(i)] = r.x;
-  out_xyz[3 * size_t(i) + 1] = r.y;
-  out_xyz[3 * size_t(i) + 2] = r.z;
-  out_d2[i] = r.d2;
-  out_found[i] = uint8_t(r.found);
+  const float qx = __ldg(p), qy = __ldg(p + 1), qz = __ldg(p + 2);
+  WarpProbe pr = warp_probe_issue(m, qx, qy, qz);
+  const NNHit r = warp_nn_finish(m, pr, qx, qy, qz);
+  if ((threadIdx.x & 31u) == 0) {
+    out_xyz[3 * size_t(i)] = r.x;
+    out_xyz[3 * size_t(i) + 1] = r.y;
+    out_xyz[3 * size_t(i) + 2] = r.z;
+    out_d2[i] = r.d2;
+    out_found[i] = uint8_t(r.found);
+  }
 }
 
 // ------------------------------------------------------------------ export
-__global__ void k_export_count(MapDev m, uint64_t n_slots, uint32_t* n_vox) {
-  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n_slots) return;
-  if (slot_key(m.slots[i]) != KEY_EMPTY) atomicAdd(n_vox, 1u);
-}
-// writes (key, count, vid) of every live slot, unordered; the host sorts by key.
-__global__ void k_export_list(MapDev m, uint64_t n_slots, uint32_t* cursor, uint64_t* keys, uint32_t* counts,
+// writes (kx, ky, kz, count, vid) of every live cell, unordered; the host sorts by key.
+__global__ void k_export_list(MapDev m, uint64_t n_buckets, uint32_t* cursor, int32_t* keys3, uint32_t* counts,
                               uint32_t* vids) {
   const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
-  if (i >= n_slots) return;
-  const uint4 s = m.slots[i];
-  const uint64_t k = slot_key(s);
-  if (k == KEY_EMPTY) return;
+  if (i >= n_buckets * 4) return;
+  const Bucket& b = m.buckets[i >> 2];
+  if (b.key == KEY_EMPTY) return;
+  const uint32_t w = b.cell[i & 3u];
+  if (w == CELL_ABSENT || w == CELL_PENDING) return;
+  int32_t kx, ky, kzq;
+  unpack_key(b.key, kx, ky, kzq);
   const uint32_t o = atomicAdd(cursor, 1u);
-  keys[o] = k;
-  counts[o] = s.w;
-  vids[o] = s.z;
+  keys3[3 * size_t(o)] = kx;
+  keys3[3 * size_t(o) + 1] = ky;
+  keys3[3 * size_t(o) + 2] = kzq * 4 + int32_t(i & 3u);
+  counts[o] = cell_cnt(w);
+  vids[o] = cell_vid(w);
 }
 
 }  // namespace mlo

@@ -92,8 +92,8 @@ struct mlo_map {
   MapDev dev{};
   MapDev alt{};  // second buffer set for filtered rebuilds (allocated on first cull)
   bool alt_ready = false;
-  uint64_t table_size = 0;
-  int32_t* head = nullptr;  // per-slot scratch list heads for insert
+  uint64_t table_size = 0;  // number of 32-byte buckets
+  int32_t* head = nullptr;  // per-cell (4 per bucket) scratch list heads for insert
 };
 
 struct mlo_dcloud {
@@ -177,12 +177,13 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
   d.cap = cap;
   d.capacity_voxels = uint32_t(p.capacity_voxels);
   d.inv_voxel = 1.0f / p.voxel_size;
+  d.voxel_size = p.voxel_size;
   d.min_dist2 = p.min_distance_between_points * p.min_distance_between_points;
   d.eig_ratio = p.max_eigen_ratio_for_planes;
   d.min_pts_plane = p.min_points_for_plane ? p.min_points_for_plane : 5;
   d.kind = p.kind;
   d.mask = table_size - 1;
-  CU(c, cudaMalloc(&d.slots, table_size * sizeof(uint4)));
+  CU(c, cudaMalloc(&d.buckets, table_size * sizeof(Bucket)));
   CU(c, cudaMalloc(&d.pts, size_t(p.capacity_voxels) * cap * sizeof(float4)));
   CU(c, cudaMalloc(&d.counters, 4 * sizeof(uint32_t)));
   d.mean = d.normal = nullptr;
@@ -193,12 +194,12 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
   return MLO_OK;
 }
 int clear_map_buffers(mlo_ctx* c, MapDev& d, uint64_t table_size) {
-  CU(c, cudaMemsetAsync(d.slots, 0xFF, table_size * sizeof(uint4), c->stream));
+  CU(c, cudaMemsetAsync(d.buckets, 0xFF, table_size * sizeof(Bucket), c->stream));
   CU(c, cudaMemsetAsync(d.counters, 0, 4 * sizeof(uint32_t), c->stream));
   return MLO_OK;
 }
 void free_map_buffers(MapDev& d) {
-  if (d.slots) cudaFree(d.slots);
+  if (d.buckets) cudaFree(d.buckets);
   if (d.pts) cudaFree(d.pts);
   if (d.counters) cudaFree(d.counters);
   if (d.mean) cudaFree(d.mean);
@@ -403,7 +404,11 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     return off;
   };
   std::vector<size_t> toff(3 * size_t(B));
-  uint32_t part_total = 0, max_blocks = 0, max_it = 0, max_inner = 1;
+  uint32_t part_total = 0, max_blocks = 0, max_blocks_acc = 0, max_it = 0, max_inner = 1;
+  // queries per warp: 32 when the batch alone fills the machine, fewer for latency-bound small batches
+  const uint64_t total_queries = offsets[B];
+  uint32_t qpw = 32;
+  while (qpw > 1 && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
   for (uint32_t b = 0; b < B; b++) {
     const mlo_icp_params& p = params[b];
     IcpProblem& P = probs[b];
@@ -439,10 +444,13 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     P.hook_min_trans = p.hook_min_trans;
     P.hook_min_rot = p.hook_min_rot_rad;
     std::memcpy(P.hook_checkpoint, p.hook_checkpoint_pose_3x4, sizeof(P.hook_checkpoint));
-    P.n_blocks = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
+    const uint32_t qpb = (ICP_BLOCK / 32) * qpw;
+    P.n_blocks = (P.n_q + qpb - 1) / qpb;
+    P.n_blocks_acc = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
     P.part_begin = part_total;
-    part_total += P.n_blocks;
+    part_total += std::max(P.n_blocks, P.n_blocks_acc);
     max_blocks = std::max(max_blocks, P.n_blocks);
+    max_blocks_acc = std::max(max_blocks_acc, P.n_blocks_acc);
     max_it = std::max(max_it, P.max_iterations);
     if (P.solver == MLO_SOLVER_GAUSS_NEWTON) max_inner = std::max(max_inner, P.gn_max_iterations);
   }
@@ -477,15 +485,16 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
 
   const size_t e_icp = prof_begin(c);
   const dim3 grid(std::max(max_blocks, 1u), B);
+  const dim3 grid_acc(std::max(max_blocks_acc, 1u), B);
   const uint32_t check_every = 4;
   for (uint32_t it = 0; it < max_it; it++) {
     const size_t e_nn = prof_begin(c);
     LAUNCH(c, k_match_accumulate, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-           c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+           c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
     prof_end(c, 3, e_nn);
     LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
     for (uint32_t inner = 1; inner < max_inner; inner++) {
-      LAUNCH(c, k_accumulate, grid, ICP_BLOCK, dP, dS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
+      LAUNCH(c, k_accumulate, grid_acc, ICP_BLOCK, dP, dS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
              c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
       LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active);
     }
@@ -591,19 +600,19 @@ int32_t mlo_voxel_index(float coord, float voxel_size) { return voxel_index_map(
 int mlo_map_create(mlo_ctx* c, const mlo_map_params* p, mlo_map** out) {
   if (!c || !p || !out) return MLO_ERR_INVALID_ARG;
   *out = nullptr;
-  if (!(p->voxel_size > 0.f) || p->capacity_voxels == 0 || p->capacity_voxels > (1ull << 27))
-    return fail(c, MLO_ERR_INVALID_ARG, "voxel_size must be > 0 and capacity_voxels in [1, 2^27]");
+  if (!(p->voxel_size > 0.f) || p->capacity_voxels == 0 || p->capacity_voxels > (1ull << 26))
+    return fail(c, MLO_ERR_INVALID_ARG, "voxel_size must be > 0 and capacity_voxels in [1, 2^26]");
   if (p->kind != MLO_MAP_HASHED_VOXEL_POINTS && p->kind != MLO_MAP_NDT) return fail(c, MLO_ERR_INVALID_ARG, "bad map kind");
   DeviceGuard g(c->device);
   auto* m = new mlo_map;
   m->ctx = c;
   m->prm = *p;
-  m->table_size = next_pow2(std::max<uint64_t>(4 * p->capacity_voxels, 1024));
+  m->table_size = next_pow2(std::max<uint64_t>(2 * p->capacity_voxels, 1024));
   int rc = alloc_map_buffers(c, *p, m->table_size, m->dev);
   if (rc == MLO_OK) rc = clear_map_buffers(c, m->dev, m->table_size);
   if (rc == MLO_OK) {
-    if (cudaMalloc(&m->head, m->table_size * sizeof(int32_t)) != cudaSuccess ||
-        cudaMemsetAsync(m->head, 0xFF, m->table_size * sizeof(int32_t), c->stream) != cudaSuccess)
+    if (cudaMalloc(&m->head, 4 * m->table_size * sizeof(int32_t)) != cudaSuccess ||
+        cudaMemsetAsync(m->head, 0xFF, 4 * m->table_size * sizeof(int32_t), c->stream) != cudaSuccess)
       rc = fail(c, MLO_ERR_CUDA, "cudaMalloc(head) failed");
   }
   if (rc != MLO_OK) {
@@ -694,7 +703,7 @@ int mlo_map_nn_single(const mlo_map* m, const float* q, uint32_t stride, uint64_
   float* dxyz = c->d_local.as<float>();
   float* dd2 = dxyz + 3 * n;
   uint8_t* df = reinterpret_cast<uint8_t*>(dd2 + n);
-  LAUNCH(c, k_nn_single, uint32_t((n + 127) / 128), 128, m->dev, c->d_in.as<float>(), stride, uint32_t(n), dxyz, dd2, df);
+  LAUNCH(c, k_nn_single, uint32_t((n * 32 + 127) / 128), 128, m->dev, c->d_in.as<float>(), stride, uint32_t(n), dxyz, dd2, df);
   CU(c, cudaMemcpyAsync(out_xyz, dxyz, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(out_d2, dd2, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(out_found, df, n, cudaMemcpyDeviceToHost, c->stream));
@@ -728,34 +737,28 @@ int mlo_map_export(const mlo_map* m, int32_t* keys, uint32_t* counts, float* xyz
   if (!keys || !counts || !xyz) return MLO_OK;
   if (nv > max_voxels || np > max_points) return fail(c, MLO_ERR_INVALID_ARG, "export buffers too small");
   if (nv == 0) return MLO_OK;
-  CU(c, c->d_local.ensure(nv * (sizeof(uint64_t) + 2 * sizeof(uint32_t)) + 64));
-  uint64_t* dk = c->d_local.as<uint64_t>();
-  uint32_t* dc = reinterpret_cast<uint32_t*>(dk + nv);
+  CU(c, c->d_local.ensure(nv * 5 * sizeof(uint32_t) + 64));
+  int32_t* dk = c->d_local.as<int32_t>();
+  uint32_t* dc = reinterpret_cast<uint32_t*>(dk + 3 * nv);
   uint32_t* dv = dc + nv;
-  uint32_t* cursor = c->d_misc.p ? c->d_misc.as<uint32_t>() + 16 : nullptr;
-  if (!cursor) {
-    CU(c, c->d_misc.ensure(256));
-    cursor = c->d_misc.as<uint32_t>() + 16;
-  }
+  CU(c, c->d_misc.ensure(256));
+  uint32_t* cursor = c->d_misc.as<uint32_t>() + 16;
   CU(c, cudaMemsetAsync(cursor, 0, sizeof(uint32_t), c->stream));
-  LAUNCH(c, k_export_list, uint32_t((m->table_size + 255) / 256), 256, m->dev, m->table_size, cursor, dk, dc, dv);
-  std::vector<uint64_t> hk(nv);
+  LAUNCH(c, k_export_list, uint32_t((m->table_size * 4 + 255) / 256), 256, m->dev, m->table_size, cursor, dk, dc, dv);
+  std::vector<int32_t> k3(3 * nv);
   std::vector<uint32_t> hc(nv), hv(nv);
-  CU(c, cudaMemcpyAsync(hk.data(), dk, nv * sizeof(uint64_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(k3.data(), dk, 3 * nv * sizeof(int32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(hc.data(), dc, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaMemcpyAsync(hv.data(), dv, nv * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  std::vector<float4> hp(size_t(nv) * m->dev.cap);
   CU(c, cudaStreamSynchronize(c->stream));
   // payload of the allocated voxels (ids are dense in [0, nv) right after a rebuild, sparse otherwise)
   uint32_t max_vid = 0;
   for (auto v : hv) max_vid = std::max(max_vid, v);
-  hp.resize(size_t(max_vid + 1) * m->dev.cap);
+  std::vector<float4> hp(size_t(max_vid + 1) * m->dev.cap);
   CU(c, cudaMemcpyAsync(hp.data(), m->dev.pts, hp.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   std::vector<uint32_t> order(nv);
   for (uint32_t i = 0; i < nv; i++) order[i] = i;
-  std::vector<int32_t> k3(3 * nv);
-  for (uint32_t i = 0; i < nv; i++) unpack_key(hk[i], k3[3 * i], k3[3 * i + 1], k3[3 * i + 2]);
   std::sort(order.begin(), order.end(), [&](uint32_t a, uint32_t b) {
     for (int k = 0; k < 3; k++)
       if (k3[3 * a + k] != k3[3 * b + k]) return k3[3 * a + k] < k3[3 * b + k];
