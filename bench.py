@@ -364,6 +364,7 @@ def main():
     for s in range(args.warmup):
         step_resident(s)
     ctx.profile_get(reset=True)
+    log(f"[bench] kernel launches before the timed region: {ctx.launch_count}")
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launch_count

@@ -124,6 +124,12 @@ int mlo_map_export(const mlo_map* map, int32_t* keys, uint32_t* counts, float* x
                    uint64_t max_points, uint64_t* n_voxels, uint64_t* n_points);
 /* The voxel index of one coordinate exactly as the device computes it (bit-exact parity probe). */
 int32_t mlo_voxel_index(float coord, float voxel_size);
+/* Host evaluations of the SE(3) routines the solve kernel uses (same source, compiled for the host):
+ * exp/log with tangent order (x y z rx ry rz), and d log(D exp(e))/de at e = 0 (6x6 row-major) used by the
+ * prior term of Solver_GaussNewton (LidarOdometry.cpp:854-877).  Pure functions, no device needed. */
+void mlo_se3_exp(const double xi[6], double pose_3x4[12]);
+void mlo_se3_log(const double pose_3x4[12], double xi[6]);
+void mlo_se3_right_jacobian_inv(const double xi[6], double J_6x6[36]);
 
 /* ------------------------------------------------------------------ filters
  * Replaces mp2p_icp_filters::FilterDecimateVoxels, DecimateMethod::FirstPoint

@@ -288,6 +288,65 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
+// Thread-per-query variant for large batches: one query per thread, map.cuh nn_single_thread (pruned,
+// 256-bit loads).  Same outputs and the same block-partial layout as k_match_accumulate.
+__global__ void __launch_bounds__(ICP_BLOCK, 4)
+    k_match_accumulate_tpq(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
+                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  const IcpProblem& P = probs[blockIdx.y];
+  if (blockIdx.x >= P.n_blocks) return;
+  const IcpState& S = states[blockIdx.y];
+  if (S.done) return;
+  __shared__ double sT[12];
+  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  __syncthreads();
+  const uint32_t it = S.it;
+  const double thr = table_at(P.thr_pt2pt, P.table_len, it);
+  const float thr2 = float(thr * thr);
+  const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
+  const double kc = table_at(P.kparam, P.table_len, it);
+  double a[NACC];
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
+  uint32_t npairs = 0, ncand = 0;
+  const uint32_t q = blockIdx.x * ICP_BLOCK + threadIdx.x;
+  if (q < P.n_q) {
+    const float4 l = __ldg(&local[P.q_begin + q]);
+    float gx, gy, gz;
+    compose_point_f(sT, l.x, l.y, l.z, gx, gy, gz);
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool paired = false;
+    if (P.matcher_mask & MLO_MATCHER_PT2PL) {
+      const PlaneHit h = nn_plane_thread(map, gx, gy, gz);
+      ncand += h.ncand;
+      if (h.found && h.dist < thr_pl) {
+        paired = true;
+        pa = make_float4(h.cx, h.cy, h.cz, 2.f);
+        pairB[P.q_begin + q] = make_float4(h.nx, h.ny, h.nz, 0.f);
+        contrib_pt2pl(sT, l.x, l.y, l.z, h.cx, h.cy, h.cz, h.nx, h.ny, h.nz, P.w_pt2pl, P.robust_kernel, kc, a);
+        npairs++;
+      }
+    }
+    if ((P.matcher_mask & MLO_MATCHER_PT2PT) && !paired) {
+      const NNHit h = nn_single_thread(map, gx, gy, gz);
+      ncand += h.ncand;
+      const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
+      if (h.found && h.d2 < lim) {
+        pa = make_float4(h.x, h.y, h.z, 1.f);
+        if (P.solver == MLO_SOLVER_GAUSS_NEWTON)
+          contrib_pt2pt(sT, l.x, l.y, l.z, h.x, h.y, h.z, P.w_pt2pt, P.robust_kernel, kc, a);
+        else
+          contrib_horn(l.x, l.y, l.z, h.x, h.y, h.z, a);
+        npairs++;
+      }
+    }
+    pairA[P.q_begin + q] = pa;
+  }
+  const uint32_t pbi = P.part_begin + blockIdx.x;
+  block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+}
+
 __global__ void __launch_bounds__(ICP_BLOCK)
     k_accumulate(const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states, const float4* __restrict__ local,
                  const float4* __restrict__ pairA, const float4* __restrict__ pairB, double* __restrict__ partials,

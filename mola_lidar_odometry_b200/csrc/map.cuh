@@ -38,7 +38,8 @@ struct MapDev {
   float4* mean;
   float4* normal;
   uint32_t* counters;  // [0] voxels allocated, [1] points stored, [2] error bits
-  uint32_t cap;
+  uint32_t cap;  // max points per voxel (logical)
+  uint32_t row;  // physical row length in float4 (cap rounded up to even: rows are 32-byte aligned)
   uint32_t capacity_voxels;
   float inv_voxel;
   float voxel_size;
@@ -148,7 +149,7 @@ MLO_D void jacobi3(double A[3][3], double V[3][3]) {
 }
 
 MLO_D void voxel_stats(const MapDev& m, uint32_t vid, uint32_t n) {
-  const float4* vp = m.pts + size_t(vid) * m.cap;
+  const float4* vp = m.pts + size_t(vid) * m.row;
   double mu[3] = {0, 0, 0};
   for (uint32_t j = 0; j < n; j++) {
     const float4 p = vp[j];
@@ -239,7 +240,7 @@ __global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__
   const uint32_t vid = cell_vid(w);
   uint32_t cnt = cell_cnt(w);
   if (vid >= m.capacity_voxels) return;  // capacity error already flagged
-  float4* vp = m.pts + size_t(vid) * m.cap;
+  float4* vp = m.pts + size_t(vid) * m.row;
   const uint32_t c0 = cnt;
   int32_t last = -1;
   while (cnt < m.cap) {
@@ -302,7 +303,7 @@ __global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_buckets, int32_t sx
     }
     nv = __shfl_sync(0xFFFFFFFFu, nv, 0);
     if (nv >= dst.capacity_voxels) continue;
-    if (lane < cnt) dst.pts[size_t(nv) * dst.cap + lane] = src.pts[size_t(ov) * src.cap + lane];
+    if (lane < cnt) dst.pts[size_t(nv) * dst.row + lane] = src.pts[size_t(ov) * src.row + lane];
     if (src.kind == MLO_MAP_NDT && lane == 0) {
       dst.mean[nv] = src.mean[ov];
       dst.normal[nv] = src.normal[ov];
@@ -319,54 +320,160 @@ struct NNHit {
   uint32_t ncand;
 };
 
-// Thread-per-query form (used by the plain query API and the NDT plane matcher).
+// 256-bit read-only loads (LDG.E.256 on sm_100a): one instruction per 32-byte bucket / per point pair.
+struct __align__(32) F8 {
+  float v[8];
+};
+MLO_D F8 ldg256_f(const void* p) {
+  F8 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=f"(r.v[0]), "=f"(r.v[1]), "=f"(r.v[2]), "=f"(r.v[3]), "=f"(r.v[4]), "=f"(r.v[5]), "=f"(r.v[6]),
+                 "=f"(r.v[7])
+               : "l"(p));
+  return r;
+}
+MLO_D BucketRO load_bucket256(const MapDev& m, uint64_t b) {
+  uint32_t x[8];
+  asm volatile("ld.global.nc.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(x[0]), "=r"(x[1]), "=r"(x[2]), "=r"(x[3]), "=r"(x[4]), "=r"(x[5]), "=r"(x[6]), "=r"(x[7])
+               : "l"(&m.buckets[b]));
+  BucketRO r;
+  r.key = (uint64_t(x[1]) << 32) | uint64_t(x[0]);
+  r.cell[0] = x[2];
+  r.cell[1] = x[3];
+  r.cell[2] = x[4];
+  r.cell[3] = x[5];
+  return r;
+}
+
+// Squared distance from q to the box of neighbour cell (kq + dd), a conservative lower bound for every
+// point stored in that cell.  Cell boxes follow the truncation-toward-zero index: cell 0 spans (-vs, vs),
+// cell c > 0 spans [c vs, (c+1) vs), cell c < 0 spans ((c-1) vs, c vs]; faces are pulled in by a few ulps
+// so a coordinate that rounds across a face is never excluded.
+MLO_D float cell_lower_bound2(float vs, const float qv[3], const int32_t kq[3], const int32_t dd[3]) {
+  float lb2 = 0.f;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    if (dd[a] == 0) continue;
+    const int32_t cc = kq[a] + dd[a];
+    float edge, gap;
+    if (dd[a] > 0) {  // lower face of cell cc
+      edge = cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs);
+      gap = edge - qv[a];
+    } else {  // upper face of cell cc
+      edge = cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs);
+      gap = qv[a] - edge;
+    }
+    gap -= 4e-6f * (fabsf(edge) + vs);
+    if (gap > 0.f) lb2 += gap * gap;
+  }
+  return lb2 * 0.99999f;
+}
+
+// Thread-per-query form: the high-MLP path of the fused ICP kernel for large batches (hundreds of
+// queries in flight per SM).  Probes: 9 columns x (1..2) buckets as 256-bit loads, issued three columns
+// at a time.  Exact pruning: the query's own cell is scanned first, a neighbour cell is read only if its
+// box can still hold a point at distance <= the running best; candidates are compared on
+// (d2, canonical order) so the result equals the sequential first-minimum scan bit for bit.
 MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
   NNHit r;
   r.x = r.y = r.z = 0.f;
   r.d2 = __int_as_float(0x7f800000);
   r.found = 0;
   r.ncand = 0;
-  const int32_t kx = voxel_index_map(qx, m.inv_voxel), ky = voxel_index_map(qy, m.inv_voxel),
-                kz = voxel_index_map(qz, m.inv_voxel);
-  if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) return r;
-#pragma unroll 1
-  for (int dx = -1; dx <= 1; dx++) {
-#pragma unroll 1
-    for (int dy = -1; dy <= 1; dy++) {
-      // the column's three cells live in one or two buckets
-      uint32_t w[3] = {CELL_ABSENT, CELL_ABSENT, CELL_ABSENT};
-      BucketRO b;
-      const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
-      if (find_column(m, pack_key(kx + dx, ky + dy, zq0), b)) {
+  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel),
+                         voxel_index_map(qz, m.inv_voxel)};
+  if (!(key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]))) return r;
+  const int32_t kz = kq[2];
+  const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
+  const bool needB = zq1 != zq0;
+  uint32_t w[27];
 #pragma unroll
-        for (int t = 0; t < 3; t++)
-          if (((kz - 1 + t) >> 2) == zq0) w[t] = b.cell[(kz - 1 + t) & 3];
+  for (int cx = 0; cx < 3; cx++) {
+    BucketRO a[3], b[3];
+    uint64_t ka[3], kb[3], ha[3], hb[3];
+#pragma unroll
+    for (int cy = 0; cy < 3; cy++) {
+      ka[cy] = pack_key(kq[0] + cx - 1, kq[1] + cy - 1, zq0);
+      ha[cy] = hash_key(ka[cy]) & m.mask;
+      a[cy] = load_bucket256(m, ha[cy]);
+    }
+    if (needB) {
+#pragma unroll
+      for (int cy = 0; cy < 3; cy++) {
+        kb[cy] = pack_key(kq[0] + cx - 1, kq[1] + cy - 1, zq1);
+        hb[cy] = hash_key(kb[cy]) & m.mask;
+        b[cy] = load_bucket256(m, hb[cy]);
       }
-      if (zq1 != zq0 && find_column(m, pack_key(kx + dx, ky + dy, zq1), b)) {
+    }
 #pragma unroll
-        for (int t = 0; t < 3; t++)
-          if (((kz - 1 + t) >> 2) == zq1) w[t] = b.cell[(kz - 1 + t) & 3];
+    for (int cy = 0; cy < 3; cy++) {
+      while (a[cy].key != ka[cy] && a[cy].key != KEY_EMPTY) {
+        ha[cy] = (ha[cy] + 1) & m.mask;
+        a[cy] = load_bucket256(m, ha[cy]);
+      }
+      if (needB) {
+        while (b[cy].key != kb[cy] && b[cy].key != KEY_EMPTY) {
+          hb[cy] = (hb[cy] + 1) & m.mask;
+          b[cy] = load_bucket256(m, hb[cy]);
+        }
       }
 #pragma unroll
       for (int t = 0; t < 3; t++) {
-        if (w[t] == CELL_ABSENT || w[t] == CELL_PENDING) continue;
-        const float4* vp = m.pts + size_t(cell_vid(w[t])) * m.cap;
-        const uint32_t c = cell_cnt(w[t]);
-        r.ncand += c;
-        for (uint32_t j = 0; j < c; j++) {
-          const float4 p = __ldg(&vp[j]);
-          const float d2 = sqr_dist(p.x, p.y, p.z, qx, qy, qz);
-          if (d2 < r.d2) {
-            r.d2 = d2;
-            r.x = p.x;
-            r.y = p.y;
-            r.z = p.z;
-            r.found = 1;
+        const int32_t z = kz - 1 + t;
+        const bool inA = (z >> 2) == zq0;
+        const bool have = inA ? (a[cy].key == ka[cy]) : (needB && b[cy].key == kb[cy]);
+        const uint32_t s = uint32_t(z & 3);
+        const uint32_t wa = s == 0 ? a[cy].cell[0] : s == 1 ? a[cy].cell[1] : s == 2 ? a[cy].cell[2] : a[cy].cell[3];
+        uint32_t wb = CELL_ABSENT;
+        if (needB) wb = s == 0 ? b[cy].cell[0] : s == 1 ? b[cy].cell[1] : s == 2 ? b[cy].cell[2] : b[cy].cell[3];
+        uint32_t ww = have ? (inA ? wa : wb) : CELL_ABSENT;
+        if (ww == CELL_PENDING) ww = CELL_ABSENT;
+        w[(cx * 3 + cy) * 3 + t] = ww;
+        if (ww != CELL_ABSENT) r.ncand += cell_cnt(ww);
+      }
+    }
+  }
+  uint32_t border = 0xFFFFFFFFu;
+  const float qv[3] = {qx, qy, qz};
+  auto scan_cell = [&](uint32_t ww, uint32_t e) {
+    const float4* row = m.pts + size_t(cell_vid(ww)) * m.row;
+    const uint32_t c = cell_cnt(ww);
+    for (uint32_t j = 0; j < c; j += 8) {
+      F8 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; u++)
+        if (j + 2 * u < c) v[u] = ldg256_f(row + j + 2 * u);
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+#pragma unroll
+        for (int hlf = 0; hlf < 2; hlf++) {
+          const uint32_t jj = j + 2 * u + hlf;
+          if (jj < c) {
+            const float px = v[u].v[4 * hlf], py = v[u].v[4 * hlf + 1], pz = v[u].v[4 * hlf + 2];
+            const float d2 = sqr_dist(px, py, pz, qx, qy, qz);
+            const uint32_t ord = e * 32u + jj;
+            if (d2 < r.d2 || (d2 == r.d2 && ord < border)) {
+              r.d2 = d2;
+              r.x = px;
+              r.y = py;
+              r.z = pz;
+              border = ord;
+            }
           }
         }
       }
     }
+  };
+  if (w[13] != CELL_ABSENT) scan_cell(w[13], 13u);
+#pragma unroll 1
+  for (int e = 0; e < 27; e++) {
+    if (e == 13) continue;
+    if (w[e] == CELL_ABSENT || cell_cnt(w[e]) == 0) continue;
+    const int32_t dd[3] = {e / 9 - 1, (e / 3) % 3 - 1, e % 3 - 1};
+    if (cell_lower_bound2(m.voxel_size, qv, kq, dd) <= r.d2) scan_cell(w[e], uint32_t(e));
   }
+  r.found = border != 0xFFFFFFFFu;
   return r;
 }
 
@@ -457,7 +564,7 @@ MLO_D NNHit warp_nn_finish(const MapDev& m, WarpProbe& p, float qx, float qy, fl
   if (w_home != CELL_ABSENT) {
     const uint32_t c = cell_cnt(w_home);
     if (lane < c) {
-      const float4 q = __ldg(m.pts + size_t(cell_vid(w_home)) * m.cap + lane);
+      const float4 q = __ldg(m.pts + size_t(cell_vid(w_home)) * m.row + lane);
       best = sqr_dist(q.x, q.y, q.z, qx, qy, qz);
       bx = q.x;
       by = q.y;
@@ -470,27 +577,10 @@ MLO_D NNHit warp_nn_finish(const MapDev& m, WarpProbe& p, float qx, float qy, fl
   }
   bool visit = my_cnt > 0 && lane != 13;
   if (visit && bound < __int_as_float(0x7f800000)) {
-    const float vs = m.voxel_size;
     const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel), p.kz};
     const float qv[3] = {qx, qy, qz};
     const int32_t dd[3] = {int32_t(lane / 9) - 1, int32_t((lane / 3) % 3) - 1, int32_t(lane % 3) - 1};
-    float lb2 = 0.f;
-#pragma unroll
-    for (int a = 0; a < 3; a++) {
-      if (dd[a] == 0) continue;
-      const int32_t cc = kq[a] + dd[a];
-      float edge, gap;
-      if (dd[a] > 0) {  // lower face of cell cc
-        edge = cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs);
-        gap = edge - qv[a];
-      } else {          // upper face of cell cc
-        edge = cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs);
-        gap = qv[a] - edge;
-      }
-      gap -= 4e-6f * (fabsf(edge) + vs);
-      if (gap > 0.f) lb2 += gap * gap;
-    }
-    visit = lb2 * 0.99999f <= bound;
+    visit = cell_lower_bound2(m.voxel_size, qv, kq, dd) <= bound;
   }
   uint32_t occ = __ballot_sync(FULL, visit);
   while (occ) {
@@ -504,7 +594,7 @@ MLO_D NNHit warp_nn_finish(const MapDev& m, WarpProbe& p, float qx, float qy, fl
         occ &= occ - 1;
         const uint32_t w = __shfl_sync(FULL, mine, e[k]);
         c[k] = cell_cnt(w);
-        if (lane < c[k]) q[k] = __ldg(m.pts + size_t(cell_vid(w)) * m.cap + lane);
+        if (lane < c[k]) q[k] = __ldg(m.pts + size_t(cell_vid(w)) * m.row + lane);
       } else {
         c[k] = 0;
         e[k] = 0;

@@ -68,6 +68,7 @@ struct mlo_ctx {
   std::string err;
   uint64_t launches = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
+  int force_kernel = 0;  // 0 auto, 1 thread-per-query, 2 warp-per-query (MLO_FORCE_KERNEL, experiments only)
   std::string dev_name;
   // scratch
   DBuf d_in, d_local, d_pairA, d_pairB, d_partials, d_partcnt, d_probs, d_states, d_tables, d_init, d_misc;
@@ -175,6 +176,7 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
   uint32_t cap = p.max_points_per_voxel;
   if (cap == 0 || cap > HARD_LIMIT_PTS) cap = HARD_LIMIT_PTS;
   d.cap = cap;
+  d.row = (cap + 1u) & ~1u;
   d.capacity_voxels = uint32_t(p.capacity_voxels);
   d.inv_voxel = 1.0f / p.voxel_size;
   d.voxel_size = p.voxel_size;
@@ -184,7 +186,7 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
   d.kind = p.kind;
   d.mask = table_size - 1;
   CU(c, cudaMalloc(&d.buckets, table_size * sizeof(Bucket)));
-  CU(c, cudaMalloc(&d.pts, size_t(p.capacity_voxels) * cap * sizeof(float4)));
+  CU(c, cudaMalloc(&d.pts, size_t(p.capacity_voxels) * d.row * sizeof(float4)));
   CU(c, cudaMalloc(&d.counters, 4 * sizeof(uint32_t)));
   d.mean = d.normal = nullptr;
   if (p.kind == MLO_MAP_NDT) {
@@ -409,6 +411,8 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   const uint64_t total_queries = offsets[B];
   uint32_t qpw = 32;
   while (qpw > 1 && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
+  // large batches: thread-per-query kernel (hundreds of queries in flight per SM); small: warp-per-query
+  const bool use_tpq = c->force_kernel == 1 || (c->force_kernel == 0 && total_queries >= uint64_t(c->sm_count) * 256);
   for (uint32_t b = 0; b < B; b++) {
     const mlo_icp_params& p = params[b];
     IcpProblem& P = probs[b];
@@ -444,7 +448,7 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     P.hook_min_trans = p.hook_min_trans;
     P.hook_min_rot = p.hook_min_rot_rad;
     std::memcpy(P.hook_checkpoint, p.hook_checkpoint_pose_3x4, sizeof(P.hook_checkpoint));
-    const uint32_t qpb = (ICP_BLOCK / 32) * qpw;
+    const uint32_t qpb = use_tpq ? ICP_BLOCK : (ICP_BLOCK / 32) * qpw;
     P.n_blocks = (P.n_q + qpb - 1) / qpb;
     P.n_blocks_acc = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
     P.part_begin = part_total;
@@ -489,8 +493,12 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   const uint32_t check_every = 4;
   for (uint32_t it = 0; it < max_it; it++) {
     const size_t e_nn = prof_begin(c);
-    LAUNCH(c, k_match_accumulate, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-           c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
+    if (use_tpq)
+      LAUNCH(c, k_match_accumulate_tpq, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+    else
+      LAUNCH(c, k_match_accumulate, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
     prof_end(c, 3, e_nn);
     LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
     for (uint32_t inner = 1; inner < max_inner; inner++) {
@@ -553,6 +561,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->cc_major = prop.major;
   c->cc_minor = prop.minor;
   c->dev_name = prop.name;
+  if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
   cudaSetDevice(cuda_device);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
@@ -595,6 +604,9 @@ void* mlo_stream(const mlo_ctx* c) { return c ? (void*)c->stream : nullptr; }
 uint64_t mlo_launch_count(const mlo_ctx* c) { return c ? c->launches : 0; }
 
 int32_t mlo_voxel_index(float coord, float voxel_size) { return voxel_index_map(coord, 1.0f / voxel_size); }
+void mlo_se3_exp(const double xi[6], double pose[12]) { se3_exp(xi, pose); }
+void mlo_se3_log(const double pose[12], double xi[6]) { se3_log(pose, xi); }
+void mlo_se3_right_jacobian_inv(const double xi[6], double J[36]) { se3_right_jacobian_inv(xi, J); }
 
 // ------------------------------------------------------------------ map
 int mlo_map_create(mlo_ctx* c, const mlo_map_params* p, mlo_map** out) {
@@ -754,7 +766,7 @@ int mlo_map_export(const mlo_map* m, int32_t* keys, uint32_t* counts, float* xyz
   // payload of the allocated voxels (ids are dense in [0, nv) right after a rebuild, sparse otherwise)
   uint32_t max_vid = 0;
   for (auto v : hv) max_vid = std::max(max_vid, v);
-  std::vector<float4> hp(size_t(max_vid + 1) * m->dev.cap);
+  std::vector<float4> hp(size_t(max_vid + 1) * m->dev.row);
   CU(c, cudaMemcpyAsync(hp.data(), m->dev.pts, hp.size() * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
   std::vector<uint32_t> order(nv);
@@ -771,7 +783,7 @@ int mlo_map_export(const mlo_map* m, int32_t* keys, uint32_t* counts, float* xyz
     counts[i] = hc[s];
     for (uint32_t j = 0; j < hc[s]; j++) {
       if (o >= max_points) return fail(c, MLO_ERR_INVALID_ARG, "export buffers too small");
-      const float4 p = hp[size_t(hv[s]) * m->dev.cap + j];
+      const float4 p = hp[size_t(hv[s]) * m->dev.row + j];
       xyz[3 * o] = p.x;
       xyz[3 * o + 1] = p.y;
       xyz[3 * o + 2] = p.z;
