@@ -276,7 +276,7 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="scans per step per GPU")
+    ap.add_argument("--batch", type=int, default=256, help="scans per step per GPU")
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
