@@ -42,6 +42,20 @@ MLO_HD void unpack_key(uint64_t k, int32_t& kx, int32_t& ky, int32_t& kz) {
   ky = int32_t((k >> 21) & 0x1FFFFFu) - KEY_BIAS;
   kz = int32_t(k & 0x1FFFFFu) - KEY_BIAS;
 }
+// 32-bit cell hash: one multiply per axis (shared between the 9 columns of a neighbourhood probe) and a
+// short avalanche; cheap on the integer pipe (the 64-bit finaliser below costs ~4x the instructions).
+MLO_HD uint32_t hash_mix(uint32_t h) {
+  h ^= h >> 15;
+  h *= 0x2C1B3C6Du;
+  h ^= h >> 12;
+  h *= 0x297A2D39u;
+  h ^= h >> 15;
+  return h;
+}
+constexpr uint32_t HASH_PX = 0x9E3779B1u, HASH_PY = 0x85EBCA77u, HASH_PZ = 0xC2B2AE3Du;
+MLO_HD uint32_t hash_cell(int32_t kx, int32_t ky, int32_t kz) {
+  return hash_mix(uint32_t(kx) * HASH_PX ^ uint32_t(ky) * HASH_PY ^ uint32_t(kz) * HASH_PZ);
+}
 // 64-bit finaliser (splitmix / murmur3 style): spreads neighbouring cells over the table.
 MLO_HD uint64_t hash_key(uint64_t k) {
   k ^= k >> 33;
@@ -64,6 +78,12 @@ MLO_HD void compose_point_f(const double* T, float lx, float ly, float lz, float
   gx = static_cast<float>(T[0] * x + T[1] * y + T[2] * z + T[3]);
   gy = static_cast<float>(T[4] * x + T[5] * y + T[6] * z + T[7]);
   gz = static_cast<float>(T[8] * x + T[9] * y + T[10] * z + T[11]);
+}
+
+MLO_HD uint32_t hash_packed(uint64_t k) {
+  int32_t kx, ky, kz;
+  unpack_key(k, kx, ky, kz);
+  return hash_cell(kx, ky, kz);
 }
 
 MLO_HD float sqr_dist(float ax, float ay, float az, float bx, float by, float bz) {

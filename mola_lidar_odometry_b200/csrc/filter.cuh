@@ -75,7 +75,7 @@ __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_hash(const DecimJob* __re
                     kz = voxel_index_filter(p.z, j.resolution);
       if (key_in_range(kx) && key_in_range(ky) && key_in_range(kz)) {
         const uint64_t key = pack_key(kx, ky, kz);
-        uint32_t h = uint32_t(hash_key(key)) & j.tab_mask;
+        uint32_t h = hash_cell(kx, ky, kz) & j.tab_mask;
         for (;;) {
           unsigned long long* kp = reinterpret_cast<unsigned long long*>(&j.tab_keys[h]);
           unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);

@@ -179,30 +179,24 @@ MLO_D void block_reduce_store(double* a, uint32_t npairs, uint32_t ncand, double
 
 // pair record: A = (gx, gy, gz | cx, cy, cz, kind) with kind 0 none, 1 pt2pt, 2 pt2pl; B = plane normal.
 //
-// Work decomposition: a warp owns `qpw` consecutive queries (qpw = 32 for throughput, smaller for
-// latency-bound small batches).  Lane t holds query t: its local point, its transformed point and, after
-// the warp-cooperative NN of that query (map.cuh: probe prefetched one query ahead), its pairing.  The
-// normal-equation terms are then computed once per query by the owning lane and butterfly-reduced.
-__global__ void __launch_bounds__(ICP_BLOCK)
-    k_match_accumulate(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
-                       const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
-                       double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
-  const IcpProblem& P = probs[blockIdx.y];
-  if (blockIdx.x >= P.n_blocks) return;
-  const IcpState& S = states[blockIdx.y];
-  if (S.done) return;
-  __shared__ double sT[12];
-  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
-  __syncthreads();
+// A "chunk" is the unit of work of one thread block: ICP_BLOCK queries (thread-per-query form) or
+// 4 warps x qpw queries (warp-per-query form).  The chunk functions below are shared by the
+// one-kernel-per-phase launch sequence and by the persistent queue-driven kernel.
+
+// Warp-per-query chunk: a warp owns `qpw` consecutive queries.  Lane t holds query t: its local point, its
+// transformed point and, after the warp-cooperative NN of that query (map.cuh: probe prefetched one query
+// ahead), its pairing.  The normal-equation terms are computed once per query by the owning lane.
+MLO_D void chunk_match_warp(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
+                            const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                            double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
   const uint32_t FULL = 0xFFFFFFFFu;
-  const uint32_t it = S.it;
   const double thr = table_at(P.thr_pt2pt, P.table_len, it);
   const float thr2 = float(thr * thr);
   const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
   const double kc = table_at(P.kparam, P.table_len, it);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
 
-  const uint32_t qbase = (blockIdx.x * (ICP_BLOCK / 32) + warp) * qpw;  // first query of this warp
+  const uint32_t qbase = (chunk * (ICP_BLOCK / 32) + warp) * qpw;  // first query of this warp
   const uint32_t nq_warp = qbase < P.n_q ? min(qpw, P.n_q - qbase) : 0u;
   const bool mine = lane < nq_warp;
   float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -284,33 +278,25 @@ __global__ void __launch_bounds__(ICP_BLOCK)
     }
     pairA[P.q_begin + qbase + lane] = pa;
   }
-  const uint32_t pbi = P.part_begin + blockIdx.x;
+  const uint32_t pbi = P.part_begin + chunk;
   block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
-// Thread-per-query variant for large batches: one query per thread, map.cuh nn_single_thread (pruned,
-// 256-bit loads).  Same outputs and the same block-partial layout as k_match_accumulate.
-__global__ void __launch_bounds__(ICP_BLOCK, 4)
-    k_match_accumulate_tpq(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
+// Thread-per-query chunk for large batches: one query per thread, map.cuh nn_single_thread (pruned,
+// 256-bit loads).  Same outputs and the same block-partial layout as the warp form.
+MLO_D void chunk_match_tpq(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                            const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                            double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
-  const IcpProblem& P = probs[blockIdx.y];
-  if (blockIdx.x >= P.n_blocks) return;
-  const IcpState& S = states[blockIdx.y];
-  if (S.done) return;
-  __shared__ double sT[12];
-  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
-  __syncthreads();
-  const uint32_t it = S.it;
   const double thr = table_at(P.thr_pt2pt, P.table_len, it);
   const float thr2 = float(thr * thr);
   const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
   const double kc = table_at(P.kparam, P.table_len, it);
+  __shared__ uint32_t s_words[27][ICP_BLOCK];  // per-thread packed cell words of the 3x3x3 neighbourhood
   double a[NACC];
 #pragma unroll
   for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
   uint32_t npairs = 0, ncand = 0;
-  const uint32_t q = blockIdx.x * ICP_BLOCK + threadIdx.x;
+  const uint32_t q = chunk * ICP_BLOCK + threadIdx.x;
   if (q < P.n_q) {
     const float4 l = __ldg(&local[P.q_begin + q]);
     float gx, gy, gz;
@@ -329,7 +315,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
       }
     }
     if ((P.matcher_mask & MLO_MATCHER_PT2PT) && !paired) {
-      const NNHit h = nn_single_thread(map, gx, gy, gz);
+      const NNHit h = nn_single_thread(map, gx, gy, gz, &s_words[0][threadIdx.x], ICP_BLOCK);
       ncand += h.ncand;
       const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
       if (h.found && h.d2 < lim) {
@@ -343,42 +329,241 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
     }
     pairA[P.q_begin + q] = pa;
   }
-  const uint32_t pbi = P.part_begin + blockIdx.x;
+  const uint32_t pbi = P.part_begin + chunk;
   block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
-__global__ void __launch_bounds__(ICP_BLOCK)
-    k_accumulate(const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states, const float4* __restrict__ local,
-                 const float4* __restrict__ pairA, const float4* __restrict__ pairB, double* __restrict__ partials,
-                 uint32_t* __restrict__ part_cnt) {
-  const IcpProblem& P = probs[blockIdx.y];
-  if (blockIdx.x >= P.n_blocks_acc) return;
-  const IcpState& S = states[blockIdx.y];
-  if (S.done || !S.inner_pending) return;
-  __shared__ double sT[12];
-  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
-  __syncthreads();
-  const double kc = table_at(P.kparam, P.table_len, S.it);
+// Work-list chunk (large batches): probes are thread-per-query (each lane keeps 9-18 independent 256-bit
+// bucket loads in flight), the 27 packed cell words of every query land in shared memory, and the candidate
+// gather is drained COOPERATIVELY from a flattened per-warp list of 8-point row segments: 8 lanes per segment
+// (one coalesced 128-byte read), 4 segments per warp instruction, 4 instructions in flight.  Each query's
+// running best is one 64-bit (d2 bits << 32 | canonical order) word updated by a shared-memory atomicMin, which
+// is exactly the sequential first-minimum rule.  Exact pruning as in map.cuh: own cell first, then only the
+// neighbour cells whose box can still beat that bound.
+constexpr uint32_t WL_CAP = 768;
+struct WarpScratch {
+  uint32_t words[27][32];
+  float q[3][32];
+  unsigned long long best[32];
+  uint16_t list[WL_CAP];
+};
+
+MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  for (uint32_t base = 0; base < n; base += 16) {
+    float4 p[4];
+    uint32_t meta[4];  // (valid << 31) | (order << 5) | q, order = e*32 + slot; q is shared by the 8 lanes of a segment
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      const uint32_t idx = base + u * 4 + grp;
+      meta[u] = 0;
+      if (idx < n) {
+        const uint32_t it = ws.list[idx];
+        const uint32_t q = it & 31u, e = (it >> 5) & 31u, slot = (it >> 10) * 8u + sub;
+        const uint32_t w = ws.words[e][q];
+        meta[u] = q;
+        if (slot < cell_cnt(w)) {
+          p[u] = __ldg(map.pts + size_t(cell_vid(w)) * map.row + slot);
+          meta[u] = 0x80000000u | ((e * 32u + slot) << 5) | q;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 4; u++) {
+      unsigned long long key = ~0ull;
+      const uint32_t q = meta[u] & 31u;
+      if (meta[u] & 0x80000000u) {
+        const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]);
+        key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {  // segmented min over the 8 lanes of the segment (uniform control flow)
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+        key = other < key ? other : key;
+      }
+      if (sub == 0 && key != ~0ull) atomicMin(&ws.best[q], key);
+    }
+  }
+  __syncwarp();
+}
+
+MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
+                          const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                          double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  __shared__ WarpScratch s_ws[ICP_BLOCK / 32];
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const double thr = table_at(P.thr_pt2pt, P.table_len, it);
+  const float thr2 = float(thr * thr);
+  const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
+  const double kc = table_at(P.kparam, P.table_len, it);
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  WarpScratch& ws = s_ws[warp];
+  const uint32_t q = chunk * ICP_BLOCK + threadIdx.x;
+  const bool mine = q < P.n_q;
+  float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
+  float gx = 0.f, gy = 0.f, gz = 0.f;
+  if (mine) {
+    l = __ldg(&local[P.q_begin + q]);
+    compose_point_f(sT, l.x, l.y, l.z, gx, gy, gz);
+  }
+  float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t ncand = 0;
+  bool paired = false;
+  if ((P.matcher_mask & MLO_MATCHER_PT2PL) && mine) {
+    const PlaneHit h = nn_plane_thread(map, gx, gy, gz);
+    ncand += h.ncand;
+    if (h.found && h.dist < thr_pl) {
+      paired = true;
+      pa = make_float4(h.cx, h.cy, h.cz, 2.f);
+      pb = make_float4(h.nx, h.ny, h.nz, 0.f);
+    }
+  }
+  if (P.matcher_mask & MLO_MATCHER_PT2PT) {
+    const bool want = mine && !paired;  // Matcher base rule: already-paired local points are skipped
+    ws.q[0][lane] = gx;
+    ws.q[1][lane] = gy;
+    ws.q[2][lane] = gz;
+    ws.best[lane] = ~0ull;
+    int32_t kq[3] = {0, 0, 0};
+    bool active = false;
+    if (want) {
+      kq[0] = voxel_index_map(gx, map.inv_voxel);
+      kq[1] = voxel_index_map(gy, map.inv_voxel);
+      kq[2] = voxel_index_map(gz, map.inv_voxel);
+      active = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
+    }
+    // ---- phase 1: probes (thread per query), words -> shared memory
+    if (active) {
+      ncand += probe_words(map, kq, &ws.words[0][lane], 32);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 27; e++) ws.words[e][lane] = CELL_ABSENT;
+    }
+    __syncwarp();
+    // ---- phase 2: own cells
+    {
+      const uint32_t wh = ws.words[13][lane];
+      const uint32_t np = (wh == CELL_ABSENT) ? 0u : (cell_cnt(wh) + 7u) >> 3;
+      uint32_t incl = np;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= uint32_t(o)) incl += y;
+      }
+      const uint32_t total = __shfl_sync(FULL, incl, 31);
+      uint32_t off = incl - np;
+      for (uint32_t k = 0; k < np; k++) ws.list[off + k] = uint16_t((k << 10) | (13u << 5) | lane);
+      __syncwarp();
+      wl_process(map, ws, total);
+    }
+    // ---- phase 3: per query, the neighbour cells that can still beat the bound from the own cell
+    uint32_t visit = 0, my_items = 0;
+    if (active) {
+      const unsigned long long b0 = ws.best[lane];
+      const float bound = (b0 == ~0ull) ? __int_as_float(0x7f800000) : __uint_as_float(uint32_t(b0 >> 32));
+      const float qv[3] = {gx, gy, gz};
+      const AxisGaps gaps = axis_gaps(map.voxel_size, qv, kq);
+#pragma unroll
+      for (int e = 0; e < 27; e++) {
+        if (e == 13) continue;
+        const uint32_t we = ws.words[e][lane];
+        if (we == CELL_ABSENT || cell_cnt(we) == 0) continue;
+        if (MLO_LB2(gaps, e) <= bound) {
+          visit |= 1u << e;
+          my_items += (cell_cnt(we) + 7u) >> 3;
+        }
+      }
+    }
+    // ---- phase 4: drain the neighbour segments, in lane ranges that fit the list
+    uint32_t start = 0;
+    while (start < 32) {
+      const uint32_t c = lane >= start ? my_items : 0u;
+      uint32_t incl = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, incl, o);
+        if (lane >= uint32_t(o)) incl += y;
+      }
+      const uint32_t end = __popc(__ballot_sync(FULL, incl <= WL_CAP));  // fits is a prefix of the lanes
+      const uint32_t total = __shfl_sync(FULL, incl, end - 1);
+      if (lane >= start && lane < end) {
+        uint32_t off = incl - c;
+        uint32_t m = visit;
+        while (m) {
+          const uint32_t e = __ffs(m) - 1;
+          m &= m - 1;
+          const uint32_t np = (cell_cnt(ws.words[e][lane]) + 7u) >> 3;
+          for (uint32_t k = 0; k < np; k++) ws.list[off++] = uint16_t((k << 10) | (e << 5) | lane);
+        }
+      }
+      __syncwarp();
+      wl_process(map, ws, total);
+      start = end;
+    }
+    // ---- result per query
+    if (active) {
+      const unsigned long long b = ws.best[lane];
+      if (b != ~0ull) {
+        const float d2 = __uint_as_float(uint32_t(b >> 32));
+        const uint32_t ord = uint32_t(b & 0xFFFFFFFFu), e = ord >> 5, slot = ord & 31u;
+        const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
+        if (d2 < lim) {
+          const float4 g = __ldg(map.pts + size_t(cell_vid(ws.words[e][lane])) * map.row + slot);
+          pa = make_float4(g.x, g.y, g.z, 1.f);
+        }
+      }
+    }
+    __syncwarp();
+  }
   double a[NACC];
 #pragma unroll
   for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
   uint32_t npairs = 0;
-  const uint32_t q = blockIdx.x * ICP_BLOCK + threadIdx.x;
+  if (mine) {
+    if (pa.w == 1.f) {
+      if (P.solver == MLO_SOLVER_GAUSS_NEWTON)
+        contrib_pt2pt(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
+      else
+        contrib_horn(l.x, l.y, l.z, pa.x, pa.y, pa.z, a);
+      npairs = 1;
+    } else if (pa.w == 2.f) {
+      contrib_pt2pl(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+      npairs = 1;
+      pairB[P.q_begin + q] = pb;
+    }
+    pairA[P.q_begin + q] = pa;
+  }
+  const uint32_t pbi = P.part_begin + chunk;
+  block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+}
+
+// Inner Gauss-Newton iterations >= 1: re-linearise over the stored pairings (no NN). Pairings were written
+// by other blocks, possibly within the same launch: read them through L2 (ld.global.cg).
+MLO_D void chunk_accumulate(const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
+                            const float4* __restrict__ local, const float4* pairA, const float4* pairB,
+                            double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  const double kc = table_at(P.kparam, P.table_len, it);
+  double a[NACC];
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
+  uint32_t npairs = 0;
+  const uint32_t q = chunk * ICP_BLOCK + threadIdx.x;
   if (q < P.n_q) {
-    const float4 pa = pairA[P.q_begin + q];
+    const float4 pa = __ldcg(&pairA[P.q_begin + q]);
     if (pa.w != 0.f) {
       const float4 l = __ldg(&local[P.q_begin + q]);
       if (pa.w == 1.f) {
         contrib_pt2pt(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
       } else {
-        const float4 nb = pairB[P.q_begin + q];
+        const float4 nb = __ldcg(&pairB[P.q_begin + q]);
         contrib_pt2pl(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, nb.x, nb.y, nb.z, P.w_pt2pl, P.robust_kernel, kc, a);
       }
       npairs++;
     }
   }
-  const uint32_t pb = P.part_begin + blockIdx.x;
-  block_reduce_store(a, npairs, 0u, partials + size_t(pb) * NACC, part_cnt + 2 * size_t(pb));
+  const uint32_t pbi = P.part_begin + chunk;
+  block_reduce_store(a, npairs, 0u, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
 // Horn's closed form from the reduced sums (Solver_Horn): dominant eigenvector of the 4x4 N matrix.
@@ -481,111 +666,178 @@ MLO_D void finish_iteration(const IcpProblem& P, IcpState& S) {
   }
 }
 
-// one warp per problem. `after_match` = 1 when the partials come from k_match_accumulate (inner 0).
-__global__ void __launch_bounds__(32)
-    k_solve(const IcpProblem* __restrict__ probs, IcpState* __restrict__ states, const double* __restrict__ partials,
-            const uint32_t* __restrict__ part_cnt, int after_match, uint32_t* __restrict__ n_active) {
-  const IcpProblem& P = probs[blockIdx.x];
-  IcpState& S = states[blockIdx.x];
-  if (S.done) return;
-  if (!after_match && !S.inner_pending) return;
-  const uint32_t lane = threadIdx.x;
-  // ordered sum over this problem's block partials: lane k owns element k
+// The solve step, executed by ONE warp: ordered sum of the problem's block partials (lane k owns element k,
+// read through L2), then lane 0 applies the prior, solves the 6x6 system, retracts and does the
+// end-of-iteration bookkeeping.  Returns (on every lane) 0 = problem finished, 1 = another inner GN
+// iteration is pending, 2 = next ICP iteration.
+__device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const double* partials, const uint32_t* part_cnt, int after_match) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u;
   double acc = 0.0;
   uint32_t cnt = 0;
   const uint32_t nblk = after_match ? P.n_blocks : P.n_blocks_acc;
   if (lane < NACC) {
-    for (uint32_t b = 0; b < nblk; b++) acc += partials[size_t(P.part_begin + b) * NACC + lane];
+    for (uint32_t b = 0; b < nblk; b++) acc += __ldcg(&partials[size_t(P.part_begin + b) * NACC + lane]);
   } else if (lane < NACC + 2) {
-    for (uint32_t b = 0; b < nblk; b++) cnt += part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)];
+    for (uint32_t b = 0; b < nblk; b++) cnt += __ldcg(&part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)]);
   }
   double a[NACC];
 #pragma unroll
-  for (int k = 0; k < int(NACC); k++) a[k] = __shfl_sync(0xFFFFFFFFu, acc, k);
-  const uint32_t npairs = __shfl_sync(0xFFFFFFFFu, cnt, NACC);
-  const uint32_t ncand = __shfl_sync(0xFFFFFFFFu, cnt, NACC + 1);
-  if (lane != 0) return;
-
-  if (after_match) {
-    S.n_pairs = npairs;
-    uint64_t pot = 0;
-    if (P.matcher_mask & MLO_MATCHER_PT2PL) pot += P.n_q;
-    if (P.matcher_mask & MLO_MATCHER_PT2PT) pot += P.n_q;
-    S.n_potential = pot;
-    S.n_query_it += P.n_q;
-    S.n_cand += ncand;
-    S.inner = 0;
-    if (npairs == 0) {
-      S.term = MLO_TERM_NO_PAIRINGS;
-      S.done = 1;
-      atomicSub(n_active, 1u);
-      return;
-    }
-  }
-  bool ok = true;
-  bool last_inner = true;
-  if (P.solver == MLO_SOLVER_HORN) {
-    ok = horn_from_sums(a, double(npairs), S.T);
-  } else {
-    double H[36], g[6];
-    int k = 0;
-    for (int i = 0; i < 6; i++)
-      for (int j = i; j < 6; j++) {
-        H[6 * i + j] = a[k];
-        H[6 * j + i] = a[k];
-        k++;
+  for (int k = 0; k < int(NACC); k++) a[k] = __shfl_sync(FULL, acc, k);
+  const uint32_t npairs = __shfl_sync(FULL, cnt, NACC);
+  const uint32_t ncand = __shfl_sync(FULL, cnt, NACC + 1);
+  int next = 0;
+  if (lane == 0) {
+    bool finished = false;
+    if (after_match) {
+      S.n_pairs = npairs;
+      uint64_t pot = 0;
+      if (P.matcher_mask & MLO_MATCHER_PT2PL) pot += P.n_q;
+      if (P.matcher_mask & MLO_MATCHER_PT2PT) pot += P.n_q;
+      S.n_potential = pot;
+      S.n_query_it += P.n_q;
+      S.n_cand += ncand;
+      S.inner = 0;
+      if (npairs == 0) {
+        S.term = MLO_TERM_NO_PAIRINGS;
+        S.done = 1;
+        finished = true;
       }
-    for (int i = 0; i < 6; i++) g[i] = a[21 + i];
-    if (P.has_prior) {
-      // e = log(prior^-1 T), J = d log(D exp(eps))/d eps ; g += J^T L e ; H += J^T L J
-      double D[12], e[6], J[36], LJ[36], Le[6];
-      pose_minus(S.T, P.prior_pose, D);
-      se3_log(D, e);
-      se3_right_jacobian_inv(e, J);
-      for (int i = 0; i < 6; i++) {
-        double s = 0;
-        for (int m = 0; m < 6; m++) s += P.prior_info[6 * i + m] * e[m];
-        Le[i] = s;
-        for (int j = 0; j < 6; j++) {
-          double t = 0;
-          for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * J[6 * m + j];
-          LJ[6 * i + j] = t;
+    }
+    if (!finished) {
+      bool ok = true;
+      bool last_inner = true;
+      if (P.solver == MLO_SOLVER_HORN) {
+        ok = horn_from_sums(a, double(npairs), S.T);
+      } else {
+        double H[36], g[6];
+        int k = 0;
+        for (int i = 0; i < 6; i++)
+          for (int j = i; j < 6; j++) {
+            H[6 * i + j] = a[k];
+            H[6 * j + i] = a[k];
+            k++;
+          }
+        for (int i = 0; i < 6; i++) g[i] = a[21 + i];
+        if (P.has_prior) {
+          // e = log(prior^-1 T), J = d log(D exp(eps))/d eps ; g += J^T L e ; H += J^T L J
+          double D[12], e[6], J[36], LJ[36], Le[6];
+          pose_minus(S.T, P.prior_pose, D);
+          se3_log(D, e);
+          se3_right_jacobian_inv(e, J);
+          for (int i = 0; i < 6; i++) {
+            double s = 0;
+            for (int m = 0; m < 6; m++) s += P.prior_info[6 * i + m] * e[m];
+            Le[i] = s;
+            for (int j = 0; j < 6; j++) {
+              double t = 0;
+              for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * J[6 * m + j];
+              LJ[6 * i + j] = t;
+            }
+          }
+          for (int i = 0; i < 6; i++) {
+            for (int m = 0; m < 6; m++) g[i] += J[6 * m + i] * Le[m];
+            for (int j = 0; j < 6; j++)
+              for (int m = 0; m < 6; m++) H[6 * i + j] += J[6 * m + i] * LJ[6 * m + j];
+          }
+        }
+        for (int i = 0; i < 36; i++) S.H[i] = H[i];
+        S.have_H = 1;
+        double mg[6], delta[6];
+        for (int i = 0; i < 6; i++) mg[i] = -g[i];
+        ok = ldlt6(H, mg, delta);
+        if (ok) {
+          double E[12], Tn[12];
+          se3_exp(delta, E);
+          pose_mul(S.T, E, Tn);
+          for (int i = 0; i < 12; i++) S.T[i] = Tn[i];
+          double dn = 0;
+          for (int i = 0; i < 6; i++) dn += delta[i] * delta[i];
+          S.inner++;
+          last_inner = (sqrt(dn) < P.gn_min_delta) || (S.inner >= P.gn_max_iterations);
         }
       }
-      for (int i = 0; i < 6; i++) {
-        for (int m = 0; m < 6; m++) g[i] += J[6 * m + i] * Le[m];
-        for (int j = 0; j < 6; j++)
-          for (int m = 0; m < 6; m++) H[6 * i + j] += J[6 * m + i] * LJ[6 * m + j];
+      if (!ok) {
+        S.term = MLO_TERM_SOLVER_ERROR;
+        S.done = 1;
+      } else if (!last_inner) {
+        S.inner_pending = 1;
+        next = 1;
+      } else {
+        finish_iteration(P, S);
+        next = S.done ? 0 : 2;
       }
     }
-    for (int i = 0; i < 36; i++) S.H[i] = H[i];
-    S.have_H = 1;
-    double mg[6], delta[6];
-    for (int i = 0; i < 6; i++) mg[i] = -g[i];
-    ok = ldlt6(H, mg, delta);
-    if (ok) {
-      double E[12], Tn[12];
-      se3_exp(delta, E);
-      pose_mul(S.T, E, Tn);
-      for (int i = 0; i < 12; i++) S.T[i] = Tn[i];
-      double dn = 0;
-      for (int i = 0; i < 6; i++) dn += delta[i] * delta[i];
-      S.inner++;
-      last_inner = (sqrt(dn) < P.gn_min_delta) || (S.inner >= P.gn_max_iterations);
-    }
   }
-  if (!ok) {
-    S.term = MLO_TERM_SOLVER_ERROR;
-    S.done = 1;
-    atomicSub(n_active, 1u);
-    return;
-  }
-  if (!last_inner) {
-    S.inner_pending = 1;
-    return;
-  }
-  finish_iteration(P, S);
-  if (S.done) atomicSub(n_active, 1u);
+  return __shfl_sync(FULL, next, 0);
+}
+
+// ------------------------------------------------------------------ one kernel per phase (launch sequence)
+__global__ void __launch_bounds__(ICP_BLOCK)
+    k_match_accumulate(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
+                       const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                       double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
+  const IcpProblem& P = probs[blockIdx.y];
+  if (blockIdx.x >= P.n_blocks) return;
+  const IcpState& S = states[blockIdx.y];
+  if (S.done) return;
+  __shared__ double sT[12];
+  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  __syncthreads();
+  chunk_match_warp(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt, qpw);
+}
+
+__global__ void __launch_bounds__(ICP_BLOCK, 4)
+    k_match_accumulate_tpq(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
+                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  const IcpProblem& P = probs[blockIdx.y];
+  if (blockIdx.x >= P.n_blocks) return;
+  const IcpState& S = states[blockIdx.y];
+  if (S.done) return;
+  __shared__ double sT[12];
+  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  __syncthreads();
+  chunk_match_tpq(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+}
+
+__global__ void __launch_bounds__(ICP_BLOCK, 8)
+    k_match_accumulate_wl(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
+                          const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                          double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  const IcpProblem& P = probs[blockIdx.y];
+  if (blockIdx.x >= P.n_blocks) return;
+  const IcpState& S = states[blockIdx.y];
+  if (S.done) return;
+  __shared__ double sT[12];
+  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  __syncthreads();
+  chunk_match_wl(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+}
+
+__global__ void __launch_bounds__(ICP_BLOCK)
+    k_accumulate(const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states, const float4* __restrict__ local,
+                 const float4* pairA, const float4* pairB, double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  const IcpProblem& P = probs[blockIdx.y];
+  if (blockIdx.x >= P.n_blocks_acc) return;
+  const IcpState& S = states[blockIdx.y];
+  if (S.done || !S.inner_pending) return;
+  __shared__ double sT[12];
+  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  __syncthreads();
+  chunk_accumulate(P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+}
+
+// one warp per problem. `after_match` = 1 when the partials come from the match phase (inner 0).
+__global__ void __launch_bounds__(32)
+    k_solve(const IcpProblem* __restrict__ probs, IcpState* __restrict__ states, const double* partials,
+            const uint32_t* part_cnt, int after_match, uint32_t* __restrict__ n_active) {
+  const IcpProblem& P = probs[blockIdx.x];
+  IcpState& S = states[blockIdx.x];
+  if (S.done) return;
+  if (!after_match && !S.inner_pending) return;
+  const int next = solve_step(P, S, partials, part_cnt, after_match);
+  if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
 __global__ void k_init_states(const IcpProblem* __restrict__ probs, IcpState* __restrict__ states, const double* __restrict__ init_poses,
@@ -610,8 +862,143 @@ __global__ void k_init_states(const IcpProblem* __restrict__ probs, IcpState* __
   if (probs[b].max_iterations == 0) {  // ICP::align with an exhausted budget (LidarOdometry.cpp:956-967)
     S.term = MLO_TERM_MAX_ITERATIONS;
     S.done = 1;
+  } else if (probs[b].n_q == 0) {      // empty local cloud: the matcher produces nothing
+    S.term = MLO_TERM_NO_PAIRINGS;
+    S.done = 1;
   } else {
     atomicAdd(n_active, 1u);
+  }
+}
+
+// ------------------------------------------------------------------ persistent, queue-driven align
+// One launch runs the whole ICP::align loop of a batch.  Work items = (problem, phase, chunk); a bounded
+// MPMC ring in global memory (ticket + per-slot sequence numbers) feeds resident thread blocks.  The block
+// that completes the last chunk of a phase runs solve_step for that problem and publishes the chunks of the
+// next phase (inner GN re-linearisation, or the match phase of the next ICP iteration), so problems advance
+// independently: no grid-wide barrier, no host round trip, no idle tail while other problems still iterate.
+struct IcpQueue {
+  uint32_t* items;
+  uint32_t* seq;
+  uint32_t mask;       // ring capacity - 1
+  uint32_t* ctrl;      // [0] head, [1] tail, [2] problems active, [3] all done, [4] error/timeout
+  uint32_t* phase_cnt; // per problem: chunks of the current phase completed
+};
+constexpr uint32_t ITEM_EXIT = 0xFFFFFFFFu;
+MLO_HD uint32_t item_make(uint32_t prob, uint32_t chunk, uint32_t phase) { return (prob << 16) | (chunk << 1) | phase; }
+
+MLO_D uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+
+// lanes of one warp publish n consecutive items (prob, phase, chunk 0..n-1)
+MLO_D void queue_push(const IcpQueue& q, uint32_t prob, uint32_t phase, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t pos = 0;
+  if (lane == 0) pos = atomicAdd(&q.ctrl[1], n);
+  pos = __shfl_sync(0xFFFFFFFFu, pos, 0);
+  for (uint32_t i = lane; i < n; i += 32) {
+    const uint32_t t = pos + i, slot = t & q.mask;
+    uint32_t spins = 0;
+    while (ld_volatile_u32(&q.seq[slot]) != t) {  // slot still holds an unconsumed older item (ring full): rare
+      __nanosleep(64);
+      if (++spins > (1u << 24)) {
+        atomicExch(&q.ctrl[4], 1u);
+        atomicExch(&q.ctrl[3], 1u);
+        break;
+      }
+    }
+    *reinterpret_cast<volatile uint32_t*>(&q.items[slot]) = item_make(prob, i, phase);
+    __threadfence();
+    *reinterpret_cast<volatile uint32_t*>(&q.seq[slot]) = t + 1;
+  }
+}
+
+// out-of-line copies for the persistent kernel: each phase keeps its own register allocation
+__device__ __noinline__ void chunk_match_tpq_ool(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it,
+                                                 uint32_t chunk, const float4* local, float4* pairA, float4* pairB,
+                                                 double* partials, uint32_t* part_cnt) {
+  chunk_match_tpq(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt);
+}
+__device__ __noinline__ void chunk_match_warp_ool(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it,
+                                                  uint32_t chunk, const float4* local, float4* pairA, float4* pairB,
+                                                  double* partials, uint32_t* part_cnt, uint32_t qpw) {
+  chunk_match_warp(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+}
+__device__ __noinline__ void chunk_accumulate_ool(const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
+                                                  const float4* local, const float4* pairA, const float4* pairB,
+                                                  double* partials, uint32_t* part_cnt) {
+  chunk_accumulate(P, sT, it, chunk, local, pairA, pairB, partials, part_cnt);
+}
+
+template <bool TPQ>
+__global__ void __launch_bounds__(ICP_BLOCK, 4)
+    k_icp_persistent(MapDev map, const IcpProblem* __restrict__ probs, IcpState* states, const float4* __restrict__ local,
+                     float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt, IcpQueue q, uint32_t qpw) {
+  __shared__ uint32_t s_item;
+  __shared__ int s_last;
+  __shared__ double sT[12];
+  __shared__ uint32_t s_it;
+  for (;;) {
+    if (threadIdx.x == 0) {
+      const uint32_t t = atomicAdd(&q.ctrl[0], 1u);
+      const uint32_t slot = t & q.mask;
+      uint32_t item = ITEM_EXIT, spins = 0;
+      for (;;) {
+        if (ld_volatile_u32(&q.seq[slot]) == t + 1) {
+          __threadfence();
+          item = ld_volatile_u32(&q.items[slot]);
+          *reinterpret_cast<volatile uint32_t*>(&q.seq[slot]) = t + q.mask + 1;  // free the slot for ticket t + capacity
+          break;
+        }
+        if (ld_volatile_u32(&q.ctrl[3])) break;  // every problem finished
+        __nanosleep(128);
+        if (++spins > (1u << 24)) {  // safety net (~seconds): never hang the device
+          atomicExch(&q.ctrl[4], 1u);
+          atomicExch(&q.ctrl[3], 1u);
+          break;
+        }
+      }
+      s_item = item;
+    }
+    __syncthreads();
+    const uint32_t item = s_item;
+    if (item == ITEM_EXIT) return;
+    const uint32_t prob = item >> 16, chunk = (item >> 1) & 0x7FFFu, phase = item & 1u;
+    const IcpProblem& P = probs[prob];
+    IcpState& S = states[prob];
+    if (threadIdx.x < 12) sT[threadIdx.x] = __ldcg(&S.T[threadIdx.x]);
+    if (threadIdx.x == 12) s_it = __ldcg(&S.it);
+    __syncthreads();
+    if (phase == 0) {
+      if (TPQ)
+        chunk_match_tpq_ool(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+      else
+        chunk_match_warp_ool(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+    } else {
+      chunk_accumulate_ool(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      __threadfence();  // partials / pairings of this chunk (ordered by the barrier) visible before the count
+      const uint32_t nblk = phase == 0 ? P.n_blocks : P.n_blocks_acc;
+      const uint32_t old = atomicAdd(&q.phase_cnt[prob], 1u);
+      s_last = (old + 1 == nblk);
+      if (s_last) atomicExch(&q.phase_cnt[prob], 0u);
+    }
+    __syncthreads();
+    if (s_last && threadIdx.x < 32) {
+      if (threadIdx.x == 0) __threadfence();  // acquire: lane 0 reads the problem state with plain loads
+      __syncwarp();
+      const int next = solve_step(P, S, partials, part_cnt, phase == 0);
+      if (threadIdx.x == 0) __threadfence();  // state of the problem visible before its next items
+      __syncwarp();
+      if (next == 1) {
+        queue_push(q, prob, 1u, P.n_blocks_acc);
+      } else if (next == 2) {
+        queue_push(q, prob, 0u, P.n_blocks);
+      } else if (threadIdx.x == 0) {
+        if (atomicSub(&q.ctrl[2], 1u) == 1u) atomicExch(&q.ctrl[3], 1u);
+      }
+    }
+    __syncthreads();
   }
 }
 

@@ -69,7 +69,7 @@ MLO_D BucketRO load_bucket(const MapDev& m, uint64_t b) {
 
 // Find the bucket of a column key; returns false if the column does not exist.
 MLO_D bool find_column(const MapDev& m, uint64_t key, BucketRO& out) {
-  uint64_t h = hash_key(key) & m.mask;
+  uint64_t h = uint64_t(hash_packed(key)) & m.mask;
   for (;;) {
     out = load_bucket(m, h);
     if (out.key == key) return true;
@@ -87,7 +87,7 @@ MLO_D uint32_t map_find_cell(const MapDev& m, int32_t kx, int32_t ky, int32_t kz
 
 // Writers: find-or-claim the bucket of `key`. Returns the bucket index or ~0 on table exhaustion.
 MLO_D uint64_t find_or_insert_column(const MapDev& m, uint64_t key) {
-  uint64_t h = hash_key(key) & m.mask;
+  uint64_t h = uint64_t(hash_packed(key)) & m.mask;
   for (uint64_t probes = 0; probes <= m.mask; probes++) {
     unsigned long long* kp = &m.buckets[h].key;
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
@@ -346,6 +346,35 @@ MLO_D BucketRO load_bucket256(const MapDev& m, uint64_t b) {
   return r;
 }
 
+// Per-axis squared gaps from q to the neighbour cells at -1 / 0 / +1 (conservative, see below): the lower
+// bound of cell (dx,dy,dz) is then g2[0][dx+1] + g2[1][dy+1] + g2[2][dz+1] — three adds per cell.
+struct AxisGaps {
+  float g2[3][3];
+};
+MLO_D AxisGaps axis_gaps(float vs, const float qv[3], const int32_t kq[3]) {
+  AxisGaps g;
+#pragma unroll
+  for (int a = 0; a < 3; a++) {
+    g.g2[a][1] = 0.f;
+    {  // dd = +1: lower face of cell kq+1
+      const int32_t cc = kq[a] + 1;
+      const float edge = cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs);
+      float gap = edge - qv[a];
+      gap -= 4e-6f * (fabsf(edge) + vs);
+      g.g2[a][2] = gap > 0.f ? gap * gap : 0.f;
+    }
+    {  // dd = -1: upper face of cell kq-1
+      const int32_t cc = kq[a] - 1;
+      const float edge = cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs);
+      float gap = qv[a] - edge;
+      gap -= 4e-6f * (fabsf(edge) + vs);
+      g.g2[a][0] = gap > 0.f ? gap * gap : 0.f;
+    }
+  }
+  return g;
+}
+#define MLO_LB2(g, e) (((g).g2[0][(e) / 9] + (g).g2[1][((e) / 3) % 3] + (g).g2[2][(e) % 3]) * 0.99999f)
+
 // Squared distance from q to the box of neighbour cell (kq + dd), a conservative lower bound for every
 // point stored in that cell.  Cell boxes follow the truncation-toward-zero index: cell 0 spans (-vs, vs),
 // cell c > 0 spans [c vs, (c+1) vs), cell c < 0 spans ((c-1) vs, c vs]; faces are pulled in by a few ulps
@@ -370,39 +399,35 @@ MLO_D float cell_lower_bound2(float vs, const float qv[3], const int32_t kq[3], 
   return lb2 * 0.99999f;
 }
 
-// Thread-per-query form: the high-MLP path of the fused ICP kernel for large batches (hundreds of
-// queries in flight per SM).  Probes: 9 columns x (1..2) buckets as 256-bit loads, issued three columns
-// at a time.  Exact pruning: the query's own cell is scanned first, a neighbour cell is read only if its
-// box can still hold a point at distance <= the running best; candidates are compared on
-// (d2, canonical order) so the result equals the sequential first-minimum scan bit for bit.
-MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
-  NNHit r;
-  r.x = r.y = r.z = 0.f;
-  r.d2 = __int_as_float(0x7f800000);
-  r.found = 0;
-  r.ncand = 0;
-  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel),
-                         voxel_index_map(qz, m.inv_voxel)};
-  if (!(key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]))) return r;
+// Probe the 3x3x3 neighbourhood of cell kq (thread per query): 9 columns x (1..2) buckets as 256-bit loads,
+// issued three columns at a time; writes the 27 packed cell words (canonical order) to ws[e * wstride] and
+// returns the number of points stored in those cells (the algorithmic candidate count).
+MLO_D uint32_t probe_words(const MapDev& m, const int32_t kq[3], uint32_t* ws, uint32_t wstride) {
   const int32_t kz = kq[2];
   const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
   const bool needB = zq1 != zq0;
-  uint32_t w[27];
+  uint32_t ncand = 0;
+  // partial hash products shared by the 9 columns
+  uint32_t hy[3];
+#pragma unroll
+  for (int cy = 0; cy < 3; cy++) hy[cy] = uint32_t(kq[1] + cy - 1) * HASH_PY;
+  const uint32_t hz0 = uint32_t(zq0) * HASH_PZ, hz1 = uint32_t(zq1) * HASH_PZ;
 #pragma unroll
   for (int cx = 0; cx < 3; cx++) {
     BucketRO a[3], b[3];
     uint64_t ka[3], kb[3], ha[3], hb[3];
+    const uint32_t hx = uint32_t(kq[0] + cx - 1) * HASH_PX;
 #pragma unroll
     for (int cy = 0; cy < 3; cy++) {
       ka[cy] = pack_key(kq[0] + cx - 1, kq[1] + cy - 1, zq0);
-      ha[cy] = hash_key(ka[cy]) & m.mask;
+      ha[cy] = uint64_t(hash_mix(hx ^ hy[cy] ^ hz0)) & m.mask;
       a[cy] = load_bucket256(m, ha[cy]);
     }
     if (needB) {
 #pragma unroll
       for (int cy = 0; cy < 3; cy++) {
         kb[cy] = pack_key(kq[0] + cx - 1, kq[1] + cy - 1, zq1);
-        hb[cy] = hash_key(kb[cy]) & m.mask;
+        hb[cy] = uint64_t(hash_mix(hx ^ hy[cy] ^ hz1)) & m.mask;
         b[cy] = load_bucket256(m, hb[cy]);
       }
     }
@@ -429,11 +454,31 @@ MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
         if (needB) wb = s == 0 ? b[cy].cell[0] : s == 1 ? b[cy].cell[1] : s == 2 ? b[cy].cell[2] : b[cy].cell[3];
         uint32_t ww = have ? (inA ? wa : wb) : CELL_ABSENT;
         if (ww == CELL_PENDING) ww = CELL_ABSENT;
-        w[(cx * 3 + cy) * 3 + t] = ww;
-        if (ww != CELL_ABSENT) r.ncand += cell_cnt(ww);
+        ws[((cx * 3 + cy) * 3 + t) * wstride] = ww;
+        if (ww != CELL_ABSENT) ncand += cell_cnt(ww);
       }
     }
   }
+  return ncand;
+}
+
+// Thread-per-query form: the high-MLP path of the fused ICP kernel for large batches (hundreds of
+// queries in flight per SM).  Probes: 9 columns x (1..2) buckets as 256-bit loads, issued three columns
+// at a time.  Exact pruning: the query's own cell is scanned first, a neighbour cell is read only if its
+// box can still hold a point at distance <= the running best; candidates are compared on
+// (d2, canonical order) so the result equals the sequential first-minimum scan bit for bit.
+// `ws` points at this thread's column of a shared-memory scratch [27][wstride] holding the 27 packed cell
+// words (dynamic indexing without local memory; unaffected by the L1 invalidation of device-scope fences).
+MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz, uint32_t* ws, uint32_t wstride) {
+  NNHit r;
+  r.x = r.y = r.z = 0.f;
+  r.d2 = __int_as_float(0x7f800000);
+  r.found = 0;
+  r.ncand = 0;
+  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel),
+                         voxel_index_map(qz, m.inv_voxel)};
+  if (!(key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]))) return r;
+  r.ncand = probe_words(m, kq, ws, wstride);
   uint32_t border = 0xFFFFFFFFu;
   const float qv[3] = {qx, qy, qz};
   auto scan_cell = [&](uint32_t ww, uint32_t e) {
@@ -465,13 +510,26 @@ MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz) {
       }
     }
   };
-  if (w[13] != CELL_ABSENT) scan_cell(w[13], 13u);
-#pragma unroll 1
+  {
+    const uint32_t wh = ws[13 * wstride];
+    if (wh != CELL_ABSENT) scan_cell(wh, 13u);
+  }
+  // Each lane walks ITS OWN compacted list of candidate cells (bit e of `todo`), so one warp iteration
+  // serves every lane's k-th visited cell: the trip count is max-over-lanes of cells visited, not the
+  // union of cells any lane visits.
+  const AxisGaps gaps = axis_gaps(m.voxel_size, qv, kq);
+  uint32_t todo = 0;
+#pragma unroll
   for (int e = 0; e < 27; e++) {
     if (e == 13) continue;
-    if (w[e] == CELL_ABSENT || cell_cnt(w[e]) == 0) continue;
-    const int32_t dd[3] = {e / 9 - 1, (e / 3) % 3 - 1, e % 3 - 1};
-    if (cell_lower_bound2(m.voxel_size, qv, kq, dd) <= r.d2) scan_cell(w[e], uint32_t(e));
+    const uint32_t we = ws[e * wstride];
+    if (we == CELL_ABSENT || cell_cnt(we) == 0) continue;
+    if (MLO_LB2(gaps, e) <= r.d2) todo |= 1u << e;
+  }
+  while (todo) {
+    const int e = __ffs(todo) - 1;
+    todo &= todo - 1;
+    scan_cell(ws[e * wstride], uint32_t(e));
   }
   r.found = border != 0xFFFFFFFFu;
   return r;
@@ -505,7 +563,7 @@ MLO_D WarpProbe warp_probe_issue(const MapDev& m, float qx, float qy, float qz) 
   const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
   p.active = p.in_range && lane < 18 && (half == 0 || zq1 != zq0);
   p.key = pack_key(kx + dx, ky + dy, half ? zq1 : zq0);
-  p.h = hash_key(p.key) & m.mask;
+  p.h = uint64_t(hash_packed(p.key)) & m.mask;
   p.b.key = KEY_EMPTY;
   p.b.cell[0] = p.b.cell[1] = p.b.cell[2] = p.b.cell[3] = CELL_ABSENT;
   if (p.active) p.b = load_bucket(m, p.h);
@@ -580,7 +638,7 @@ MLO_D NNHit warp_nn_finish(const MapDev& m, WarpProbe& p, float qx, float qy, fl
     const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel), p.kz};
     const float qv[3] = {qx, qy, qz};
     const int32_t dd[3] = {int32_t(lane / 9) - 1, int32_t((lane / 3) % 3) - 1, int32_t(lane % 3) - 1};
-    visit = cell_lower_bound2(m.voxel_size, qv, kq, dd) <= bound;
+    visit = cell_lower_bound2(m.voxel_size, qv, kq, dd) <= bound;  // one cell per lane: the direct form
   }
   uint32_t occ = __ballot_sync(FULL, visit);
   while (occ) {

@@ -69,11 +69,13 @@ struct mlo_ctx {
   uint64_t launches = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   int force_kernel = 0;  // 0 auto, 1 thread-per-query, 2 warp-per-query (MLO_FORCE_KERNEL, experiments only)
+  bool use_persistent = true;  // MLO_PERSISTENT=0 selects the one-kernel-per-phase launch sequence
+  int persistent_blocks = 0;
   std::string dev_name;
   // scratch
   DBuf d_in, d_local, d_pairA, d_pairB, d_partials, d_partcnt, d_probs, d_states, d_tables, d_init, d_misc;
   DBuf d_f_tab, d_f_pslot, d_f_flags, d_f_blk, d_f_jobs, d_f_cnt, d_f_stage1, d_f_map, d_f_icp;
-  DBuf d_ins_g, d_ins_slot, d_ins_next;
+  DBuf d_ins_g, d_ins_slot, d_ins_next, d_queue;
   HBuf h_misc, h_states, h_stage;
   // profiling
   bool prof_on = false;
@@ -412,7 +414,8 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   uint32_t qpw = 32;
   while (qpw > 1 && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
   // large batches: thread-per-query kernel (hundreds of queries in flight per SM); small: warp-per-query
-  const bool use_tpq = c->force_kernel == 1 || (c->force_kernel == 0 && total_queries >= uint64_t(c->sm_count) * 256);
+  const bool use_tpq = c->force_kernel == 1 || c->force_kernel == 3 ||
+                       (c->force_kernel == 0 && total_queries >= uint64_t(c->sm_count) * 256);
   for (uint32_t b = 0; b < B; b++) {
     const mlo_icp_params& p = params[b];
     IcpProblem& P = probs[b];
@@ -491,9 +494,62 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   const dim3 grid(std::max(max_blocks, 1u), B);
   const dim3 grid_acc(std::max(max_blocks_acc, 1u), B);
   const uint32_t check_every = 4;
-  for (uint32_t it = 0; it < max_it; it++) {
+  bool persistent = c->use_persistent && B < 65536 && max_blocks < 32768 && max_blocks_acc < 32768;
+  if (persistent) {
+    // ---- one launch for the whole align loop: queue of (problem, phase, chunk) items
+    std::vector<uint32_t> items;
+    uint32_t n_act = 0;
+    for (uint32_t b = 0; b < B; b++) {
+      if (probs[b].max_iterations == 0 || probs[b].n_q == 0) continue;
+      n_act++;
+      for (uint32_t ch = 0; ch < probs[b].n_blocks; ch++) items.push_back(item_make(b, ch, 0u));
+    }
+    if (n_act) {
+      const uint32_t qcap = uint32_t(next_pow2(std::max<uint64_t>(2ull * part_total, 1024)));
+      std::vector<uint32_t> seq(qcap);
+      for (uint32_t i = 0; i < qcap; i++) seq[i] = i < items.size() ? i + 1 : i;
+      items.resize(qcap, 0u);
+      CU(c, c->d_queue.ensure((2ull * qcap + 8 + B) * sizeof(uint32_t)));
+      uint32_t* dq = c->d_queue.as<uint32_t>();
+      IcpQueue q;
+      q.items = dq;
+      q.seq = dq + qcap;
+      q.ctrl = dq + 2ull * qcap;
+      q.phase_cnt = dq + 2ull * qcap + 8;
+      q.mask = qcap - 1;
+      uint32_t n_items = 0;
+      for (uint32_t i = 0; i < qcap; i++)
+        if (seq[i] == i + 1) n_items++;
+      const uint32_t h_ctrl[8] = {0u, n_items, n_act, 0u, 0u, 0u, 0u, 0u};
+      CU(c, cudaMemcpyAsync(q.items, items.data(), qcap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(q.seq, seq.data(), qcap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(q.ctrl, h_ctrl, sizeof(h_ctrl), cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaMemsetAsync(q.phase_cnt, 0, B * sizeof(uint32_t), c->stream));
+      if (c->persistent_blocks == 0) {
+        int per_sm = 0;
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true>, ICP_BLOCK, 0));
+        c->persistent_blocks = std::max(1, per_sm) * c->sm_count;
+      }
+      const uint32_t nblk = std::min<uint32_t>(uint32_t(c->persistent_blocks), std::max<uint32_t>(part_total, 1u));
+      const size_t e_nn = prof_begin(c);
+      if (use_tpq)
+        LAUNCH(c, k_icp_persistent<true>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+               c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, 0u);
+      else
+        LAUNCH(c, k_icp_persistent<false>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+               c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, qpw);
+      prof_end(c, 3, e_nn);
+      CU(c, cudaMemcpyAsync(h_active, q.ctrl + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+      CU(c, cudaStreamSynchronize(c->stream));
+      if (*h_active != 0) return fail(c, MLO_ERR_CUDA, "persistent ICP kernel timed out waiting on its work queue");
+    }
+  }
+  for (uint32_t it = 0; !persistent && it < max_it; it++) {
     const size_t e_nn = prof_begin(c);
-    if (use_tpq)
+    if (use_tpq && c->force_kernel != 1)
+      LAUNCH(c, k_match_accumulate_wl, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+    else if (use_tpq)
       LAUNCH(c, k_match_accumulate_tpq, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
              c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
     else
@@ -562,6 +618,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->cc_minor = prop.minor;
   c->dev_name = prop.name;
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
+  if (const char* pk = getenv("MLO_PERSISTENT")) c->use_persistent = atoi(pk) != 0;
   cudaSetDevice(cuda_device);
   if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
     delete c;
@@ -577,7 +634,7 @@ void mlo_destroy(mlo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DBuf* b : {&c->d_in, &c->d_local, &c->d_pairA, &c->d_pairB, &c->d_partials, &c->d_partcnt, &c->d_probs, &c->d_states,
                   &c->d_tables, &c->d_init, &c->d_misc, &c->d_f_tab, &c->d_f_pslot, &c->d_f_flags, &c->d_f_blk, &c->d_f_jobs,
-                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next})
+                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue})
     b->release();
   c->h_misc.release();
   c->h_states.release();
