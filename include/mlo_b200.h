@@ -235,6 +235,18 @@ int mlo_scan_register_batch(mlo_ctx* ctx, const mlo_map* map, uint32_t n_scans, 
                             uint32_t stride_floats, const uint64_t* offsets, const mlo_filter1_params* fps,
                             const double* init_poses_3x4, const mlo_icp_params* ips, mlo_icp_result* out);
 
+/* Pipelined host-buffer path: two staging slots on a dedicated copy stream.  mlo_stage_upload_async registers
+ * the H2D of one batch of raw clouds (pinned host memory recommended; the buffer must stay valid until the slot
+ * is consumed) into `slot` (0/1) and returns at once; the transfer itself is enqueued by the next compute call
+ * of this context right after that call's own small parameter uploads, so it overlaps that call's ICP loop
+ * (the H2D copy engine serves transfers in submission order).  mlo_scan_register_batch_staged runs
+ * filter -> align on the batch staged in `slot` once its copy has landed.  Registering batch k+1 before
+ * consuming batch k therefore hides its transfer behind the compute of batch k. */
+int mlo_stage_upload_async(mlo_ctx* ctx, int slot, const float* raw_pts, uint32_t stride_floats, uint32_t n_scans,
+                           const uint64_t* offsets);
+int mlo_scan_register_batch_staged(mlo_ctx* ctx, const mlo_map* map, int slot, const mlo_filter1_params* fps,
+                                   const double* init_poses_3x4, const mlo_icp_params* ips, mlo_icp_result* out);
+
 /* ------------------------------------------------------------------ device-resident handles
  * Same operations with inputs already resident in HBM (bench.py "value"; pipelines that keep
  * scans on the device).  A mlo_dcloud is a device float4 array owned by the library. */

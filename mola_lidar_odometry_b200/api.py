@@ -163,6 +163,19 @@ class Context:
                                                     init_poses.ctypes.data, parr, out))
         return list(out)
 
+    def stage_upload_async(self, slot: int, flat: np.ndarray, offs: np.ndarray, stride: int):
+        """Enqueue the H2D of one batch (flat float32 array, pinned memory recommended) into staging slot 0/1."""
+        self.check(self.lib.mlo_stage_upload_async(self.h, slot, flat.ctypes.data, stride, len(offs) - 1, offs.ctypes.data))
+
+    def scan_register_batch_staged(self, lmap, slot: int, fps, init_poses, params):
+        B = len(fps)
+        init_poses = _pose(init_poses).reshape(B, 12)
+        farr = (Filter1Params * B)(*fps)
+        parr = self._params_array(params)
+        out = (IcpResult * B)()
+        self.check(self.lib.mlo_scan_register_batch_staged(self.h, lmap.h, slot, farr, init_poses.ctypes.data, parr, out))
+        return list(out)
+
     def upload_batch(self, clouds: Sequence[np.ndarray]) -> "DeviceClouds":
         flat, offs, stride = self._concat(clouds)
         h = C.c_void_p()

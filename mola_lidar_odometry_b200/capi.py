@@ -177,6 +177,8 @@ _SIGNATURES = {
     "mlo_scan_register": (C.c_int, [_vp, _vp, _vp, _u32, _u64, C.POINTER(Filter1Params), _vp, C.POINTER(IcpParams),
                                     C.c_int, _f, C.POINTER(IcpResult)]),
     "mlo_scan_register_batch": (C.c_int, [_vp, _vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),
+    "mlo_stage_upload_async": (C.c_int, [_vp, C.c_int, _vp, _u32, _u32, _vp]),
+    "mlo_scan_register_batch_staged": (C.c_int, [_vp, _vp, C.c_int, _vp, _vp, _vp, _vp]),
     "mlo_dcloud_upload": (C.c_int, [_vp, _vp, _u32, _u64, C.POINTER(_vp)]),
     "mlo_dcloud_upload_batch": (C.c_int, [_vp, _vp, _u32, _u32, _vp, C.POINTER(_vp)]),
     "mlo_dcloud_destroy": (None, [_vp]),

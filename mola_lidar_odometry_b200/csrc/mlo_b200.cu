@@ -69,7 +69,19 @@ struct mlo_ctx {
   uint64_t launches = 0;
   int sm_count = 0, cc_major = 0, cc_minor = 0;
   int force_kernel = 0;  // 0 auto, 1 thread-per-query, 2 warp-per-query (MLO_FORCE_KERNEL, experiments only)
+  // two staging slots for the pipelined host-buffer path
+  cudaStream_t copy_stream = nullptr;
+  struct Stage {
+    DBuf buf;
+    cudaEvent_t ready = nullptr;
+    std::vector<uint64_t> offsets;
+    uint32_t stride = 0;
+    bool pending = false;
+    const float* deferred_src = nullptr;  // upload requested but not yet enqueued (see issue_stage_upload)
+  } stage[2];
   bool use_persistent = true;  // MLO_PERSISTENT=0 selects the one-kernel-per-phase launch sequence
+  bool persistent_forced = false;
+  int consuming_slot = -1;  // staging slot read by the compute call in progress
   int persistent_blocks = 0;
   std::string dev_name;
   // scratch
@@ -390,6 +402,35 @@ int upload_strided(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t n, DB
   return MLO_OK;
 }
 
+int issue_stage_upload(mlo_ctx* c, int slot) {
+  auto& st = c->stage[slot];
+  if (!st.deferred_src) return MLO_OK;
+  const float* raw = st.deferred_src;
+  st.deferred_src = nullptr;
+  const uint64_t total = st.offsets.back();
+  const size_t bytes = std::max<size_t>(total * st.stride * sizeof(float), 16);
+  // the slot may still be read by work enqueued earlier on the main stream: order the copy after it
+  CU(c, cudaEventRecord(st.ready, c->stream));
+  CU(c, cudaStreamWaitEvent(c->copy_stream, st.ready, 0));
+  if (st.buf.cap < bytes) {
+    CU(c, cudaStreamSynchronize(c->stream));
+    CU(c, cudaStreamSynchronize(c->copy_stream));
+    CU(c, st.buf.ensure(bytes));
+  }
+  if (total)
+    CU(c, cudaMemcpyAsync(st.buf.p, raw, total * st.stride * sizeof(float), cudaMemcpyHostToDevice, c->copy_stream));
+  CU(c, cudaEventRecord(st.ready, c->copy_stream));
+  return MLO_OK;
+}
+int issue_deferred_uploads(mlo_ctx* c, int except_slot) {
+  for (int s = 0; s < 2; s++)
+    if (s != except_slot) {
+      int rc = issue_stage_upload(c, s);
+      if (rc != MLO_OK) return rc;
+    }
+  return MLO_OK;
+}
+
 // The batched align driver over device-resident float4 local points.
 int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64_t* offsets, const mlo_map* map,
                        const double* init_poses, const mlo_icp_params* params, mlo_icp_result* out) {
@@ -490,11 +531,18 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   IcpState* dS = c->d_states.as<IcpState>();
   LAUNCH(c, k_init_states, (B + 127) / 128, 128, dP, dS, c->d_init.as<double>(), B, d_active);
 
+  {  // all small uploads of this call are enqueued: now start the deferred transfer of the next staged batch
+    int rc = issue_deferred_uploads(c, c->consuming_slot);
+    if (rc != MLO_OK) return rc;
+  }
   const size_t e_icp = prof_begin(c);
   const dim3 grid(std::max(max_blocks, 1u), B);
   const dim3 grid_acc(std::max(max_blocks_acc, 1u), B);
   const uint32_t check_every = 4;
-  bool persistent = c->use_persistent && B < 65536 && max_blocks < 32768 && max_blocks_acc < 32768;
+  // the queue-driven kernel wins while a launch sequence would be latency/launch-bound (small batches);
+  // for large batches one kernel per phase streams better (profiles/README.md)
+  bool persistent = c->use_persistent && (c->persistent_forced || total_queries < uint64_t(c->sm_count) * 1024) && B < 65536 &&
+                    max_blocks < 32768 && max_blocks_acc < 32768;
   if (persistent) {
     // ---- one launch for the whole align loop: queue of (problem, phase, chunk) items
     std::vector<uint32_t> items;
@@ -618,9 +666,15 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->cc_minor = prop.minor;
   c->dev_name = prop.name;
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
-  if (const char* pk = getenv("MLO_PERSISTENT")) c->use_persistent = atoi(pk) != 0;
+  if (const char* pk = getenv("MLO_PERSISTENT")) {
+    c->use_persistent = atoi(pk) != 0;
+    c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
+  }
   cudaSetDevice(cuda_device);
-  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) {
+  if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->stage[0].ready, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&c->stage[1].ready, cudaEventDisableTiming) != cudaSuccess) {
     delete c;
     return MLO_ERR_CUDA;
   }
@@ -640,6 +694,12 @@ void mlo_destroy(mlo_ctx* c) {
   c->h_states.release();
   c->h_stage.release();
   for (auto e : c->ev_pool) cudaEventDestroy(e);
+  cudaStreamSynchronize(c->copy_stream);
+  for (auto& st : c->stage) {
+    st.buf.release();
+    if (st.ready) cudaEventDestroy(st.ready);
+  }
+  cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -1072,6 +1132,38 @@ int mlo_scan_register_batch(mlo_ctx* c, const mlo_map* map, uint32_t B, const fl
   int rc = upload_strided(c, raw, stride, offsets[B], c->d_in);
   if (rc != MLO_OK) return rc;
   return scan_register_device(c, map, B, c->d_in.as<float>(), stride, offsets, fps, init_poses, ips, out, nullptr);
+}
+
+int mlo_stage_upload_async(mlo_ctx* c, int slot, const float* raw, uint32_t stride, uint32_t B, const uint64_t* offsets) {
+  if (!c || !raw || !offsets || B == 0 || slot < 0 || slot > 1) return MLO_ERR_INVALID_ARG;
+  if (stride != 3 && stride != 4) return fail(c, MLO_ERR_INVALID_ARG, "stride_floats must be 3 or 4");
+  auto& st = c->stage[slot];
+  st.offsets.assign(offsets, offsets + B + 1);
+  st.stride = stride;
+  st.pending = true;
+  // Deferred: the transfer is enqueued by the next compute call of this context right after that call's own
+  // small parameter uploads (the H2D copy engine serves transfers in submission order, so a 1 GB transfer
+  // submitted first would stall them), or at the latest when this slot is consumed.
+  st.deferred_src = raw;
+  return MLO_OK;
+}
+
+int mlo_scan_register_batch_staged(mlo_ctx* c, const mlo_map* map, int slot, const mlo_filter1_params* fps,
+                                   const double* init_poses, const mlo_icp_params* ips, mlo_icp_result* out) {
+  if (!c || !map || !fps || !init_poses || !ips || !out || slot < 0 || slot > 1) return MLO_ERR_INVALID_ARG;
+  if (map->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "map belongs to another context");
+  auto& st = c->stage[slot];
+  if (!st.pending) return fail(c, MLO_ERR_INVALID_ARG, "nothing staged in this slot");
+  DeviceGuard g(c->device);
+  int rc = issue_stage_upload(c, slot);  // not yet enqueued (no compute call ran in between): do it now
+  if (rc != MLO_OK) return rc;
+  CU(c, cudaStreamWaitEvent(c->stream, st.ready, 0));
+  st.pending = false;
+  c->consuming_slot = slot;
+  rc = scan_register_device(c, map, uint32_t(st.offsets.size() - 1), st.buf.as<float>(), st.stride, st.offsets.data(), fps,
+                            init_poses, ips, out, nullptr);
+  c->consuming_slot = -1;
+  return rc;
 }
 
 int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t stride, uint64_t n, const mlo_filter1_params* fp,
