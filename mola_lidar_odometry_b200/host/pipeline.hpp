@@ -1,0 +1,682 @@
+// pipeline.hpp — C++ host mirror of the reference's plugin surface for the hot path, over a backend.
+//
+// Mirrors (same names / YAML keys / argument meaning / error behaviour, re-implemented from the call sites):
+//   mp2p_icp::ICP + Parameters + Results          pipelines/lidar3d-default.yaml:169-182, LidarOdometry.cpp:961-962
+//   mp2p_icp::Matcher_Points_DistanceThreshold    default.yaml:196-204
+//   mp2p_icp::Matcher_Point2Plane                 lidar3d-ndt.yaml:195-200
+//   mp2p_icp::Solver_GaussNewton / Solver_Horn    default.yaml:185-190, extras/icp-pipeline_no_motion_model.yaml:24-29
+//   mp2p_icp::QualityEvaluator_PairedRatio        default.yaml:206-209
+//   mp2p_icp_filters::FilterDecimateVoxels / FilterByRange / FilterBoundingBox   default.yaml:285-319
+//   mola::HashedVoxelPointCloud / mola::NDT       default.yaml:228-242, ndt.yaml:234-254
+//   mola::LidarOdometry::onLidarImpl (caller contract of the hot path)           LidarOdometry.cpp:627-1206
+// The Backend supplies the arithmetic: BackendGpu (backend_gpu.hpp, the CUDA C ABI) in the product;
+// oracle/backend_oracle.hpp exists only so tests can run the SAME orchestrator over the CPU oracle.
+// Errors: std::runtime_error, like the reference's MRPT exceptions that its worker latches (LidarOdometry.cpp:614-619).
+#pragma once
+#include <algorithm>
+#include <array>
+#include <cmath>
+#include <cstring>
+#include <memory>
+#include <optional>
+#include <string>
+#include <vector>
+
+#include "formula.hpp"
+#include "mlo_b200.h"
+#include "yaml_lite.hpp"
+
+namespace mlo_host {
+
+using Pose = std::array<double, 12>;  // 3x4 row-major [R|t]
+
+inline Pose pose_identity() { return {1, 0, 0, 0, 0, 1, 0, 0, 0, 0, 1, 0}; }
+inline Pose pose_compose(const Pose& a, const Pose& b) {
+  Pose c{};
+  for (int r = 0; r < 3; r++) {
+    for (int k = 0; k < 3; k++) c[4 * r + k] = a[4 * r] * b[k] + a[4 * r + 1] * b[4 + k] + a[4 * r + 2] * b[8 + k];
+    c[4 * r + 3] = a[4 * r] * b[3] + a[4 * r + 1] * b[7] + a[4 * r + 2] * b[11] + a[4 * r + 3];
+  }
+  return c;
+}
+inline Pose pose_inverse(const Pose& a) {
+  Pose c{};
+  for (int r = 0; r < 3; r++)
+    for (int k = 0; k < 3; k++) c[4 * r + k] = a[4 * k + r];
+  for (int r = 0; r < 3; r++) c[4 * r + 3] = -(c[4 * r] * a[3] + c[4 * r + 1] * a[7] + c[4 * r + 2] * a[11]);
+  return c;
+}
+inline Pose pose_minus(const Pose& a, const Pose& b) { return pose_compose(pose_inverse(b), a); }  // MRPT "a - b"
+inline double norm3(const double* v) { return std::sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]); }
+// yaw/pitch/roll of the rotation block (MRPT CPose3D convention), for the robot_yaw/pitch/roll variables
+inline void pose_ypr(const Pose& p, double& yaw, double& pitch, double& roll) {
+  pitch = std::atan2(-p[8], std::hypot(p[0], p[4]));
+  yaw = std::atan2(p[4], p[0]);
+  roll = std::atan2(p[9], p[10]);
+}
+
+// ------------------------------------------------------------------------------------------------ plugin params
+struct Matcher_Points_DistanceThreshold {
+  Formula threshold{"1.0"};
+  double thresholdAngularDeg = 0;
+  int pairingsPerPoint = 1;
+  bool allowMatchAlreadyMatchedGlobalPoints = true;
+  double weight = 1.0;
+  std::string global_layer = "localmap", local_layer = "decimated_for_icp";
+  void initialize(const YamlNode& p) {
+    threshold = Formula(p.at("threshold").str());
+    thresholdAngularDeg = p["thresholdAngularDeg"].num(0);
+    pairingsPerPoint = int(p["pairingsPerPoint"].num(1));
+    allowMatchAlreadyMatchedGlobalPoints = p["allowMatchAlreadyMatchedGlobalPoints"].boolean(true);
+    if (pairingsPerPoint != 1) throw std::runtime_error("Matcher_Points_DistanceThreshold: only pairingsPerPoint=1 is supported");
+    const YamlNode& lm = p["pointLayerMatches"];
+    if (lm.isSeq() && !lm.seq.empty()) {
+      global_layer = lm.seq[0]["global"].str_or(global_layer);
+      local_layer = lm.seq[0]["local"].str_or(local_layer);
+      weight = lm.seq[0]["weight"].num(1.0);
+    }
+  }
+};
+struct Matcher_Point2Plane {
+  Formula distanceThreshold{"1.0"};
+  double weight = 1.0;
+  void initialize(const YamlNode& p) {
+    distanceThreshold = Formula(p.at("distanceThreshold").str());
+    const YamlNode& lm = p["pointLayerMatches"];
+    if (lm.isSeq() && !lm.seq.empty()) weight = lm.seq[0]["weight"].num(1.0);
+  }
+};
+struct Solver_GaussNewton {
+  uint32_t maxIterations = 2;
+  int robustKernel = MLO_KERNEL_NONE;
+  Formula robustKernelParam{"1.0"};
+  double minDelta = 1e-7;
+  void initialize(const YamlNode& p) {
+    maxIterations = uint32_t(p["maxIterations"].num(2));
+    const std::string k = p["robustKernel"].str_or("RobustKernel::None");
+    if (k == "RobustKernel::GemanMcClure") robustKernel = MLO_KERNEL_GEMAN_MCCLURE;
+    else if (k == "RobustKernel::Cauchy") robustKernel = MLO_KERNEL_CAUCHY;
+    else if (k == "RobustKernel::None") robustKernel = MLO_KERNEL_NONE;
+    else throw std::runtime_error("Solver_GaussNewton: unknown robustKernel '" + k + "'");
+    if (p.has("robustKernelParam")) robustKernelParam = Formula(p["robustKernelParam"].str());
+    minDelta = p["minDelta"].num(1e-7);
+  }
+};
+struct Solver_Horn {
+  double runUntilTranslationCorrectionSmallerThan = 0;
+  void initialize(const YamlNode& p) {
+    runUntilTranslationCorrectionSmallerThan = p["runUntilTranslationCorrectionSmallerThan"].num(0);
+  }
+};
+struct QualityEvaluator_PairedRatio {
+  void initialize(const YamlNode&) {}  // no parameters required (default.yaml:208-209): reuses the ICP pairings
+};
+
+struct Parameters {  // mp2p_icp::Parameters (default.yaml:172-182)
+  uint32_t maxIterations = 300;
+  double minAbsStep_trans = 1e-4, minAbsStep_rot = 5e-5;
+};
+struct Results {  // mp2p_icp::Results as consumed at LidarOdometry.cpp:964-1011
+  Pose optimal_tf_mean = pose_identity();
+  std::array<double, 36> optimal_tf_cov{};
+  double quality = 0;
+  uint32_t nIterations = 0;
+  int terminationReason = MLO_TERM_UNDEFINED;
+  uint64_t nPairings = 0;
+};
+struct IterationHook {  // the lambda of LidarOdometry.cpp:923-952 expressed as data
+  bool enabled = false;
+  Pose checkpoint = pose_identity();
+  double min_trans = 0.15, min_rot_rad = 0.75 * M_PI / 180.0;
+};
+struct Prior {
+  Pose mean = pose_identity();
+  std::array<double, 36> cov_inv{};
+};
+
+template <class Backend>
+class ICP {
+ public:
+  Parameters params;
+  std::optional<Solver_GaussNewton> gn;
+  std::optional<Solver_Horn> horn;
+  std::optional<Matcher_Points_DistanceThreshold> m_pt2pt;
+  std::optional<Matcher_Point2Plane> m_pt2pl;
+  QualityEvaluator_PairedRatio quality;
+  IterationHook hook;
+  ParameterSource* source = nullptr;
+
+  // mp2p_icp::icp_pipeline_from_yaml (LidarOdometry.cpp:115-122)
+  void initialize(const YamlNode& n) {
+    const std::string cn = n["class_name"].str_or("mp2p_icp::ICP");
+    if (cn != "mp2p_icp::ICP" && cn != "mlo_b200::ICP") throw std::runtime_error("unsupported ICP class_name '" + cn + "'");
+    const YamlNode& p = n["params"];
+    params.maxIterations = uint32_t(p["maxIterations"].num(300));
+    params.minAbsStep_trans = p["minAbsStep_trans"].num(1e-4);
+    params.minAbsStep_rot = p["minAbsStep_rot"].num(5e-5);
+    for (const YamlNode& s : n.at("solvers").seq) {
+      const std::string c = s.at("class").str();
+      if (c == "mp2p_icp::Solver_GaussNewton") { gn.emplace(); gn->initialize(s["params"]); }
+      else if (c == "mp2p_icp::Solver_Horn") { horn.emplace(); horn->initialize(s["params"]); }
+      else throw std::runtime_error("unsupported solver class '" + c + "'");
+    }
+    for (const YamlNode& m : n.at("matchers").seq) {
+      const std::string c = m.at("class").str();
+      if (c == "mp2p_icp::Matcher_Points_DistanceThreshold") { m_pt2pt.emplace(); m_pt2pt->initialize(m["params"]); }
+      else if (c == "mp2p_icp::Matcher_Point2Plane") { m_pt2pl.emplace(); m_pt2pl->initialize(m["params"]); }
+      else throw std::runtime_error("unsupported matcher class '" + c + "'");
+    }
+    for (const YamlNode& q : n["quality"].seq) {
+      if (q.at("class").str() != "mp2p_icp::QualityEvaluator_PairedRatio")
+        throw std::runtime_error("unsupported quality evaluator '" + q["class"].str() + "'");
+      quality.initialize(q["params"]);
+    }
+    if (!gn && !horn) throw std::runtime_error("ICP: no solver defined");
+    if (!m_pt2pt && !m_pt2pl) throw std::runtime_error("ICP: no matcher defined");
+  }
+  void attachToParameterSource(ParameterSource& ps) { source = &ps; }
+  void setIterationHook(const IterationHook& h) { hook = h; }
+
+  // mp2p_icp::ICP::align(local, global, init, params, result, prior) — call site LidarOdometry.cpp:961-962.
+  void align(Backend& be, const float* local_xyz, uint64_t n_local, void* global_map, const Pose& init, const Parameters& p,
+             Results& out, const std::optional<Prior>& prior = std::nullopt) {
+    if (!source) throw std::runtime_error("ICP::align: not attached to a ParameterSource");
+    mlo_icp_params q;
+    std::memset(&q, 0, sizeof(q));
+    q.max_iterations = p.maxIterations;
+    q.min_abs_step_trans = p.minAbsStep_trans;
+    q.min_abs_step_rot = p.minAbsStep_rot;
+    q.solver = (gn ? MLO_SOLVER_GAUSS_NEWTON : MLO_SOLVER_HORN);
+    q.gn_max_iterations = gn ? gn->maxIterations : 1;
+    q.gn_min_delta = gn ? gn->minDelta : 1e-7;
+    q.robust_kernel = gn ? gn->robustKernel : MLO_KERNEL_NONE;
+    q.matcher_mask = (m_pt2pt ? MLO_MATCHER_PT2PT : 0u) | (m_pt2pl ? MLO_MATCHER_PT2PL : 0u);
+    q.pt2pt_weight = m_pt2pt ? m_pt2pt->weight : 1.0;
+    q.pt2pl_weight = m_pt2pl ? m_pt2pl->weight : 1.0;
+    q.threshold_angular_deg = m_pt2pt ? m_pt2pt->thresholdAngularDeg : 0.0;
+    // formulas are re-realised per ICP_ITERATION: tabulate them
+    const uint32_t len = std::max<uint32_t>(1, std::min<uint32_t>(p.maxIterations, 64));
+    std::vector<double> t1(len, 0.0), t2(len, 0.0), t3(len, 1.0);
+    const double saved_it = source->has("ICP_ITERATION") ? source->get("ICP_ITERATION") : 0.0;
+    for (uint32_t it = 0; it < len; it++) {
+      source->updateVariable("ICP_ITERATION", double(it));
+      if (m_pt2pt) t1[it] = m_pt2pt->threshold.eval(*source);
+      if (m_pt2pl) t2[it] = m_pt2pl->distanceThreshold.eval(*source);
+      if (gn) t3[it] = gn->robustKernelParam.eval(*source);
+    }
+    source->updateVariable("ICP_ITERATION", saved_it);
+    q.table_len = len;
+    q.pt2pt_threshold_by_iter = t1.data();
+    q.pt2pl_threshold_by_iter = t2.data();
+    q.kernel_param_by_iter = t3.data();
+    const Pose I = pose_identity();
+    std::memcpy(q.prior_pose_3x4, I.data(), sizeof(q.prior_pose_3x4));
+    if (prior) {
+      q.has_prior = 1;
+      std::memcpy(q.prior_pose_3x4, prior->mean.data(), sizeof(q.prior_pose_3x4));
+      std::memcpy(q.prior_info_6x6, prior->cov_inv.data(), sizeof(q.prior_info_6x6));
+    }
+    q.hook_enabled = hook.enabled ? 1 : 0;
+    q.hook_min_trans = hook.min_trans;
+    q.hook_min_rot_rad = hook.min_rot_rad;
+    std::memcpy(q.hook_checkpoint_pose_3x4, hook.checkpoint.data(), sizeof(q.hook_checkpoint_pose_3x4));
+    mlo_icp_result r;
+    be.icp_align(local_xyz, n_local, global_map, init.data(), q, r);
+    std::memcpy(out.optimal_tf_mean.data(), r.pose_3x4, sizeof(r.pose_3x4));
+    std::memcpy(out.optimal_tf_cov.data(), r.cov_6x6, sizeof(r.cov_6x6));
+    out.quality = r.quality;
+    out.nIterations = r.n_iterations;
+    out.terminationReason = r.termination;
+    out.nPairings = r.n_pairings;
+  }
+};
+
+// observations_filter_1st_pass (default.yaml:278-319): the four filters of the default pipelines, recognised by class
+// and realised into the fused device filter (decimate -> by-range -> bbox-outside -> decimate).
+struct FilterPipeline1st {
+  Formula res_map{"0.2"}, res_icp{"0.6"}, range_min{"0"}, range_max{"1e9"};
+  Formula bb_min[3], bb_max[3];
+  uint32_t min_pts_map = 2000, min_pts_icp = 2000;
+  bool has_range = false, has_bbox = false;
+  void initialize(const YamlNode& seq) {
+    int decim = 0;
+    for (const YamlNode& f : seq.seq) {
+      const std::string c = f.at("class_name").str();
+      const YamlNode& p = f["params"];
+      if (c == "mp2p_icp_filters::FilterDecimateVoxels") {
+        const std::string m = p["decimate_method"].str_or("DecimateMethod::FirstPoint");
+        if (m != "DecimateMethod::FirstPoint") throw std::runtime_error("FilterDecimateVoxels: only DecimateMethod::FirstPoint is supported");
+        (decim == 0 ? res_map : res_icp) = Formula(p.at("voxel_filter_resolution").str());
+        (decim == 0 ? min_pts_map : min_pts_icp) = uint32_t(p["minimum_input_points_to_filter"].num(0));
+        decim++;
+      } else if (c == "mp2p_icp_filters::FilterByRange") {
+        has_range = true;
+        range_min = Formula(p.at("range_min").str());
+        range_max = Formula(p.at("range_max").str());
+      } else if (c == "mp2p_icp_filters::FilterBoundingBox") {
+        has_bbox = true;
+        for (int k = 0; k < 3; k++) {
+          bb_min[k] = Formula(p.at("bounding_box_min").seq.at(k).str());
+          bb_max[k] = Formula(p.at("bounding_box_max").seq.at(k).str());
+        }
+      } else {
+        throw std::runtime_error("observations_filter_1st_pass: unsupported filter '" + c + "'");
+      }
+    }
+    if (decim != 2) throw std::runtime_error("observations_filter_1st_pass: expected two FilterDecimateVoxels stages");
+  }
+  mlo_filter1_params realize(const ParameterSource& ps) const {
+    mlo_filter1_params f;
+    std::memset(&f, 0, sizeof(f));
+    f.for_map.voxel_filter_resolution = float(res_map.eval(ps));
+    f.for_map.minimum_input_points_to_filter = min_pts_map;
+    f.for_icp.voxel_filter_resolution = float(res_icp.eval(ps));
+    f.for_icp.minimum_input_points_to_filter = min_pts_icp;
+    if (has_range) {
+      f.for_icp.use_range = 1;
+      f.for_icp.range_min = float(range_min.eval(ps));
+      f.for_icp.range_max = float(range_max.eval(ps));
+    }
+    if (has_bbox) {
+      f.for_icp.use_bbox_outside = 1;
+      for (int k = 0; k < 3; k++) {
+        f.for_icp.bbox_min[k] = float(bb_min[k].eval(ps));
+        f.for_icp.bbox_max[k] = float(bb_max[k].eval(ps));
+      }
+    }
+    return f;
+  }
+};
+
+// metric_map_definition (default.yaml:228-242 / ndt.yaml:234-254)
+struct LocalMapDefinition {
+  int kind = MLO_MAP_HASHED_VOXEL_POINTS;
+  Formula voxel_size{"1.0"}, remove_voxels_farther_than{"0"};
+  uint32_t max_points_per_voxel = 20;
+  double min_distance_between_points = 0, max_eigen_ratio_for_planes = 0.05;
+  uint64_t capacity_voxels = 1u << 20;
+  void initialize(const YamlNode& def) {
+    const std::string c = def.at("class").str();
+    if (c == "mola::HashedVoxelPointCloud") kind = MLO_MAP_HASHED_VOXEL_POINTS;
+    else if (c == "mola::NDT") kind = MLO_MAP_NDT;
+    else throw std::runtime_error("unsupported metric map class '" + c + "'");
+    voxel_size = Formula(def.at("creationOpts").at("voxel_size").str());
+    const YamlNode& io = def["insertOpts"];
+    max_points_per_voxel = uint32_t(io["max_points_per_voxel"].num(20));
+    min_distance_between_points = io["min_distance_between_points"].num(0);
+    if (io.has("remove_voxels_farther_than")) remove_voxels_farther_than = Formula(io["remove_voxels_farther_than"].str());
+    max_eigen_ratio_for_planes = io["max_eigen_ratio_for_planes"].num(0.05);
+    if (def.has("capacity_voxels")) capacity_voxels = uint64_t(def["capacity_voxels"].num());  // extension key (device budget)
+  }
+};
+
+// ------------------------------------------------------------------------------------------------ orchestrator
+struct LidarOdometryParams {  // the subset of LidarOdometry::Parameters around the hot path (LidarOdometry.cpp:125-321)
+  double min_time_between_scans = 1e-3;
+  double max_sensor_range_filter_coefficient = 0.95, absolute_minimum_sensor_range = 5.0;
+  bool optimize_twist = true;
+  double optimize_twist_rerun_min_trans = 0.15, optimize_twist_rerun_min_rot_deg = 0.75;
+  bool local_map_updates_enabled = true;
+  Formula min_translation_between_keyframes{"1.0"}, min_rotation_between_keyframes{"30"}, max_distance_to_keep_keyframes{"0"};
+  uint32_t check_for_removal_every_n = 100;
+  double min_icp_goodness = 0.25;
+  bool adaptive_enabled = true;
+  double initial_sigma = 2.0, min_motion = 0.1, maximum_sigma = 3.0, kp = 2.0, alpha = 0.9;
+  double max_time_to_use_velocity_model = 0.75;
+};
+
+struct ScanOutput {
+  bool processed = false, icp_ran = false, icp_good = false, map_updated = false;
+  Pose pose = pose_identity();
+  double quality = 0, sigma = 0, est_max_range = 0;
+  uint32_t icp_iterations = 0, icp_runs = 0;
+  int termination = MLO_TERM_UNDEFINED;
+  uint64_t n_map_layer = 0, n_icp_layer = 0;
+};
+
+template <class Backend>
+class LidarOdometryT {
+ public:
+  explicit LidarOdometryT(Backend& be) : be_(be) {}
+  ~LidarOdometryT() {
+    if (map_) be_.destroy_map(map_);
+  }
+  LidarOdometryParams params_;
+  ParameterSource parameter_source;
+
+  // mola::LidarOdometry::initialize_frontend (LidarOdometry.cpp:246-476), hot-path subset
+  void initialize(const YamlNode& cfg) {
+    const YamlNode& p = cfg.at("params");
+    params_.min_time_between_scans = p["min_time_between_scans"].num(1e-3);
+    params_.max_sensor_range_filter_coefficient = p["max_sensor_range_filter_coefficient"].num(0.95);
+    params_.absolute_minimum_sensor_range = p["absolute_minimum_sensor_range"].num(5.0);
+    params_.optimize_twist = p["optimize_twist"].boolean(true);
+    params_.optimize_twist_rerun_min_trans = p["optimize_twist_rerun_min_trans"].num(0.15);
+    params_.optimize_twist_rerun_min_rot_deg = p["optimize_twist_rerun_min_rot_deg"].num(0.75);
+    const YamlNode& lm = p["local_map_updates"];
+    params_.local_map_updates_enabled = lm["enabled"].boolean(true);
+    params_.min_translation_between_keyframes = Formula(lm.at("min_translation_between_keyframes").str());
+    params_.min_rotation_between_keyframes = Formula(lm.at("min_rotation_between_keyframes").str());
+    if (lm.has("max_distance_to_keep_keyframes")) params_.max_distance_to_keep_keyframes = Formula(lm["max_distance_to_keep_keyframes"].str());
+    params_.check_for_removal_every_n = uint32_t(lm["check_for_removal_every_n"].num(100));
+    params_.min_icp_goodness = p["min_icp_goodness"].num(0.25);
+    const YamlNode& at = p["adaptive_threshold"];
+    params_.adaptive_enabled = at["enabled"].boolean(true);
+    params_.initial_sigma = at["initial_sigma"].num(2.0);
+    params_.min_motion = at["min_motion"].num(0.1);
+    params_.maximum_sigma = at["maximum_sigma"].num(3.0);
+    params_.kp = at["kp"].num(2.0);
+    params_.alpha = at["alpha"].num(0.9);
+    if (cfg.has("navstate_fuse_params"))
+      params_.max_time_to_use_velocity_model = cfg["navstate_fuse_params"]["max_time_to_use_velocity_model"].num(0.75);
+    icp_.initialize(cfg.at("icp_settings_with_vel"));
+    icp_.attachToParameterSource(parameter_source);
+    filter1_.initialize(cfg.at("observations_filter_1st_pass"));
+    bool found = false;
+    for (const YamlNode& g : cfg.at("localmap_generator").seq)
+      if (g["params"].has("metric_map_definition")) {
+        mapdef_.initialize(g["params"]["metric_map_definition"]);
+        found = true;
+      }
+    if (!found) throw std::runtime_error("localmap_generator: no metric_map_definition");
+    reset_state();
+  }
+
+  void reset_state() {
+    if (map_) be_.destroy_map(map_);
+    map_ = nullptr;
+    map_points_ = 0;
+    trajectory_.clear();
+    keyframes_.clear();
+    last_lidar_pose_ = pose_identity();
+    fused_.clear();
+    sigma_ = 0;
+    est_max_range_.reset();
+    inst_max_range_.reset();
+    last_obs_time_.reset();
+    last_icp_was_good_ = true;
+    last_icp_quality_ = 0.0;
+    removal_counter_ = 0;
+  }
+
+  const std::vector<std::pair<double, Pose>>& estimatedTrajectory() const { return trajectory_; }
+  double adaptiveSigma() const { return sigma_; }
+  void* localMap() const { return map_; }
+
+  // mola::LidarOdometry::onLidarImpl for one point cloud (LidarOdometry.cpp:627-1206); deskew off (row f1).
+  ScanOutput onLidar(const float* pts, uint32_t stride, uint64_t n, double stamp) {
+    ScanOutput out;
+    if (last_obs_time_ && stamp - *last_obs_time_ < params_.min_time_between_scans) return out;  // :643-657
+    const std::optional<double> last_obs = last_obs_time_;
+    last_obs_time_ = stamp;
+    out.processed = true;
+    if (!est_max_range_) {  // doInitializeEstimatedMaxSensorRange, :1487-1513
+      const double r = std::max(bbox_radius(pts, stride, n), params_.absolute_minimum_sensor_range);
+      if (n) est_max_range_ = r;
+    }
+    const auto motion = estimated_navstate(stamp);  // :808-815
+    updatePipelineDynamicVariables(motion);         // :692
+    // 1st-pass filter (:732-735); 2nd pass is the identity with deskew skipped (:737-741)
+    const mlo_filter1_params f1 = filter1_.realize(parameter_source);
+    be_.filter_1st_pass(pts, stride, n, f1, map_layer_, icp_layer_);
+    out.n_map_layer = map_layer_.size() / 3;
+    out.n_icp_layer = icp_layer_.size() / 3;
+    doUpdateEstimatedMaxSensorRange();  // :744-769 (first points layer of the observation = decimated_for_icp)
+    out.est_max_range = est_max_range_.value_or(0.0);
+
+    bool updateLocalMap = false;
+    const bool hasMotionModel = motion.has_value();
+    if (!map_ || map_points_ == 0) {
+      // first point cloud: no ICP, seed the map at the origin (:817-839)
+      updateLocalMap = true;
+      trajectory_.emplace_back(stamp, last_lidar_pose_);
+      fuse_pose(stamp, pose_identity());
+    } else {
+      Pose init = hasMotionModel ? motion->pose : last_lidar_pose_;  // :852-897 (prior term: see DESIGN.md, f2)
+      const Pose init_guess = init;
+      const Pose last_keyframe_pose = last_lidar_pose_;  // :904
+      const double since_last = last_icp_time_ ? stamp - *last_icp_time_ : 0.0;
+      last_icp_time_ = stamp;
+      Parameters ip = icp_.params;
+      uint32_t remaining = ip.maxIterations;
+      Results r;
+      IterationHook hook;
+      hook.enabled = params_.optimize_twist;
+      hook.min_trans = params_.optimize_twist_rerun_min_trans;
+      hook.min_rot_rad = params_.optimize_twist_rerun_min_rot_deg * M_PI / 180.0;
+      Pose current_solution = init;
+      do {  // :954-1007
+        ip.maxIterations = remaining;
+        hook.checkpoint = current_solution;
+        icp_.setIterationHook(hook);
+        icp_.align(be_, icp_layer_.data(), icp_layer_.size() / 3, map_, current_solution, ip, r);
+        out.icp_runs++;
+        remaining = r.nIterations <= remaining ? remaining - r.nIterations : 0;
+        if (r.terminationReason == MLO_TERM_HOOK_REQUEST) {
+          current_solution = r.optimal_tf_mean;  // the hook stored the new checkpoint (:949)
+          if (since_last > 0) {  // re-estimate the twist (:973-992); re-deskew is the identity here
+            const Pose incr = pose_minus(r.optimal_tf_mean, last_keyframe_pose);
+            double xi[6];
+            be_.se3_log(incr.data(), xi);
+            double w[3];
+            rot_log(incr, w);
+            twist_ = {incr[3] / since_last, incr[7] / since_last, incr[11] / since_last, w[0] / since_last,
+                      w[1] / since_last, w[2] / since_last};
+            updatePipelineTwistVariables();
+          }
+        }
+      } while (r.terminationReason == MLO_TERM_HOOK_REQUEST);
+      out.icp_ran = true;
+      out.quality = r.quality;
+      out.icp_iterations = r.nIterations;
+      out.termination = r.terminationReason;
+      const bool icpIsGood = r.quality >= params_.min_icp_goodness;  // :1026
+      last_icp_was_good_ = icpIsGood;
+      last_icp_quality_ = r.quality;
+      out.icp_good = icpIsGood;
+      if (icpIsGood) {
+        last_lidar_pose_ = r.optimal_tf_mean;
+        fuse_pose(stamp, r.optimal_tf_mean);
+        trajectory_.emplace_back(stamp, last_lidar_pose_);
+      } else {
+        fused_.clear();  // navstate_fuse.reset()
+      }
+      if (params_.adaptive_enabled) doUpdateAdaptiveThreshold(pose_minus(r.optimal_tf_mean, init_guess), motion);  // :1052-1063
+      // keyframe decision (:1066-1115)
+      double dist = 0, rot = 0;
+      const bool isFirst = closest_keyframe(last_lidar_pose_, dist, rot);
+      const double min_t = params_.min_translation_between_keyframes.eval(parameter_source);
+      const double min_r = params_.min_rotation_between_keyframes.eval(parameter_source) * M_PI / 180.0;
+      updateLocalMap = icpIsGood && params_.local_map_updates_enabled && hasMotionModel && (isFirst || dist > min_t || rot > min_r);
+      if (updateLocalMap) {
+        keyframes_.push_back(last_lidar_pose_);
+        const double keep = params_.max_distance_to_keep_keyframes.eval(parameter_source);
+        if (keep > 0 && removal_counter_++ >= params_.check_for_removal_every_n) {
+          removal_counter_ = 0;
+          std::vector<Pose> kept;
+          for (const Pose& k : keyframes_) {
+            const double d[3] = {k[3] - last_lidar_pose_[3], k[7] - last_lidar_pose_[7], k[11] - last_lidar_pose_[11]};
+            if (norm3(d) <= keep) kept.push_back(k);
+          }
+          keyframes_.swap(kept);
+        }
+      }
+    }
+    // bad first ICP: restart from scratch (:1150-1158)
+    if (!last_icp_was_good_ && trajectory_.size() == 1) {
+      if (map_) be_.map_clear(map_);
+      map_points_ = 0;
+      trajectory_.clear();
+      keyframes_.clear();
+      updateLocalMap = false;
+      last_icp_was_good_ = true;
+    }
+    if (updateLocalMap) {  // :1161-1206
+      updatePipelineDynamicVariables(motion);  // robot_x.. for FilterMerge
+      if (!map_) {
+        mlo_map_params mp;
+        std::memset(&mp, 0, sizeof(mp));
+        mp.kind = mapdef_.kind;
+        mp.voxel_size = float(mapdef_.voxel_size.eval(parameter_source));
+        mp.max_points_per_voxel = mapdef_.max_points_per_voxel;
+        mp.min_distance_between_points = float(mapdef_.min_distance_between_points);
+        mp.max_eigen_ratio_for_planes = float(mapdef_.max_eigen_ratio_for_planes);
+        mp.min_points_for_plane = 5;
+        mp.capacity_voxels = mapdef_.capacity_voxels;
+        map_ = be_.create_map(mp);
+        cull_dist_ = float(mapdef_.remove_voxels_farther_than.eval(parameter_source));
+      }
+      be_.map_insert(map_, map_layer_.data(), map_layer_.size() / 3, last_lidar_pose_.data());
+      if (cull_dist_ > 0) {
+        const double s[3] = {last_lidar_pose_[3], last_lidar_pose_[7], last_lidar_pose_[11]};
+        be_.map_cull(map_, s, cull_dist_);
+      }
+      uint64_t nv = 0;
+      be_.map_stats(map_, nv, map_points_);
+      out.map_updated = true;
+    }
+    (void)last_obs;
+    out.pose = last_lidar_pose_;
+    out.sigma = sigma_;
+    return out;
+  }
+
+ private:
+  struct NavState {
+    Pose pose;
+    std::array<double, 6> twist;
+  };
+  // Constant-velocity stand-in for mola::NavStateFuse (external, row f2): body-frame twist from the last two fused
+  // poses; valid while the newest fused pose is younger than max_time_to_use_velocity_model.
+  std::optional<NavState> estimated_navstate(double stamp) {
+    if (fused_.size() < 2) return std::nullopt;
+    const auto& a = fused_[fused_.size() - 2];
+    const auto& b = fused_.back();
+    const double dt0 = b.first - a.first, dt = stamp - b.first;
+    if (dt0 <= 0 || dt > params_.max_time_to_use_velocity_model) return std::nullopt;
+    const Pose rel = pose_minus(b.second, a.second);
+    double xi[6];
+    be_.se3_log(rel.data(), xi);
+    NavState ns;
+    for (int k = 0; k < 6; k++) ns.twist[k] = xi[k] / dt0;
+    double step[6];
+    for (int k = 0; k < 6; k++) step[k] = ns.twist[k] * dt;
+    Pose d;
+    be_.se3_exp(step, d.data());
+    ns.pose = pose_compose(b.second, d);
+    return ns;
+  }
+  void fuse_pose(double stamp, const Pose& p) {
+    fused_.emplace_back(stamp, p);
+    if (fused_.size() > 8) fused_.erase(fused_.begin());
+  }
+  void rot_log(const Pose& p, double w[3]) {
+    Pose r = p;
+    r[3] = r[7] = r[11] = 0.0;
+    double xi[6];
+    be_.se3_log(r.data(), xi);
+    w[0] = xi[3];
+    w[1] = xi[4];
+    w[2] = xi[5];
+  }
+  static double bbox_radius(const float* p, uint32_t stride, uint64_t n) {
+    if (!n) return 0.0;
+    float mn[3] = {p[0], p[1], p[2]}, mx[3] = {p[0], p[1], p[2]};
+    for (uint64_t i = 1; i < n; i++)
+      for (int k = 0; k < 3; k++) {
+        mn[k] = std::min(mn[k], p[i * stride + k]);
+        mx[k] = std::max(mx[k], p[i * stride + k]);
+      }
+    const double a[3] = {mn[0], mn[1], mn[2]}, b[3] = {mx[0], mx[1], mx[2]};
+    return std::max(norm3(a), norm3(b));
+  }
+  void doUpdateEstimatedMaxSensorRange() {  // :1515-1546
+    if (!est_max_range_ || icp_layer_.empty()) return;
+    const double radius = std::max(bbox_radius(icp_layer_.data(), 3, icp_layer_.size() / 3), params_.absolute_minimum_sensor_range);
+    inst_max_range_ = radius;
+    const double a = params_.max_sensor_range_filter_coefficient;
+    est_max_range_ = *est_max_range_ * a + radius * (1.0 - a);
+  }
+  void doUpdateAdaptiveThreshold(const Pose& err, const std::optional<NavState>& motion) {  // :1449-1485
+    if (!est_max_range_) return;
+    const double max_range = *est_max_range_;
+    double w[3];
+    rot_log(err, w);
+    const double theta = norm3(w);
+    const double t[3] = {err[3], err[7], err[11]};
+    const double model_error = norm3(t) + 2.0 * max_range * std::sin(theta / 2.0);
+    double rot_error = 0;
+    if (motion) rot_error = 0.1 * norm3(&motion->twist[3]) * max_range;
+    const double gain = std::min(std::max(params_.kp * (1.0 - last_icp_quality_), 0.1), params_.kp);
+    const double new_sigma = (model_error + rot_error) * gain;
+    if (sigma_ == 0) sigma_ = params_.initial_sigma;
+    sigma_ = params_.alpha * sigma_ + (1.0 - params_.alpha) * new_sigma;
+    sigma_ = std::min(std::max(sigma_, params_.min_motion), params_.maximum_sigma);
+  }
+  void updatePipelineTwistVariables() {  // :1571-1579
+    static const char* names[6] = {"vx", "vy", "vz", "wx", "wy", "wz"};
+    for (int k = 0; k < 6; k++) parameter_source.updateVariable(names[k], twist_[k]);
+  }
+  void updatePipelineDynamicVariables(const std::optional<NavState>& motion) {  // :1581-1635
+    twist_ = motion ? motion->twist : std::array<double, 6>{0, 0, 0, 0, 0, 0};
+    updatePipelineTwistVariables();
+    double yaw, pitch, roll;
+    pose_ypr(last_lidar_pose_, yaw, pitch, roll);
+    parameter_source.updateVariable("robot_x", last_lidar_pose_[3]);
+    parameter_source.updateVariable("robot_y", last_lidar_pose_[7]);
+    parameter_source.updateVariable("robot_z", last_lidar_pose_[11]);
+    parameter_source.updateVariable("robot_yaw", yaw);
+    parameter_source.updateVariable("robot_pitch", pitch);
+    parameter_source.updateVariable("robot_roll", roll);
+    parameter_source.updateVariable("ADAPTIVE_THRESHOLD_SIGMA", sigma_ != 0 ? sigma_ : params_.initial_sigma);
+    parameter_source.updateVariable("ICP_ITERATION", 0);
+    for (const char* v : {"icp_iterations", "SENSOR_TIME_OFFSET", "twistCorrectionCount"})
+      if (!parameter_source.has(v)) parameter_source.updateVariable(v, 0);
+    if (est_max_range_) parameter_source.updateVariable("ESTIMATED_SENSOR_MAX_RANGE", *est_max_range_);
+    parameter_source.updateVariable("INSTANTANEOUS_SENSOR_MAX_RANGE", inst_max_range_ ? *inst_max_range_ : 20.0);
+  }
+  // mola::SearchablePoseList::check: distance to the closest stored keyframe; true when the list is empty
+  bool closest_keyframe(const Pose& p, double& dist, double& rot) {
+    if (keyframes_.empty()) {
+      dist = rot = 0;
+      return true;
+    }
+    double best = 1e300;
+    const Pose* bk = nullptr;
+    for (const Pose& k : keyframes_) {
+      const double d[3] = {k[3] - p[3], k[7] - p[7], k[11] - p[11]};
+      const double n = norm3(d);
+      if (n < best) {
+        best = n;
+        bk = &k;
+      }
+    }
+    const Pose rel = pose_minus(p, *bk);
+    const double t[3] = {rel[3], rel[7], rel[11]};
+    dist = norm3(t);
+    double w[3];
+    rot_log(rel, w);
+    rot = norm3(w);
+    return false;
+  }
+
+  Backend& be_;
+  ICP<Backend> icp_;
+  FilterPipeline1st filter1_;
+  LocalMapDefinition mapdef_;
+  void* map_ = nullptr;
+  uint64_t map_points_ = 0;
+  float cull_dist_ = 0;
+  std::vector<float> map_layer_, icp_layer_;
+  std::vector<std::pair<double, Pose>> trajectory_, fused_;
+  std::vector<Pose> keyframes_;
+  Pose last_lidar_pose_ = pose_identity();
+  std::array<double, 6> twist_{};
+  double sigma_ = 0;
+  std::optional<double> est_max_range_, inst_max_range_, last_obs_time_, last_icp_time_;
+  bool last_icp_was_good_ = true;
+  double last_icp_quality_ = 0;
+  uint32_t removal_counter_ = 0;
+};
+
+}  // namespace mlo_host

@@ -1,0 +1,122 @@
+"""ctypes view of include/mlo_b200_host.h: the C++ host layer (pipeline YAML + LidarOdometry caller contract)."""
+from __future__ import annotations
+
+import ctypes as C
+from pathlib import Path
+
+import numpy as np
+
+from . import capi
+from .api import Context, MloError, _pts
+
+PIPELINES = Path(__file__).resolve().parent.parent / "pipelines"
+
+
+class ScanOutput(C.Structure):
+    _fields_ = [("processed", C.c_int32), ("icp_ran", C.c_int32), ("icp_good", C.c_int32), ("map_updated", C.c_int32),
+                ("pose_3x4", C.c_double * 12), ("quality", C.c_double), ("sigma", C.c_double),
+                ("est_max_range", C.c_double), ("icp_iterations", C.c_uint32), ("icp_runs", C.c_uint32),
+                ("termination", C.c_int32), ("n_map_layer", C.c_uint64), ("n_icp_layer", C.c_uint64)]
+
+    @property
+    def pose(self):
+        return np.array(self.pose_3x4[:]).reshape(3, 4)
+
+
+_vp, _u32, _u64 = C.c_void_p, C.c_uint32, C.c_uint64
+HOST_SIGNATURES = {
+    "mlo_lo_create": (C.c_int, [_vp, C.c_char_p, C.c_int, C.POINTER(_vp)]),
+    "mlo_lo_destroy": (None, [_vp]),
+    "mlo_lo_last_error": (C.c_char_p, [_vp]),
+    "mlo_lo_on_lidar": (C.c_int, [_vp, _vp, _u32, _u64, C.c_double, C.POINTER(ScanOutput)]),
+    "mlo_lo_trajectory": (C.c_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64)]),
+    "mlo_lo_reset": (C.c_int, [_vp]),
+    "mlo_host_last_error": (C.c_char_p, []),
+    "mlo_host_icp_tables": (C.c_int, [C.c_char_p, C.c_double, _u32, _vp, _vp, _vp, C.POINTER(capi.IcpParams)]),
+    "mlo_host_filter1": (C.c_int, [C.c_char_p, C.c_double, C.c_double, C.POINTER(capi.Filter1Params)]),
+    "mlo_host_mapdef": (C.c_int, [C.c_char_p, C.c_double, C.POINTER(capi.MapParams), C.POINTER(C.c_float)]),
+    "mlo_host_eval_formula": (C.c_int, [C.c_char_p, C.POINTER(C.c_char_p), _vp, _u32, C.POINTER(C.c_double)]),
+}
+_BOUND = False
+
+
+def lib():
+    global _BOUND
+    L = capi.load()
+    if not _BOUND:
+        for name, (res, args) in HOST_SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype, fn.argtypes = res, args
+        _BOUND = True
+    return L
+
+
+def _host_check(rc):
+    if rc != 0:
+        raise MloError(rc, lib().mlo_host_last_error().decode())
+
+
+def icp_tables(yaml_text: str, sigma: float, n_it: int):
+    t1, t2, t3 = np.zeros(n_it), np.zeros(n_it), np.zeros(n_it)
+    sc = capi.IcpParams()
+    _host_check(lib().mlo_host_icp_tables(yaml_text.encode(), sigma, n_it, t1.ctypes.data, t2.ctypes.data, t3.ctypes.data,
+                                          C.byref(sc)))
+    return t1, t2, t3, sc
+
+
+def filter1(yaml_text: str, est: float, inst: float) -> capi.Filter1Params:
+    f = capi.Filter1Params()
+    _host_check(lib().mlo_host_filter1(yaml_text.encode(), est, inst, C.byref(f)))
+    return f
+
+
+def mapdef(yaml_text: str, est: float):
+    m, cull = capi.MapParams(), C.c_float()
+    _host_check(lib().mlo_host_mapdef(yaml_text.encode(), est, C.byref(m), C.byref(cull)))
+    return m, cull.value
+
+
+def eval_formula(expr: str, **variables) -> float:
+    names = (C.c_char_p * len(variables))(*[k.encode() for k in variables])
+    vals = np.array(list(variables.values()), dtype=np.float64)
+    out = C.c_double()
+    _host_check(lib().mlo_host_eval_formula(expr.encode(), names, vals.ctypes.data, len(variables), C.byref(out)))
+    return out.value
+
+
+class LidarOdometry:
+    """mola::LidarOdometry (hot-path subset) on one GPU context: initialize(yaml) then on_lidar(cloud, stamp)."""
+
+    def __init__(self, ctx: Context, yaml_path_or_text, is_text: bool = False):
+        self.ctx = ctx
+        h = _vp()
+        rc = lib().mlo_lo_create(ctx.h, str(yaml_path_or_text).encode(), int(is_text), C.byref(h))
+        if rc != 0:
+            raise MloError(rc, lib().mlo_lo_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().mlo_lo_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def on_lidar(self, pts, stamp: float) -> ScanOutput:
+        pts = _pts(pts)
+        out = ScanOutput()
+        rc = lib().mlo_lo_on_lidar(self.h, pts.ctypes.data, pts.shape[1], len(pts), stamp, C.byref(out))
+        if rc != 0:
+            raise MloError(rc, lib().mlo_lo_last_error(self.h).decode())
+        return out
+
+    def trajectory(self):
+        n = _u64()
+        lib().mlo_lo_trajectory(self.h, None, None, 0, C.byref(n))
+        st, ps = np.zeros(n.value), np.zeros((n.value, 3, 4))
+        lib().mlo_lo_trajectory(self.h, st.ctypes.data, ps.ctypes.data, n.value, C.byref(n))
+        return st, ps

@@ -217,3 +217,34 @@ def scan_register(omap: OracleMap, raw, fp: Filter1Params, init_pose, params: Ic
                             C.byref(params), int(insert), cull_dist, pool.h if pool else None, C.byref(res),
                             ms.ctypes.data)
     return res, ms
+
+
+class OracleLidarOdometry:
+    """The product's C++ host orchestrator instantiated over the CPU oracle (oracle_lo_capi.cpp) — for
+    trajectory-level parity tests and the sequence CPU baseline."""
+
+    def __init__(self, yaml_path_or_text, is_text: bool = False):
+        from mola_lidar_odometry_b200.host_api import ScanOutput
+        L = lib()
+        L.orc_lo_create.restype = _vp
+        L.orc_lo_create.argtypes = [C.c_char_p, C.c_int]
+        L.orc_lo_destroy.argtypes = [_vp]
+        L.orc_lo_on_lidar.restype = C.c_int
+        L.orc_lo_on_lidar.argtypes = [_vp, _vp, _u32, _u64, C.c_double, C.POINTER(ScanOutput)]
+        self._out_t = ScanOutput
+        self.h = L.orc_lo_create(str(yaml_path_or_text).encode(), int(is_text))
+        if not self.h:
+            raise RuntimeError("orc_lo_create failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_lo_destroy(self.h)
+            self.h = None
+
+    def on_lidar(self, pts, stamp: float):
+        pts = _f32(pts)
+        out = self._out_t()
+        rc = lib().orc_lo_on_lidar(self.h, pts.ctypes.data, pts.shape[1], len(pts), stamp, C.byref(out))
+        if rc != 0:
+            raise RuntimeError("orc_lo_on_lidar failed")
+        return out
