@@ -113,7 +113,7 @@ def test_lidar_odometry_caller_contract_on_oracle(built, scene, traj):
     outs = _run(lo, scene, traj, 8)
     assert not outs[0].icp_ran and outs[0].map_updated
     assert outs[1].icp_ran and outs[1].icp_good and not outs[1].map_updated     # no motion model yet (LidarOdometry.cpp:1088)
-    assert all(o.icp_good for o in outs[2:]) and sum(o.map_updated for o in outs[2:]) >= 4
+    assert all(o.icp_good for o in outs[2:]) and sum(o.map_updated for o in outs[2:]) >= 1  # keyframe rule: (0.001+0.1|w|)*R
     assert all(o.icp_runs == 1 for o in outs[1:])                               # optimize_twist off: no hook re-runs
     # adaptive sigma after the first ICP (LidarOdometry.cpp:1449-1485): init guess = identity, no twist yet
     o1 = outs[1]
