@@ -50,7 +50,7 @@ def log(*a):
 class Workload:
     def __init__(self, n_query: int, seed: int, threads: int):
         self.scene = synth.Scene(42)
-        self.traj = synth.trajectory_T00(4541, seed=7)
+        self.traj = synth.trajectory_T00(8000, seed=7)  # T00-shaped drive, long enough to cover 2^20 voxels
         self.T0 = self.traj[0]
         self.fp = capi.filter1_default(EST_RANGE)
         self.threads = threads

@@ -323,6 +323,7 @@ struct LidarOdometryParams {  // the subset of LidarOdometry::Parameters around 
   bool adaptive_enabled = true;
   double initial_sigma = 2.0, min_motion = 0.1, maximum_sigma = 3.0, kp = 2.0, alpha = 0.9;
   double max_time_to_use_velocity_model = 0.75;
+  std::array<double, 6> initial_twist{};  // navstate_fuse_params.initial_twist (default.yaml:139): vx vy vz wx wy wz
 };
 
 struct ScanOutput {
@@ -368,7 +369,12 @@ class LidarOdometryT {
     params_.kp = at["kp"].num(2.0);
     params_.alpha = at["alpha"].num(0.9);
     if (cfg.has("navstate_fuse_params"))
-      params_.max_time_to_use_velocity_model = cfg["navstate_fuse_params"]["max_time_to_use_velocity_model"].num(0.75);
+    {
+      const YamlNode& nf = cfg["navstate_fuse_params"];
+      params_.max_time_to_use_velocity_model = nf["max_time_to_use_velocity_model"].num(0.75);
+      if (nf["initial_twist"].isSeq())
+        for (size_t k = 0; k < 6 && k < nf["initial_twist"].seq.size(); k++) params_.initial_twist[k] = nf["initial_twist"].seq[k].num(0.0);
+    }
     icp_.initialize(cfg.at("icp_settings_with_vel"));
     icp_.attachToParameterSource(parameter_source);
     filter1_.initialize(cfg.at("observations_filter_1st_pass"));
@@ -549,6 +555,20 @@ class LidarOdometryT {
   // Constant-velocity stand-in for mola::NavStateFuse (external, row f2): body-frame twist from the last two fused
   // poses; valid while the newest fused pose is younger than max_time_to_use_velocity_model.
   std::optional<NavState> estimated_navstate(double stamp) {
+    if (fused_.size() == 1) {  // only the initial pose is known: extrapolate with the configured initial twist, if any
+      bool any = false;
+      for (double v : params_.initial_twist) any = any || v != 0.0;
+      const double dt = stamp - fused_.back().first;
+      if (!any || dt > params_.max_time_to_use_velocity_model) return std::nullopt;
+      NavState ns;
+      ns.twist = params_.initial_twist;
+      double step[6];
+      for (int k = 0; k < 6; k++) step[k] = ns.twist[k] * dt;
+      Pose d;
+      be_.se3_exp(step, d.data());
+      ns.pose = pose_compose(fused_.back().second, d);
+      return ns;
+    }
     if (fused_.size() < 2) return std::nullopt;
     const auto& a = fused_[fused_.size() - 2];
     const auto& b = fused_.back();

@@ -50,7 +50,7 @@ SENSOR_HEIGHT = 1.73
 class Scene:
     """Scene S(seed): street grid with buildings, poles and parked cars."""
 
-    def __init__(self, seed: int = 42, extent_m: float = 1500.0, n_poles: int = 2000, n_cars: int = 1500):
+    def __init__(self, seed: int = 42, extent_m: float = 1500.0, n_poles: int = 8000, n_cars: int = 6000):
         self._h = _lib().synth_scene_create(seed, extent_m, n_poles, n_cars)
         self.extent = extent_m
 
@@ -156,27 +156,41 @@ def _street_path(rng: np.random.Generator, length_m: float, extent_m: float, ds:
             heading, skip = h2, rad
     path = np.concatenate(chunks, 0)
     path[:, 2] = np.unwrap(path[:, 2])
-    return path
+    # clothoid-like corners: smooth the heading over ~6 m of arc length and re-integrate the position, so the yaw
+    # rate ramps up and down instead of stepping (a vehicle cannot change curvature instantly)
+    k = np.exp(-0.5 * (np.arange(-int(9.0 / ds), int(9.0 / ds) + 1) * ds / 3.0) ** 2)
+    k /= k.sum()
+    pad = len(k) // 2
+    yaw = np.convolve(np.pad(path[:, 2], pad, mode="edge"), k, mode="valid")
+    x = path[0, 0] + np.concatenate([[0.0], np.cumsum(np.cos(yaw[:-1]) * ds)])
+    y = path[0, 1] + np.concatenate([[0.0], np.cumsum(np.sin(yaw[:-1]) * ds)])
+    return np.stack([x, y, yaw], 1)
 
 
-def trajectory_T00(n_poses: int = 4541, seed: int = 7, extent_m: float = 1500.0, dt: float = 0.1) -> np.ndarray:
+def trajectory_T00(n_poses: int = 4541, seed: int = 7, extent_m: float = 1500.0, dt: float = 0.1, v0: float = 8.0) -> np.ndarray:
     """KITTI-00-shaped drive: straights and 90-degree turns on a street grid, an Ornstein-Uhlenbeck speed
     profile in [0, 15] m/s, smoothed 0.2-degree pitch/roll noise.  Returns [n,3,4] sensor->world poses
     (world: ground z = 0, sensor at 1.73 m)."""
     rng = np.random.default_rng(seed)
     ds = 0.02
     path = _street_path(rng, n_poses * dt * 15.0 + 100.0, extent_m, ds)
-    v = np.empty(n_poses)
-    vv = 8.0
+    # speed: Ornstein-Uhlenbeck around 12.5 m/s on straights, braking to ~3 m/s for the 6 m-radius corners
+    # (yaw rate <= ~30 deg/s like KITTI; 8 m/s through such a corner would be 76 deg/s)
+    turning = np.abs(np.gradient(path[:, 2])) > 1e-9
+    look = int(9.0 / ds)
+    csum = np.concatenate([[0], np.cumsum(turning)])
+    s_now, vv = 0.0, float(v0)
+    xyyaw = np.empty((n_poses, 3))
     for k in range(n_poses):
-        vv += 0.05 * (9.0 - vv) + 0.35 * rng.standard_normal()
-        vv = min(15.0, max(0.0, vv))
-        v[k] = vv
-    s = np.concatenate([[0.0], np.cumsum(v[:-1] * dt)])
-    f = s / ds
-    i0 = np.minimum(f.astype(np.int64), len(path) - 2)
-    w = (f - i0)[:, None]
-    xyyaw = path[i0] * (1 - w) + path[i0 + 1] * w
+        f = s_now / ds
+        i0 = min(int(f), len(path) - 2)
+        w = f - i0
+        xyyaw[k] = path[i0] * (1 - w) + path[i0 + 1] * w
+        near_turn = csum[min(i0 + look, len(path))] - csum[max(i0 - int(2.0 / ds), 0)] > 0
+        target = 3.0 if near_turn else 12.5
+        vv += (0.15 if near_turn else 0.06) * (target - vv) + 0.35 * rng.standard_normal() * (0.3 if near_turn else 1.0)
+        vv = min(15.0, max(0.5 if k else vv, vv))
+        s_now += max(vv, 0.0) * dt
     pr = rng.standard_normal((n_poses, 2))
     k = np.exp(-0.5 * (np.arange(-20, 21) / 6.0) ** 2)
     k /= np.sqrt((k ** 2).sum())
