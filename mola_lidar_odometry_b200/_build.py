@@ -42,8 +42,8 @@ def _nvcc() -> str:
 
 def build_cuda(force: bool = False, verbose: bool = False) -> Path:
     srcs = sorted(CSRC.glob("*.cu")) + sorted((PKG / "host").glob("*.cpp"))
-    deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((PKG / "host").glob("*.h")) + [
-        ROOT / "include" / "mlo_b200.h"]
+    deps = srcs + sorted(CSRC.glob("*.cuh")) + sorted(CSRC.glob("*.h")) + sorted((PKG / "host").glob("*.h")) + sorted((PKG / "host").glob("*.hpp")) + [
+        ROOT / "include" / "mlo_b200.h", ROOT / "include" / "mlo_b200_host.h"]
     if force or _newer(LIB_CUDA, deps):
         cmd = [_nvcc(), *NVCC_FLAGS, "-I", str(ROOT / "include"), "-I", str(CSRC), "-I", str(PKG / "host"),
                "-o", str(LIB_CUDA), *map(str, srcs), "-lcudart"]
