@@ -928,6 +928,28 @@ __device__ __noinline__ void chunk_accumulate_ool(const IcpProblem& P, const dou
   chunk_accumulate(P, sT, it, chunk, local, pairA, pairB, partials, part_cnt);
 }
 
+// Build the work queue on the device from the current problem states (used when a launch sequence hands its
+// tail of still-active problems over to the persistent kernel): every slot first gets seq = index (free), then
+// each active problem appends the chunks of its next match phase.
+__global__ void k_queue_reset(IcpQueue q, uint32_t n_problems) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= q.mask) q.seq[i] = i;
+  if (i < n_problems) q.phase_cnt[i] = 0;
+  if (i < 8) q.ctrl[i] = 0;
+}
+__global__ void k_queue_build(const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states, IcpQueue q,
+                              uint32_t n_problems) {
+  const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= n_problems || states[b].done) return;
+  const uint32_t n = probs[b].n_blocks;
+  const uint32_t pos = atomicAdd(&q.ctrl[1], n);
+  for (uint32_t i = 0; i < n; i++) {
+    q.items[(pos + i) & q.mask] = item_make(b, i, 0u);
+    q.seq[(pos + i) & q.mask] = pos + i + 1;
+  }
+  atomicAdd(&q.ctrl[2], 1u);
+}
+
 template <bool TPQ>
 __global__ void __launch_bounds__(ICP_BLOCK, 4)
     k_icp_persistent(MapDev map, const IcpProblem* __restrict__ probs, IcpState* states, const float4* __restrict__ local,

@@ -81,6 +81,7 @@ struct mlo_ctx {
   } stage[2];
   bool use_persistent = true;  // MLO_PERSISTENT=0 selects the one-kernel-per-phase launch sequence
   bool persistent_forced = false;
+  bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
   int consuming_slot = -1;  // staging slot read by the compute call in progress
   int persistent_blocks = 0;
   std::string dev_name;
@@ -614,6 +615,41 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
       CU(c, cudaMemcpyAsync(h_active, d_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
       if (*h_active == 0) break;
+      // Tail hand-over: once few problems remain, a launch sequence is latency-bound (each iteration still costs
+      // four launches); the queue-driven kernel finishes the stragglers in one launch.
+      const uint64_t avg_q = total_queries / std::max<uint32_t>(B, 1);
+      if (c->use_persistent && c->tail_handover && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * 512 &&
+          B < 65536 && max_blocks < 32768 && max_blocks_acc < 32768) {
+        const uint32_t qcap = uint32_t(next_pow2(std::max<uint64_t>(2ull * part_total, 1024)));
+        CU(c, c->d_queue.ensure((2ull * qcap + 8 + B) * sizeof(uint32_t)));
+        uint32_t* dq = c->d_queue.as<uint32_t>();
+        IcpQueue q;
+        q.items = dq;
+        q.seq = dq + qcap;
+        q.ctrl = dq + 2ull * qcap;
+        q.phase_cnt = dq + 2ull * qcap + 8;
+        q.mask = qcap - 1;
+        LAUNCH(c, k_queue_reset, (std::max(qcap, B) + 255) / 256, 256, q, B);
+        LAUNCH(c, k_queue_build, (B + 127) / 128, 128, dP, dS, q, B);
+        if (c->persistent_blocks == 0) {
+          int per_sm = 0;
+          CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true>, ICP_BLOCK, 0));
+          c->persistent_blocks = std::max(1, per_sm) * c->sm_count;
+        }
+        const uint32_t nblk = std::min<uint32_t>(uint32_t(c->persistent_blocks), std::max<uint32_t>(part_total, 1u));
+        const size_t e_nn = prof_begin(c);
+        if (use_tpq)
+          LAUNCH(c, k_icp_persistent<true>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+                 c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, 0u);
+        else
+          LAUNCH(c, k_icp_persistent<false>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+                 c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, qpw);
+        prof_end(c, 3, e_nn);
+        CU(c, cudaMemcpyAsync(h_active, q.ctrl + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+        CU(c, cudaStreamSynchronize(c->stream));
+        if (*h_active != 0) return fail(c, MLO_ERR_CUDA, "persistent ICP kernel timed out waiting on its work queue");
+        break;
+      }
     }
   }
   prof_end(c, 1, e_icp);
@@ -666,6 +702,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->cc_minor = prop.minor;
   c->dev_name = prop.name;
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
+  if (const char* th = getenv("MLO_TAIL_HANDOVER")) c->tail_handover = atoi(th) != 0;
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)

@@ -172,28 +172,38 @@ MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
 MLO_HD bool ldlt6(const double* H, const double* b, double* x) {
   double L[36];
   double D[6];
+#pragma unroll
   for (int i = 0; i < 36; i++) L[i] = 0.0;
+#pragma unroll
   for (int j = 0; j < 6; j++) {
     double d = H[6 * j + j];
+#pragma unroll
     for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k] * D[k];
     if (!(d > 0.0) || !(d < 1e300)) return false;
     D[j] = d;
     L[6 * j + j] = 1.0;
+#pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double s = H[6 * i + j];
+#pragma unroll
       for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k] * D[k];
       L[6 * i + j] = s / d;
     }
   }
   double y[6];
+#pragma unroll
   for (int i = 0; i < 6; i++) {
     double s = b[i];
+#pragma unroll
     for (int k = 0; k < i; k++) s -= L[6 * i + k] * y[k];
     y[i] = s;
   }
+#pragma unroll
   for (int i = 0; i < 6; i++) y[i] /= D[i];
+#pragma unroll
   for (int i = 5; i >= 0; i--) {
     double s = y[i];
+#pragma unroll
     for (int k = i + 1; k < 6; k++) s -= L[6 * k + i] * x[k];
     x[i] = s;
   }
