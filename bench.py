@@ -269,6 +269,132 @@ def run_reference(args, rank: int):
     print(json.dumps(line), flush=True)
 
 
+# ---------------------------------------------------------------------------------------------- sequence workloads
+def run_sequences(args, rank, local_rank, world):
+    """BASELINE configs[2]/[3]/[4]: S independent T00-shaped sequences per GPU, each through the full odometry loop of
+    the C++ host layer (filter -> motion-model guess -> ICP -> quality gate -> adaptive sigma -> keyframe -> map
+    insert + cull) with the pipeline YAML; one host thread + one context (stream) per sequence, like the reference's
+    one worker per LidarOdometry.  The CPU arm runs the SAME orchestrator over the oracle backend."""
+    os.environ.setdefault("MOLA_OPTIMIZE_TWIST", "false")   # benchmark settings of SURVEY.md §8(d): deskew is row f1
+    os.environ.setdefault("MOLA_INITIAL_VX", "8.0")
+    ndt = args.workload == "ndt"
+    yaml_path = ROOT / "pipelines" / ("lidar3d-ndt.yaml" if ndt else "lidar3d-default.yaml")
+    sensor = synth.O128 if ndt else synth.K64
+    cores = os.cpu_count() or 1
+    S, N = args.sequences, args.scans
+    scene = synth.Scene(42)
+    seeds = [7 + rank * S + i for i in range(S)]
+    trajs = [synth.trajectory_T00(N + 5, seed=sd) for sd in seeds]
+    with ThreadPoolExecutor(max(1, cores // max(1, world))) as ex:
+        scans = [list(ex.map(lambda k, tr=tr, sd=sd: scene.scan(tr[k], sensor, scan_seed=sd * 100000 + k), range(N)))
+                 for tr, sd in zip(trajs, seeds)]
+    from oracle import oracle_py as O
+
+    def drive(make_lo, s_idx, res):
+        lo = make_lo()
+        t0 = time.perf_counter()
+        poses, its = [], 0
+        for k in range(N):
+            o = lo.on_lidar(scans[s_idx][k], 0.1 * k)
+            poses.append(o.pose.copy())
+            its += int(o.icp_iterations)
+        res[s_idx] = (time.perf_counter() - t0, np.stack(poses), its)
+
+    def run_all(make_lo, n_threads):
+        res = [None] * S
+        t0 = time.perf_counter()
+        pending = list(range(S))
+        lock = threading.Lock()
+
+        def worker():
+            while True:
+                with lock:
+                    if not pending:
+                        return
+                    i = pending.pop(0)
+                drive(make_lo, i, res)
+        th = [threading.Thread(target=worker) for _ in range(n_threads)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+        return time.perf_counter() - t0, res
+
+    line = {"metric": "scans/sec", "unit": "scans/s", "n_gpus": world, "steps": 1, "warmup": 0, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32 distances / f64 normal equations", "data": "synthetic",
+            "config": {"workload": ("config[3]: T00 x O128, lidar3d-ndt.yaml" if ndt else
+                                    "config[2]/[4]: T00 x K64 sequences, lidar3d-default.yaml, full odometry loop"),
+                       "sequences_per_gpu": S, "scans_per_sequence": N, "points_per_scan": int(np.mean([len(x) for x in scans[0]]))}}
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        wall, res = run_all(lambda: O.OracleLidarOdometry(yaml_path), min(cores, S))
+        line.update({"impl": "reference", "value": S * N / wall, "ms_per_step": wall * 1e3,
+                     "cpu_baseline": {"value": S * N / wall, "unit": "scans/s", "cores": min(cores, S), "kind": "port",
+                                      "sample": f"{S} sequences x {N} scans, one thread per sequence"},
+                     "e2e": {"value": S * N / wall, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                     "gpu_launches": 0})
+        print(json.dumps(line), flush=True)
+        return
+    import torch
+    import torch.distributed as dist
+    from mola_lidar_odometry_b200.api import Context
+    from mola_lidar_odometry_b200.host_api import LidarOdometry
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    ctxs = []
+
+    def make_gpu():
+        c = Context(local_rank)
+        ctxs.append(c)
+        return LidarOdometry(c, yaml_path)
+    run_all(make_gpu, S)                      # warm-up pass (allocations, first-touch)
+    l0 = sum(c.launch_count for c in ctxs)
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall, res = run_all(make_gpu, S)
+    torch.cuda.synchronize()
+    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    wall_max = float(t[0])
+    launches = sum(c.launch_count for c in ctxs) - l0
+    value = world * S * N / wall_max
+    cpu, parity = None, None
+    if rank == 0 and not args.no_cpu_baseline:
+        n_cpu = min(S, max(1, cores // 2))
+        cwall, cres = run_all(lambda: O.OracleLidarOdometry(yaml_path), min(cores, S))
+        cpu = {"value": S * N / cwall, "unit": "scans/s", "cores": min(cores, S), "kind": "port",
+               "sample": f"{S} sequences x {N} scans, one thread per sequence (same C++ orchestrator over the oracle backend)"}
+        dt, dr, ape_gt = [], [], []
+        for i in range(S):
+            gp, cp = res[i][1], cres[i][1]
+            for k in range(N):
+                e = O.pose_error(gp[k], cp[k])
+                dt.append(e[0])
+                dr.append(e[1])
+            gt = np.stack([synth.relative(trajs[i][0], trajs[i][k]) for k in range(N)])
+            ape_gt.append(float(np.sqrt(np.mean(np.sum((gp[:, :, 3] - gt[:, :, 3]) ** 2, axis=1)))))
+        parity = {"max_trans_m": float(max(dt)), "max_rot_deg": float(max(dr)),
+                  "ape_rmse_vs_oracle_m": float(np.sqrt(np.mean(np.square(dt)))), "ape_rmse_vs_gt_m": float(np.mean(ape_gt)),
+                  "mean_icp_iterations": float(np.mean([r[2] for r in res]) / max(1, N - 1))}
+    if rank == 0:
+        line.update({"value": value, "ms_per_step": wall_max * 1e3,
+                     "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": int(sum(x.nbytes for sc in scans for x in sc)),
+                             "d2h_bytes_per_step": int(S * N * 400), "note": "host buffers in, host results out on every scan"},
+                     "gpu_launches": int(launches), "cpu_baseline": cpu, "quality": parity,
+                     "roofline": None})
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+    for c in ctxs:
+        c.close()
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -280,12 +406,20 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="config1", choices=["config1", "sequence", "ndt"],
+                    help="config1 = the headline (default); sequence = BASELINE configs[2]/[4] full odometry loop; "
+                         "ndt = configs[3] (lidar3d-ndt.yaml, O128 sensor)")
+    ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (sequence/ndt workloads)")
+    ap.add_argument("--scans", type=int, default=120, help="scans per sequence (sequence/ndt workloads)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
+    if args.workload != "config1":
+        run_sequences(args, rank, local_rank, world)
+        return
     if args.impl == "reference":
         run_reference(args, rank)
         return

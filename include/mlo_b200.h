@@ -117,6 +117,11 @@ int mlo_map_cull(mlo_map* map, const double sensor_xyz[3], float remove_farther_
  * out_xyz: n*3 floats, out_d2: n floats (+inf when nothing found), out_found: n bytes. */
 int mlo_map_nn_single(const mlo_map* map, const float* q, uint32_t stride_floats, uint64_t n, float* out_xyz,
                       float* out_d2, uint8_t* out_found);
+/* mola::NDT nearest-plane query (Matcher_Point2Plane's map interface, pipelines/lidar3d-ndt.yaml:195-200): among
+ * the 3x3x3 cells around key(q), the planar voxel with the smallest |n.(q - mean)|.  NDT maps only.
+ * out_mean / out_normal: n*3 floats, out_dist: n floats (+inf when none), out_found: n bytes. */
+int mlo_map_nn_plane(const mlo_map* map, const float* q, uint32_t stride_floats, uint64_t n, float* out_mean,
+                     float* out_normal, float* out_dist, uint8_t* out_found);
 int mlo_map_stats(const mlo_map* map, uint64_t* n_voxels, uint64_t* n_points);
 /* Flat export, sorted by (kx,ky,kz): keys 3*i32 per voxel, counts u32 per voxel, then points
  * (x,y,z f32) in stored slot order.  Pass NULL buffers to query sizes only. */

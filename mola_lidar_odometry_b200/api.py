@@ -273,6 +273,15 @@ class LocalMap:
                                                       d2.ctypes.data, f.ctypes.data))
         return xyz[:n], d2[:n], f[:n].astype(bool)
 
+    def nn_plane(self, q):
+        q = _pts(q)
+        n = len(q)
+        mean, nrm = np.empty((max(n, 1), 3), np.float32), np.empty((max(n, 1), 3), np.float32)
+        d, f = np.empty(max(n, 1), np.float32), np.empty(max(n, 1), np.uint8)
+        self.ctx.check(self.ctx.lib.mlo_map_nn_plane(self.h, q.ctypes.data, q.shape[1], n, mean.ctypes.data,
+                                                     nrm.ctypes.data, d.ctypes.data, f.ctypes.data))
+        return mean[:n], nrm[:n], d[:n], f[:n].astype(bool)
+
     def export(self):
         nv, npts = C.c_uint64(), C.c_uint64()
         self.ctx.check(self.ctx.lib.mlo_map_export(self.h, None, None, None, 0, 0, C.byref(nv), C.byref(npts)))

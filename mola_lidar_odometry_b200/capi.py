@@ -161,6 +161,7 @@ _SIGNATURES = {
     "mlo_map_insert_soa": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp]),
     "mlo_map_cull": (C.c_int, [_vp, _vp, _f]),
     "mlo_map_nn_single": (C.c_int, [_vp, _vp, _u32, _u64, _vp, _vp, _vp]),
+    "mlo_map_nn_plane": (C.c_int, [_vp, _vp, _u32, _u64, _vp, _vp, _vp, _vp]),
     "mlo_map_stats": (C.c_int, [_vp, C.POINTER(_u64), C.POINTER(_u64)]),
     "mlo_map_export": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _u64, C.POINTER(_u64), C.POINTER(_u64)]),
     "mlo_voxel_index": (C.c_int32, [_f, _f]),

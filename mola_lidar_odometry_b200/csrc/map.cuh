@@ -755,6 +755,22 @@ __global__ void k_nn_single(MapDev m, const float* __restrict__ q, uint32_t stri
   }
 }
 
+__global__ void k_nn_plane(MapDev m, const float* __restrict__ q, uint32_t stride, uint32_t n, float* __restrict__ out_mean,
+                           float* __restrict__ out_normal, float* __restrict__ out_dist, uint8_t* __restrict__ out_found) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float* p = q + size_t(i) * stride;
+  const PlaneHit h = nn_plane_thread(m, __ldg(p), __ldg(p + 1), __ldg(p + 2));
+  out_mean[3 * size_t(i)] = h.cx;
+  out_mean[3 * size_t(i) + 1] = h.cy;
+  out_mean[3 * size_t(i) + 2] = h.cz;
+  out_normal[3 * size_t(i)] = h.nx;
+  out_normal[3 * size_t(i) + 1] = h.ny;
+  out_normal[3 * size_t(i) + 2] = h.nz;
+  out_dist[i] = h.dist;
+  out_found[i] = uint8_t(h.found);
+}
+
 // ------------------------------------------------------------------ export
 // writes (kx, ky, kz, count, vid) of every live cell, unordered; the host sorts by key.
 __global__ void k_export_list(MapDev m, uint64_t n_buckets, uint32_t* cursor, int32_t* keys3, uint32_t* counts,

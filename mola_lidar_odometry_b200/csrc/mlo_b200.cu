@@ -878,6 +878,30 @@ int mlo_map_nn_single(const mlo_map* m, const float* q, uint32_t stride, uint64_
   return MLO_OK;
 }
 
+int mlo_map_nn_plane(const mlo_map* m, const float* q, uint32_t stride, uint64_t n, float* out_mean, float* out_normal,
+                     float* out_dist, uint8_t* out_found) {
+  if (!m || (n && (!q || !out_mean || !out_normal || !out_dist || !out_found))) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = m->ctx;
+  if (m->prm.kind != MLO_MAP_NDT) return fail(c, MLO_ERR_UNSUPPORTED, "nearest-plane queries need an NDT map");
+  DeviceGuard g(c->device);
+  if (n == 0) return MLO_OK;
+  int rc = upload_strided(c, q, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  CU(c, c->d_local.ensure(n * (7 * sizeof(float) + 1) + 64));
+  float* dm = c->d_local.as<float>();
+  float* dn = dm + 3 * n;
+  float* dd = dn + 3 * n;
+  uint8_t* df = reinterpret_cast<uint8_t*>(dd + n);
+  LAUNCH(c, k_nn_plane, uint32_t((n + 127) / 128), 128, m->dev, c->d_in.as<float>(), stride, uint32_t(n), dm, dn, dd, df);
+  CU(c, cudaMemcpyAsync(out_mean, dm, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_normal, dn, 3 * n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_dist, dd, n * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaMemcpyAsync(out_found, df, n, cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+
 int mlo_map_stats(const mlo_map* m, uint64_t* n_voxels, uint64_t* n_points) {
   if (!m) return MLO_ERR_INVALID_ARG;
   mlo_ctx* c = m->ctx;

@@ -325,3 +325,51 @@ def test_scan_register_batch_and_resident(ctx, world):
         _check_result(res[i], orr)
         assert np.array_equal(res[i].pose, res2[i].pose)  # same decomposition: bit-identical
     assert ctx.launch_count > 0
+
+
+# ------------------------------------------------------------------------------------------------ NDT / point-to-plane
+def test_ndt_map_and_plane_query_bit_exact(ctx, world):
+    """mola::NDT (ndt.yaml:234-254): insert with min_distance_between_points 0.2 and the hard point limit, per-voxel
+    mean / normal / planarity, nearest-plane query — all bit-exact against the oracle."""
+    g, o = _mk_maps(ctx, 1.0, 0, 0.2, 1 << 16, kind=capi.MAP_NDT)
+    for fr in world["frames"][:10]:
+        g.insert(fr["map_layer"], fr["gt"])
+        o.insert(fr["map_layer"], fr["gt"])
+    assert g.stats() == o.stats()
+    _assert_maps_equal(g, o)
+    fr = world["frames"][10]
+    R, t = fr["gt"][:, :3], fr["gt"][:, 3]
+    q = (fr["icp_layer"].astype(np.float64) @ R.T + t).astype(np.float32)
+    gm, gn, gd, gf = g.nn_plane(q)
+    om, on, od, of = o.nn_plane(q)
+    assert np.array_equal(gf, of) and gf.mean() > 0.3
+    assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+    assert np.array_equal(gm[gf].view(np.uint32), om[of].view(np.uint32))
+    assert np.array_equal(gn[gf].view(np.uint32), on[of].view(np.uint32))
+    # culling keeps the statistics of the surviving voxels
+    s = fr["gt"][:, 3]
+    g.cull(s, 25.0)
+    o.cull(s, 25.0)
+    _assert_maps_equal(g, o)
+    gm, gn, gd, gf = g.nn_plane(q)
+    om, on, od, of = o.nn_plane(q)
+    assert np.array_equal(gf, of) and np.array_equal(gd.view(np.uint32), od.view(np.uint32))
+
+
+def test_icp_ndt_pipeline_parity(ctx, world):
+    """lidar3d-ndt.yaml ICP: Matcher_Point2Plane first, Matcher_Points_DistanceThreshold for the rest, GN x1."""
+    g, o = _build_pair(ctx, world, 12, voxel=1.0, cap=0, min_dist=0.2, kind=capi.MAP_NDT)
+    rng = np.random.default_rng(31)
+    for k in (12, 15, 19):
+        fr = world["frames"][k]
+        init = synth.perturb(fr["gt"], rng, 0.3, 1.0)
+        ip = capi.IcpParamsOwner(sigma=2.0, pipeline="ndt")
+        gr = ctx.icp_align(fr["icp_layer"], g, init, ip.p)
+        orr = O.icp_align(o, fr["icp_layer"], init, ip.p)
+        _check_result(gr, orr)
+        assert gr.n_potential_pairings == 2 * len(fr["icp_layer"])
+    # a point-to-plane matcher against a plain point map is rejected, not silently ignored
+    g2, _ = _build_pair(ctx, world, 2)
+    from mola_lidar_odometry_b200.api import MloError
+    with pytest.raises(MloError):
+        ctx.icp_align(world["frames"][3]["icp_layer"], g2, np.eye(4)[:3], capi.IcpParamsOwner(sigma=2.0, pipeline="ndt").p)
