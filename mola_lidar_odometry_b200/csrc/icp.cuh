@@ -625,27 +625,27 @@ MLO_D bool horn_from_sums(const double* a, double n, double* T) {
 
 // End-of-iteration bookkeeping of mp2p_icp::ICP::align: step measure against prev and
 // prev-prev, hook-as-data, stall test, iteration counter, MaxIterations.
-MLO_D void finish_iteration(const IcpProblem& P, IcpState& S) {
+// step measure of the new pose against a reference pose: norms of the two halves of log_SE3(ref^-1 T)
+MLO_D void step_measure(const double* T, const double* ref, double& dt, double& dr) {
   double D[12], d[6];
-  pose_minus(S.T, S.prev, D);
+  pose_minus(T, ref, D);
   se3_log(D, d);
-  double dt = nrm3(d), dr = nrm3(d + 3);
-  if (S.has_prev2) {
-    double d2[6];
-    pose_minus(S.T, S.prev2, D);
-    se3_log(D, d2);
-    dt = fmin(dt, nrm3(d2));
-    dr = fmin(dr, nrm3(d2 + 3));
-  }
+  dt = nrm3(d);
+  dr = nrm3(d + 3);
+}
+
+// executed by lane 0 after the step measures (vs prev on lane 0, vs prev-prev on lane 1) have been combined
+MLO_D void finish_iteration(const IcpProblem& P, IcpState& S, double* T, double* prev, double* prev2, double dt, double dr) {
+#pragma unroll
   for (int k = 0; k < 12; k++) {
-    S.prev2[k] = S.prev[k];
-    S.prev[k] = S.T[k];
+    prev2[k] = prev[k];
+    prev[k] = T[k];
   }
   S.has_prev2 = 1;
   S.inner_pending = 0;
   if (P.hook_enabled) {
-    double w[3];
-    pose_minus(S.T, P.hook_checkpoint, D);
+    double D[12], w[3];
+    pose_minus(T, P.hook_checkpoint, D);
     so3_log_of_pose(D, w);
     const double tt[3] = {D[3], D[7], D[11]};
     if (nrm3(tt) > P.hook_min_trans || nrm3(w) > P.hook_min_rot) {
@@ -677,7 +677,17 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
   uint32_t cnt = 0;
   const uint32_t nblk = after_match ? P.n_blocks : P.n_blocks_acc;
   if (lane < NACC) {
-    for (uint32_t b = 0; b < nblk; b++) acc += __ldcg(&partials[size_t(P.part_begin + b) * NACC + lane]);
+    // sequential (deterministic) order, eight L2 loads in flight at a time
+    const double* base = partials + size_t(P.part_begin) * NACC + lane;
+    uint32_t b = 0;
+    for (; b + 8 <= nblk; b += 8) {
+      double v[8];
+#pragma unroll
+      for (int u = 0; u < 8; u++) v[u] = __ldcg(base + size_t(b + u) * NACC);
+#pragma unroll
+      for (int u = 0; u < 8; u++) acc += v[u];
+    }
+    for (; b < nblk; b++) acc += __ldcg(base + size_t(b) * NACC);
   } else if (lane < NACC + 2) {
     for (uint32_t b = 0; b < nblk; b++) cnt += __ldcg(&part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)]);
   }
@@ -686,6 +696,14 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
   for (int k = 0; k < int(NACC); k++) a[k] = __shfl_sync(FULL, acc, k);
   const uint32_t npairs = __shfl_sync(FULL, cnt, NACC);
   const uint32_t ncand = __shfl_sync(FULL, cnt, NACC + 1);
+  // stage T / prev / prev2 (36 contiguous doubles of the state) in shared memory: one coalesced read and one
+  // coalesced write-back by the whole warp instead of ~100 serial global accesses by lane 0
+  __shared__ double s_pose[36];
+  for (uint32_t i = lane; i < 36; i += 32) s_pose[i] = __ldcg(&S.T[0] + i);
+  __syncwarp();
+  double* const sT = s_pose;
+  double* const sPrev = s_pose + 12;
+  double* const sPrev2 = s_pose + 24;
   int next = 0;
   if (lane == 0) {
     bool finished = false;
@@ -708,7 +726,7 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
       bool ok = true;
       bool last_inner = true;
       if (P.solver == MLO_SOLVER_HORN) {
-        ok = horn_from_sums(a, double(npairs), S.T);
+        ok = horn_from_sums(a, double(npairs), sT);
       } else {
         double H[36], g[6];
         int k = 0;
@@ -722,7 +740,7 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
         if (P.has_prior) {
           // e = log(prior^-1 T), J = d log(D exp(eps))/d eps ; g += J^T L e ; H += J^T L J
           double D[12], e[6], J[36], LJ[36], Le[6];
-          pose_minus(S.T, P.prior_pose, D);
+          pose_minus(sT, P.prior_pose, D);
           se3_log(D, e);
           se3_right_jacobian_inv(e, J);
           for (int i = 0; i < 6; i++) {
@@ -749,8 +767,9 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
         if (ok) {
           double E[12], Tn[12];
           se3_exp(delta, E);
-          pose_mul(S.T, E, Tn);
-          for (int i = 0; i < 12; i++) S.T[i] = Tn[i];
+          pose_mul(sT, E, Tn);
+#pragma unroll
+          for (int i = 0; i < 12; i++) sT[i] = Tn[i];
           double dn = 0;
           for (int i = 0; i < 6; i++) dn += delta[i] * delta[i];
           S.inner++;
@@ -764,11 +783,26 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
         S.inner_pending = 1;
         next = 1;
       } else {
-        finish_iteration(P, S);
-        next = S.done ? 0 : 2;
+        next = 3;  // retraction done, this was the last inner iteration: end-of-iteration bookkeeping follows
       }
     }
   }
+  next = __shfl_sync(FULL, next, 0);
+  if (next == 3) {
+    // lanes 0 and 1 evaluate the two SE(3) logs of the stall / oscillation test concurrently
+    __syncwarp();
+    const int has2 = __shfl_sync(FULL, lane == 0 ? S.has_prev2 : 0, 0);
+    double dt = 1e300, dr = 1e300;
+    if (lane == 0) step_measure(sT, sPrev, dt, dr);
+    if (lane == 1 && has2) step_measure(sT, sPrev2, dt, dr);
+    const double dt1 = __shfl_sync(FULL, dt, 1), dr1 = __shfl_sync(FULL, dr, 1);
+    if (lane == 0) {
+      finish_iteration(P, S, sT, sPrev, sPrev2, fmin(dt, dt1), fmin(dr, dr1));
+      next = S.done ? 0 : 2;
+    }
+  }
+  __syncwarp();
+  for (uint32_t i = lane; i < 36; i += 32) (&S.T[0])[i] = s_pose[i];
   return __shfl_sync(FULL, next, 0);
 }
 

@@ -454,7 +454,8 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   // queries per warp: 32 when the batch alone fills the machine, fewer for latency-bound small batches
   const uint64_t total_queries = offsets[B];
   uint32_t qpw = 32;
-  while (qpw > 1 && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
+  const uint32_t qpw_floor = total_queries >= 256 ? 4u : 1u;  // below 4 the per-block reduction dominates the chunk
+  while (qpw > qpw_floor && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
   // large batches: thread-per-query kernel (hundreds of queries in flight per SM); small: warp-per-query
   const bool use_tpq = c->force_kernel == 1 || c->force_kernel == 3 ||
                        (c->force_kernel == 0 && total_queries >= uint64_t(c->sm_count) * 256);

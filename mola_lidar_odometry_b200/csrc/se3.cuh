@@ -44,10 +44,10 @@ MLO_HD void pose_minus(const double* A, const double* B, double* C) {
 
 // Rodrigues coefficients with series near zero: a = sin(t)/t, b = (1-cos t)/t^2, c = (t - sin t)/t^3
 MLO_HD void rodrigues_coeffs(double t2, double& a, double& b, double& c) {
-  if (t2 < 1e-10) {
-    a = 1.0 - t2 * (1.0 / 6.0);
-    b = 0.5 - t2 * (1.0 / 24.0);
-    c = (1.0 / 6.0) - t2 * (1.0 / 120.0);
+  if (t2 < 2.5e-3) {  // |phi| < 0.05 rad: Taylor series to t^8, truncation error < 1e-18 (no sin/cos calls)
+    a = 1.0 - t2 * (1.0 / 6.0) * (1.0 - t2 * (1.0 / 20.0) * (1.0 - t2 * (1.0 / 42.0) * (1.0 - t2 * (1.0 / 72.0))));
+    b = 0.5 * (1.0 - t2 * (1.0 / 12.0) * (1.0 - t2 * (1.0 / 30.0) * (1.0 - t2 * (1.0 / 56.0) * (1.0 - t2 * (1.0 / 90.0)))));
+    c = (1.0 / 6.0) * (1.0 - t2 * (1.0 / 20.0) * (1.0 - t2 * (1.0 / 42.0) * (1.0 - t2 * (1.0 / 72.0) * (1.0 - t2 * (1.0 / 110.0)))));
   } else {
     const double t = sqrt(t2);
     a = sin(t) / t;
@@ -95,7 +95,14 @@ MLO_HD void so3_log_of_pose(const double* T, double* w) {
   }
   if (qw < 0) { qw = -qw; qx = -qx; qy = -qy; qz = -qz; }
   const double vn = sqrt(qx * qx + qy * qy + qz * qz);
-  const double k = (vn < 1e-10) ? 2.0 / qw : 2.0 * atan2(vn, qw) / vn;
+  double k;
+  if (vn < 0.03 * qw) {  // small angle: 2 atan(x)/vn with x = vn/qw, alternating series to x^14 (error < 1e-20)
+    const double x2 = (vn / qw) * (vn / qw);
+    const double ser = 1.0 - x2 * ((1.0 / 3.0) - x2 * ((1.0 / 5.0) - x2 * ((1.0 / 7.0) - x2 * ((1.0 / 9.0) - x2 * ((1.0 / 11.0) - x2 * (1.0 / 13.0))))));
+    k = 2.0 * ser / qw;
+  } else {
+    k = 2.0 * atan2(vn, qw) / vn;
+  }
   w[0] = k * qx; w[1] = k * qy; w[2] = k * qz;
 }
 
@@ -106,7 +113,8 @@ MLO_HD void se3_log(const double* T, double* xi) {
   const double t2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
   // V^-1 = I - W/2 + d W^2,  d = (1 - t sin t / (2 (1 - cos t))) / t^2
   double d;
-  if (t2 < 1e-12) d = (1.0 / 12.0) + t2 * (1.0 / 720.0);
+  if (t2 < 2.5e-3)  // series of (1 - (t/2) cot(t/2)) / t^2 (Bernoulli numbers), truncation error < 1e-18 for |phi| < 0.05
+    d = (1.0 / 12.0) + t2 * ((1.0 / 720.0) + t2 * ((1.0 / 30240.0) + t2 * ((1.0 / 1209600.0) + t2 * (1.0 / 47900160.0))));
   else { const double t = sqrt(t2); d = (1.0 - (t * sin(t)) / (2.0 * (1.0 - cos(t)))) / t2; }
   const double tt[3] = {T[3], T[7], T[11]};
   double a[3], b[3];
@@ -181,13 +189,14 @@ MLO_HD bool ldlt6(const double* H, const double* b, double* x) {
     for (int k = 0; k < j; k++) d -= L[6 * j + k] * L[6 * j + k] * D[k];
     if (!(d > 0.0) || !(d < 1e300)) return false;
     D[j] = d;
+    const double inv_d = 1.0 / d;
     L[6 * j + j] = 1.0;
 #pragma unroll
     for (int i = j + 1; i < 6; i++) {
       double s = H[6 * i + j];
 #pragma unroll
       for (int k = 0; k < j; k++) s -= L[6 * i + k] * L[6 * j + k] * D[k];
-      L[6 * i + j] = s / d;
+      L[6 * i + j] = s * inv_d;
     }
   }
   double y[6];
