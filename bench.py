@@ -542,8 +542,18 @@ def main():
     alg_bytes = 16 * qi + 27 * 16 * qi + 16 * P + 27 * 8 * nb
     nn_ms = prof.nn_kernel_ms
     achieved = (alg_bytes / 1e9) / (nn_ms * 1e-3) if nn_ms > 0 else 0.0
+    traffic, traffic_note = None, None
+    try:
+        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        traffic = tj["dram_bytes_per_launch"]
+        traffic_note = (f"ncu --set full capture of one full-activity launch at B=512 ({tj['capture'].split(' ')[0]}); "
+                        f"algorithmic bytes of that launch: {tj['algorithmic_bytes_same_launch']:.3g}")
+    except Exception:
+        pass
+    persistent_used = prof.nn_kernel_launches <= 2 * args.steps
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": None, "kernel": "k_match_accumulate",
+                "traffic": traffic, "traffic_note": traffic_note,
+                "kernel": "k_icp_persistent" if persistent_used else "k_match_accumulate_wl (+ k_icp_persistent for the tail)",
                 "peak_source": "MEASURED_PEAKS.json hbm_gbs (measured)" if peaks else "fallback 6650 GB/s",
                 "bytes_per_launch": alg_bytes / max(1, prof.nn_kernel_launches),
                 "avg_launch_us": 1e3 * nn_ms / max(1, prof.nn_kernel_launches),
