@@ -164,6 +164,15 @@ int mlo_filter_1st_pass(mlo_ctx* ctx, const float* pts, uint32_t stride_floats, 
                         const mlo_filter1_params* p, float* out_map_xyz, uint64_t* out_map_n, float* out_icp_xyz,
                         uint64_t* out_icp_n);
 
+/* The same 1st pass carrying one extra per-point channel `t` (per-point timestamps of CPointsMapXYZIRT; NULL = zeros):
+ * outputs are x, y, z, t (4 floats per point), the "..._skewed" layers that FilterDeskew consumes. */
+int mlo_filter_1st_pass_xyzt(mlo_ctx* ctx, const float* pts, uint32_t stride_floats, const float* t, uint64_t n,
+                             const mlo_filter1_params* p, float* out_map_xyzt, uint64_t* out_map_n, float* out_icp_xyzt,
+                             uint64_t* out_icp_n);
+/* mp2p_icp_filters::FilterDeskew (pipelines/lidar3d-default.yaml:328-350; re-run inside the ICP loop at
+ * LidarOdometry.cpp:999): p' = exp_SO3(w t) p + v t with twist = (vx vy vz wx wy wz) and t the 4th input float. */
+int mlo_deskew(mlo_ctx* ctx, const float* xyzt, uint64_t n, const double twist[6], float* out_xyz);
+
 /* ------------------------------------------------------------------ ICP
  * Replaces mp2p_icp::ICP::align as called at LidarOdometry.cpp:961-962 with the object graph of
  * pipelines/lidar3d-default.yaml:162-209 (ndt: pipelines/lidar3d-ndt.yaml:162-216):

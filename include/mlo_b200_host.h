@@ -26,6 +26,10 @@ void mlo_lo_destroy(mlo_lo* lo);
 const char* mlo_lo_last_error(const mlo_lo* lo);
 /* LidarOdometry::onNewObservation + spin until !isBusy (apps/mola-lidar-odometry-cli.cpp:494-521): one cloud. */
 int mlo_lo_on_lidar(mlo_lo* lo, const float* pts, uint32_t stride_floats, uint64_t n, double stamp_s, mlo_lo_scan_output* out);
+/* The same with the per-point time channel `t` [s, relative] of a CPointsMapXYZIRT cloud: enables FilterAdjustTimestamps +
+ * FilterDeskew + the twist re-estimation loop of LidarOdometry.cpp:923-1005 (unless MOLA_SKIP_DESKEW / optimize_twist off). */
+int mlo_lo_on_lidar_t(mlo_lo* lo, const float* pts, uint32_t stride_floats, const float* t, uint64_t n, double stamp_s,
+                      mlo_lo_scan_output* out);
 /* LidarOdometry::estimatedTrajectory (LidarOdometry.cpp:1425) */
 int mlo_lo_trajectory(const mlo_lo* lo, double* stamps, double* poses_3x4, uint64_t max_n, uint64_t* n);
 int mlo_lo_reset(mlo_lo* lo); /* LidarOdometry::reset (LidarOdometry.cpp:495) */

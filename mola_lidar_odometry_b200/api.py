@@ -97,6 +97,26 @@ class Context:
                                                 a.ctypes.data, C.byref(na), b.ctypes.data, C.byref(nb)))
         return a[:na.value].copy(), b[:nb.value].copy()
 
+    def filter_1st_pass_xyzt(self, pts, t, fp: Filter1Params):
+        """1st-pass filter carrying per-point timestamps: returns the two '_skewed' layers as [n,4] x,y,z,t."""
+        pts = _pts(pts)
+        t = None if t is None else np.ascontiguousarray(t, dtype=np.float32)
+        a = np.empty((max(len(pts), 1), 4), np.float32)
+        b = np.empty((max(len(pts), 1), 4), np.float32)
+        na, nb = C.c_uint64(), C.c_uint64()
+        self.check(self.lib.mlo_filter_1st_pass_xyzt(self.h, pts.ctypes.data, pts.shape[1], None if t is None else t.ctypes.data,
+                                                     len(pts), C.byref(fp), a.ctypes.data, C.byref(na), b.ctypes.data,
+                                                     C.byref(nb)))
+        return a[:na.value].copy(), b[:nb.value].copy()
+
+    def deskew(self, xyzt, twist) -> np.ndarray:
+        xyzt = np.ascontiguousarray(xyzt, dtype=np.float32)
+        assert xyzt.ndim == 2 and xyzt.shape[1] == 4
+        tw = np.ascontiguousarray(twist, dtype=np.float64)
+        out = np.empty((max(len(xyzt), 1), 3), np.float32)
+        self.check(self.lib.mlo_deskew(self.h, xyzt.ctypes.data, len(xyzt), tw.ctypes.data, out.ctypes.data))
+        return out[:len(xyzt)]
+
     # ---- ICP
     def icp_align(self, local, lmap: "LocalMap", init_pose, params: IcpParams) -> IcpResult:
         local, init_pose = _pts(local), _pose(init_pose)

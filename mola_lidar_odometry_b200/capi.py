@@ -171,6 +171,9 @@ _SIGNATURES = {
     "mlo_voxel_decimate_first": (C.c_int, [_vp, _vp, _u32, _u64, C.POINTER(DecimateParams), _vp, C.POINTER(_u64)]),
     "mlo_filter_1st_pass": (C.c_int, [_vp, _vp, _u32, _u64, C.POINTER(Filter1Params), _vp, C.POINTER(_u64), _vp,
                                       C.POINTER(_u64)]),
+    "mlo_filter_1st_pass_xyzt": (C.c_int, [_vp, _vp, _u32, _vp, _u64, C.POINTER(Filter1Params), _vp, C.POINTER(_u64), _vp,
+                                           C.POINTER(_u64)]),
+    "mlo_deskew": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "mlo_icp_params_default": (None, [C.POINTER(IcpParams)]),
     "mlo_icp_align": (C.c_int, [_vp, _vp, _u32, _u64, _vp, _vp, C.POINTER(IcpParams), C.POINTER(IcpResult)]),
     "mlo_icp_align_soa": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, C.POINTER(IcpParams), C.POINTER(IcpResult)]),

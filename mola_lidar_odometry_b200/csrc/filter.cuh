@@ -12,6 +12,8 @@ namespace mlo {
 
 struct DecimJob {
   const float* in;         // first input point
+  const float* in_t;       // optional per-point channel carried in .w (timestamps for FilterDeskew), else nullptr
+  int32_t keep_w;          // carry .w of the input (stride 4) through to the outputs
   uint32_t in_stride;      // floats per point (3 or 4)
   uint32_t n_in_static;    // input size when n_in_dev == nullptr
   const uint32_t* n_in_dev;  // input size produced on device by the previous stage
@@ -186,7 +188,11 @@ __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_scatter(const DecimJob* _
   float4 p = make_float4(0, 0, 0, 0);
   if (i < n) {
     f = j.flags[i];
-    if (f) p = load_point(j.in, j.in_stride, i);
+    if (f) {
+      p = load_point(j.in, j.in_stride, i);
+      if (j.in_t) p.w = __ldg(j.in_t + i);
+      else if (!j.keep_w) p.w = 0.f;
+    }
   }
   __shared__ uint32_t wcnt[2][DECIM_BLOCK / 32];
   const uint32_t ba = __ballot_sync(0xFFFFFFFFu, f & 1u), bb = __ballot_sync(0xFFFFFFFFu, f & 2u);
@@ -201,12 +207,41 @@ __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_scatter(const DecimJob* _
     offB += wcnt[1][w];
   }
   const uint32_t lt = (1u << lane) - 1u;
-  if ((f & 1u) && j.outA) j.outA[offA + __popc(ba & lt)] = make_float4(p.x, p.y, p.z, 0.f);
+  if ((f & 1u) && j.outA) j.outA[offA + __popc(ba & lt)] = p;
   if (f & 2u) {
     const uint32_t o = offB + __popc(bb & lt);
-    j.outB[o] = make_float4(p.x, p.y, p.z, 0.f);
+    j.outB[o] = p;
     if (j.outB_idx) j.outB_idx[o] = i;
   }
+}
+
+// mp2p_icp_filters::FilterDeskew (pipelines/lidar3d-default.yaml:328-350): p' = exp_SO3(w t) p + v t, t = in.w.
+// Same operation order and the same small-angle series as the CPU statement (bit-exact for |w t| < 0.05 rad).
+MLO_D void deskew_coeffs(double th2, double& A, double& B) {
+  if (th2 < 2.5e-3) {
+    A = 1.0 - th2 * (1.0 / 6.0) * (1.0 - th2 * (1.0 / 20.0) * (1.0 - th2 * (1.0 / 42.0) * (1.0 - th2 * (1.0 / 72.0))));
+    B = 0.5 * (1.0 - th2 * (1.0 / 12.0) * (1.0 - th2 * (1.0 / 30.0) * (1.0 - th2 * (1.0 / 56.0) * (1.0 - th2 * (1.0 / 90.0)))));
+  } else {
+    const double th = sqrt(th2);
+    A = sin(th) / th;
+    B = (1.0 - cos(th)) / th2;
+  }
+}
+struct Twist6 {
+  double v[6];
+};
+__global__ void k_deskew(const float4* __restrict__ in, uint32_t n, Twist6 tw, float4* __restrict__ out) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const float4 p = __ldg(&in[i]);
+  const double x = p.x, y = p.y, z = p.z, t = p.w;
+  const double wx = tw.v[3] * t, wy = tw.v[4] * t, wz = tw.v[5] * t;
+  double A, B;
+  deskew_coeffs(wx * wx + wy * wy + wz * wz, A, B);
+  const double cx = wy * z - wz * y, cy = wz * x - wx * z, cz = wx * y - wy * x;
+  const double dx = wy * cz - wz * cy, dy = wz * cx - wx * cz, dz = wx * cy - wy * cx;
+  out[i] = make_float4(static_cast<float>(x + A * cx + B * dx + tw.v[0] * t), static_cast<float>(y + A * cy + B * dy + tw.v[1] * t),
+                       static_cast<float>(z + A * cz + B * dz + tw.v[2] * t), p.w);
 }
 
 }  // namespace mlo

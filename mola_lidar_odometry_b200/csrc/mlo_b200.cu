@@ -88,7 +88,7 @@ struct mlo_ctx {
   // scratch
   DBuf d_in, d_local, d_pairA, d_pairB, d_partials, d_partcnt, d_probs, d_states, d_tables, d_init, d_misc;
   DBuf d_f_tab, d_f_pslot, d_f_flags, d_f_blk, d_f_jobs, d_f_cnt, d_f_stage1, d_f_map, d_f_icp;
-  DBuf d_ins_g, d_ins_slot, d_ins_next, d_queue;
+  DBuf d_ins_g, d_ins_slot, d_ins_next, d_queue, d_tchan;
   HBuf h_misc, h_states, h_stage;
   // profiling
   bool prof_on = false;
@@ -298,7 +298,8 @@ struct FilterBatch {
 constexpr uint32_t CNT_STRIDE = 8;
 
 int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n_clouds, const uint64_t* offsets,
-                     const mlo_filter1_params* fps, bool single_decimate_idx, uint32_t* d_idx_out, FilterBatch& fb) {
+                     const mlo_filter1_params* fps, bool single_decimate_idx, uint32_t* d_idx_out, FilterBatch& fb,
+                     const float* d_t = nullptr) {
   fb.n_clouds = n_clouds;
   fb.out_off.assign(offsets, offsets + n_clouds + 1);
   const uint64_t total = offsets[n_clouds];
@@ -349,6 +350,7 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
     }
     DecimJob& j1 = hj[b];
     j1.in = d_raw + offsets[b] * stride;
+    j1.in_t = d_t ? d_t + offsets[b] : nullptr;
     j1.in_stride = stride;
     j1.n_in_static = n;
     fill_decim(j1, fps[b].for_map, single_decimate_idx);
@@ -359,6 +361,7 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
     DecimJob& j2 = hj[n_clouds + b];
     j2.in = reinterpret_cast<const float*>(c->d_f_stage1.as<float4>() + offsets[b]);
     j2.in_stride = 4;
+    j2.keep_w = d_t ? 1 : 0;
     j2.n_in_dev = cnt + b * CNT_STRIDE + 0;
     fill_decim(j2, fps[b].for_icp, true);
     j2.npred = cnt + b * CNT_STRIDE + 4;
@@ -726,7 +729,7 @@ void mlo_destroy(mlo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DBuf* b : {&c->d_in, &c->d_local, &c->d_pairA, &c->d_pairB, &c->d_partials, &c->d_partcnt, &c->d_probs, &c->d_states,
                   &c->d_tables, &c->d_init, &c->d_misc, &c->d_f_tab, &c->d_f_pslot, &c->d_f_flags, &c->d_f_blk, &c->d_f_jobs,
-                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue})
+                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan})
     b->release();
   c->h_misc.release();
   c->h_states.release();
@@ -1048,6 +1051,60 @@ int mlo_filter_1st_pass(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t 
   }
   prof_collect(c);
   return MLO_OK;
+}
+
+int mlo_filter_1st_pass_xyzt(mlo_ctx* c, const float* pts, uint32_t stride, const float* t, uint64_t n,
+                             const mlo_filter1_params* p, float* out_map_xyzt, uint64_t* out_map_n, float* out_icp_xyzt,
+                             uint64_t* out_icp_n) {
+  if (!c || !p || !out_map_n || !out_icp_n || (n && !pts)) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(c->device);
+  *out_map_n = *out_icp_n = 0;
+  if (n == 0) return MLO_OK;
+  int rc = upload_strided(c, pts, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  const float* d_t = nullptr;
+  if (t) {
+    CU(c, c->d_tchan.ensure(n * sizeof(float)));
+    CU(c, cudaMemcpyAsync(c->d_tchan.p, t, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+    d_t = c->d_tchan.as<float>();
+  }
+  const uint64_t offs[2] = {0, n};
+  FilterBatch fb;
+  const size_t e0 = prof_begin(c);
+  rc = run_filter_batch(c, c->d_in.as<float>(), stride, 1, offs, p, false, nullptr, fb, d_t);
+  prof_end(c, 0, e0);
+  if (rc != MLO_OK) return rc;
+  uint32_t h[CNT_STRIDE];
+  CU(c, cudaMemcpyAsync(h, c->d_f_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  if (h[5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  *out_map_n = h[1];
+  *out_icp_n = h[2];
+  if (out_map_xyzt && h[1])
+    CU(c, cudaMemcpyAsync(out_map_xyzt, c->d_f_map.p, size_t(h[1]) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  if (out_icp_xyzt && h[2])
+    CU(c, cudaMemcpyAsync(out_icp_xyzt, c->d_f_icp.p, size_t(h[2]) * sizeof(float4), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  prof_collect(c);
+  return MLO_OK;
+}
+
+int mlo_deskew(mlo_ctx* c, const float* xyzt, uint64_t n, const double twist[6], float* out_xyz) {
+  if (!c || !twist || (n && (!xyzt || !out_xyz))) return MLO_ERR_INVALID_ARG;
+  DeviceGuard g(c->device);
+  if (n == 0) return MLO_OK;
+  CU(c, c->d_in.ensure(n * sizeof(float4)));
+  CU(c, c->d_local.ensure(n * sizeof(float4)));
+  CU(c, cudaMemcpyAsync(c->d_in.p, xyzt, n * sizeof(float4), cudaMemcpyHostToDevice, c->stream));
+  Twist6 tw;
+  std::memcpy(tw.v, twist, sizeof(tw.v));
+  const size_t e0 = prof_begin(c);
+  LAUNCH(c, k_deskew, uint32_t((n + 255) / 256), 256, c->d_in.as<float4>(), uint32_t(n), tw, c->d_local.as<float4>());
+  prof_end(c, 0, e0);
+  CU(c, cudaGetLastError());
+  int rc = download_xyz(c, c->d_local.as<float4>(), n, out_xyz);
+  prof_collect(c);
+  return rc;
 }
 
 // ------------------------------------------------------------------ ICP

@@ -36,6 +36,19 @@ struct BackendGpu {
     map_xyz.resize(3 * na);
     icp_xyz.resize(3 * nb);
   }
+  void filter_1st_pass_xyzt(const float* pts, uint32_t stride, const float* t, uint64_t n, const mlo_filter1_params& f,
+                            std::vector<float>& map_xyzt, std::vector<float>& icp_xyzt) {
+    map_xyzt.resize(4 * n);
+    icp_xyzt.resize(4 * n);
+    uint64_t na = 0, nb = 0;
+    check(mlo_filter_1st_pass_xyzt(ctx, pts, stride, t, n, &f, map_xyzt.data(), &na, icp_xyzt.data(), &nb));
+    map_xyzt.resize(4 * na);
+    icp_xyzt.resize(4 * nb);
+  }
+  void deskew(const float* xyzt, uint64_t n, const double* twist, std::vector<float>& out_xyz) {
+    out_xyz.resize(3 * n);
+    check(mlo_deskew(ctx, xyzt, n, twist, out_xyz.data()));
+  }
   void icp_align(const float* xyz, uint64_t n, void* map, const double* init, const mlo_icp_params& p, mlo_icp_result& r) {
     check(mlo_icp_align(ctx, xyz, 3, n, static_cast<mlo_map*>(map), init, &p, &r));
   }

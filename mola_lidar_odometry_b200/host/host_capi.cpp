@@ -42,9 +42,14 @@ void mlo_lo_destroy(mlo_lo* lo) { delete lo; }
 const char* mlo_lo_last_error(const mlo_lo* lo) { return lo ? lo->err.c_str() : g_err.c_str(); }
 
 int mlo_lo_on_lidar(mlo_lo* lo, const float* pts, uint32_t stride, uint64_t n, double stamp, mlo_lo_scan_output* out) {
+  return mlo_lo_on_lidar_t(lo, pts, stride, nullptr, n, stamp, out);
+}
+
+int mlo_lo_on_lidar_t(mlo_lo* lo, const float* pts, uint32_t stride, const float* t, uint64_t n, double stamp,
+                      mlo_lo_scan_output* out) {
   if (!lo || !out || (n && !pts) || (stride != 3 && stride != 4)) return MLO_ERR_INVALID_ARG;
   try {
-    const ScanOutput s = lo->lo.onLidar(pts, stride, n, stamp);
+    const ScanOutput s = lo->lo.onLidar(pts, stride, n, stamp, t);
     out->processed = s.processed;
     out->icp_ran = s.icp_ran;
     out->icp_good = s.icp_good;

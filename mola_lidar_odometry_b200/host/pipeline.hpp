@@ -324,6 +324,9 @@ struct LidarOdometryParams {  // the subset of LidarOdometry::Parameters around 
   double initial_sigma = 2.0, min_motion = 0.1, maximum_sigma = 3.0, kp = 2.0, alpha = 0.9;
   double max_time_to_use_velocity_model = 0.75;
   std::array<double, 6> initial_twist{};  // navstate_fuse_params.initial_twist (default.yaml:139): vx vy vz wx wy wz
+  // observations_filter_2nd_pass FilterDeskew (default.yaml:328-350) + FilterAdjustTimestamps (:267-275)
+  bool skip_deskew = false, silently_ignore_no_timestamps = true;
+  bool timestamps_middle_is_zero = true;  // TimestampAdjustMethod::MiddleIsZero (else EarliestIsZero)
 };
 
 struct ScanOutput {
@@ -375,6 +378,19 @@ class LidarOdometryT {
       if (nf["initial_twist"].isSeq())
         for (size_t k = 0; k < 6 && k < nf["initial_twist"].seq.size(); k++) params_.initial_twist[k] = nf["initial_twist"].seq[k].num(0.0);
     }
+    if (cfg.has("observations_filter_2nd_pass"))
+      for (const YamlNode& f : cfg["observations_filter_2nd_pass"].seq)
+        if (f["class_name"].str_or("") == "mp2p_icp_filters::FilterDeskew") {
+          params_.skip_deskew = f["params"]["skip_deskew"].boolean(false);
+          params_.silently_ignore_no_timestamps = f["params"]["silently_ignore_no_timestamps"].boolean(true);
+        }
+    if (cfg.has("observations_filter_adjust_timestamps"))
+      for (const YamlNode& f : cfg["observations_filter_adjust_timestamps"].seq) {
+        const std::string m = f["params"]["method"].str_or("TimestampAdjustMethod::MiddleIsZero");
+        if (m == "TimestampAdjustMethod::MiddleIsZero") params_.timestamps_middle_is_zero = true;
+        else if (m == "TimestampAdjustMethod::EarliestIsZero") params_.timestamps_middle_is_zero = false;
+        else throw std::runtime_error("FilterAdjustTimestamps: unsupported method '" + m + "'");
+      }
     icp_.initialize(cfg.at("icp_settings_with_vel"));
     icp_.attachToParameterSource(parameter_source);
     filter1_.initialize(cfg.at("observations_filter_1st_pass"));
@@ -410,7 +426,8 @@ class LidarOdometryT {
   void* localMap() const { return map_; }
 
   // mola::LidarOdometry::onLidarImpl for one point cloud (LidarOdometry.cpp:627-1206); deskew off (row f1).
-  ScanOutput onLidar(const float* pts, uint32_t stride, uint64_t n, double stamp) {
+  // `t` = optional per-point timestamps [s] relative to the scan stamp (CPointsMapXYZIRT "t" channel)
+  ScanOutput onLidar(const float* pts, uint32_t stride, uint64_t n, double stamp, const float* t = nullptr) {
     ScanOutput out;
     if (last_obs_time_ && stamp - *last_obs_time_ < params_.min_time_between_scans) return out;  // :643-657
     const std::optional<double> last_obs = last_obs_time_;
@@ -424,7 +441,26 @@ class LidarOdometryT {
     updatePipelineDynamicVariables(motion);         // :692
     // 1st-pass filter (:732-735); 2nd pass is the identity with deskew skipped (:737-741)
     const mlo_filter1_params f1 = filter1_.realize(parameter_source);
-    be_.filter_1st_pass(pts, stride, n, f1, map_layer_, icp_layer_);
+    if (!t && !params_.skip_deskew && !params_.silently_ignore_no_timestamps)
+      throw std::runtime_error("FilterDeskew: the point cloud has no per-point timestamps (silently_ignore_no_timestamps is false)");
+    const bool do_deskew = t && !params_.skip_deskew && n > 0;
+    if (do_deskew) {
+      // FilterAdjustTimestamps (:267-275) on the raw layer, then the 1st pass keeps t through both decimations and
+      // the 2nd pass deskews the two '_skewed' layers with the current twist variables (:328-350)
+      adj_t_.assign(t, t + n);
+      float tmin = adj_t_[0], tmax = adj_t_[0];
+      for (float v : adj_t_) {
+        tmin = std::min(tmin, v);
+        tmax = std::max(tmax, v);
+      }
+      const float shift = (params_.timestamps_middle_is_zero ? 0.5f * (tmin + tmax) : tmin) -
+                          float(parameter_source.has("SENSOR_TIME_OFFSET") ? parameter_source.get("SENSOR_TIME_OFFSET") : 0.0);
+      for (float& v : adj_t_) v -= shift;
+      be_.filter_1st_pass_xyzt(pts, stride, adj_t_.data(), n, f1, map_skewed_, icp_skewed_);
+      apply_deskew();
+    } else {
+      be_.filter_1st_pass(pts, stride, n, f1, map_layer_, icp_layer_);
+    }
     out.n_map_layer = map_layer_.size() / 3;
     out.n_icp_layer = icp_layer_.size() / 3;
     doUpdateEstimatedMaxSensorRange();  // :744-769 (first points layer of the observation = decimated_for_icp)
@@ -469,6 +505,7 @@ class LidarOdometryT {
             twist_ = {incr[3] / since_last, incr[7] / since_last, incr[11] / since_last, w[0] / since_last,
                       w[1] / since_last, w[2] / since_last};
             updatePipelineTwistVariables();
+            if (do_deskew) apply_deskew();  // re-apply the 2nd pass with the new twist (:996-1001)
           }
         }
       } while (r.terminationReason == MLO_TERM_HOOK_REQUEST);
@@ -586,6 +623,10 @@ class LidarOdometryT {
     ns.pose = pose_compose(b.second, d);
     return ns;
   }
+  void apply_deskew() {
+    be_.deskew(map_skewed_.data(), map_skewed_.size() / 4, twist_.data(), map_layer_);
+    be_.deskew(icp_skewed_.data(), icp_skewed_.size() / 4, twist_.data(), icp_layer_);
+  }
   void fuse_pose(double stamp, const Pose& p) {
     fused_.emplace_back(stamp, p);
     if (fused_.size() > 8) fused_.erase(fused_.begin());
@@ -687,7 +728,7 @@ class LidarOdometryT {
   void* map_ = nullptr;
   uint64_t map_points_ = 0;
   float cull_dist_ = 0;
-  std::vector<float> map_layer_, icp_layer_;
+  std::vector<float> map_layer_, icp_layer_, map_skewed_, icp_skewed_, adj_t_;
   std::vector<std::pair<double, Pose>> trajectory_, fused_;
   std::vector<Pose> keyframes_;
   Pose last_lidar_pose_ = pose_identity();

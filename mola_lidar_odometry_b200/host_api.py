@@ -29,6 +29,7 @@ HOST_SIGNATURES = {
     "mlo_lo_destroy": (None, [_vp]),
     "mlo_lo_last_error": (C.c_char_p, [_vp]),
     "mlo_lo_on_lidar": (C.c_int, [_vp, _vp, _u32, _u64, C.c_double, C.POINTER(ScanOutput)]),
+    "mlo_lo_on_lidar_t": (C.c_int, [_vp, _vp, _u32, _vp, _u64, C.c_double, C.POINTER(ScanOutput)]),
     "mlo_lo_trajectory": (C.c_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "mlo_lo_reset": (C.c_int, [_vp]),
     "mlo_host_last_error": (C.c_char_p, []),
@@ -106,10 +107,14 @@ class LidarOdometry:
         except Exception:
             pass
 
-    def on_lidar(self, pts, stamp: float) -> ScanOutput:
+    def on_lidar(self, pts, stamp: float, t=None) -> ScanOutput:
         pts = _pts(pts)
         out = ScanOutput()
-        rc = lib().mlo_lo_on_lidar(self.h, pts.ctypes.data, pts.shape[1], len(pts), stamp, C.byref(out))
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=np.float32)
+            assert len(t) == len(pts)
+        rc = lib().mlo_lo_on_lidar_t(self.h, pts.ctypes.data, pts.shape[1], None if t is None else t.ctypes.data, len(pts),
+                                     stamp, C.byref(out))
         if rc != 0:
             raise MloError(rc, lib().mlo_lo_last_error(self.h).decode())
         return out

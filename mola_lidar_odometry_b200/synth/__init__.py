@@ -27,6 +27,9 @@ def _lib():
         L.synth_scan.restype = C.c_uint64
         L.synth_scan.argtypes = [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_double, C.c_double, C.c_double,
                                  C.c_double, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.synth_scan_skewed.restype = C.c_uint64
+        L.synth_scan_skewed.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_int, C.c_int, C.c_double,
+                                        C.c_double, C.c_double, C.c_double, C.c_uint64, C.c_void_p, C.c_void_p, C.c_uint64]
         _LIB = L
     return _LIB
 
@@ -71,6 +74,35 @@ class Scene:
         if with_time:
             return out[:n].copy(), t[:n].copy()
         return out[:n].copy()
+
+
+def scan_skewed(scene: "Scene", pose_world, twist_body, sensor: Sensor = None, scan_seed: int = 1000, sweep_s: float = 0.1):
+    """A sweep taken while the sensor moves with body-frame twist (vx vy vz wx wy wz); pose_world is the pose at the
+    middle of the sweep.  Returns (float32 [n,4] x,y,z,intensity in the instantaneous sensor frames, float32 [n] t)."""
+    sensor = sensor or K64
+    pose = np.ascontiguousarray(np.asarray(pose_world, dtype=np.float64)[:3, :4])
+    tw = np.ascontiguousarray(twist_body, dtype=np.float64)
+    cap = sensor.n_beams * sensor.n_az
+    out = np.empty((cap, 4), dtype=np.float32)
+    t = np.empty(cap, dtype=np.float32)
+    n = _lib().synth_scan_skewed(scene._h, pose.ctypes.data, tw.ctypes.data, sweep_s, sensor.n_beams, sensor.n_az,
+                                 sensor.el_top_deg, sensor.el_bot_deg, sensor.max_range, sensor.noise_sigma, scan_seed,
+                                 out.ctypes.data, t.ctypes.data, cap)
+    return out[:n].copy(), t[:n].copy()
+
+
+def body_twists(traj: np.ndarray, dt: float = 0.1) -> np.ndarray:
+    """Body-frame twist at every pose of a trajectory (central differences of log(T_k^-1 T_k+1))."""
+    from scipy.spatial.transform import Rotation as Rot
+    n = len(traj)
+    tw = np.zeros((n, 6))
+    for k in range(n):
+        a, b = traj[max(k - 1, 0)], traj[min(k + 1, n - 1)]
+        span = (min(k + 1, n - 1) - max(k - 1, 0)) * dt
+        rel = relative(a, b)
+        tw[k, :3] = rel[:, 3] / span                      # small-step approximation of the SE(3) log
+        tw[k, 3:] = Rot.from_matrix(rel[:, :3]).as_rotvec() / span
+    return tw
 
 
 def rot_zyx(yaw: float, pitch: float = 0.0, roll: float = 0.0) -> np.ndarray:

@@ -167,15 +167,61 @@ void synth_scene_counts(void* s, int* n_boxes, int* n_cyls) {
 
 // pose: 3x4 row-major sensor->world.  Returns the number of returns written (<= max_pts).
 // out_t (optional): per-point relative time (az/2pi - 0.5) * 0.1 s.
+static uint64_t scan_impl(void* scene, const double* pose, const double* twist, double sweep_s, int n_beams, int n_az,
+                          double el_top_deg, double el_bot_deg, double max_range, double noise_sigma, uint64_t scan_seed,
+                          float* out_xyzi, float* out_t, uint64_t max_pts);
+
 uint64_t synth_scan(void* scene, const double* pose, int n_beams, int n_az, double el_top_deg, double el_bot_deg,
                     double max_range, double noise_sigma, uint64_t scan_seed, float* out_xyzi, float* out_t,
                     uint64_t max_pts) {
+  return scan_impl(scene, pose, nullptr, 0.1, n_beams, n_az, el_top_deg, el_bot_deg, max_range, noise_sigma, scan_seed,
+                   out_xyzi, out_t, max_pts);
+}
+
+// A spinning sensor moving with body-frame twist (vx vy vz wx wy wz) during the sweep: the ray of azimuth step a is
+// cast at time t = (az/2pi) * sweep_s (t = 0 at the middle of the sweep) from pose(t) = pose * exp(twist * t), and the
+// return is reported in the sensor frame of THAT instant, which is what FilterDeskew undoes.
+uint64_t synth_scan_skewed(void* scene, const double* pose, const double* twist, double sweep_s, int n_beams, int n_az,
+                           double el_top_deg, double el_bot_deg, double max_range, double noise_sigma, uint64_t scan_seed,
+                           float* out_xyzi, float* out_t, uint64_t max_pts) {
+  return scan_impl(scene, pose, twist, sweep_s, n_beams, n_az, el_top_deg, el_bot_deg, max_range, noise_sigma, scan_seed,
+                   out_xyzi, out_t, max_pts);
+}
+
+static void se3_exp_small(const double* xi, double t, double* P) {  // P = exp(xi * t) as 3x4
+  const double v[3] = {xi[0] * t, xi[1] * t, xi[2] * t}, w[3] = {xi[3] * t, xi[4] * t, xi[5] * t};
+  const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2], th = std::sqrt(th2);
+  double A, B, C;
+  if (th < 1e-6) { A = 1 - th2 / 6; B = 0.5 - th2 / 24; C = 1.0 / 6 - th2 / 120; }
+  else { A = std::sin(th) / th; B = (1 - std::cos(th)) / th2; C = (th - std::sin(th)) / (th2 * th); }
+  const double W[9] = {0, -w[2], w[1], w[2], 0, -w[0], -w[1], w[0], 0};
+  double W2[9];
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) W2[3 * i + j] = W[3 * i] * W[j] + W[3 * i + 1] * W[3 + j] + W[3 * i + 2] * W[6 + j];
+  for (int i = 0; i < 3; i++) {
+    double tr = v[i];
+    for (int j = 0; j < 3; j++) {
+      P[4 * i + j] = (i == j) + A * W[3 * i + j] + B * W2[3 * i + j];
+      tr += (B * W[3 * i + j] + C * W2[3 * i + j]) * v[j];
+    }
+    P[4 * i + 3] = tr;
+  }
+}
+
+static uint64_t scan_impl(void* scene, const double* pose_mid, const double* twist, double sweep_s, int n_beams, int n_az,
+                          double el_top_deg, double el_bot_deg, double max_range, double noise_sigma, uint64_t scan_seed,
+                          float* out_xyzi, float* out_t, uint64_t max_pts) {
   const Scene& S = *static_cast<Scene*>(scene);
-  const double o[3] = {pose[3], pose[7], pose[11]};
+  const double o_mid[3] = {pose_mid[3], pose_mid[7], pose_mid[11]};
+  const double* pose = pose_mid;
+  const double* o = o_mid;
+  const double bin_margin = twist ? 1.5 : 0.0;  // the origin moves during the sweep: widen the bearing bins
   // cull primitives by distance and bucket by bearing
   constexpr int NB = 360;
   std::vector<std::vector<int>> bb(NB), cb(NB), sb(NB);
   auto add = [&](std::vector<std::vector<int>>& bins, int id, double cx, double cy, double rad) {
+    (void)0;
+    rad += bin_margin;
     const double dx = cx - o[0], dy = cy - o[1];
     const double dist = std::sqrt(dx * dx + dy * dy);
     if (dist - rad > max_range) return;
@@ -195,8 +241,21 @@ uint64_t synth_scan(void* scene, const double* pose, int n_beams, int n_az, doub
   for (size_t i = 0; i < S.sphs.size(); i++) add(sb, int(i), S.sphs[i].cx, S.sphs[i].cy, S.sphs[i].r);
 
   uint64_t n = 0;
+  double pose_t[12], o_t[3];
   for (int a = 0; a < n_az; a++) {
     const double az = -M_PI + 2.0 * M_PI * (double(a) + 0.5) / n_az;
+    if (twist) {  // pose at the instant this azimuth column is fired
+      double E[12];
+      se3_exp_small(twist, (az / (2.0 * M_PI)) * sweep_s, E);
+      for (int r = 0; r < 3; r++) {
+        for (int c = 0; c < 3; c++)
+          pose_t[4 * r + c] = pose_mid[4 * r] * E[c] + pose_mid[4 * r + 1] * E[4 + c] + pose_mid[4 * r + 2] * E[8 + c];
+        pose_t[4 * r + 3] = pose_mid[4 * r] * E[3] + pose_mid[4 * r + 1] * E[7] + pose_mid[4 * r + 2] * E[11] + pose_mid[4 * r + 3];
+      }
+      o_t[0] = pose_t[3]; o_t[1] = pose_t[7]; o_t[2] = pose_t[11];
+      pose = pose_t;
+      o = o_t;
+    }
     for (int b = 0; b < n_beams; b++) {
       const double el = (el_top_deg + (el_bot_deg - el_top_deg) * (n_beams > 1 ? double(b) / (n_beams - 1) : 0.0)) * M_PI / 180.0;
       const double ds[3] = {std::cos(el) * std::cos(az), std::cos(el) * std::sin(az), std::sin(el)};
@@ -227,7 +286,7 @@ uint64_t synth_scan(void* scene, const double* pose, int n_beams, int n_az, doub
       out_xyzi[4 * n + 1] = float(r * ds[1]);
       out_xyzi[4 * n + 2] = float(r * ds[2]);
       out_xyzi[4 * n + 3] = float(u01(splitmix(h2 + 7)));
-      if (out_t) out_t[n] = float((az / (2.0 * M_PI)) * 0.1);
+      if (out_t) out_t[n] = float((az / (2.0 * M_PI)) * sweep_s);
       n++;
     }
   }

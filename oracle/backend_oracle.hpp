@@ -12,6 +12,9 @@ void orc_filter_1st_pass(const float* pts, uint32_t stride, uint64_t n, const ml
                          uint64_t* out_map_n, float* out_icp_xyz, uint64_t* out_icp_n);
 void orc_icp_align(void* map, const float* local, uint32_t stride, uint64_t n, const double* init_pose, const mlo_icp_params* p,
                    mlo_icp_result* out, void* pool, double* trace_poses, uint32_t* trace_pairs, uint32_t trace_cap);
+void orc_filter_1st_pass_xyzt(const float* pts, uint32_t stride, const float* t, uint64_t n, const mlo_filter1_params* p,
+                              float* out_map_xyzt, uint64_t* out_map_n, float* out_icp_xyzt, uint64_t* out_icp_n);
+void orc_deskew(const float* xyzt, uint64_t n, const double* twist, float* out_xyz);
 void* orc_map_create(const mlo_map_params* p);
 void orc_map_destroy(void* m);
 void orc_map_clear(void* m);
@@ -37,6 +40,19 @@ struct BackendOracle {
     orc_filter_1st_pass(pts, stride, n, &f, a.data(), &na, b.data(), &nb);
     a.resize(3 * na);
     b.resize(3 * nb);
+  }
+  void filter_1st_pass_xyzt(const float* pts, uint32_t stride, const float* t, uint64_t n, const mlo_filter1_params& f,
+                            std::vector<float>& a, std::vector<float>& b) {
+    a.resize(4 * n);
+    b.resize(4 * n);
+    uint64_t na = 0, nb = 0;
+    orc_filter_1st_pass_xyzt(pts, stride, t, n, &f, a.data(), &na, b.data(), &nb);
+    a.resize(4 * na);
+    b.resize(4 * nb);
+  }
+  void deskew(const float* xyzt, uint64_t n, const double* twist, std::vector<float>& out_xyz) {
+    out_xyz.resize(3 * n);
+    orc_deskew(xyzt, n, twist, out_xyz.data());
   }
   void icp_align(const float* xyz, uint64_t n, void* map, const double* init, const mlo_icp_params& p, mlo_icp_result& r) {
     orc_icp_align(map, xyz, 3, n, init, &p, &r, nullptr, nullptr, nullptr, 0);

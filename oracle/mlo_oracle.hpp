@@ -510,6 +510,35 @@ inline void decimate_first(const float* p, uint32_t stride, size_t n, const Deci
   }
 }
 
+// ---------------------------------------------------------------- FilterDeskew
+// mp2p_icp_filters::FilterDeskew (pipelines/lidar3d-default.yaml:328-350): per point with relative time
+// t, p' = exp_SO3(w t) p + v t.  Rotation coefficients by the Taylor series to t^8 for |w t| < 0.05 rad (exact to
+// < 1e-18 there) so that the device reproduces them bit for bit; libm beyond.  Double arithmetic, float result.
+inline void deskew_coeffs(double th2, double& A, double& B) {
+  if (th2 < 2.5e-3) {
+    A = 1.0 - th2 * (1.0 / 6.0) * (1.0 - th2 * (1.0 / 20.0) * (1.0 - th2 * (1.0 / 42.0) * (1.0 - th2 * (1.0 / 72.0))));
+    B = 0.5 * (1.0 - th2 * (1.0 / 12.0) * (1.0 - th2 * (1.0 / 30.0) * (1.0 - th2 * (1.0 / 56.0) * (1.0 - th2 * (1.0 / 90.0)))));
+  } else {
+    const double th = std::sqrt(th2);
+    A = std::sin(th) / th;
+    B = (1.0 - std::cos(th)) / th2;
+  }
+}
+inline void deskew(const float* xyzt, size_t n, const double twist[6], float* out_xyz) {
+  for (size_t i = 0; i < n; i++) {
+    const double x = xyzt[4 * i], y = xyzt[4 * i + 1], z = xyzt[4 * i + 2], t = xyzt[4 * i + 3];
+    const double wx = twist[3] * t, wy = twist[4] * t, wz = twist[5] * t;
+    double A, B;
+    deskew_coeffs(wx * wx + wy * wy + wz * wz, A, B);
+    // R p = p + A (w x p) + B (w x (w x p))
+    const double cx = wy * z - wz * y, cy = wz * x - wx * z, cz = wx * y - wy * x;
+    const double dx = wy * cz - wz * cy, dy = wz * cx - wx * cz, dz = wx * cy - wy * cx;
+    out_xyz[3 * i] = static_cast<float>(x + A * cx + B * dx + twist[0] * t);
+    out_xyz[3 * i + 1] = static_cast<float>(y + A * cy + B * dy + twist[1] * t);
+    out_xyz[3 * i + 2] = static_cast<float>(z + A * cz + B * dz + twist[2] * t);
+  }
+}
+
 // ---------------------------------------------------------------- ICP
 struct IcpParams {
   uint32_t max_iterations = 300;

@@ -168,6 +168,34 @@ void orc_filter_1st_pass(const float* pts, uint32_t stride, uint64_t n, const ml
       for (int k = 0; k < 3; k++) out_icp_xyz[3 * i + k] = b[size_t(k2[i]) * 3 + k];
 }
 
+// the same 1st pass carrying one extra per-point channel (timestamps): outputs are x, y, z, t
+void orc_filter_1st_pass_xyzt(const float* pts, uint32_t stride, const float* t, uint64_t n, const mlo_filter1_params* p,
+                              float* out_map_xyzt, uint64_t* out_map_n, float* out_icp_xyzt, uint64_t* out_icp_n) {
+  std::vector<uint32_t> k1, k2;
+  DecimateParams d1 = convert(&p->for_map);
+  d1.use_range = d1.use_bbox_outside = false;
+  decimate_first(pts, stride, n, d1, k1);
+  DecimateParams pred = convert(&p->for_icp);
+  std::vector<float> b;
+  for (uint32_t i : k1) {
+    const float* q = pts + size_t(i) * stride;
+    if (predicate_keep(pred, q[0], q[1], q[2])) {
+      b.insert(b.end(), q, q + 3);
+      b.push_back(t ? t[i] : 0.f);
+    }
+  }
+  *out_map_n = b.size() / 4;
+  if (out_map_xyzt) std::memcpy(out_map_xyzt, b.data(), b.size() * sizeof(float));
+  DecimateParams d2 = pred;
+  d2.use_range = d2.use_bbox_outside = false;
+  decimate_first(b.data(), 4, b.size() / 4, d2, k2);
+  *out_icp_n = k2.size();
+  if (out_icp_xyzt)
+    for (size_t i = 0; i < k2.size(); i++)
+      for (int k = 0; k < 4; k++) out_icp_xyzt[4 * i + k] = b[size_t(k2[i]) * 4 + k];
+}
+void orc_deskew(const float* xyzt, uint64_t n, const double* twist, float* out_xyz) { deskew(xyzt, n, twist, out_xyz); }
+
 void orc_icp_align(void* map, const float* local, uint32_t stride, uint64_t n, const double* init_pose,
                    const mlo_icp_params* p, mlo_icp_result* out, void* pool, double* trace_poses,
                    uint32_t* trace_pairs, uint32_t trace_cap) {

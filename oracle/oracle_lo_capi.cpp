@@ -29,10 +29,14 @@ void* orc_lo_create(const char* yaml, int is_text) {
   }
 }
 void orc_lo_destroy(void* h) { delete static_cast<orc_lo*>(h); }
+int orc_lo_on_lidar_t(void* h, const float* pts, uint32_t stride, const float* t, uint64_t n, double stamp, mlo_lo_scan_output* out);
 int orc_lo_on_lidar(void* h, const float* pts, uint32_t stride, uint64_t n, double stamp, mlo_lo_scan_output* out) {
+  return orc_lo_on_lidar_t(h, pts, stride, nullptr, n, stamp, out);
+}
+int orc_lo_on_lidar_t(void* h, const float* pts, uint32_t stride, const float* t, uint64_t n, double stamp, mlo_lo_scan_output* out) {
   auto* o = static_cast<orc_lo*>(h);
   try {
-    const ScanOutput s = o->lo.onLidar(pts, stride, n, stamp);
+    const ScanOutput s = o->lo.onLidar(pts, stride, n, stamp, t);
     out->processed = s.processed;
     out->icp_ran = s.icp_ran;
     out->icp_good = s.icp_good;

@@ -194,6 +194,29 @@ def filter_1st_pass(pts, fp: Filter1Params):
     return a[:na.value].copy(), b[:nb.value].copy()
 
 
+def filter_1st_pass_xyzt(pts, t, fp: Filter1Params):
+    pts = _f32(pts)
+    t = None if t is None else np.ascontiguousarray(t, dtype=np.float32)
+    a, b = np.empty((len(pts), 4), np.float32), np.empty((len(pts), 4), np.float32)
+    na, nb = _u64(), _u64()
+    L = lib()
+    L.orc_filter_1st_pass_xyzt.argtypes = [_vp, _u32, _vp, _u64, C.POINTER(Filter1Params), _vp, C.POINTER(_u64), _vp,
+                                           C.POINTER(_u64)]
+    L.orc_filter_1st_pass_xyzt(pts.ctypes.data, pts.shape[1], None if t is None else t.ctypes.data, len(pts), C.byref(fp),
+                               a.ctypes.data, C.byref(na), b.ctypes.data, C.byref(nb))
+    return a[:na.value].copy(), b[:nb.value].copy()
+
+
+def deskew(xyzt, twist):
+    xyzt = np.ascontiguousarray(xyzt, dtype=np.float32)
+    tw = np.ascontiguousarray(twist, dtype=np.float64)
+    out = np.empty((len(xyzt), 3), np.float32)
+    L = lib()
+    L.orc_deskew.argtypes = [_vp, _u64, _vp, _vp]
+    L.orc_deskew(xyzt.ctypes.data, len(xyzt), tw.ctypes.data, out.ctypes.data)
+    return out
+
+
 def icp_align(omap: OracleMap, local, init_pose, params: IcpParams, pool: Pool | None = None, trace: bool = False):
     local, init_pose = _f32(local), _pose(init_pose)
     res = IcpResult()
@@ -229,8 +252,8 @@ class OracleLidarOdometry:
         L.orc_lo_create.restype = _vp
         L.orc_lo_create.argtypes = [C.c_char_p, C.c_int]
         L.orc_lo_destroy.argtypes = [_vp]
-        L.orc_lo_on_lidar.restype = C.c_int
-        L.orc_lo_on_lidar.argtypes = [_vp, _vp, _u32, _u64, C.c_double, C.POINTER(ScanOutput)]
+        L.orc_lo_on_lidar_t.restype = C.c_int
+        L.orc_lo_on_lidar_t.argtypes = [_vp, _vp, _u32, _vp, _u64, C.c_double, C.POINTER(ScanOutput)]
         self._out_t = ScanOutput
         self.h = L.orc_lo_create(str(yaml_path_or_text).encode(), int(is_text))
         if not self.h:
@@ -241,10 +264,13 @@ class OracleLidarOdometry:
             lib().orc_lo_destroy(self.h)
             self.h = None
 
-    def on_lidar(self, pts, stamp: float):
+    def on_lidar(self, pts, stamp: float, t=None):
         pts = _f32(pts)
         out = self._out_t()
-        rc = lib().orc_lo_on_lidar(self.h, pts.ctypes.data, pts.shape[1], len(pts), stamp, C.byref(out))
+        if t is not None:
+            t = np.ascontiguousarray(t, dtype=np.float32)
+        rc = lib().orc_lo_on_lidar_t(self.h, pts.ctypes.data, pts.shape[1], None if t is None else t.ctypes.data, len(pts),
+                                     stamp, C.byref(out))
         if rc != 0:
             raise RuntimeError("orc_lo_on_lidar failed")
         return out

@@ -373,3 +373,21 @@ def test_icp_ndt_pipeline_parity(ctx, world):
     from mola_lidar_odometry_b200.api import MloError
     with pytest.raises(MloError):
         ctx.icp_align(world["frames"][3]["icp_layer"], g2, np.eye(4)[:3], capi.IcpParamsOwner(sigma=2.0, pipeline="ndt").p)
+
+
+# ------------------------------------------------------------------------------------------------ FilterDeskew (row f1)
+def test_deskew_and_xyzt_filter_bit_exact(ctx, world):
+    raw = world["frames"][5]["raw"]
+    rng = np.random.default_rng(12)
+    t = rng.uniform(-0.05, 0.05, len(raw)).astype(np.float32)
+    ga, gb = ctx.filter_1st_pass_xyzt(raw, t, world["fp"])
+    oa, ob = O.filter_1st_pass_xyzt(raw, t, world["fp"])
+    assert np.array_equal(ga.view(np.uint32), oa.view(np.uint32)) and np.array_equal(gb.view(np.uint32), ob.view(np.uint32))
+    for twist in ([8.0, 0.2, -0.1, 0.01, -0.02, 0.5], [0, 0, 0, 0, 0, 0], [15.0, 0, 0, 0, 0, -0.9]):
+        gd, od = ctx.deskew(ga, twist), O.deskew(oa, twist)
+        assert np.array_equal(gd.view(np.uint32), od.view(np.uint32))       # small-angle series: bit-exact
+    # large angles take the libm branch: tolerance test (floating point, 1e-5 m)
+    big = ga.copy()
+    big[:, 3] = 1.0
+    assert np.allclose(ctx.deskew(big, [1, 2, 3, 0.3, -0.4, 1.2]), O.deskew(big, [1, 2, 3, 0.3, -0.4, 1.2]), atol=1e-5)
+    assert len(ctx.deskew(np.zeros((0, 4), np.float32), [0] * 6)) == 0

@@ -177,3 +177,37 @@ def test_lidar_odometry_gpu_ndt_pipeline(ctx, scene, traj):
         assert (a.icp_good, a.map_updated) == (b.icp_good, b.map_updated)
         assert a.quality == pytest.approx(b.quality, abs=2e-3)
     g.close()
+
+
+@pytest.mark.gpu
+def test_lidar_odometry_gpu_deskew_and_twist_loop(ctx, scene, traj, monkeypatch):
+    """Row f1: skewed sweeps with per-point timestamps, FilterAdjustTimestamps + FilterDeskew + the twist re-estimation
+    loop (optimize_twist on, LidarOdometry.cpp:923-1005) — GPU backend vs oracle backend, same orchestrator."""
+    from mola_lidar_odometry_b200.host_api import LidarOdometry
+    from oracle import oracle_py as O
+    monkeypatch.setenv("MOLA_OPTIMIZE_TWIST", "true")
+    monkeypatch.setenv("MOLA_SKIP_DESKEW", "false")
+    tw = synth.body_twists(traj)
+    g, o = LidarOdometry(ctx, DEFAULT_YAML), O.OracleLidarOdometry(DEFAULT_YAML)
+    runs = 0
+    for k in range(30):
+        raw, t = synth.scan_skewed(scene, traj[k], tw[k], scan_seed=1000 + k)
+        a, b = g.on_lidar(raw, 0.1 * k, t), o.on_lidar(raw, 0.1 * k, t)
+        et, er = O.pose_error(a.pose, b.pose)
+        assert et <= 1e-3 and er <= 1e-2, (k, et, er)
+        assert (a.icp_good, a.map_updated, a.icp_runs, a.n_icp_layer) == (b.icp_good, b.map_updated, b.icp_runs, b.n_icp_layer)
+        runs += a.icp_runs
+    assert runs >= 29
+    gt = synth.relative(traj[0], traj[29])
+    assert O.pose_error(a.pose, gt)[0] < 0.6
+    g.close()
+
+
+def test_deskew_requires_timestamps_when_not_ignored(built, scene, traj, monkeypatch):
+    from oracle import oracle_py as O
+    monkeypatch.setenv("MOLA_IGNORE_NO_POINT_STAMPS", "false")
+    monkeypatch.setenv("MOLA_SKIP_DESKEW", "false")
+    lo = O.OracleLidarOdometry(DEFAULT_YAML)
+    raw = scene.scan(traj[0], scan_seed=1000)
+    with pytest.raises(RuntimeError):                       # the reference's rosbag2 test fails the same way
+        lo.on_lidar(raw, 0.0)                               # (test_lidar_odometry_rosbag2.cpp, MOLA_IGNORE_NO_POINT_STAMPS=false)

@@ -221,3 +221,33 @@ def test_ndt_plane_detection(built):
     assert f[0] and abs(abs(nrm[0, 2]) - 1.0) < 1e-3 and abs(d[0] - 0.3) < 0.01
     assert not f[1]                                                  # isotropic blob is not a plane
     assert f[2] and abs(d[2] - 1.2) < 0.01                           # found from the neighbouring cell
+
+
+def test_deskew_known_answers(built):
+    """FilterDeskew: p' = exp_SO3(w t) p + v t."""
+    pts = np.array([[10.0, 0.0, 1.0, 0.05], [10.0, 0.0, 1.0, -0.05], [0.0, 5.0, 0.0, 0.0], [3.0, 4.0, 5.0, 0.02]], np.float32)
+    # pure translation
+    d = O.deskew(pts, [8.0, -2.0, 0.5, 0, 0, 0])
+    assert np.allclose(d[0], [10.4, -0.1, 1.025], atol=1e-6) and np.allclose(d[1], [9.6, 0.1, 0.975], atol=1e-6)
+    assert np.array_equal(d[2], pts[2, :3])                                 # t = 0: untouched
+    # pure yaw rate 1 rad/s: rotation by w*t about z
+    d = O.deskew(pts, [0, 0, 0, 0, 0, 1.0])
+    for i in (0, 1, 3):
+        a = float(pts[i, 3])
+        R = np.array([[np.cos(a), -np.sin(a), 0], [np.sin(a), np.cos(a), 0], [0, 0, 1]])
+        assert np.allclose(d[i], R @ pts[i, :3].astype(np.float64), atol=2e-6)
+    # large angle uses the libm branch and stays a rotation
+    big = np.array([[1.0, 2.0, 3.0, 1.0]], np.float32)
+    d = O.deskew(big, [0, 0, 0, 0.3, -0.4, 1.2])
+    assert np.linalg.norm(d[0]) == pytest.approx(np.linalg.norm(big[0, :3]), rel=1e-6)
+
+
+def test_filter_xyzt_carries_timestamps(built, world):
+    raw = world["frames"][2]["raw"]
+    t = np.linspace(-0.05, 0.05, len(raw)).astype(np.float32)
+    a, b = O.filter_1st_pass_xyzt(raw, t, world["fp"])
+    a0, b0 = O.filter_1st_pass(raw, world["fp"])
+    assert np.array_equal(a[:, :3], a0) and np.array_equal(b[:, :3], b0)
+    # the carried channel is the timestamp of the surviving input point
+    lut = {tuple(p): tt for p, tt in zip(map(tuple, raw[:, :3]), t)}
+    assert all(lut[tuple(p[:3])] == p[3] for p in a[::50])
