@@ -71,7 +71,21 @@ def build_oracle(force: bool = False) -> Path:
     return LIB_ORACLE
 
 
+CLI_BIN = ROOT / "apps" / "mlo-lidar-odometry-cli"
+
+
+def build_cli(force: bool = False) -> Path:
+    """apps/mlo-lidar-odometry-cli: the offline driver (reference: apps/mola-lidar-odometry-cli.cpp) over libmlo_b200.so."""
+    src = ROOT / "apps" / "mlo-lidar-odometry-cli.cpp"
+    if force or _newer(CLI_BIN, [src, ROOT / "include" / "mlo_b200_host.h", LIB_CUDA]):
+        cmd = ["g++", "-O2", "-std=c++17", "-I", str(ROOT / "include"), str(src), "-o", str(CLI_BIN), "-L", str(PKG),
+               "-lmlo_b200", f"-Wl,-rpath,{PKG}", "-Wl,-rpath,$ORIGIN/../mola_lidar_odometry_b200"]
+        subprocess.run(cmd, check=True)
+    return CLI_BIN
+
+
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_synth(force)
     build_cuda(force, verbose)
     build_oracle(force)
+    build_cli(force)
