@@ -115,10 +115,58 @@ def stream_map(wl: Workload, filt, insert, stats, tag: str):
     raise RuntimeError("trajectory exhausted before reaching 2^20 voxels")
 
 
-def build_gpu_map(ctx, wl: Workload, capacity: int):
+def build_gpu_map(ctx, wl: Workload, capacity: int, rank: int = 0, world: int = 1):
+    """Every rank ends with the same map.  With several ranks the scan synthesis + device filtering of each chunk
+    of 64 poses is split across ranks and the decimated layers are all-gathered over NCCL (set-up only: the timed
+    region has no collective)."""
     from mola_lidar_odometry_b200.api import LocalMap
     gmap = LocalMap(ctx, MAP_VOXEL, MAP_CAP, 0.0, capacity)
-    layers = stream_map(wl, lambda scans: [ctx.filter_1st_pass(r, wl.fp)[0] for r in scans], gmap.insert, gmap.stats, "device")
+    if world == 1:
+        layers = stream_map(wl, lambda scans: [ctx.filter_1st_pass(r, wl.fp)[0] for r in scans], gmap.insert, gmap.stats,
+                            "device")
+        return gmap, layers
+    import torch
+    import torch.distributed as dist
+    MAXP = 16384
+    gen_all = wl.gen_scans
+
+    def gen_share(idxs):       # stream_map asks for the scans of a chunk: produce only this rank's share
+        mine = idxs[rank::world]
+        return [(i, s) for i, s in zip(mine, gen_all(mine))] if mine else []
+
+    def filt_shared(tagged):
+        n_chunk = filt_shared.chunk_len
+        per = (n_chunk + world - 1) // world
+        buf = torch.zeros((per, MAXP, 3), dtype=torch.float32, device="cuda")
+        cnt = torch.zeros((per,), dtype=torch.int32, device="cuda")
+        for j, (_, raw) in enumerate(tagged):
+            a = ctx.filter_1st_pass(raw, wl.fp)[0]
+            assert len(a) <= MAXP
+            buf[j, :len(a)] = torch.from_numpy(a).cuda()
+            cnt[j] = len(a)
+        bufs = [torch.empty_like(buf) for _ in range(world)]
+        cnts = [torch.empty_like(cnt) for _ in range(world)]
+        dist.all_gather(bufs, buf)
+        dist.all_gather(cnts, cnt)
+        out = []
+        for i in range(n_chunk):                      # chunk position i was produced by rank i % world as its item i // world
+            r, j = i % world, i // world
+            n = int(cnts[r][j])
+            out.append(bufs[r][j, :n].cpu().numpy())
+        return out
+
+    class _Shim:
+        """Adapts stream_map's (gen, filt) protocol: gen returns a tagged share, filt gathers the whole chunk."""
+    orig_gen = wl.gen_scans
+
+    def gen_hook(idxs, seed0=1000):
+        filt_shared.chunk_len = len(idxs)
+        return gen_share(list(idxs))
+    wl.gen_scans = gen_hook
+    try:
+        layers = stream_map(wl, filt_shared, gmap.insert, gmap.stats, f"device[rank {rank}]")
+    finally:
+        wl.gen_scans = orig_gen
     return gmap, layers
 
 
@@ -441,7 +489,7 @@ def main():
     B = args.batch
     n_windows = 4
     wl = Workload(B * n_windows, seed=args.seed + rank, threads=threads)
-    gmap, layers = build_gpu_map(ctx, wl, TARGET_VOXELS)
+    gmap, layers = build_gpu_map(ctx, wl, TARGET_VOXELS, rank, world)
     scans, gts, inits = wl.query_set(layers[-1][0])
     fps = [wl.fp] * B
     owners = [capi.IcpParamsOwner(sigma=SIGMA) for _ in range(B)]
