@@ -46,6 +46,17 @@ def log(*a):
     print(*a, file=sys.stderr, flush=True)
 
 
+# stdout carries exactly ONE JSON line: native libraries (e.g. "NCCL version ..." banners) also write to fd 1, so the
+# real stdout is kept aside and fd 1 is pointed at stderr for everything else.
+_REAL_STDOUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
+
+
+def emit(line: dict):
+    _REAL_STDOUT.write(json.dumps(line) + "\n")
+    _REAL_STDOUT.flush()
+
+
 # ---------------------------------------------------------------------------------------------- workload
 class Workload:
     def __init__(self, n_query: int, seed: int, threads: int):
@@ -314,7 +325,7 @@ def run_reference(args, rank: int):
                              "sample": f"{n} scans, {per_step} per step, {cores} independent scans in flight"},
             "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------- sequence workloads
@@ -382,7 +393,7 @@ def run_sequences(args, rank, local_rank, world):
                                       "sample": f"{S} sequences x {N} scans, one thread per sequence"},
                      "e2e": {"value": S * N / wall, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                      "gpu_launches": 0})
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
     import torch
     import torch.distributed as dist
@@ -435,7 +446,7 @@ def run_sequences(args, rank, local_rank, world):
                              "d2h_bytes_per_step": int(S * N * 400), "note": "host buffers in, host results out on every scan"},
                      "gpu_launches": int(launches), "cpu_baseline": cpu, "quality": parity,
                      "roofline": None})
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
@@ -643,7 +654,7 @@ def main():
                 "quality": {"mean_iterations": float(np.mean(iters)), "max_err_vs_gt_m": max(e[0] for e in err_gt),
                             "median_err_vs_gt_m": float(np.median([e[0] for e in err_gt])), "parity_vs_oracle": parity},
                 "timing": {"device_ms_total": ms_dev, "wall_ms_total": ms_wall}}
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
