@@ -46,6 +46,7 @@ struct IcpProblem {
   uint32_t part_begin;    // first partial block of this problem
   uint32_t n_blocks;      // blocks of k_match_accumulate (4 warps x qpw queries each)
   uint32_t n_blocks_acc;  // blocks of k_accumulate (ICP_BLOCK queries each)
+  uint32_t n_blocks_pers; // match chunks of the persistent kernel (its own chunk geometry)
 };
 
 struct IcpState {
@@ -174,6 +175,27 @@ MLO_D void block_reduce_store(double* a, uint32_t npairs, uint32_t ncand, double
     }
     part_cnt[0] = p;
     part_cnt[1] = c;
+  }
+}
+
+// one-warp variant (blocks of 32 threads: no block barrier, every warp writes its own partial)
+MLO_D void warp_reduce_store(double* a, uint32_t npairs, uint32_t ncand, double* part, uint32_t* part_cnt) {
+  const uint32_t lane = threadIdx.x & 31;
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) {
+    double v = a[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == uint32_t(k)) part[k] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    npairs += __shfl_xor_sync(0xFFFFFFFFu, npairs, o);
+    ncand += __shfl_xor_sync(0xFFFFFFFFu, ncand, o);
+  }
+  if (lane == 0) {
+    part_cnt[0] = npairs;
+    part_cnt[1] = ncand;
   }
 }
 
@@ -387,10 +409,12 @@ MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
   __syncwarp();
 }
 
+constexpr uint32_t WL_BLOCK = 32;  // the work-list kernel runs one warp per block: a chunk is 32 queries
+template <int NWARPS>
 MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
-  __shared__ WarpScratch s_ws[ICP_BLOCK / 32];
+  __shared__ WarpScratch s_ws[NWARPS];
   const uint32_t FULL = 0xFFFFFFFFu;
   const double thr = table_at(P.thr_pt2pt, P.table_len, it);
   const float thr2 = float(thr * thr);
@@ -398,7 +422,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
   const double kc = table_at(P.kparam, P.table_len, it);
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   WarpScratch& ws = s_ws[warp];
-  const uint32_t q = chunk * ICP_BLOCK + threadIdx.x;
+  const uint32_t q = chunk * (32u * NWARPS) + threadIdx.x;
   const bool mine = q < P.n_q;
   float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
   float gx = 0.f, gy = 0.f, gz = 0.f;
@@ -535,7 +559,10 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
     pairA[P.q_begin + q] = pa;
   }
   const uint32_t pbi = P.part_begin + chunk;
-  block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+  if (NWARPS == 1)
+    warp_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+  else
+    block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
 // Inner Gauss-Newton iterations >= 1: re-linearise over the stored pairings (no NN). Pairings were written
@@ -670,12 +697,13 @@ MLO_D void finish_iteration(const IcpProblem& P, IcpState& S, double* T, double*
 // read through L2), then lane 0 applies the prior, solves the 6x6 system, retracts and does the
 // end-of-iteration bookkeeping.  Returns (on every lane) 0 = problem finished, 1 = another inner GN
 // iteration is pending, 2 = next ICP iteration.
-__device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const double* partials, const uint32_t* part_cnt, int after_match) {
+__device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const double* partials, const uint32_t* part_cnt, int after_match,
+                                       uint32_t nblk_match) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u;
   double acc = 0.0;
   uint32_t cnt = 0;
-  const uint32_t nblk = after_match ? P.n_blocks : P.n_blocks_acc;
+  const uint32_t nblk = after_match ? nblk_match : P.n_blocks_acc;
   if (lane < NACC) {
     // sequential (deterministic) order, eight L2 loads in flight at a time
     const double* base = partials + size_t(P.part_begin) * NACC + lane;
@@ -835,7 +863,23 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
   chunk_match_tpq(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
+// four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
 __global__ void __launch_bounds__(ICP_BLOCK, 8)
+    k_match_accumulate_wl4(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
+                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
+                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+  const IcpProblem& P = probs[blockIdx.y];
+  if (blockIdx.x >= P.n_blocks) return;
+  const IcpState& S = states[blockIdx.y];
+  if (S.done) return;
+  __shared__ double sT[12];
+  if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  __syncthreads();
+  chunk_match_wl<4>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+}
+
+template <int MIN_BLOCKS>
+__global__ void __launch_bounds__(WL_BLOCK, MIN_BLOCKS)
     k_match_accumulate_wl(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
@@ -846,7 +890,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 8)
   __shared__ double sT[12];
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
   __syncthreads();
-  chunk_match_wl(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  chunk_match_wl<1>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
 __global__ void __launch_bounds__(ICP_BLOCK)
@@ -870,7 +914,7 @@ __global__ void __launch_bounds__(32)
   IcpState& S = states[blockIdx.x];
   if (S.done) return;
   if (!after_match && !S.inner_pending) return;
-  const int next = solve_step(P, S, partials, part_cnt, after_match);
+  const int next = solve_step(P, S, partials, part_cnt, after_match, P.n_blocks);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -975,7 +1019,7 @@ __global__ void k_queue_build(const IcpProblem* __restrict__ probs, const IcpSta
                               uint32_t n_problems) {
   const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= n_problems || states[b].done) return;
-  const uint32_t n = probs[b].n_blocks;
+  const uint32_t n = probs[b].n_blocks_pers;
   const uint32_t pos = atomicAdd(&q.ctrl[1], n);
   for (uint32_t i = 0; i < n; i++) {
     q.items[(pos + i) & q.mask] = item_make(b, i, 0u);
@@ -1034,7 +1078,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
     __syncthreads();
     if (threadIdx.x == 0) {
       __threadfence();  // partials / pairings of this chunk (ordered by the barrier) visible before the count
-      const uint32_t nblk = phase == 0 ? P.n_blocks : P.n_blocks_acc;
+      const uint32_t nblk = phase == 0 ? P.n_blocks_pers : P.n_blocks_acc;
       const uint32_t old = atomicAdd(&q.phase_cnt[prob], 1u);
       s_last = (old + 1 == nblk);
       if (s_last) atomicExch(&q.phase_cnt[prob], 0u);
@@ -1043,13 +1087,13 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
     if (s_last && threadIdx.x < 32) {
       if (threadIdx.x == 0) __threadfence();  // acquire: lane 0 reads the problem state with plain loads
       __syncwarp();
-      const int next = solve_step(P, S, partials, part_cnt, phase == 0);
+      const int next = solve_step(P, S, partials, part_cnt, phase == 0, P.n_blocks_pers);
       if (threadIdx.x == 0) __threadfence();  // state of the problem visible before its next items
       __syncwarp();
       if (next == 1) {
         queue_push(q, prob, 1u, P.n_blocks_acc);
       } else if (next == 2) {
-        queue_push(q, prob, 0u, P.n_blocks);
+        queue_push(q, prob, 0u, P.n_blocks_pers);
       } else if (threadIdx.x == 0) {
         if (atomicSub(&q.ctrl[2], 1u) == 1u) atomicExch(&q.ctrl[3], 1u);
       }

@@ -273,38 +273,34 @@ __global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__
 // ------------------------------------------------------------------ cull (filtered rebuild)
 // insertOpts.remove_voxels_farther_than (default.yaml:238): keep voxels whose per-axis cell distance
 // to the sensor's cell is <= ceil(dist * voxel_size_inv); survivors are re-hashed into `dst`.
-// One warp per source bucket; lanes cooperate on the payload copies.
+// One thread per source bucket (most are empty: the table is sized for a low load factor); the thread of a live
+// bucket re-inserts its cells and copies their payload rows.
 __global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_buckets, int32_t sx, int32_t sy, int32_t sz, int32_t d,
                           int32_t use_filter) {
-  const uint64_t warp = (uint64_t(blockIdx.x) * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t lane = threadIdx.x & 31u;
-  if (warp >= n_buckets) return;
-  const Bucket b = src.buckets[warp];
-  if (b.key == KEY_EMPTY) return;
+  const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
+  if (i >= n_buckets) return;
+  const unsigned long long key = src.buckets[i].key;
+  if (key == KEY_EMPTY) return;
+  const Bucket b = src.buckets[i];
   int32_t kx, ky, kzq;
-  unpack_key(b.key, kx, ky, kzq);
+  unpack_key(key, kx, ky, kzq);
   for (int sub = 0; sub < 4; sub++) {
     const uint32_t w = b.cell[sub];
     if (w == CELL_ABSENT || w == CELL_PENDING) continue;
     const int32_t kz = kzq * 4 + sub;
     if (use_filter && (abs(kx - sx) > d || abs(ky - sy) > d || abs(kz - sz) > d)) continue;
     const uint32_t cnt = cell_cnt(w), ov = cell_vid(w);
-    uint32_t nv = 0xFFFFFFFFu;
-    if (lane == 0) {
-      const uint64_t c = find_or_insert_cell(dst, kx, ky, kz);
-      if (c != ~0ull) {
-        uint32_t* cp = &dst.buckets[c >> 2].cell[c & 3u];
-        nv = cell_vid(*reinterpret_cast<volatile uint32_t*>(cp));
-        if (nv < dst.capacity_voxels) {
-          *cp = cell_make(nv, cnt);
-          atomicAdd(&dst.counters[1], cnt);
-        }
-      }
-    }
-    nv = __shfl_sync(0xFFFFFFFFu, nv, 0);
+    const uint64_t c = find_or_insert_cell(dst, kx, ky, kz);
+    if (c == ~0ull) continue;
+    uint32_t* cp = &dst.buckets[c >> 2].cell[c & 3u];
+    const uint32_t nv = cell_vid(*reinterpret_cast<volatile uint32_t*>(cp));
     if (nv >= dst.capacity_voxels) continue;
-    if (lane < cnt) dst.pts[size_t(nv) * dst.row + lane] = src.pts[size_t(ov) * src.row + lane];
-    if (src.kind == MLO_MAP_NDT && lane == 0) {
+    *cp = cell_make(nv, cnt);
+    atomicAdd(&dst.counters[1], cnt);
+    const float4* sp = src.pts + size_t(ov) * src.row;
+    float4* dp = dst.pts + size_t(nv) * dst.row;
+    for (uint32_t j = 0; j < cnt; j++) dp[j] = sp[j];
+    if (src.kind == MLO_MAP_NDT) {
       dst.mean[nv] = src.mean[ov];
       dst.normal[nv] = src.normal[ov];
     }

@@ -81,6 +81,9 @@ struct mlo_ctx {
   } stage[2];
   bool use_persistent = true;  // MLO_PERSISTENT=0 selects the one-kernel-per-phase launch sequence
   bool persistent_forced = false;
+  int wl_min_blocks = 32;  // MLO_WL_MIN_BLOCKS (one-warp blocks per SM)
+  int wl_warps = 4;        // MLO_WL_WARPS: 4 = four-warp blocks (default), 1 = one-warp blocks (A/B: slower)
+  int table_factor = 8;    // MLO_TABLE_FACTOR: hash buckets per voxel of capacity (load factor ~0.08: fewer re-probes): occupancy target of the work-list kernel (register budget), experiments
   bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
   int consuming_slot = -1;  // staging slot read by the compute call in progress
   int persistent_blocks = 0;
@@ -264,7 +267,7 @@ int map_rebuild(mlo_map* m, bool use_filter, int32_t sx, int32_t sy, int32_t sz,
   }
   int rc = clear_map_buffers(c, m->alt, m->table_size);
   if (rc != MLO_OK) return rc;
-  const uint64_t threads = m->table_size * 32;
+  const uint64_t threads = m->table_size;
   LAUNCH(c, k_rebuild, uint32_t((threads + 255) / 256), 256, m->dev, m->alt, m->table_size, sx, sy, sz, d,
          use_filter ? 1 : 0);
   CU(c, cudaGetLastError());
@@ -497,11 +500,14 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     P.hook_min_trans = p.hook_min_trans;
     P.hook_min_rot = p.hook_min_rot_rad;
     std::memcpy(P.hook_checkpoint, p.hook_checkpoint_pose_3x4, sizeof(P.hook_checkpoint));
-    const uint32_t qpb = use_tpq ? ICP_BLOCK : (ICP_BLOCK / 32) * qpw;
+    const bool use_wl = use_tpq && c->force_kernel != 1;
+    const uint32_t qpb_pers = use_tpq ? ICP_BLOCK : (ICP_BLOCK / 32) * qpw;  // persistent kernel: tpq or warp chunks
+    const uint32_t qpb = use_wl ? (c->wl_warps == 4 ? ICP_BLOCK : WL_BLOCK) : qpb_pers;  // launch sequence: work-list chunks
     P.n_blocks = (P.n_q + qpb - 1) / qpb;
+    P.n_blocks_pers = (P.n_q + qpb_pers - 1) / qpb_pers;
     P.n_blocks_acc = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
     P.part_begin = part_total;
-    part_total += std::max(P.n_blocks, P.n_blocks_acc);
+    part_total += std::max(std::max(P.n_blocks, P.n_blocks_pers), P.n_blocks_acc);
     max_blocks = std::max(max_blocks, P.n_blocks);
     max_blocks_acc = std::max(max_blocks_acc, P.n_blocks_acc);
     max_it = std::max(max_it, P.max_iterations);
@@ -547,7 +553,7 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   // the queue-driven kernel wins while a launch sequence would be latency/launch-bound (small batches);
   // for large batches one kernel per phase streams better (profiles/README.md)
   bool persistent = c->use_persistent && (c->persistent_forced || total_queries < uint64_t(c->sm_count) * 1024) && B < 65536 &&
-                    max_blocks < 32768 && max_blocks_acc < 32768;
+                    max_blocks < 32768 && max_blocks_acc < 32768;  // (chunk counts of the persistent geometry are <= these)
   if (persistent) {
     // ---- one launch for the whole align loop: queue of (problem, phase, chunk) items
     std::vector<uint32_t> items;
@@ -555,7 +561,7 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     for (uint32_t b = 0; b < B; b++) {
       if (probs[b].max_iterations == 0 || probs[b].n_q == 0) continue;
       n_act++;
-      for (uint32_t ch = 0; ch < probs[b].n_blocks; ch++) items.push_back(item_make(b, ch, 0u));
+      for (uint32_t ch = 0; ch < probs[b].n_blocks_pers; ch++) items.push_back(item_make(b, ch, 0u));
     }
     if (n_act) {
       const uint32_t qcap = uint32_t(next_pow2(std::max<uint64_t>(2ull * part_total, 1024)));
@@ -599,9 +605,19 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   }
   for (uint32_t it = 0; !persistent && it < max_it; it++) {
     const size_t e_nn = prof_begin(c);
-    if (use_tpq && c->force_kernel != 1)
-      LAUNCH(c, k_match_accumulate_wl, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+    if (use_tpq && c->force_kernel != 1) {
+#define MLO_WL_LAUNCH(MB)                                                                                              \
+  LAUNCH(c, k_match_accumulate_wl<MB>, grid, WL_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),            \
+         c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
+      if (c->wl_warps == 4)
+        LAUNCH(c, k_match_accumulate_wl4, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
+               c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+      else switch (c->wl_min_blocks) {
+        case 16: MLO_WL_LAUNCH(16); break;
+        case 24: MLO_WL_LAUNCH(24); break;
+        default: MLO_WL_LAUNCH(32); break;
+      }
+    }
     else if (use_tpq)
       LAUNCH(c, k_match_accumulate_tpq, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
              c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
@@ -707,6 +723,9 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->dev_name = prop.name;
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
   if (const char* th = getenv("MLO_TAIL_HANDOVER")) c->tail_handover = atoi(th) != 0;
+  if (const char* wb = getenv("MLO_WL_MIN_BLOCKS")) c->wl_min_blocks = atoi(wb);
+  if (const char* ww = getenv("MLO_WL_WARPS")) c->wl_warps = atoi(ww);
+  if (const char* tf = getenv("MLO_TABLE_FACTOR")) c->table_factor = std::max(1, atoi(tf));
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
@@ -777,7 +796,7 @@ int mlo_map_create(mlo_ctx* c, const mlo_map_params* p, mlo_map** out) {
   auto* m = new mlo_map;
   m->ctx = c;
   m->prm = *p;
-  m->table_size = next_pow2(std::max<uint64_t>(2 * p->capacity_voxels, 1024));
+  m->table_size = next_pow2(std::max<uint64_t>(uint64_t(c->table_factor) * p->capacity_voxels, 1024));
   int rc = alloc_map_buffers(c, *p, m->table_size, m->dev);
   if (rc == MLO_OK) rc = clear_map_buffers(c, m->dev, m->table_size);
   if (rc == MLO_OK) {
