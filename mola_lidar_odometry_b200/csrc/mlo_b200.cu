@@ -71,6 +71,12 @@ struct mlo_ctx {
   int force_kernel = 0;  // 0 auto, 1 thread-per-query, 2 warp-per-query (MLO_FORCE_KERNEL, experiments only)
   // two staging slots for the pipelined host-buffer path
   cudaStream_t copy_stream = nullptr;
+  // Large batches run their launch sequence as `stream_groups` independent halves on separate streams so that the
+  // latency-bound one-warp-per-problem solve of one group overlaps the bandwidth-bound match kernel of the other.
+  static constexpr int MAX_GROUPS = 4;
+  cudaStream_t aux_stream[MAX_GROUPS - 1] = {nullptr, nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[MAX_GROUPS - 1] = {nullptr, nullptr, nullptr};
+  int stream_groups = 3;  // MLO_STREAM_GROUPS (A/B at B=512: 1: 21.5k, 2: 22.5k, 3: 22.9k, 4: 22.8k scans/s)
   struct Stage {
     DBuf buf;
     cudaEvent_t ready = nullptr;
@@ -138,6 +144,11 @@ int fail(mlo_ctx* c, int code, const std::string& msg) {
   do {                                                 \
     kern<<<grid, block, 0, (ctx)->stream>>>(__VA_ARGS__); \
     (ctx)->launches++;                                 \
+  } while (0)
+#define LAUNCH_ON(ctx, strm, kern, grid, block, ...) \
+  do {                                               \
+    kern<<<grid, block, 0, strm>>>(__VA_ARGS__);     \
+    (ctx)->launches++;                               \
   } while (0)
 
 struct DeviceGuard {
@@ -603,34 +614,55 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
       if (*h_active != 0) return fail(c, MLO_ERR_CUDA, "persistent ICP kernel timed out waiting on its work queue");
     }
   }
+  // stream groups: contiguous slices of the batch, each with its own launch sequence (group 0 on the context stream)
+  // (per-kernel timing needs the kernel alone on the device: one group while profiling)
+  const uint32_t n_groups = (!persistent && use_tpq && B >= 64 && !c->prof_on) ? uint32_t(c->stream_groups) : 1u;
+  auto group_stream = [&](uint32_t g) { return g == 0 ? c->stream : c->aux_stream[g - 1]; };
+  if (n_groups > 1) {
+    CU(c, cudaEventRecord(c->ev_fork, c->stream));
+    for (uint32_t g = 1; g < n_groups; g++) CU(c, cudaStreamWaitEvent(c->aux_stream[g - 1], c->ev_fork, 0));
+  }
   for (uint32_t it = 0; !persistent && it < max_it; it++) {
-    const size_t e_nn = prof_begin(c);
-    if (use_tpq && c->force_kernel != 1) {
+    for (uint32_t g = 0; g < n_groups; g++) {
+      const uint32_t g0 = uint32_t(uint64_t(B) * g / n_groups), g1 = uint32_t(uint64_t(B) * (g + 1) / n_groups);
+      const uint32_t Bg = g1 - g0;
+      if (Bg == 0) continue;
+      cudaStream_t sg = group_stream(g);
+      const IcpProblem* gP = dP + g0;
+      IcpState* gS = dS + g0;
+      const dim3 grid_g(grid.x, Bg), grid_acc_g(grid_acc.x, Bg);
+      const size_t e_nn = g == 0 ? prof_begin(c) : 0;
+      if (use_tpq && c->force_kernel != 1) {
 #define MLO_WL_LAUNCH(MB)                                                                                              \
-  LAUNCH(c, k_match_accumulate_wl<MB>, grid, WL_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),            \
-         c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
-      if (c->wl_warps == 4)
-        LAUNCH(c, k_match_accumulate_wl4, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-               c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
-      else switch (c->wl_min_blocks) {
-        case 16: MLO_WL_LAUNCH(16); break;
-        case 24: MLO_WL_LAUNCH(24); break;
-        default: MLO_WL_LAUNCH(32); break;
+  LAUNCH_ON(c, sg, k_match_accumulate_wl<MB>, grid_g, WL_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),   \
+            c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
+        if (c->wl_warps == 4)
+          LAUNCH_ON(c, sg, k_match_accumulate_wl4, grid_g, ICP_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),
+                    c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+        else switch (c->wl_min_blocks) {
+          case 16: MLO_WL_LAUNCH(16); break;
+          case 24: MLO_WL_LAUNCH(24); break;
+          default: MLO_WL_LAUNCH(32); break;
+        }
+      } else if (use_tpq)
+        LAUNCH_ON(c, sg, k_match_accumulate_tpq, grid_g, ICP_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),
+                  c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+      else
+        LAUNCH_ON(c, sg, k_match_accumulate, grid_g, ICP_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),
+                  c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
+      if (g == 0) prof_end(c, 3, e_nn);
+      LAUNCH_ON(c, sg, k_solve, Bg, 32, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
+      for (uint32_t inner = 1; inner < max_inner; inner++) {
+        LAUNCH_ON(c, sg, k_accumulate, grid_acc_g, ICP_BLOCK, gP, gS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
+                  c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+        LAUNCH_ON(c, sg, k_solve, Bg, 32, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active);
       }
     }
-    else if (use_tpq)
-      LAUNCH(c, k_match_accumulate_tpq, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
-    else
-      LAUNCH(c, k_match_accumulate, grid, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
-    prof_end(c, 3, e_nn);
-    LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
-    for (uint32_t inner = 1; inner < max_inner; inner++) {
-      LAUNCH(c, k_accumulate, grid_acc, ICP_BLOCK, dP, dS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
-             c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
-      LAUNCH(c, k_solve, B, 32, dP, dS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active);
-    }
+    if (((it % check_every) == check_every - 1 || it + 1 == max_it) && n_groups > 1)
+      for (uint32_t g = 1; g < n_groups; g++) {  // join: the context stream waits for every group
+        CU(c, cudaEventRecord(c->ev_join[g - 1], c->aux_stream[g - 1]));
+        CU(c, cudaStreamWaitEvent(c->stream, c->ev_join[g - 1], 0));
+      }
     if ((it % check_every) == check_every - 1 || it + 1 == max_it) {
       CU(c, cudaMemcpyAsync(h_active, d_active, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
@@ -726,6 +758,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* wb = getenv("MLO_WL_MIN_BLOCKS")) c->wl_min_blocks = atoi(wb);
   if (const char* ww = getenv("MLO_WL_WARPS")) c->wl_warps = atoi(ww);
   if (const char* tf = getenv("MLO_TABLE_FACTOR")) c->table_factor = std::max(1, atoi(tf));
+  if (const char* sg = getenv("MLO_STREAM_GROUPS")) c->stream_groups = std::min(int(mlo_ctx::MAX_GROUPS), std::max(1, atoi(sg)));
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
@@ -735,6 +768,14 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
       cudaStreamCreateWithFlags(&c->copy_stream, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->stage[0].ready, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&c->stage[1].ready, cudaEventDisableTiming) != cudaSuccess) {
+    delete c;
+    return MLO_ERR_CUDA;
+  }
+  bool ok = cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int g = 0; ok && g < mlo_ctx::MAX_GROUPS - 1; g++)
+    ok = cudaStreamCreateWithFlags(&c->aux_stream[g], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&c->ev_join[g], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
     delete c;
     return MLO_ERR_CUDA;
   }
@@ -759,6 +800,11 @@ void mlo_destroy(mlo_ctx* c) {
     st.buf.release();
     if (st.ready) cudaEventDestroy(st.ready);
   }
+  for (int g = 0; g < mlo_ctx::MAX_GROUPS - 1; g++) {
+    if (c->aux_stream[g]) cudaStreamSynchronize(c->aux_stream[g]), cudaStreamDestroy(c->aux_stream[g]);
+    if (c->ev_join[g]) cudaEventDestroy(c->ev_join[g]);
+  }
+  if (c->ev_fork) cudaEventDestroy(c->ev_fork);
   cudaStreamDestroy(c->copy_stream);
   cudaStreamDestroy(c->stream);
   delete c;
