@@ -332,8 +332,9 @@ def run_reference(args, rank: int):
 def run_sequences(args, rank, local_rank, world):
     """BASELINE configs[2]/[3]/[4]: S independent T00-shaped sequences per GPU, each through the full odometry loop of
     the C++ host layer (filter -> motion-model guess -> ICP -> quality gate -> adaptive sigma -> keyframe -> map
-    insert + cull) with the pipeline YAML; one host thread + one context (stream) per sequence, like the reference's
-    one worker per LidarOdometry.  The CPU arm runs the SAME orchestrator over the oracle backend."""
+    insert + cull) with the pipeline YAML.  GPU arm: the S sequences advance in lock step as one fleet (one device
+    pass per phase over S local maps).  CPU arm: the SAME orchestrator over the oracle backend, one thread per
+    sequence like the reference's one worker per LidarOdometry / process per sequence."""
     os.environ.setdefault("MOLA_OPTIMIZE_TWIST", "false")   # benchmark settings of SURVEY.md §8(d): deskew is row f1
     os.environ.setdefault("MOLA_INITIAL_VX", "8.0")
     ndt = args.workload == "ndt"
@@ -398,30 +399,62 @@ def run_sequences(args, rank, local_rank, world):
     import torch
     import torch.distributed as dist
     from mola_lidar_odometry_b200.api import Context
-    from mola_lidar_odometry_b200.host_api import LidarOdometry
+    from mola_lidar_odometry_b200.host_api import LidarOdometryFleet
     torch.cuda.set_device(local_rank)
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    ctxs = []
+    # the S sequences of this GPU advance in lock step as one fleet: one filter pass, one align pass over S local maps
+    # and one insert pass per step (mlo_fleet_* / mlo_scanset_*); raw scans sit in pinned host memory
+    pinned = []
+    for sc in scans:
+        row = []
+        for x in sc:
+            tns = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).pin_memory()
+            row.append(tns)
+        pinned.append(row)
+    views = [[tns.numpy() for tns in row] for row in pinned]
+    ctx = Context(local_rank)
+    ctxs = [ctx]
 
-    def make_gpu():
-        c = Context(local_rank)
-        ctxs.append(c)
-        return LidarOdometry(c, yaml_path)
-    run_all(make_gpu, S)                      # warm-up pass (allocations, first-touch)
-    l0 = sum(c.launch_count for c in ctxs)
+    def run_fleet(profile=False):
+        fleet = LidarOdometryFleet(ctx, yaml_path, S)
+        poses = [[] for _ in range(S)]
+        its = [0] * S
+        if profile:
+            ctx.profile_enable(True)
+            ctx.profile_get(True)
+        t0 = time.perf_counter()
+        for k in range(N):
+            outs = fleet.on_lidar([views[s][k] for s in range(S)], [0.1 * k] * S)
+            for s in range(S):
+                poses[s].append(outs[s].pose.copy())
+                its[s] += int(outs[s].icp_iterations)
+        wall = time.perf_counter() - t0
+        host_phases = fleet.phase_times()
+        prof = None
+        if profile:
+            pr = ctx.profile_get(True)
+            ctx.profile_enable(False)
+            prof = {"filter_1st_ms_per_step": pr.filter_1st_ms / N, "run_icp_ms_per_step": pr.run_icp_ms / N,
+                    "update_local_map_ms_per_step": pr.update_local_map_ms / N, "wall_ms_per_step": wall * 1e3 / N}
+        fleet.close()
+        return wall, [(wall, np.stack(poses[s]), its[s]) for s in range(S)], prof, host_phases
+    run_fleet()                               # warm-up pass (allocations, first-touch)
+    l0 = ctx.launch_count
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    wall, res = run_all(make_gpu, S)
+    wall, res, _, host_phases = run_fleet()
     torch.cuda.synchronize()
+    launches = ctx.launch_count - l0
     t = torch.tensor([wall], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     wall_max = float(t[0])
-    launches = sum(c.launch_count for c in ctxs) - l0
     value = world * S * N / wall_max
+    _, _, phase_profile, _ = run_fleet(profile=True)
+    phase_profile = {"device_events_pass": phase_profile, "host_wall_timed_pass": host_phases}
     cpu, parity = None, None
     if rank == 0 and not args.no_cpu_baseline:
         n_cpu = min(S, max(1, cores // 2))
@@ -443,9 +476,10 @@ def run_sequences(args, rank, local_rank, world):
     if rank == 0:
         line.update({"value": value, "ms_per_step": wall_max * 1e3,
                      "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": int(sum(x.nbytes for sc in scans for x in sc)),
-                             "d2h_bytes_per_step": int(S * N * 400), "note": "host buffers in, host results out on every scan"},
+                             "d2h_bytes_per_step": int(S * N * 400),
+                             "note": "pinned host scans in, host results out on every lock step (mlo_fleet_on_lidar)"},
                      "gpu_launches": int(launches), "cpu_baseline": cpu, "quality": parity,
-                     "roofline": None})
+                     "phases": phase_profile, "roofline": None})
         emit(line)
     if world > 1:
         dist.barrier()

@@ -276,6 +276,55 @@ int mlo_scan_register_batch_resident(mlo_ctx* ctx, const mlo_map* map, const mlo
 int mlo_icp_align_batch_resident(mlo_ctx* ctx, const mlo_dcloud* local_batch, const mlo_map* global,
                                  const double* init_poses_3x4, const mlo_icp_params* params, mlo_icp_result* out);
 
+/* ------------------------------------------------------------------ scan sets: device-resident scan layers
+ * The layers an observation is reduced to by the 1st/2nd pass filters ("decimated_for_map", "decimated_for_icp" and
+ * their "_skewed" inputs, pipelines/lidar3d-default.yaml:278-350) stay in HBM between the calls that the reference makes
+ * on them (apply_filter_pipeline at LidarOdometry.cpp:732-741, ICP::align at :961, the merge pipeline at :1197), and
+ * every call works on MANY scans at once: a set of n_slots scans belonging to independent LidarOdometry instances
+ * (one sequence each) that advance in lock step.  Only the raw clouds go up and only counts,
+ * bounding boxes and ICP results come back.  One set belongs to one context; calls are stream-ordered. */
+typedef struct mlo_scanset mlo_scanset;
+typedef struct mlo_scan_job {
+  uint32_t slot;          /* which scan of the set this cloud becomes */
+  const float* pts;       /* host, array-of-structs */
+  const float* t;         /* host per-point times (CPointsMapXYZIRT "t") or NULL */
+  uint64_t n;
+  mlo_filter1_params fp;  /* observations_filter_1st_pass realised for this scan */
+} mlo_scan_job;
+typedef struct mlo_scan_info {
+  uint64_t n_map, n_icp;          /* sizes of the two layers */
+  float icp_min[3], icp_max[3];   /* bounding box of the ICP layer (doUpdateEstimatedMaxSensorRange, :1515-1546) */
+} mlo_scan_info;
+typedef struct mlo_align_job {
+  uint32_t slot;
+  const mlo_map* map;             /* the local map of the sequence this scan belongs to */
+  double init_pose_3x4[12];
+  mlo_icp_params params;
+} mlo_align_job;
+typedef struct mlo_insert_job {
+  uint32_t slot;
+  mlo_map* map;
+  double pose_3x4[12];
+  float cull_farther_than;        /* insertOpts.remove_voxels_farther_than, 0 = off */
+} mlo_insert_job;
+typedef struct mlo_map_counts { uint64_t n_voxels, n_points; } mlo_map_counts;
+
+int mlo_scanset_create(mlo_ctx* ctx, uint32_t n_slots, mlo_scanset** out);
+void mlo_scanset_destroy(mlo_scanset* set);
+/* 1st-pass filter of n_jobs raw clouds (all with the same stride); replaces the previous contents of the WHOLE set
+ * (slots without a job become empty).  With any job carrying `t`, the layers are the "_skewed" ones and
+ * mlo_scanset_deskew must run before align/insert.  info[j] describes job j. */
+int mlo_scanset_filter(mlo_scanset* set, uint32_t n_jobs, const mlo_scan_job* jobs, uint32_t stride_floats,
+                       mlo_scan_info* info);
+/* FilterDeskew of the listed slots with one twist (vx vy vz wx wy wz) each; info[i] is refreshed for slots[i]. */
+int mlo_scanset_deskew(mlo_scanset* set, uint32_t n, const uint32_t* slots, const double* twists6, mlo_scan_info* info);
+/* ICP::align of the listed scans, each against its own map, in one device pass. */
+int mlo_scanset_align(mlo_scanset* set, uint32_t n_jobs, const mlo_align_job* jobs, mlo_icp_result* out);
+/* Map-layer insert (+ cull) of the listed scans into their maps; one synchronisation for all of them. */
+int mlo_scanset_insert(mlo_scanset* set, uint32_t n_jobs, const mlo_insert_job* jobs, mlo_map_counts* out);
+/* Copy one layer of one slot back (tests): layer 0 = map layer, 1 = ICP layer; xyz packed. */
+int mlo_scanset_download(mlo_scanset* set, uint32_t slot, int layer, float* out_xyz, uint64_t max_points, uint64_t* n);
+
 /* Per-kernel device time (ms, CUDA events on the context stream) accumulated since the last reset,
  * for the three profiler buckets of the reference (LidarOdometry.cpp:732,916,1162) and the
  * dominant kernel.  Timing is only collected when enabled (it adds event records). */

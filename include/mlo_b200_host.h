@@ -34,6 +34,22 @@ int mlo_lo_on_lidar_t(mlo_lo* lo, const float* pts, uint32_t stride_floats, cons
 int mlo_lo_trajectory(const mlo_lo* lo, double* stamps, double* poses_3x4, uint64_t max_n, uint64_t* n);
 int mlo_lo_reset(mlo_lo* lo); /* LidarOdometry::reset (LidarOdometry.cpp:495) */
 
+/* A fleet of n_sequences independent LidarOdometry instances advanced in lock step on one context: every phase of the
+ * per-scan path (filter, ICP::align, map merge) is ONE device pass over all sequences, each with its own local map
+ * (mlo_scanset_* in mlo_b200.h).  The reference runs independent sequences as separate processes
+ * (eval/cli_kitti.sh:23); results per sequence are those of mlo_lo_on_lidar. */
+typedef struct mlo_fleet mlo_fleet;
+int mlo_fleet_create(mlo_ctx* ctx, const char* yaml, int is_text, uint32_t n_sequences, mlo_fleet** out);
+void mlo_fleet_destroy(mlo_fleet* f);
+const char* mlo_fleet_last_error(const mlo_fleet* f);
+/* One lock step: cloud i -> sequence i (pts[i] == NULL leaves sequence i idle; t may be NULL, or hold NULL entries). */
+int mlo_fleet_on_lidar(mlo_fleet* f, const float* const* pts, uint32_t stride_floats, const uint64_t* n, const double* stamps_s,
+                       const float* const* t, mlo_lo_scan_output* out);
+/* Host wall time [ms] per phase accumulated since the last reset: [0] per-scan host logic before the filter,
+ * [1] filter pass, [2] deskew passes, [3] align passes, [4] host logic after ICP, [5] insert pass, [6] lock steps. */
+int mlo_fleet_phase_times(mlo_fleet* f, double out_ms[8], int reset);
+int mlo_fleet_trajectory(const mlo_fleet* f, uint32_t sequence, double* stamps, double* poses_3x4, uint64_t max_n, uint64_t* n);
+
 /* Pure host helpers (no device): parse the pipeline YAML and realise its formulas for given variable values. */
 const char* mlo_host_last_error(void);
 int mlo_host_icp_tables(const char* yaml_text, double sigma, uint32_t n_iterations, double* thr_pt2pt, double* thr_pt2pl,

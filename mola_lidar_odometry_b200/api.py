@@ -238,6 +238,80 @@ class DeviceClouds:
             pass
 
 
+class ScanSet:
+    """Device-resident layers of n_slots scans (mlo_scanset_*): filter -> (deskew) -> align -> insert, each ONE device
+    pass over all listed scans, every scan against its own local map (fleets of independent sequences)."""
+
+    def __init__(self, ctx: Context, n_slots: int):
+        self.ctx, self.n_slots = ctx, n_slots
+        h = C.c_void_p()
+        ctx.check(ctx.lib.mlo_scanset_create(ctx.h, n_slots, C.byref(h)))
+        self.h = h
+        self._keep = None
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            self.ctx.lib.mlo_scanset_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def filter(self, slots: Sequence[int], clouds: Sequence[np.ndarray], fps: Sequence[Filter1Params], ts=None):
+        clouds = [_pts(c) for c in clouds]
+        stride = clouds[0].shape[1] if clouds else 3
+        assert all(c.shape[1] == stride for c in clouds)
+        ts = [None] * len(clouds) if ts is None else [None if t is None else np.ascontiguousarray(t, dtype=np.float32) for t in ts]
+        jobs = (capi.ScanJob * max(1, len(clouds)))()
+        for j, (sl, c, fp, t) in enumerate(zip(slots, clouds, fps, ts)):
+            jobs[j].slot, jobs[j].pts, jobs[j].n, jobs[j].fp = sl, c.ctypes.data, len(c), fp
+            jobs[j].t = None if t is None else t.ctypes.data
+        info = (capi.ScanInfo * max(1, len(clouds)))()
+        self.ctx.check(self.ctx.lib.mlo_scanset_filter(self.h, len(clouds), jobs, stride, info))
+        return list(info)[:len(clouds)]
+
+    def deskew(self, slots: Sequence[int], twists):
+        sl = np.ascontiguousarray(slots, dtype=np.uint32)
+        tw = np.ascontiguousarray(twists, dtype=np.float64).reshape(len(sl), 6)
+        info = (capi.ScanInfo * max(1, len(sl)))()
+        self.ctx.check(self.ctx.lib.mlo_scanset_deskew(self.h, len(sl), sl.ctypes.data, tw.ctypes.data, info))
+        return list(info)[:len(sl)]
+
+    def align(self, slots: Sequence[int], maps: Sequence["LocalMap"], init_poses, params: Sequence[IcpParams]):
+        n = len(slots)
+        jobs = (capi.AlignJob * max(1, n))()
+        init = _pose(init_poses).reshape(n, 12)
+        for j in range(n):
+            jobs[j].slot, jobs[j].map, jobs[j].params = slots[j], maps[j].h, params[j]
+            jobs[j].init_pose_3x4[:] = init[j].tolist()
+        out = (IcpResult * max(1, n))()
+        self.ctx.check(self.ctx.lib.mlo_scanset_align(self.h, n, jobs, out))
+        return list(out)[:n]
+
+    def insert(self, slots: Sequence[int], maps: Sequence["LocalMap"], poses, cull=None):
+        n = len(slots)
+        jobs = (capi.InsertJob * max(1, n))()
+        ps = _pose(poses).reshape(n, 12)
+        for j in range(n):
+            jobs[j].slot, jobs[j].map = slots[j], maps[j].h
+            jobs[j].pose_3x4[:] = ps[j].tolist()
+            jobs[j].cull_farther_than = 0.0 if cull is None else float(cull[j])
+        out = (capi.MapCounts * max(1, n))()
+        self.ctx.check(self.ctx.lib.mlo_scanset_insert(self.h, n, jobs, out))
+        return [(o.n_voxels, o.n_points) for o in list(out)[:n]]
+
+    def download(self, slot: int, layer: int) -> np.ndarray:
+        n = C.c_uint64()
+        self.ctx.check(self.ctx.lib.mlo_scanset_download(self.h, slot, layer, None, 0, C.byref(n)))
+        out = np.zeros((n.value, 3), dtype=np.float32)
+        if n.value:
+            self.ctx.check(self.ctx.lib.mlo_scanset_download(self.h, slot, layer, out.ctypes.data, n.value, C.byref(n)))
+        return out
+
+
 class LocalMap:
     """Hash-voxel local map in HBM: mola::HashedVoxelPointCloud (kind 0) or mola::NDT (kind 1)."""
 

@@ -71,6 +71,26 @@ class Profile(C.Structure):
                 ("nn_candidate_points", C.c_uint64), ("nn_blocks", C.c_uint64)]
 
 
+class ScanJob(C.Structure):
+    _fields_ = [("slot", C.c_uint32), ("pts", C.c_void_p), ("t", C.c_void_p), ("n", C.c_uint64), ("fp", Filter1Params)]
+
+
+class ScanInfo(C.Structure):
+    _fields_ = [("n_map", C.c_uint64), ("n_icp", C.c_uint64), ("icp_min", C.c_float * 3), ("icp_max", C.c_float * 3)]
+
+
+class AlignJob(C.Structure):
+    _fields_ = [("slot", C.c_uint32), ("map", C.c_void_p), ("init_pose_3x4", C.c_double * 12), ("params", IcpParams)]
+
+
+class InsertJob(C.Structure):
+    _fields_ = [("slot", C.c_uint32), ("map", C.c_void_p), ("pose_3x4", C.c_double * 12), ("cull_farther_than", C.c_float)]
+
+
+class MapCounts(C.Structure):
+    _fields_ = [("n_voxels", C.c_uint64), ("n_points", C.c_uint64)]
+
+
 def decimate_params(resolution: float, min_points: int = 2000, range_minmax=None, bbox_outside=None) -> DecimateParams:
     p = DecimateParams()
     p.voxel_filter_resolution = resolution
@@ -189,6 +209,13 @@ _SIGNATURES = {
     "mlo_dcloud_size": (_u64, [_vp]),
     "mlo_scan_register_batch_resident": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp]),
     "mlo_icp_align_batch_resident": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp]),
+    "mlo_scanset_create": (C.c_int, [_vp, C.c_uint32, C.POINTER(_vp)]),
+    "mlo_scanset_destroy": (None, [_vp]),
+    "mlo_scanset_filter": (C.c_int, [_vp, C.c_uint32, C.POINTER(ScanJob), C.c_uint32, C.POINTER(ScanInfo)]),
+    "mlo_scanset_deskew": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.POINTER(ScanInfo)]),
+    "mlo_scanset_align": (C.c_int, [_vp, C.c_uint32, C.POINTER(AlignJob), C.POINTER(IcpResult)]),
+    "mlo_scanset_insert": (C.c_int, [_vp, C.c_uint32, C.POINTER(InsertJob), C.POINTER(MapCounts)]),
+    "mlo_scanset_download": (C.c_int, [_vp, C.c_uint32, C.c_int, _vp, C.c_uint64, C.POINTER(C.c_uint64)]),
     "mlo_profile_enable": (C.c_int, [_vp, C.c_int]),
     "mlo_profile_get": (C.c_int, [_vp, C.POINTER(Profile), C.c_int]),
 }

@@ -25,6 +25,7 @@ constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int32_t KEY_BIAS = 1 << 20;  // 21 bits per axis
 constexpr uint32_t HARD_LIMIT_PTS = 32; // upstream HARDLIMIT_MAX_POINTS_PER_VOXEL
 enum : uint32_t { ERR_CAPACITY = 1u, ERR_KEY_RANGE = 2u };  // device-side error bits
+constexpr uint32_t MAP_COUNTERS = 8;  // u32 words of MapDev::counters (map.cuh)
 
 // mola::HashedVoxelPointCloud::coordToGlobalIdx (pipelines/lidar3d-default.yaml:233 voxel_size):
 // static_cast<int32_t>(coord * voxel_size_inv), truncation toward zero.

@@ -47,7 +47,17 @@ struct IcpProblem {
   uint32_t n_blocks;      // blocks of k_match_accumulate (4 warps x qpw queries each)
   uint32_t n_blocks_acc;  // blocks of k_accumulate (ICP_BLOCK queries each)
   uint32_t n_blocks_pers; // match chunks of the persistent kernel (its own chunk geometry)
+  uint32_t map_idx;       // index into the launch's map table (fleet launches: one local map per sequence)
 };
+
+// Fleet launches (independent sequences advanced in lock step) give every problem its own local map: the
+// descriptor of problem P is staged from maps[P.map_idx] into shared memory once per block / work item.
+MLO_D void stage_map(MapDev& dst, const MapDev* __restrict__ maps, uint32_t idx) {
+  static_assert(sizeof(MapDev) % 4 == 0, "MapDev is copied word by word");
+  const uint32_t* src = reinterpret_cast<const uint32_t*>(&maps[idx]);
+  uint32_t* d = reinterpret_cast<uint32_t*>(&dst);
+  if (threadIdx.x < sizeof(MapDev) / 4) d[threadIdx.x] = __ldg(&src[threadIdx.x]);
+}
 
 struct IcpState {
   double T[12], prev[12], prev2[12];
@@ -835,18 +845,22 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const d
 }
 
 // ------------------------------------------------------------------ one kernel per phase (launch sequence)
+template <bool MULTI>
 __global__ void __launch_bounds__(ICP_BLOCK)
-    k_match_accumulate(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
-                       const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
-                       double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
+    k_match_accumulate(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
+                       const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,
+                       float4* __restrict__ pairB, double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
   const IcpProblem& P = probs[blockIdx.y];
   if (blockIdx.x >= P.n_blocks) return;
   const IcpState& S = states[blockIdx.y];
   if (S.done) return;
   __shared__ double sT[12];
+  __shared__ MapDev sMap;
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  if (MULTI) stage_map(sMap, maps, P.map_idx);
   __syncthreads();
-  chunk_match_warp(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt, qpw);
+  if constexpr (MULTI) chunk_match_warp(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt, qpw);
+  else chunk_match_warp(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt, qpw);
 }
 
 __global__ void __launch_bounds__(ICP_BLOCK, 4)
@@ -864,18 +878,22 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
 }
 
 // four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
+template <bool MULTI>
 __global__ void __launch_bounds__(ICP_BLOCK, 8)
-    k_match_accumulate_wl4(MapDev map, const IcpProblem* __restrict__ probs, const IcpState* __restrict__ states,
-                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
-                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
+    k_match_accumulate_wl4(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
+                           const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,
+                           float4* __restrict__ pairB, double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
   const IcpProblem& P = probs[blockIdx.y];
   if (blockIdx.x >= P.n_blocks) return;
   const IcpState& S = states[blockIdx.y];
   if (S.done) return;
   __shared__ double sT[12];
+  __shared__ MapDev sMap;
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
+  if (MULTI) stage_map(sMap, maps, P.map_idx);
   __syncthreads();
-  chunk_match_wl<4>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  if constexpr (MULTI) chunk_match_wl<4>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  else chunk_match_wl<4>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
 template <int MIN_BLOCKS>
@@ -990,16 +1008,19 @@ MLO_D void queue_push(const IcpQueue& q, uint32_t prob, uint32_t phase, uint32_t
 }
 
 // out-of-line copies for the persistent kernel: each phase keeps its own register allocation
+template <int TAG>
 __device__ __noinline__ void chunk_match_tpq_ool(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it,
                                                  uint32_t chunk, const float4* local, float4* pairA, float4* pairB,
                                                  double* partials, uint32_t* part_cnt) {
   chunk_match_tpq(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt);
 }
+template <int TAG>
 __device__ __noinline__ void chunk_match_warp_ool(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it,
                                                   uint32_t chunk, const float4* local, float4* pairA, float4* pairB,
                                                   double* partials, uint32_t* part_cnt, uint32_t qpw) {
   chunk_match_warp(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
 }
+template <int TAG>
 __device__ __noinline__ void chunk_accumulate_ool(const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                                                   const float4* local, const float4* pairA, const float4* pairB,
                                                   double* partials, uint32_t* part_cnt) {
@@ -1028,10 +1049,12 @@ __global__ void k_queue_build(const IcpProblem* __restrict__ probs, const IcpSta
   atomicAdd(&q.ctrl[2], 1u);
 }
 
-template <bool TPQ>
+template <bool TPQ, bool MULTI>
 __global__ void __launch_bounds__(ICP_BLOCK, 4)
-    k_icp_persistent(MapDev map, const IcpProblem* __restrict__ probs, IcpState* states, const float4* __restrict__ local,
-                     float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt, IcpQueue q, uint32_t qpw) {
+    k_icp_persistent(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs, IcpState* states,
+                     const float4* __restrict__ local, float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt,
+                     IcpQueue q, uint32_t qpw) {
+  __shared__ MapDev sMap;
   __shared__ uint32_t s_item;
   __shared__ int s_last;
   __shared__ double sT[12];
@@ -1066,14 +1089,16 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
     IcpState& S = states[prob];
     if (threadIdx.x < 12) sT[threadIdx.x] = __ldcg(&S.T[threadIdx.x]);
     if (threadIdx.x == 12) s_it = __ldcg(&S.it);
+    if (MULTI && phase == 0) stage_map(sMap, maps, P.map_idx);
     __syncthreads();
     if (phase == 0) {
-      if (TPQ)
-        chunk_match_tpq_ool(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
-      else
-        chunk_match_warp_ool(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+      constexpr int TAG = (TPQ ? 2 : 0) + (MULTI ? 1 : 0);  // one out-of-line copy per kernel instance
+      if constexpr (TPQ && MULTI) chunk_match_tpq_ool<TAG>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+      else if constexpr (TPQ) chunk_match_tpq_ool<TAG>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+      else if constexpr (MULTI) chunk_match_warp_ool<TAG>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+      else chunk_match_warp_ool<TAG>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
     } else {
-      chunk_accumulate_ool(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+      chunk_accumulate_ool<(TPQ ? 2 : 0) + (MULTI ? 1 : 0)>(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -10,8 +10,12 @@
 //   pts[capacity*cap]   float4 (x, y, z, 0): the <= cap points of voxel v at [v*cap, v*cap+count),
 //                       64-byte aligned rows, read as one coalesced warp load per cell.
 //   mean/normal[capacity] float4, NDT only: (mean xyz, is_plane) and (unit normal xyz, 0).
-// n_buckets = next power of two >= 2 * capacity_voxels.  No tombstones: culling is a filtered rebuild
-// into a second set of buffers.
+//   vkey[capacity]      u64 packed (kx, ky, kz) of voxel v, or KEY_EMPTY once v was culled; free_ids[capacity] is the
+//                       stack of culled voxel ids that the next inserts reuse before bumping counters[0].
+// n_buckets = table_factor * capacity_voxels (power of two).  Culling (insertOpts.remove_voxels_farther_than) is in
+// place: one thread per voxel id tests its key, clears the cell word of an out-of-range voxel and pushes the id on
+// the free stack; the emptied column buckets stay claimed (they keep probe chains intact) and are only compacted
+// by a rebuild into the second buffer set once claimed columns exceed half of the table.
 #pragma once
 #include "common.cuh"
 
@@ -37,7 +41,10 @@ struct MapDev {
   float4* pts;
   float4* mean;
   float4* normal;
-  uint32_t* counters;  // [0] voxels allocated, [1] points stored, [2] error bits
+  unsigned long long* vkey;  // per voxel id: packed (kx,ky,kz), KEY_EMPTY = culled
+  uint32_t* free_ids;        // stack of reusable voxel ids (counters[3] entries)
+  uint32_t* counters;  // [0] voxel ids handed out (high-water mark), [1] points stored, [2] error bits,
+                       // [3] free-stack size (int), [4] column buckets claimed, [5] voxels removed by the last cull
   uint32_t cap;  // max points per voxel (logical)
   uint32_t row;  // physical row length in float4 (cap rounded up to even: rows are 32-byte aligned)
   uint32_t capacity_voxels;
@@ -91,7 +98,10 @@ MLO_D uint64_t find_or_insert_column(const MapDev& m, uint64_t key) {
   for (uint64_t probes = 0; probes <= m.mask; probes++) {
     unsigned long long* kp = &m.buckets[h].key;
     unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-    if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+    if (cur == KEY_EMPTY) {
+      cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+      if (cur == KEY_EMPTY) atomicAdd(&m.counters[4], 1u);
+    }
     if (cur == KEY_EMPTY || cur == key) return h;
     h = (h + 1) & m.mask;
   }
@@ -108,8 +118,21 @@ MLO_D uint64_t find_or_insert_cell(const MapDev& m, int32_t kx, int32_t ky, int3
   uint32_t* cp = &m.buckets[b].cell[sub];
   if (*reinterpret_cast<volatile uint32_t*>(cp) == CELL_ABSENT) {
     if (atomicCAS(cp, CELL_ABSENT, CELL_PENDING) == CELL_ABSENT) {
-      const uint32_t v = atomicAdd(&m.counters[0], 1u);
-      if (v >= m.capacity_voxels) atomicOr(&m.counters[2], ERR_CAPACITY);
+      // payload id: reuse a culled voxel's row if the free stack has one (no pushes run concurrently with inserts)
+      uint32_t v;
+      int* fn = reinterpret_cast<int*>(&m.counters[3]);
+      int f = -1;
+      if (*reinterpret_cast<volatile int*>(fn) > 0) {
+        f = atomicSub(fn, 1) - 1;
+        if (f < 0) atomicAdd(fn, 1);  // lost the race for the last entry: undo
+      }
+      if (f >= 0) {
+        v = m.free_ids[f];
+      } else {
+        v = atomicAdd(&m.counters[0], 1u);
+        if (v >= m.capacity_voxels) atomicOr(&m.counters[2], ERR_CAPACITY);
+      }
+      if (v < m.capacity_voxels) m.vkey[v] = pack_key(kx, ky, kz);
       atomicExch(cp, cell_make(v, 0u));
     }
   }
@@ -305,6 +328,36 @@ __global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_buckets, int32_t sx
       dst.normal[nv] = src.normal[ov];
     }
   }
+}
+
+// In-place cull: one thread per voxel id below the high-water mark.  An out-of-range voxel loses its cell word
+// (the column bucket stays claimed), its id goes on the free stack and its points leave the statistics.
+__global__ void k_cull_inplace(MapDev m, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
+  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t hwm = min(*reinterpret_cast<volatile uint32_t*>(&m.counters[0]), m.capacity_voxels);
+  if (v >= hwm) return;
+  const unsigned long long key = m.vkey[v];
+  if (key == KEY_EMPTY) return;
+  int32_t kx, ky, kz;
+  unpack_key(key, kx, ky, kz);
+  if (!(abs(kx - sx) > d || abs(ky - sy) > d || abs(kz - sz) > d)) return;
+  const unsigned long long ck = column_key(kx, ky, kz);
+  uint64_t h = uint64_t(hash_packed(ck)) & m.mask;
+  for (uint64_t probes = 0; probes <= m.mask; probes++) {
+    const unsigned long long cur = m.buckets[h].key;
+    if (cur == ck) break;
+    if (cur == KEY_EMPTY) return;  // cannot happen: the voxel's column exists
+    h = (h + 1) & m.mask;
+  }
+  uint32_t* cp = &m.buckets[h].cell[kz & 3];
+  const uint32_t w = *cp;
+  if (w == CELL_ABSENT || cell_vid(w) != v) return;
+  *cp = CELL_ABSENT;
+  m.vkey[v] = KEY_EMPTY;
+  atomicSub(&m.counters[1], cell_cnt(w));
+  atomicAdd(&m.counters[5], 1u);
+  const int slot = atomicAdd(reinterpret_cast<int*>(&m.counters[3]), 1);
+  m.free_ids[slot] = v;
 }
 
 // ------------------------------------------------------------------ nearest neighbour

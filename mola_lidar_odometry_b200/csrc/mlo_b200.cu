@@ -97,7 +97,7 @@ struct mlo_ctx {
   // scratch
   DBuf d_in, d_local, d_pairA, d_pairB, d_partials, d_partcnt, d_probs, d_states, d_tables, d_init, d_misc;
   DBuf d_f_tab, d_f_pslot, d_f_flags, d_f_blk, d_f_jobs, d_f_cnt, d_f_stage1, d_f_map, d_f_icp;
-  DBuf d_ins_g, d_ins_slot, d_ins_next, d_queue, d_tchan;
+  DBuf d_ins_g, d_ins_slot, d_ins_next, d_queue, d_tchan, d_maps;
   HBuf h_misc, h_states, h_stage;
   // profiling
   bool prof_on = false;
@@ -119,6 +119,7 @@ struct mlo_map {
   bool alt_ready = false;
   uint64_t table_size = 0;  // number of 32-byte buckets
   int32_t* head = nullptr;  // per-cell (4 per bucket) scratch list heads for insert
+  uint64_t n_voxels = 0, n_points = 0;  // as of the last digest of the device counters
 };
 
 struct mlo_dcloud {
@@ -126,6 +127,23 @@ struct mlo_dcloud {
   float4* pts = nullptr;
   uint64_t n = 0;
   std::vector<uint64_t> offsets;  // n_clouds + 1
+};
+
+// Device-resident layers of n_slots scans (include/mlo_b200.h "scan sets").  A filter call packs its raw clouds
+// back to back; slot s keeps (offset, sizes) of where its layers sit in the shared buffers.
+struct mlo_scanset {
+  mlo_ctx* ctx = nullptr;
+  struct Slot {
+    bool valid = false;
+    uint64_t off = 0;  // in points, common to every buffer
+    uint32_t n_raw = 0, n_map = 0, n_icp = 0;
+  };
+  std::vector<Slot> slots;
+  bool skewed = false;     // the last filter call produced "_skewed" layers (x, y, z, t)
+  bool deskewed = false;   // ... and mlo_scanset_deskew has produced the final layers since
+  DBuf raw, tchan, mapS, icpS, mapL, icpL, cnt, bbox_jobs, bbox_out;
+  const float4* map_layer() const { return mapL.as<float4>(); }
+  const float4* icp_layer() const { return icpL.as<float4>(); }
 };
 
 namespace {
@@ -216,7 +234,9 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
   d.mask = table_size - 1;
   CU(c, cudaMalloc(&d.buckets, table_size * sizeof(Bucket)));
   CU(c, cudaMalloc(&d.pts, size_t(p.capacity_voxels) * d.row * sizeof(float4)));
-  CU(c, cudaMalloc(&d.counters, 4 * sizeof(uint32_t)));
+  CU(c, cudaMalloc(&d.counters, MAP_COUNTERS * sizeof(uint32_t)));
+  CU(c, cudaMalloc(&d.vkey, size_t(p.capacity_voxels) * sizeof(unsigned long long)));
+  CU(c, cudaMalloc(&d.free_ids, size_t(p.capacity_voxels) * sizeof(uint32_t)));
   d.mean = d.normal = nullptr;
   if (p.kind == MLO_MAP_NDT) {
     CU(c, cudaMalloc(&d.mean, size_t(p.capacity_voxels) * sizeof(float4)));
@@ -226,11 +246,13 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
 }
 int clear_map_buffers(mlo_ctx* c, MapDev& d, uint64_t table_size) {
   CU(c, cudaMemsetAsync(d.buckets, 0xFF, table_size * sizeof(Bucket), c->stream));
-  CU(c, cudaMemsetAsync(d.counters, 0, 4 * sizeof(uint32_t), c->stream));
+  CU(c, cudaMemsetAsync(d.counters, 0, MAP_COUNTERS * sizeof(uint32_t), c->stream));
   return MLO_OK;
 }
 void free_map_buffers(MapDev& d) {
   if (d.buckets) cudaFree(d.buckets);
+  if (d.vkey) cudaFree(d.vkey);
+  if (d.free_ids) cudaFree(d.free_ids);
   if (d.pts) cudaFree(d.pts);
   if (d.counters) cudaFree(d.counters);
   if (d.mean) cudaFree(d.mean);
@@ -238,17 +260,29 @@ void free_map_buffers(MapDev& d) {
   d = MapDev{};
 }
 
-int check_map_errors(mlo_map* m) {
+int map_rebuild(mlo_map* m, bool use_filter, int32_t sx, int32_t sy, int32_t sz, int32_t d);
+
+// Interpret one host copy of a map's counters (after a stream synchronize): error bits, statistics and the
+// compaction trigger (claimed column buckets above half of the table -> rebuild into the second buffer set).
+int digest_map_counters(mlo_map* m, const uint32_t* h) {
   mlo_ctx* c = m->ctx;
-  CU(c, c->h_misc.ensure(64));
-  uint32_t* h = c->h_misc.as<uint32_t>();
-  CU(c, cudaMemcpyAsync(h, m->dev.counters, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
   if (h[2] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
   if ((h[2] & ERR_CAPACITY) || h[0] > m->dev.capacity_voxels)
     return fail(c, MLO_ERR_CAPACITY, "map voxel capacity exhausted (" + std::to_string(h[0]) + " > " +
                                          std::to_string(m->dev.capacity_voxels) + ")");
+  m->n_voxels = uint64_t(h[0]) - uint64_t(h[3]);
+  m->n_points = h[1];
+  if (uint64_t(h[4]) * 2 > m->table_size) return map_rebuild(m, false, 0, 0, 0, 0);
   return MLO_OK;
+}
+
+int check_map_errors(mlo_map* m) {
+  mlo_ctx* c = m->ctx;
+  CU(c, c->h_misc.ensure(64));
+  uint32_t* h = c->h_misc.as<uint32_t>();
+  CU(c, cudaMemcpyAsync(h, m->dev.counters, MAP_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  return digest_map_counters(m, h);
 }
 
 // device-side insert of n points already on the device (float array with stride)
@@ -265,6 +299,15 @@ int map_insert_device(mlo_map* m, const float* d_pts, uint32_t stride, uint64_t 
          c->d_ins_slot.as<uint32_t>(), m->head, c->d_ins_next.as<int32_t>());
   LAUNCH(c, k_insert_commit, nb, 256, m->dev, uint32_t(n), c->d_ins_g.as<float4>(), c->d_ins_slot.as<uint32_t>(),
          m->head, c->d_ins_next.as<int32_t>());
+  CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+
+// in-place cull (no host synchronisation): thread per voxel id, early exit above the device-side high-water mark
+int map_cull_device(mlo_map* m, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
+  mlo_ctx* c = m->ctx;
+  CU(c, cudaMemsetAsync(m->dev.counters + 5, 0, sizeof(uint32_t), c->stream));
+  LAUNCH(c, k_cull_inplace, uint32_t((uint64_t(m->dev.capacity_voxels) + 255) / 256), 256, m->dev, sx, sy, sz, d);
   CU(c, cudaGetLastError());
   return MLO_OK;
 }
@@ -308,6 +351,10 @@ struct FilterBatch {
   uint32_t n_clouds = 0;
   std::vector<uint64_t> out_off;  // per-cloud output offset (== raw offset: outputs never exceed inputs)
   uint32_t max_n = 0;
+  // where the layers and the counters go; null = the context's scratch (d_f_map / d_f_icp / d_f_cnt)
+  DBuf* out_map = nullptr;
+  DBuf* out_icp = nullptr;
+  DBuf* out_cnt = nullptr;
 };
 constexpr uint32_t CNT_STRIDE = 8;
 
@@ -336,16 +383,19 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
   CU(c, c->d_f_pslot.ensure(2 * total * sizeof(uint32_t)));
   CU(c, c->d_f_flags.ensure(2 * total));
   CU(c, c->d_f_blk.ensure(2 * blk_total * 4 * sizeof(uint32_t)));
-  CU(c, c->d_f_cnt.ensure(size_t(n_clouds) * CNT_STRIDE * sizeof(uint32_t)));
+  DBuf& b_map = fb.out_map ? *fb.out_map : c->d_f_map;
+  DBuf& b_icp = fb.out_icp ? *fb.out_icp : c->d_f_icp;
+  DBuf& b_cnt = fb.out_cnt ? *fb.out_cnt : c->d_f_cnt;
+  CU(c, b_cnt.ensure(size_t(n_clouds) * CNT_STRIDE * sizeof(uint32_t)));
   CU(c, c->d_f_stage1.ensure(total * sizeof(float4)));
-  CU(c, c->d_f_map.ensure(total * sizeof(float4)));
-  CU(c, c->d_f_icp.ensure(total * sizeof(float4)));
+  CU(c, b_map.ensure(total * sizeof(float4)));
+  CU(c, b_icp.ensure(total * sizeof(float4)));
   CU(c, c->d_f_jobs.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
   CU(c, c->h_stage.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
 
   uint64_t* keys = c->d_f_tab.as<uint64_t>();
   uint32_t* firsts = reinterpret_cast<uint32_t*>(keys + 2 * tab_total);
-  uint32_t* cnt = c->d_f_cnt.as<uint32_t>();
+  uint32_t* cnt = b_cnt.as<uint32_t>();
   DecimJob* hj = c->h_stage.as<DecimJob>();
   for (uint32_t b = 0; b < n_clouds; b++) {
     const uint32_t n = uint32_t(offsets[b + 1] - offsets[b]);
@@ -379,9 +429,9 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
     j2.n_in_dev = cnt + b * CNT_STRIDE + 0;
     fill_decim(j2, fps[b].for_icp, true);
     j2.npred = cnt + b * CNT_STRIDE + 4;
-    j2.outA = c->d_f_map.as<float4>() + offsets[b];
+    j2.outA = b_map.as<float4>() + offsets[b];
     j2.nA = cnt + b * CNT_STRIDE + 1;
-    j2.outB = c->d_f_icp.as<float4>() + offsets[b];
+    j2.outB = b_icp.as<float4>() + offsets[b];
     j2.nB = cnt + b * CNT_STRIDE + 2;
   }
   const int n_stages = single_decimate_idx ? 1 : 2;
@@ -411,6 +461,39 @@ __global__ void k_soa_to_float4(const float* __restrict__ x, const float* __rest
   const uint64_t i = uint64_t(blockIdx.x) * blockDim.x + threadIdx.x;
   if (i >= n) return;
   dst[i] = make_float4(x[i], y[i], z[i], 0.f);
+}
+
+// axis-aligned bounding box of each listed cloud (one block per cloud): out[6*j] = min xyz, max xyz
+struct BBoxJob {
+  const float4* p;
+  uint32_t n;
+};
+__global__ void __launch_bounds__(256) k_bbox(const BBoxJob* __restrict__ jobs, float* __restrict__ out) {
+  const BBoxJob j = jobs[blockIdx.x];
+  float mn[3] = {INFINITY, INFINITY, INFINITY}, mx[3] = {-INFINITY, -INFINITY, -INFINITY};
+  for (uint32_t i = threadIdx.x; i < j.n; i += blockDim.x) {
+    const float4 p = __ldg(&j.p[i]);
+    mn[0] = fminf(mn[0], p.x); mn[1] = fminf(mn[1], p.y); mn[2] = fminf(mn[2], p.z);
+    mx[0] = fmaxf(mx[0], p.x); mx[1] = fmaxf(mx[1], p.y); mx[2] = fmaxf(mx[2], p.z);
+  }
+  __shared__ float s[8][6];
+  for (int k = 0; k < 3; k++)
+    for (int o = 16; o > 0; o >>= 1) {
+      mn[k] = fminf(mn[k], __shfl_xor_sync(0xFFFFFFFFu, mn[k], o));
+      mx[k] = fmaxf(mx[k], __shfl_xor_sync(0xFFFFFFFFu, mx[k], o));
+    }
+  const uint32_t w = threadIdx.x >> 5;
+  if ((threadIdx.x & 31u) == 0)
+    for (int k = 0; k < 3; k++) {
+      s[w][k] = mn[k];
+      s[w][3 + k] = mx[k];
+    }
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float v = s[0][threadIdx.x];
+    for (uint32_t q = 1; q < blockDim.x / 32; q++) v = threadIdx.x < 3 ? fminf(v, s[q][threadIdx.x]) : fmaxf(v, s[q][threadIdx.x]);
+    out[6 * blockIdx.x + threadIdx.x] = v;
+  }
 }
 
 int upload_strided(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t n, DBuf& dst) {
@@ -449,10 +532,44 @@ int issue_deferred_uploads(mlo_ctx* c, int except_slot) {
   return MLO_OK;
 }
 
-// The batched align driver over device-resident float4 local points.
-int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64_t* offsets, const mlo_map* map,
-                       const double* init_poses, const mlo_icp_params* params, mlo_icp_result* out) {
+void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const MapDev& map, const MapDev* d_maps,
+                       const IcpProblem* dP, IcpState* dS, const float4* d_local, const IcpQueue& q, uint32_t qpw) {
+#define MLO_PERS(T, M, QPW)                                                                                              \
+  LAUNCH(c, (k_icp_persistent<T, M>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),            \
+         c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW)
+  if (tpq && multi) MLO_PERS(true, true, 0u);
+  else if (tpq) MLO_PERS(true, false, 0u);
+  else if (multi) MLO_PERS(false, true, qpw);
+  else MLO_PERS(false, false, qpw);
+#undef MLO_PERS
+}
+
+// The batched align driver over device-resident float4 local points.  Problem b reads local points
+// [q_begin[b], q_begin[b] + n_q[b]) of d_local and matches against maps[b] (all equal: the read-only-map batch of
+// config[1]; different: a fleet of independent sequences advanced in lock step, one local map each).
+int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64_t* q_begin, const uint32_t* n_q,
+                     const mlo_map* const* maps, const double* init_poses, const mlo_icp_params* params, mlo_icp_result* out) {
   if (B == 0) return MLO_OK;
+  // ---- map table
+  std::vector<const mlo_map*> uniq;
+  std::vector<uint32_t> map_idx(B, 0);
+  for (uint32_t b = 0; b < B; b++) {
+    if (!maps[b]) return fail(c, MLO_ERR_INVALID_ARG, "null map");
+    size_t k = 0;
+    while (k < uniq.size() && uniq[k] != maps[b]) k++;
+    if (k == uniq.size()) uniq.push_back(maps[b]);
+    map_idx[b] = uint32_t(k);
+  }
+  const bool multi = uniq.size() > 1;
+  const mlo_map* map = uniq[0];
+  const MapDev* d_maps = nullptr;
+  if (multi) {
+    std::vector<MapDev> hm(uniq.size());
+    for (size_t k = 0; k < uniq.size(); k++) hm[k] = uniq[k]->dev;
+    CU(c, c->d_maps.ensure(hm.size() * sizeof(MapDev)));
+    CU(c, cudaMemcpyAsync(c->d_maps.p, hm.data(), hm.size() * sizeof(MapDev), cudaMemcpyHostToDevice, c->stream));
+    d_maps = c->d_maps.as<MapDev>();
+  }
   // ---- problems + tables
   std::vector<IcpProblem> probs(B);
   std::vector<double> tables;
@@ -469,7 +586,11 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   std::vector<size_t> toff(3 * size_t(B));
   uint32_t part_total = 0, max_blocks = 0, max_blocks_acc = 0, max_it = 0, max_inner = 1;
   // queries per warp: 32 when the batch alone fills the machine, fewer for latency-bound small batches
-  const uint64_t total_queries = offsets[B];
+  uint64_t total_queries = 0, q_end = 0;
+  for (uint32_t b = 0; b < B; b++) {
+    total_queries += n_q[b];
+    q_end = std::max(q_end, q_begin[b] + n_q[b]);
+  }
   uint32_t qpw = 32;
   const uint32_t qpw_floor = total_queries >= 256 ? 4u : 1u;  // below 4 the per-block reduction dominates the chunk
   while (qpw > qpw_floor && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
@@ -480,14 +601,15 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     const mlo_icp_params& p = params[b];
     IcpProblem& P = probs[b];
     std::memset(&P, 0, sizeof(P));
-    if ((p.matcher_mask & MLO_MATCHER_PT2PL) && map->prm.kind != MLO_MAP_NDT)
+    if ((p.matcher_mask & MLO_MATCHER_PT2PL) && maps[b]->prm.kind != MLO_MAP_NDT)
       return fail(c, MLO_ERR_UNSUPPORTED, "Matcher_Point2Plane needs an NDT map");
     if (p.solver == MLO_SOLVER_HORN && (p.matcher_mask & MLO_MATCHER_PT2PL))
       return fail(c, MLO_ERR_UNSUPPORTED, "Solver_Horn handles point-to-point pairings only");
     if (p.table_len == 0 || !p.pt2pt_threshold_by_iter || !p.kernel_param_by_iter)
       if (p.matcher_mask & MLO_MATCHER_PT2PT) return fail(c, MLO_ERR_INVALID_ARG, "missing per-iteration tables");
-    P.q_begin = offsets[b];
-    P.n_q = uint32_t(offsets[b + 1] - offsets[b]);
+    P.q_begin = q_begin[b];
+    P.n_q = n_q[b];
+    P.map_idx = map_idx[b];
     P.max_iterations = p.max_iterations;
     P.min_abs_step_trans = p.min_abs_step_trans;
     P.min_abs_step_rot = p.min_abs_step_rot;
@@ -511,9 +633,9 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     P.hook_min_trans = p.hook_min_trans;
     P.hook_min_rot = p.hook_min_rot_rad;
     std::memcpy(P.hook_checkpoint, p.hook_checkpoint_pose_3x4, sizeof(P.hook_checkpoint));
-    const bool use_wl = use_tpq && c->force_kernel != 1;
+    const bool use_wl = use_tpq && (multi || c->force_kernel != 1);
     const uint32_t qpb_pers = use_tpq ? ICP_BLOCK : (ICP_BLOCK / 32) * qpw;  // persistent kernel: tpq or warp chunks
-    const uint32_t qpb = use_wl ? (c->wl_warps == 4 ? ICP_BLOCK : WL_BLOCK) : qpb_pers;  // launch sequence: work-list chunks
+    const uint32_t qpb = use_wl ? ((multi || c->wl_warps == 4) ? ICP_BLOCK : WL_BLOCK) : qpb_pers;  // launch sequence: work-list chunks
     P.n_blocks = (P.n_q + qpb - 1) / qpb;
     P.n_blocks_pers = (P.n_q + qpb_pers - 1) / qpb_pers;
     P.n_blocks_acc = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
@@ -533,7 +655,7 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
     probs[b].thr_pt2pl = toff[3 * b + 1] == size_t(-1) ? nullptr : base + toff[3 * b + 1];
     probs[b].kparam = toff[3 * b + 2] == size_t(-1) ? nullptr : base + toff[3 * b + 2];
   }
-  const uint64_t total_q = offsets[B];
+  const uint64_t total_q = q_end;
   CU(c, c->d_probs.ensure(B * sizeof(IcpProblem)));
   CU(c, c->d_states.ensure(B * sizeof(IcpState)));
   CU(c, c->d_init.ensure(B * 12 * sizeof(double)));
@@ -597,17 +719,12 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
       CU(c, cudaMemsetAsync(q.phase_cnt, 0, B * sizeof(uint32_t), c->stream));
       if (c->persistent_blocks == 0) {
         int per_sm = 0;
-        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true>, ICP_BLOCK, 0));
+        CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true, true>, ICP_BLOCK, 0));
         c->persistent_blocks = std::max(1, per_sm) * c->sm_count;
       }
       const uint32_t nblk = std::min<uint32_t>(uint32_t(c->persistent_blocks), std::max<uint32_t>(part_total, 1u));
       const size_t e_nn = prof_begin(c);
-      if (use_tpq)
-        LAUNCH(c, k_icp_persistent<true>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-               c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, 0u);
-      else
-        LAUNCH(c, k_icp_persistent<false>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-               c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, qpw);
+      launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
       prof_end(c, 3, e_nn);
       CU(c, cudaMemcpyAsync(h_active, q.ctrl + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
@@ -632,13 +749,19 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
       IcpState* gS = dS + g0;
       const dim3 grid_g(grid.x, Bg), grid_acc_g(grid_acc.x, Bg);
       const size_t e_nn = g == 0 ? prof_begin(c) : 0;
-      if (use_tpq && c->force_kernel != 1) {
+      if (multi && use_tpq) {
+        LAUNCH_ON(c, sg, k_match_accumulate_wl4<true>, grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,
+                  c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+      } else if (multi) {
+        LAUNCH_ON(c, sg, k_match_accumulate<true>, grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,
+                  c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
+      } else if (use_tpq && c->force_kernel != 1) {
 #define MLO_WL_LAUNCH(MB)                                                                                              \
   LAUNCH_ON(c, sg, k_match_accumulate_wl<MB>, grid_g, WL_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),   \
             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
         if (c->wl_warps == 4)
-          LAUNCH_ON(c, sg, k_match_accumulate_wl4, grid_g, ICP_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),
-                    c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+          LAUNCH_ON(c, sg, k_match_accumulate_wl4<false>, grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,
+                    c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
         else switch (c->wl_min_blocks) {
           case 16: MLO_WL_LAUNCH(16); break;
           case 24: MLO_WL_LAUNCH(24); break;
@@ -648,8 +771,8 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
         LAUNCH_ON(c, sg, k_match_accumulate_tpq, grid_g, ICP_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),
                   c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
       else
-        LAUNCH_ON(c, sg, k_match_accumulate, grid_g, ICP_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),
-                  c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
+        LAUNCH_ON(c, sg, k_match_accumulate<false>, grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,
+                  c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
       if (g == 0) prof_end(c, 3, e_nn);
       LAUNCH_ON(c, sg, k_solve, Bg, 32, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
       for (uint32_t inner = 1; inner < max_inner; inner++) {
@@ -685,17 +808,12 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
         LAUNCH(c, k_queue_build, (B + 127) / 128, 128, dP, dS, q, B);
         if (c->persistent_blocks == 0) {
           int per_sm = 0;
-          CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true>, ICP_BLOCK, 0));
+          CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true, true>, ICP_BLOCK, 0));
           c->persistent_blocks = std::max(1, per_sm) * c->sm_count;
         }
         const uint32_t nblk = std::min<uint32_t>(uint32_t(c->persistent_blocks), std::max<uint32_t>(part_total, 1u));
         const size_t e_nn = prof_begin(c);
-        if (use_tpq)
-          LAUNCH(c, k_icp_persistent<true>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-                 c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, 0u);
-        else
-          LAUNCH(c, k_icp_persistent<false>, nblk, ICP_BLOCK, map->dev, dP, dS, d_local, c->d_pairA.as<float4>(),
-                 c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, qpw);
+        launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
         prof_end(c, 3, e_nn);
         CU(c, cudaMemcpyAsync(h_active, q.ctrl + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
@@ -730,6 +848,15 @@ int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint
   }
   prof_collect(c);
   return MLO_OK;
+}
+
+int align_batch_device(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64_t* offsets, const mlo_map* map,
+                       const double* init_poses, const mlo_icp_params* params, mlo_icp_result* out) {
+  std::vector<uint64_t> qb(offsets, offsets + B);
+  std::vector<uint32_t> nq(B);
+  for (uint32_t b = 0; b < B; b++) nq[b] = uint32_t(offsets[b + 1] - offsets[b]);
+  std::vector<const mlo_map*> maps(B, map);
+  return align_batch_core(c, B, d_local, qb.data(), nq.data(), maps.data(), init_poses, params, out);
 }
 
 }  // namespace
@@ -789,7 +916,7 @@ void mlo_destroy(mlo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DBuf* b : {&c->d_in, &c->d_local, &c->d_pairA, &c->d_pairB, &c->d_partials, &c->d_partcnt, &c->d_probs, &c->d_states,
                   &c->d_tables, &c->d_init, &c->d_misc, &c->d_f_tab, &c->d_f_pslot, &c->d_f_flags, &c->d_f_blk, &c->d_f_jobs,
-                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan})
+                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan, &c->d_maps})
     b->release();
   c->h_misc.release();
   c->h_states.release();
@@ -918,7 +1045,7 @@ int mlo_map_cull(mlo_map* m, const double sensor[3], float dist) {
                 sz = voxel_index_map(float(sensor[2]), inv);
   const int32_t d = int32_t(std::ceil(dist * inv));
   const size_t e0 = prof_begin(c);
-  int rc = map_rebuild(m, true, sx, sy, sz, d);
+  int rc = map_cull_device(m, sx, sy, sz, d);
   prof_end(c, 2, e0);
   if (rc != MLO_OK) return rc;
   rc = check_map_errors(m);
@@ -975,10 +1102,10 @@ int mlo_map_stats(const mlo_map* m, uint64_t* n_voxels, uint64_t* n_points) {
   if (!m) return MLO_ERR_INVALID_ARG;
   mlo_ctx* c = m->ctx;
   DeviceGuard g(c->device);
-  uint32_t h[4];
+  uint32_t h[MAP_COUNTERS];
   CU(c, cudaMemcpyAsync(h, m->dev.counters, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  if (n_voxels) *n_voxels = std::min<uint32_t>(h[0], m->dev.capacity_voxels);
+  if (n_voxels) *n_voxels = uint64_t(std::min<uint32_t>(h[0], m->dev.capacity_voxels)) - h[3];
   if (n_points) *n_points = h[1];
   return MLO_OK;
 }
@@ -1281,21 +1408,16 @@ static int scan_register_device(mlo_ctx* c, const mlo_map* map, uint32_t B, cons
   std::vector<uint32_t> h(size_t(B) * CNT_STRIDE);
   CU(c, cudaMemcpyAsync(h.data(), c->d_f_cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
-  // compact the per-cloud ICP layers into one contiguous problem array (offsets of the align batch)
-  std::vector<uint64_t> qoff(B + 1, 0);
+  // the ICP layers stay where the filter wrote them (at the raw offsets): problem b = [offsets[b], offsets[b] + n_icp)
+  std::vector<uint64_t> qb(offsets, offsets + B);
+  std::vector<uint32_t> nq(B);
+  std::vector<const mlo_map*> maps(B, map);
   for (uint32_t b = 0; b < B; b++) {
     if (h[b * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
-    qoff[b + 1] = qoff[b] + h[b * CNT_STRIDE + 2];
+    nq[b] = h[b * CNT_STRIDE + 2];
     if (map_layer_n) (*map_layer_n)[b] = h[b * CNT_STRIDE + 1];
   }
-  CU(c, c->d_local.ensure(std::max<uint64_t>(qoff[B], 1) * sizeof(float4)));
-  for (uint32_t b = 0; b < B; b++) {
-    const uint64_t nb = qoff[b + 1] - qoff[b];
-    if (nb)
-      CU(c, cudaMemcpyAsync(c->d_local.as<float4>() + qoff[b], c->d_f_icp.as<float4>() + offsets[b], nb * sizeof(float4),
-                            cudaMemcpyDeviceToDevice, c->stream));
-  }
-  return align_batch_device(c, B, c->d_local.as<float4>(), qoff.data(), map, init_poses, ips, out);
+  return align_batch_core(c, B, c->d_f_icp.as<float4>(), qb.data(), nq.data(), maps.data(), init_poses, ips, out);
 }
 
 int mlo_scan_register_batch_resident(mlo_ctx* c, const mlo_map* map, const mlo_dcloud* raw, const mlo_filter1_params* fps,
@@ -1369,8 +1491,8 @@ int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t strid
     if (cull_farther_than > 0.f) {
       const double s[3] = {out->pose_3x4[3], out->pose_3x4[7], out->pose_3x4[11]};
       const float inv = map->dev.inv_voxel;
-      rc = map_rebuild(map, true, voxel_index_map(float(s[0]), inv), voxel_index_map(float(s[1]), inv),
-                       voxel_index_map(float(s[2]), inv), int32_t(std::ceil(cull_farther_than * inv)));
+      rc = map_cull_device(map, voxel_index_map(float(s[0]), inv), voxel_index_map(float(s[1]), inv),
+                           voxel_index_map(float(s[2]), inv), int32_t(std::ceil(cull_farther_than * inv)));
       if (rc != MLO_OK) return rc;
     }
     prof_end(c, 2, e0);
@@ -1378,6 +1500,232 @@ int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t strid
     prof_collect(c);
   }
   return rc;
+}
+
+// ------------------------------------------------------------------ scan sets (device-resident layers, fleets)
+static int scanset_bbox(mlo_scanset* set, uint32_t n, const uint32_t* slots, mlo_scan_info* info) {
+  mlo_ctx* c = set->ctx;
+  if (n == 0) return MLO_OK;
+  std::vector<BBoxJob> jobs(n);
+  for (uint32_t i = 0; i < n; i++) {
+    const auto& sl = set->slots[slots[i]];
+    jobs[i].p = set->icp_layer() + sl.off;
+    jobs[i].n = sl.valid ? sl.n_icp : 0;
+  }
+  CU(c, set->bbox_jobs.ensure(n * sizeof(BBoxJob)));
+  CU(c, set->bbox_out.ensure(n * 6 * sizeof(float)));
+  CU(c, cudaMemcpyAsync(set->bbox_jobs.p, jobs.data(), n * sizeof(BBoxJob), cudaMemcpyHostToDevice, c->stream));
+  LAUNCH(c, k_bbox, n, 256, set->bbox_jobs.as<BBoxJob>(), set->bbox_out.as<float>());
+  std::vector<float> h(6 * size_t(n));
+  CU(c, cudaMemcpyAsync(h.data(), set->bbox_out.p, h.size() * sizeof(float), cudaMemcpyDeviceToHost, c->stream));
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  for (uint32_t i = 0; i < n; i++) {
+    const auto& sl = set->slots[slots[i]];
+    info[i].n_map = sl.n_map;
+    info[i].n_icp = sl.n_icp;
+    for (int k = 0; k < 3; k++) {
+      info[i].icp_min[k] = sl.n_icp ? h[6 * i + k] : 0.f;
+      info[i].icp_max[k] = sl.n_icp ? h[6 * i + 3 + k] : 0.f;
+    }
+  }
+  return MLO_OK;
+}
+
+int mlo_scanset_create(mlo_ctx* c, uint32_t n_slots, mlo_scanset** out) {
+  if (!c || !out || n_slots == 0) return MLO_ERR_INVALID_ARG;
+  auto* s = new mlo_scanset();
+  s->ctx = c;
+  s->slots.resize(n_slots);
+  *out = s;
+  return MLO_OK;
+}
+
+void mlo_scanset_destroy(mlo_scanset* s) {
+  if (!s) return;
+  DeviceGuard g(s->ctx->device);
+  cudaStreamSynchronize(s->ctx->stream);
+  for (DBuf* b : {&s->raw, &s->tchan, &s->mapS, &s->icpS, &s->mapL, &s->icpL, &s->cnt, &s->bbox_jobs, &s->bbox_out}) b->release();
+  delete s;
+}
+
+int mlo_scanset_filter(mlo_scanset* set, uint32_t n_jobs, const mlo_scan_job* jobs, uint32_t stride, mlo_scan_info* info) {
+  if (!set || (n_jobs && (!jobs || !info))) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = set->ctx;
+  if (stride != 3 && stride != 4) return fail(c, MLO_ERR_INVALID_ARG, "stride_floats must be 3 or 4");
+  DeviceGuard g(c->device);
+  for (auto& sl : set->slots) sl = mlo_scanset::Slot{};
+  set->skewed = set->deskewed = false;
+  if (n_jobs == 0) return MLO_OK;
+  std::vector<uint64_t> off(n_jobs + 1, 0);
+  std::vector<mlo_filter1_params> fps(n_jobs);
+  bool any_t = false;
+  for (uint32_t j = 0; j < n_jobs; j++) {
+    if (jobs[j].slot >= set->slots.size() || (jobs[j].n && !jobs[j].pts)) return fail(c, MLO_ERR_INVALID_ARG, "bad scan job");
+    if (set->slots[jobs[j].slot].valid) return fail(c, MLO_ERR_INVALID_ARG, "two jobs for one slot");
+    set->slots[jobs[j].slot].valid = true;
+    off[j + 1] = off[j] + jobs[j].n;
+    fps[j] = jobs[j].fp;
+    any_t = any_t || (jobs[j].t && jobs[j].n);
+  }
+  const uint64_t total = off[n_jobs];
+  CU(c, set->raw.ensure(std::max<size_t>(total * stride * sizeof(float), 16)));
+  for (uint32_t j = 0; j < n_jobs; j++)
+    if (jobs[j].n)
+      CU(c, cudaMemcpyAsync(set->raw.as<float>() + off[j] * stride, jobs[j].pts, jobs[j].n * stride * sizeof(float),
+                            cudaMemcpyHostToDevice, c->stream));
+  const float* d_t = nullptr;
+  if (any_t) {
+    CU(c, set->tchan.ensure(std::max<size_t>(total * sizeof(float), 16)));
+    for (uint32_t j = 0; j < n_jobs; j++) {
+      if (!jobs[j].n) continue;
+      if (jobs[j].t)
+        CU(c, cudaMemcpyAsync(set->tchan.as<float>() + off[j], jobs[j].t, jobs[j].n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
+      else
+        CU(c, cudaMemsetAsync(set->tchan.as<float>() + off[j], 0, jobs[j].n * sizeof(float), c->stream));
+    }
+    d_t = set->tchan.as<float>();
+  }
+  FilterBatch fb;
+  fb.out_map = any_t ? &set->mapS : &set->mapL;
+  fb.out_icp = any_t ? &set->icpS : &set->icpL;
+  fb.out_cnt = &set->cnt;
+  const size_t e0 = prof_begin(c);
+  int rc = run_filter_batch(c, set->raw.as<float>(), stride, n_jobs, off.data(), fps.data(), false, nullptr, fb, d_t);
+  prof_end(c, 0, e0);
+  if (rc != MLO_OK) return rc;
+  std::vector<uint32_t> h(size_t(n_jobs) * CNT_STRIDE, 0u);
+  if (total) {
+    CU(c, cudaMemcpyAsync(h.data(), set->cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+  }
+  std::vector<uint32_t> sl_idx(n_jobs);
+  for (uint32_t j = 0; j < n_jobs; j++) {
+    if (h[j * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+    auto& sl = set->slots[jobs[j].slot];
+    sl.off = off[j];
+    sl.n_raw = uint32_t(jobs[j].n);
+    sl.n_map = h[j * CNT_STRIDE + 1];
+    sl.n_icp = h[j * CNT_STRIDE + 2];
+    sl_idx[j] = jobs[j].slot;
+  }
+  set->skewed = any_t;
+  if (any_t) {
+    // the final layers do not exist before mlo_scanset_deskew: report sizes only
+    CU(c, set->mapL.ensure(std::max<size_t>(total, 1) * sizeof(float4)));
+    CU(c, set->icpL.ensure(std::max<size_t>(total, 1) * sizeof(float4)));
+    for (uint32_t j = 0; j < n_jobs; j++) {
+      info[j] = mlo_scan_info{};
+      info[j].n_map = set->slots[jobs[j].slot].n_map;
+      info[j].n_icp = set->slots[jobs[j].slot].n_icp;
+    }
+    prof_collect(c);
+    return MLO_OK;
+  }
+  rc = scanset_bbox(set, n_jobs, sl_idx.data(), info);
+  prof_collect(c);
+  return rc;
+}
+
+int mlo_scanset_deskew(mlo_scanset* set, uint32_t n, const uint32_t* slots, const double* twists6, mlo_scan_info* info) {
+  if (!set || (n && (!slots || !twists6 || !info))) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = set->ctx;
+  DeviceGuard g(c->device);
+  if (!set->skewed) return fail(c, MLO_ERR_INVALID_ARG, "the set holds no skewed layers (filter ran without timestamps)");
+  const size_t e0 = prof_begin(c);
+  for (uint32_t i = 0; i < n; i++) {
+    if (slots[i] >= set->slots.size() || !set->slots[slots[i]].valid) return fail(c, MLO_ERR_INVALID_ARG, "bad slot");
+    const auto& sl = set->slots[slots[i]];
+    Twist6 tw;
+    std::memcpy(tw.v, twists6 + 6 * size_t(i), sizeof(tw.v));
+    if (sl.n_map)
+      LAUNCH(c, k_deskew, (sl.n_map + 255) / 256, 256, set->mapS.as<float4>() + sl.off, sl.n_map, tw, set->mapL.as<float4>() + sl.off);
+    if (sl.n_icp)
+      LAUNCH(c, k_deskew, (sl.n_icp + 255) / 256, 256, set->icpS.as<float4>() + sl.off, sl.n_icp, tw, set->icpL.as<float4>() + sl.off);
+  }
+  prof_end(c, 0, e0);
+  set->deskewed = true;
+  int rc = scanset_bbox(set, n, slots, info);
+  prof_collect(c);
+  return rc;
+}
+
+int mlo_scanset_align(mlo_scanset* set, uint32_t n_jobs, const mlo_align_job* jobs, mlo_icp_result* out) {
+  if (!set || (n_jobs && (!jobs || !out))) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = set->ctx;
+  DeviceGuard g(c->device);
+  if (set->skewed && !set->deskewed) return fail(c, MLO_ERR_INVALID_ARG, "skewed layers: call mlo_scanset_deskew first");
+  std::vector<uint64_t> qb(n_jobs);
+  std::vector<uint32_t> nq(n_jobs);
+  std::vector<const mlo_map*> maps(n_jobs);
+  std::vector<double> init(12 * size_t(n_jobs));
+  std::vector<mlo_icp_params> prm(n_jobs);
+  for (uint32_t j = 0; j < n_jobs; j++) {
+    if (jobs[j].slot >= set->slots.size() || !set->slots[jobs[j].slot].valid || !jobs[j].map)
+      return fail(c, MLO_ERR_INVALID_ARG, "bad align job");
+    if (jobs[j].map->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "map belongs to another context");
+    const auto& sl = set->slots[jobs[j].slot];
+    qb[j] = sl.off;
+    nq[j] = sl.n_icp;
+    maps[j] = jobs[j].map;
+    std::memcpy(&init[12 * size_t(j)], jobs[j].init_pose_3x4, 12 * sizeof(double));
+    prm[j] = jobs[j].params;
+  }
+  return align_batch_core(c, n_jobs, set->icp_layer(), qb.data(), nq.data(), maps.data(), init.data(), prm.data(), out);
+}
+
+int mlo_scanset_insert(mlo_scanset* set, uint32_t n_jobs, const mlo_insert_job* jobs, mlo_map_counts* out) {
+  if (!set || (n_jobs && !jobs)) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = set->ctx;
+  DeviceGuard g(c->device);
+  if (set->skewed && !set->deskewed) return fail(c, MLO_ERR_INVALID_ARG, "skewed layers: call mlo_scanset_deskew first");
+  if (n_jobs == 0) return MLO_OK;
+  CU(c, c->h_misc.ensure(std::max<size_t>(256, size_t(n_jobs) * MAP_COUNTERS * sizeof(uint32_t))));
+  uint32_t* h = c->h_misc.as<uint32_t>();
+  const size_t e0 = prof_begin(c);
+  for (uint32_t j = 0; j < n_jobs; j++) {
+    if (jobs[j].slot >= set->slots.size() || !set->slots[jobs[j].slot].valid || !jobs[j].map)
+      return fail(c, MLO_ERR_INVALID_ARG, "bad insert job");
+    mlo_map* m = jobs[j].map;
+    if (m->ctx != c) return fail(c, MLO_ERR_INVALID_ARG, "map belongs to another context");
+    const auto& sl = set->slots[jobs[j].slot];
+    int rc = map_insert_device(m, reinterpret_cast<const float*>(set->map_layer() + sl.off), 4, sl.n_map, jobs[j].pose_3x4);
+    if (rc != MLO_OK) return rc;
+    if (jobs[j].cull_farther_than > 0.f) {
+      const float inv = m->dev.inv_voxel;
+      rc = map_cull_device(m, voxel_index_map(float(jobs[j].pose_3x4[3]), inv), voxel_index_map(float(jobs[j].pose_3x4[7]), inv),
+                           voxel_index_map(float(jobs[j].pose_3x4[11]), inv), int32_t(std::ceil(jobs[j].cull_farther_than * inv)));
+      if (rc != MLO_OK) return rc;
+    }
+    CU(c, cudaMemcpyAsync(h + size_t(j) * MAP_COUNTERS, m->dev.counters, MAP_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost,
+                          c->stream));
+  }
+  prof_end(c, 2, e0);
+  CU(c, cudaStreamSynchronize(c->stream));
+  CU(c, cudaGetLastError());
+  std::vector<uint32_t> hc(h, h + size_t(n_jobs) * MAP_COUNTERS);  // digest may reuse h_misc (rebuild path)
+  for (uint32_t j = 0; j < n_jobs; j++) {
+    int rc = digest_map_counters(jobs[j].map, &hc[size_t(j) * MAP_COUNTERS]);
+    if (rc != MLO_OK) return rc;
+    if (out) {
+      out[j].n_voxels = jobs[j].map->n_voxels;
+      out[j].n_points = jobs[j].map->n_points;
+    }
+  }
+  prof_collect(c);
+  return MLO_OK;
+}
+
+int mlo_scanset_download(mlo_scanset* set, uint32_t slot, int layer, float* out_xyz, uint64_t max_points, uint64_t* n) {
+  if (!set || !n || slot >= set->slots.size() || (layer != 0 && layer != 1)) return MLO_ERR_INVALID_ARG;
+  mlo_ctx* c = set->ctx;
+  DeviceGuard g(c->device);
+  const auto& sl = set->slots[slot];
+  *n = sl.valid ? (layer == 0 ? sl.n_map : sl.n_icp) : 0;
+  if (!out_xyz || *n == 0) return MLO_OK;
+  if (*n > max_points) return fail(c, MLO_ERR_INVALID_ARG, "download buffer too small");
+  if (set->skewed && !set->deskewed) return fail(c, MLO_ERR_INVALID_ARG, "skewed layers: call mlo_scanset_deskew first");
+  return download_xyz(c, (layer == 0 ? set->map_layer() : set->icp_layer()) + sl.off, *n, out_xyz);
 }
 
 // ------------------------------------------------------------------ profiling

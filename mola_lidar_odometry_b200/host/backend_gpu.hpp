@@ -27,30 +27,25 @@ struct BackendGpu {
   }
   void map_cull(void* m, const double* sensor, float dist) { check(mlo_map_cull(static_cast<mlo_map*>(m), sensor, dist)); }
   void map_stats(void* m, uint64_t& nv, uint64_t& np) { check(mlo_map_stats(static_cast<mlo_map*>(m), &nv, &np)); }
-  void filter_1st_pass(const float* pts, uint32_t stride, uint64_t n, const mlo_filter1_params& f, std::vector<float>& map_xyz,
-                       std::vector<float>& icp_xyz) {
-    map_xyz.resize(3 * n);
-    icp_xyz.resize(3 * n);
-    uint64_t na = 0, nb = 0;
-    check(mlo_filter_1st_pass(ctx, pts, stride, n, &f, map_xyz.data(), &na, icp_xyz.data(), &nb));
-    map_xyz.resize(3 * na);
-    icp_xyz.resize(3 * nb);
+  // scan sets: the layers of an observation stay in HBM between the filter, align and insert calls
+  using ScanSet = mlo_scanset;
+  ScanSet* scanset_create(uint32_t n_slots) {
+    mlo_scanset* s = nullptr;
+    check(mlo_scanset_create(ctx, n_slots, &s));
+    return s;
   }
-  void filter_1st_pass_xyzt(const float* pts, uint32_t stride, const float* t, uint64_t n, const mlo_filter1_params& f,
-                            std::vector<float>& map_xyzt, std::vector<float>& icp_xyzt) {
-    map_xyzt.resize(4 * n);
-    icp_xyzt.resize(4 * n);
-    uint64_t na = 0, nb = 0;
-    check(mlo_filter_1st_pass_xyzt(ctx, pts, stride, t, n, &f, map_xyzt.data(), &na, icp_xyzt.data(), &nb));
-    map_xyzt.resize(4 * na);
-    icp_xyzt.resize(4 * nb);
+  void scanset_destroy(ScanSet* s) { mlo_scanset_destroy(s); }
+  void scanset_filter(ScanSet* s, uint32_t n, const mlo_scan_job* jobs, uint32_t stride, mlo_scan_info* info) {
+    check(mlo_scanset_filter(s, n, jobs, stride, info));
   }
-  void deskew(const float* xyzt, uint64_t n, const double* twist, std::vector<float>& out_xyz) {
-    out_xyz.resize(3 * n);
-    check(mlo_deskew(ctx, xyzt, n, twist, out_xyz.data()));
+  void scanset_deskew(ScanSet* s, uint32_t n, const uint32_t* slots, const double* twists6, mlo_scan_info* info) {
+    check(mlo_scanset_deskew(s, n, slots, twists6, info));
   }
-  void icp_align(const float* xyz, uint64_t n, void* map, const double* init, const mlo_icp_params& p, mlo_icp_result& r) {
-    check(mlo_icp_align(ctx, xyz, 3, n, static_cast<mlo_map*>(map), init, &p, &r));
+  void scanset_align(ScanSet* s, uint32_t n, const mlo_align_job* jobs, mlo_icp_result* out) {
+    check(mlo_scanset_align(s, n, jobs, out));
+  }
+  void scanset_insert(ScanSet* s, uint32_t n, const mlo_insert_job* jobs, mlo_map_counts* out) {
+    check(mlo_scanset_insert(s, n, jobs, out));
   }
   void se3_exp(const double* xi, double* pose) { mlo_se3_exp(xi, pose); }
   void se3_log(const double* pose, double* xi) { mlo_se3_log(pose, xi); }

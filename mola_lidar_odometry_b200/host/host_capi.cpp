@@ -2,6 +2,7 @@
 #include <cstring>
 #include <memory>
 #include <string>
+#include <vector>
 
 #include "backend_gpu.hpp"
 #include "mlo_b200_host.h"
@@ -17,7 +18,30 @@ struct mlo_lo {
   explicit mlo_lo(mlo_ctx* c) : be(c), lo(be) {}
 };
 
+struct mlo_fleet {
+  BackendGpu be;
+  LidarOdometryFleetT<BackendGpu> fleet;
+  std::string err;
+  std::vector<ScanOutput> tmp;
+  mlo_fleet(mlo_ctx* c, uint32_t n) : be(c), fleet(be, n), tmp(n) {}
+};
+
 namespace {
+void put_output(const ScanOutput& s, mlo_lo_scan_output* out) {
+  out->processed = s.processed;
+  out->icp_ran = s.icp_ran;
+  out->icp_good = s.icp_good;
+  out->map_updated = s.map_updated;
+  std::memcpy(out->pose_3x4, s.pose.data(), sizeof(out->pose_3x4));
+  out->quality = s.quality;
+  out->sigma = s.sigma;
+  out->est_max_range = s.est_max_range;
+  out->icp_iterations = s.icp_iterations;
+  out->icp_runs = s.icp_runs;
+  out->termination = s.termination;
+  out->n_map_layer = s.n_map_layer;
+  out->n_icp_layer = s.n_icp_layer;
+}
 thread_local std::string g_err;
 YamlNode load_cfg(const char* yaml, int is_text) { return is_text ? yaml_parse(yaml) : yaml_load_file(yaml); }
 }  // namespace
@@ -49,20 +73,7 @@ int mlo_lo_on_lidar_t(mlo_lo* lo, const float* pts, uint32_t stride, const float
                       mlo_lo_scan_output* out) {
   if (!lo || !out || (n && !pts) || (stride != 3 && stride != 4)) return MLO_ERR_INVALID_ARG;
   try {
-    const ScanOutput s = lo->lo.onLidar(pts, stride, n, stamp, t);
-    out->processed = s.processed;
-    out->icp_ran = s.icp_ran;
-    out->icp_good = s.icp_good;
-    out->map_updated = s.map_updated;
-    std::memcpy(out->pose_3x4, s.pose.data(), sizeof(out->pose_3x4));
-    out->quality = s.quality;
-    out->sigma = s.sigma;
-    out->est_max_range = s.est_max_range;
-    out->icp_iterations = s.icp_iterations;
-    out->icp_runs = s.icp_runs;
-    out->termination = s.termination;
-    out->n_map_layer = s.n_map_layer;
-    out->n_icp_layer = s.n_icp_layer;
+    put_output(lo->lo.onLidar(pts, stride, n, stamp, t), out);
     return MLO_OK;
   } catch (const std::exception& e) {
     lo->err = e.what();  // the reference latches this as fatal_error (LidarOdometry.cpp:614-619)
@@ -93,6 +104,54 @@ int mlo_lo_reset(mlo_lo* lo) {
   }
 }
 
+int mlo_fleet_create(mlo_ctx* ctx, const char* yaml, int is_text, uint32_t n_sequences, mlo_fleet** out) {
+  if (!ctx || !yaml || !out || n_sequences == 0) return MLO_ERR_INVALID_ARG;
+  *out = nullptr;
+  try {
+    auto f = std::make_unique<mlo_fleet>(ctx, n_sequences);
+    f->fleet.initialize(load_cfg(yaml, is_text));
+    *out = f.release();
+    return MLO_OK;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return MLO_ERR_INVALID_ARG;
+  }
+}
+void mlo_fleet_destroy(mlo_fleet* f) { delete f; }
+const char* mlo_fleet_last_error(const mlo_fleet* f) { return f ? f->err.c_str() : g_err.c_str(); }
+
+int mlo_fleet_on_lidar(mlo_fleet* f, const float* const* pts, uint32_t stride, const uint64_t* n, const double* stamps,
+                       const float* const* t, mlo_lo_scan_output* out) {
+  if (!f || !pts || !n || !stamps || !out || (stride != 3 && stride != 4)) return MLO_ERR_INVALID_ARG;
+  try {
+    f->fleet.onLidarBatch(pts, stride, n, stamps, t, f->tmp.data());
+    for (uint32_t i = 0; i < f->fleet.size(); i++) put_output(f->tmp[i], &out[i]);
+    return MLO_OK;
+  } catch (const std::exception& e) {
+    f->err = e.what();
+    return MLO_ERR_CUDA;
+  }
+}
+
+int mlo_fleet_phase_times(mlo_fleet* f, double out_ms[8], int reset) {
+  if (!f || !out_ms) return MLO_ERR_INVALID_ARG;
+  for (int k = 0; k < 8; k++) out_ms[k] = f->fleet.phase_ms[k];
+  if (reset) f->fleet.phase_ms.fill(0.0);
+  return MLO_OK;
+}
+
+int mlo_fleet_trajectory(const mlo_fleet* f, uint32_t sequence, double* stamps, double* poses, uint64_t max_n, uint64_t* n) {
+  if (!f || !n || sequence >= const_cast<mlo_fleet*>(f)->fleet.size()) return MLO_ERR_INVALID_ARG;
+  const auto& t = const_cast<mlo_fleet*>(f)->fleet.sequence(sequence).estimatedTrajectory();
+  *n = t.size();
+  if (!stamps || !poses) return MLO_OK;
+  for (uint64_t i = 0; i < t.size() && i < max_n; i++) {
+    stamps[i] = t[i].first;
+    std::memcpy(poses + 12 * i, t[i].second.data(), 12 * sizeof(double));
+  }
+  return MLO_OK;
+}
+
 const char* mlo_host_last_error(void) { return g_err.c_str(); }
 
 int mlo_host_icp_tables(const char* yaml_text, double sigma, uint32_t n_it, double* t1, double* t2, double* t3, mlo_icp_params* sc) {
@@ -100,7 +159,7 @@ int mlo_host_icp_tables(const char* yaml_text, double sigma, uint32_t n_it, doub
     const YamlNode cfg = yaml_parse(yaml_text);
     const YamlNode& icp = cfg.has("icp_settings_with_vel") ? cfg["icp_settings_with_vel"] : cfg;
     struct Dummy {};
-    ICP<Dummy> o;
+    ICP<Dummy> o;  // only the YAML -> formula part is used here
     o.initialize(icp);
     ParameterSource ps;
     ps.updateVariable("ADAPTIVE_THRESHOLD_SIGMA", sigma);

@@ -15,6 +15,7 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <chrono>
 #include <cmath>
 #include <cstring>
 #include <memory>
@@ -177,11 +178,12 @@ class ICP {
   void attachToParameterSource(ParameterSource& ps) { source = &ps; }
   void setIterationHook(const IterationHook& h) { hook = h; }
 
-  // mp2p_icp::ICP::align(local, global, init, params, result, prior) — call site LidarOdometry.cpp:961-962.
-  void align(Backend& be, const float* local_xyz, uint64_t n_local, void* global_map, const Pose& init, const Parameters& p,
-             Results& out, const std::optional<Prior>& prior = std::nullopt) {
+  // mp2p_icp::ICP::align(local, global, init, params, result, prior) — call site LidarOdometry.cpp:961-962 — is split in
+  // two so that a fleet of sequences can put the aligns of one lock step into ONE device pass: make_params() realises
+  // the plugin objects into the POD the C ABI takes (tables live in this object until the call returns),
+  // read_result() turns the POD result into mp2p_icp::Results.
+  void make_params(const Parameters& p, const std::optional<Prior>& prior, mlo_icp_params& q) {
     if (!source) throw std::runtime_error("ICP::align: not attached to a ParameterSource");
-    mlo_icp_params q;
     std::memset(&q, 0, sizeof(q));
     q.max_iterations = p.maxIterations;
     q.min_abs_step_trans = p.minAbsStep_trans;
@@ -196,19 +198,21 @@ class ICP {
     q.threshold_angular_deg = m_pt2pt ? m_pt2pt->thresholdAngularDeg : 0.0;
     // formulas are re-realised per ICP_ITERATION: tabulate them
     const uint32_t len = std::max<uint32_t>(1, std::min<uint32_t>(p.maxIterations, 64));
-    std::vector<double> t1(len, 0.0), t2(len, 0.0), t3(len, 1.0);
+    t1_.assign(len, 0.0);
+    t2_.assign(len, 0.0);
+    t3_.assign(len, 1.0);
     const double saved_it = source->has("ICP_ITERATION") ? source->get("ICP_ITERATION") : 0.0;
     for (uint32_t it = 0; it < len; it++) {
       source->updateVariable("ICP_ITERATION", double(it));
-      if (m_pt2pt) t1[it] = m_pt2pt->threshold.eval(*source);
-      if (m_pt2pl) t2[it] = m_pt2pl->distanceThreshold.eval(*source);
-      if (gn) t3[it] = gn->robustKernelParam.eval(*source);
+      if (m_pt2pt) t1_[it] = m_pt2pt->threshold.eval(*source);
+      if (m_pt2pl) t2_[it] = m_pt2pl->distanceThreshold.eval(*source);
+      if (gn) t3_[it] = gn->robustKernelParam.eval(*source);
     }
     source->updateVariable("ICP_ITERATION", saved_it);
     q.table_len = len;
-    q.pt2pt_threshold_by_iter = t1.data();
-    q.pt2pl_threshold_by_iter = t2.data();
-    q.kernel_param_by_iter = t3.data();
+    q.pt2pt_threshold_by_iter = t1_.data();
+    q.pt2pl_threshold_by_iter = t2_.data();
+    q.kernel_param_by_iter = t3_.data();
     const Pose I = pose_identity();
     std::memcpy(q.prior_pose_3x4, I.data(), sizeof(q.prior_pose_3x4));
     if (prior) {
@@ -220,8 +224,8 @@ class ICP {
     q.hook_min_trans = hook.min_trans;
     q.hook_min_rot_rad = hook.min_rot_rad;
     std::memcpy(q.hook_checkpoint_pose_3x4, hook.checkpoint.data(), sizeof(q.hook_checkpoint_pose_3x4));
-    mlo_icp_result r;
-    be.icp_align(local_xyz, n_local, global_map, init.data(), q, r);
+  }
+  static void read_result(const mlo_icp_result& r, Results& out) {
     std::memcpy(out.optimal_tf_mean.data(), r.pose_3x4, sizeof(r.pose_3x4));
     std::memcpy(out.optimal_tf_cov.data(), r.cov_6x6, sizeof(r.cov_6x6));
     out.quality = r.quality;
@@ -229,6 +233,9 @@ class ICP {
     out.terminationReason = r.termination;
     out.nPairings = r.n_pairings;
   }
+
+ private:
+  std::vector<double> t1_, t2_, t3_;
 };
 
 // observations_filter_1st_pass (default.yaml:278-319): the four filters of the default pipelines, recognised by class
@@ -344,7 +351,10 @@ class LidarOdometryT {
   explicit LidarOdometryT(Backend& be) : be_(be) {}
   ~LidarOdometryT() {
     if (map_) be_.destroy_map(map_);
+    if (set_) be_.scanset_destroy(set_);
   }
+  LidarOdometryT(const LidarOdometryT&) = delete;
+  LidarOdometryT& operator=(const LidarOdometryT&) = delete;
   LidarOdometryParams params_;
   ParameterSource parameter_source;
 
@@ -425,26 +435,42 @@ class LidarOdometryT {
   double adaptiveSigma() const { return sigma_; }
   void* localMap() const { return map_; }
 
-  // mola::LidarOdometry::onLidarImpl for one point cloud (LidarOdometry.cpp:627-1206); deskew off (row f1).
-  // `t` = optional per-point timestamps [s] relative to the scan stamp (CPointsMapXYZIRT "t" channel)
-  ScanOutput onLidar(const float* pts, uint32_t stride, uint64_t n, double stamp, const float* t = nullptr) {
-    ScanOutput out;
-    if (last_obs_time_ && stamp - *last_obs_time_ < params_.min_time_between_scans) return out;  // :643-657
-    const std::optional<double> last_obs = last_obs_time_;
+  // ---------------------------------------------------------------------------------------------------------------
+  // mola::LidarOdometry::onLidarImpl for one point cloud (LidarOdometry.cpp:627-1206), cut into phases at the points
+  // where the reference calls into its plugins (filter pipelines :732-741, ICP::align :961, merge pipeline :1197).
+  // Between phases the scan's layers stay in the backend's scan set (device memory for BackendGpu); a fleet
+  // (LidarOdometryFleetT below) runs the same phase of many sequences with ONE backend call.
+  //   begin_scan -> [filter] -> after_filter -> ([deskew] -> after_deskew)
+  //     -> while icp_pending(): make_align_job -> [align] -> on_align_result -> ([deskew])
+  //     -> after_icp -> ([insert] -> after_insert) -> finish_scan
+  // `t` = optional per-point timestamps [s] relative to the scan stamp (CPointsMapXYZIRT "t" channel).
+
+  // Phase A.  Returns false when the observation is dropped (:643-657); otherwise `job` describes the filter call.
+  bool begin_scan(const float* pts, uint32_t stride, uint64_t n, double stamp, const float* t, mlo_scan_job& job) {
+    out_ = ScanOutput{};
+    icp_pending_ = false;
+    needs_deskew_ = false;
+    insert_pending_ = false;
+    if (last_obs_time_ && stamp - *last_obs_time_ < params_.min_time_between_scans) return false;  // :643-657
     last_obs_time_ = stamp;
-    out.processed = true;
+    stamp_ = stamp;
+    out_.processed = true;
     if (!est_max_range_) {  // doInitializeEstimatedMaxSensorRange, :1487-1513
       const double r = std::max(bbox_radius(pts, stride, n), params_.absolute_minimum_sensor_range);
       if (n) est_max_range_ = r;
     }
-    const auto motion = estimated_navstate(stamp);  // :808-815
-    updatePipelineDynamicVariables(motion);         // :692
-    // 1st-pass filter (:732-735); 2nd pass is the identity with deskew skipped (:737-741)
-    const mlo_filter1_params f1 = filter1_.realize(parameter_source);
+    motion_ = estimated_navstate(stamp);      // :808-815
+    updatePipelineDynamicVariables(motion_);  // :692
+    // 1st-pass filter (:732-735); the 2nd pass is the identity with deskew skipped (:737-741)
+    std::memset(&job, 0, sizeof(job));
+    job.fp = filter1_.realize(parameter_source);
     if (!t && !params_.skip_deskew && !params_.silently_ignore_no_timestamps)
       throw std::runtime_error("FilterDeskew: the point cloud has no per-point timestamps (silently_ignore_no_timestamps is false)");
-    const bool do_deskew = t && !params_.skip_deskew && n > 0;
-    if (do_deskew) {
+    do_deskew_ = t && !params_.skip_deskew && n > 0;
+    job.pts = pts;
+    job.n = n;
+    job.t = nullptr;
+    if (do_deskew_) {
       // FilterAdjustTimestamps (:267-275) on the raw layer, then the 1st pass keeps t through both decimations and
       // the 2nd pass deskews the two '_skewed' layers with the current twist variables (:328-350)
       adj_t_.assign(t, t + n);
@@ -456,75 +482,82 @@ class LidarOdometryT {
       const float shift = (params_.timestamps_middle_is_zero ? 0.5f * (tmin + tmax) : tmin) -
                           float(parameter_source.has("SENSOR_TIME_OFFSET") ? parameter_source.get("SENSOR_TIME_OFFSET") : 0.0);
       for (float& v : adj_t_) v -= shift;
-      be_.filter_1st_pass_xyzt(pts, stride, adj_t_.data(), n, f1, map_skewed_, icp_skewed_);
-      apply_deskew();
-    } else {
-      be_.filter_1st_pass(pts, stride, n, f1, map_layer_, icp_layer_);
+      job.t = adj_t_.data();
     }
-    out.n_map_layer = map_layer_.size() / 3;
-    out.n_icp_layer = icp_layer_.size() / 3;
-    doUpdateEstimatedMaxSensorRange();  // :744-769 (first points layer of the observation = decimated_for_icp)
-    out.est_max_range = est_max_range_.value_or(0.0);
-
-    bool updateLocalMap = false;
-    const bool hasMotionModel = motion.has_value();
-    if (!map_ || map_points_ == 0) {
-      // first point cloud: no ICP, seed the map at the origin (:817-839)
-      updateLocalMap = true;
-      trajectory_.emplace_back(stamp, last_lidar_pose_);
-      fuse_pose(stamp, pose_identity());
-    } else {
-      Pose init = hasMotionModel ? motion->pose : last_lidar_pose_;  // :852-897 (prior term: see DESIGN.md, f2)
-      const Pose init_guess = init;
-      const Pose last_keyframe_pose = last_lidar_pose_;  // :904
-      const double since_last = last_icp_time_ ? stamp - *last_icp_time_ : 0.0;
-      last_icp_time_ = stamp;
-      Parameters ip = icp_.params;
-      uint32_t remaining = ip.maxIterations;
-      Results r;
-      IterationHook hook;
-      hook.enabled = params_.optimize_twist;
-      hook.min_trans = params_.optimize_twist_rerun_min_trans;
-      hook.min_rot_rad = params_.optimize_twist_rerun_min_rot_deg * M_PI / 180.0;
-      Pose current_solution = init;
-      do {  // :954-1007
-        ip.maxIterations = remaining;
-        hook.checkpoint = current_solution;
-        icp_.setIterationHook(hook);
-        icp_.align(be_, icp_layer_.data(), icp_layer_.size() / 3, map_, current_solution, ip, r);
-        out.icp_runs++;
-        remaining = r.nIterations <= remaining ? remaining - r.nIterations : 0;
-        if (r.terminationReason == MLO_TERM_HOOK_REQUEST) {
-          current_solution = r.optimal_tf_mean;  // the hook stored the new checkpoint (:949)
-          if (since_last > 0) {  // re-estimate the twist (:973-992); re-deskew is the identity here
-            const Pose incr = pose_minus(r.optimal_tf_mean, last_keyframe_pose);
-            double xi[6];
-            be_.se3_log(incr.data(), xi);
-            double w[3];
-            rot_log(incr, w);
-            twist_ = {incr[3] / since_last, incr[7] / since_last, incr[11] / since_last, w[0] / since_last,
-                      w[1] / since_last, w[2] / since_last};
-            updatePipelineTwistVariables();
-            if (do_deskew) apply_deskew();  // re-apply the 2nd pass with the new twist (:996-1001)
-          }
-        }
-      } while (r.terminationReason == MLO_TERM_HOOK_REQUEST);
-      out.icp_ran = true;
-      out.quality = r.quality;
-      out.icp_iterations = r.nIterations;
-      out.termination = r.terminationReason;
+    return true;
+  }
+  // Phase C.  With deskew on, the layers only exist after the deskew call: ask for it.
+  void after_filter(const mlo_scan_info& info) {
+    if (do_deskew_) {
+      needs_deskew_ = true;
+      first_deskew_ = true;
+      return;
+    }
+    on_layers(info);
+  }
+  bool needs_deskew() const { return needs_deskew_; }
+  const std::array<double, 6>& deskew_twist() const { return twist_; }
+  void after_deskew(const mlo_scan_info& info) {
+    needs_deskew_ = false;
+    if (first_deskew_) {
+      first_deskew_ = false;
+      on_layers(info);
+    }
+  }
+  bool icp_pending() const { return icp_pending_; }
+  // Phase D: one ICP::align call of the do/while at :954-1007
+  void make_align_job(mlo_align_job& job) {
+    ip_.maxIterations = remaining_;
+    hook_.checkpoint = current_solution_;
+    icp_.setIterationHook(hook_);
+    std::memset(&job, 0, sizeof(job));
+    job.map = static_cast<const mlo_map*>(map_);
+    std::memcpy(job.init_pose_3x4, current_solution_.data(), sizeof(job.init_pose_3x4));
+    icp_.make_params(ip_, std::nullopt, job.params);
+  }
+  void on_align_result(const mlo_icp_result& res) {
+    Results& r = result_;
+    ICP<Backend>::read_result(res, r);
+    out_.icp_runs++;
+    total_iterations_ += r.nIterations;
+    remaining_ = r.nIterations <= remaining_ ? remaining_ - r.nIterations : 0;
+    if (r.terminationReason == MLO_TERM_HOOK_REQUEST) {
+      current_solution_ = r.optimal_tf_mean;  // the hook stored the new checkpoint (:949)
+      if (since_last_ > 0) {  // re-estimate the twist (:973-992), then re-apply the 2nd pass with it (:996-1001)
+        const Pose incr = pose_minus(r.optimal_tf_mean, last_keyframe_pose_);
+        double w[3];
+        rot_log(incr, w);
+        twist_ = {incr[3] / since_last_, incr[7] / since_last_, incr[11] / since_last_, w[0] / since_last_, w[1] / since_last_,
+                  w[2] / since_last_};
+        updatePipelineTwistVariables();
+        if (do_deskew_) needs_deskew_ = true;
+      }
+      return;  // still pending: the loop runs again with the remaining budget
+    }
+    icp_pending_ = false;
+  }
+  // Phase E: gating, adaptive sigma, keyframe decision (:1011-1158).  Returns true when a map insert must follow.
+  bool after_icp(mlo_insert_job& job) {
+    bool updateLocalMap = first_scan_;
+    const bool hasMotionModel = motion_.has_value();
+    if (!first_scan_) {
+      const Results& r = result_;
+      out_.icp_ran = true;
+      out_.quality = r.quality;
+      out_.icp_iterations = r.nIterations;
+      out_.termination = r.terminationReason;
       const bool icpIsGood = r.quality >= params_.min_icp_goodness;  // :1026
       last_icp_was_good_ = icpIsGood;
       last_icp_quality_ = r.quality;
-      out.icp_good = icpIsGood;
+      out_.icp_good = icpIsGood;
       if (icpIsGood) {
         last_lidar_pose_ = r.optimal_tf_mean;
-        fuse_pose(stamp, r.optimal_tf_mean);
-        trajectory_.emplace_back(stamp, last_lidar_pose_);
+        fuse_pose(stamp_, r.optimal_tf_mean);
+        trajectory_.emplace_back(stamp_, last_lidar_pose_);
       } else {
         fused_.clear();  // navstate_fuse.reset()
       }
-      if (params_.adaptive_enabled) doUpdateAdaptiveThreshold(pose_minus(r.optimal_tf_mean, init_guess), motion);  // :1052-1063
+      if (params_.adaptive_enabled) doUpdateAdaptiveThreshold(pose_minus(r.optimal_tf_mean, init_guess_), motion_);  // :1052-1063
       // keyframe decision (:1066-1115)
       double dist = 0, rot = 0;
       const bool isFirst = closest_keyframe(last_lidar_pose_, dist, rot);
@@ -555,7 +588,7 @@ class LidarOdometryT {
       last_icp_was_good_ = true;
     }
     if (updateLocalMap) {  // :1161-1206
-      updatePipelineDynamicVariables(motion);  // robot_x.. for FilterMerge
+      updatePipelineDynamicVariables(motion_);  // robot_x.. for FilterMerge
       if (!map_) {
         mlo_map_params mp;
         std::memset(&mp, 0, sizeof(mp));
@@ -569,22 +602,90 @@ class LidarOdometryT {
         map_ = be_.create_map(mp);
         cull_dist_ = float(mapdef_.remove_voxels_farther_than.eval(parameter_source));
       }
-      be_.map_insert(map_, map_layer_.data(), map_layer_.size() / 3, last_lidar_pose_.data());
-      if (cull_dist_ > 0) {
-        const double s[3] = {last_lidar_pose_[3], last_lidar_pose_[7], last_lidar_pose_[11]};
-        be_.map_cull(map_, s, cull_dist_);
-      }
-      uint64_t nv = 0;
-      be_.map_stats(map_, nv, map_points_);
-      out.map_updated = true;
+      std::memset(&job, 0, sizeof(job));
+      job.map = static_cast<mlo_map*>(map_);
+      std::memcpy(job.pose_3x4, last_lidar_pose_.data(), sizeof(job.pose_3x4));
+      job.cull_farther_than = cull_dist_ > 0 ? cull_dist_ : 0.f;
+      insert_pending_ = true;
     }
-    (void)last_obs;
-    out.pose = last_lidar_pose_;
-    out.sigma = sigma_;
-    return out;
+    return updateLocalMap;
+  }
+  void after_insert(const mlo_map_counts& cnt) {
+    map_points_ = cnt.n_points;
+    out_.map_updated = true;
+    insert_pending_ = false;
+  }
+  ScanOutput finish_scan() {
+    out_.pose = last_lidar_pose_;
+    out_.sigma = sigma_;
+    return out_;
   }
 
+  // One sequence on its own: the phases back to back on a one-slot scan set.
+  ScanOutput onLidar(const float* pts, uint32_t stride, uint64_t n, double stamp, const float* t = nullptr) {
+    if (!set_) set_ = be_.scanset_create(1);
+    mlo_scan_job fj;
+    if (!begin_scan(pts, stride, n, stamp, t, fj)) return finish_dropped();
+    fj.slot = 0;
+    mlo_scan_info info;
+    be_.scanset_filter(set_, 1, &fj, stride, &info);
+    after_filter(info);
+    const uint32_t slot0 = 0;
+    auto deskew = [&] {
+      be_.scanset_deskew(set_, 1, &slot0, twist_.data(), &info);
+      after_deskew(info);
+    };
+    if (needs_deskew()) deskew();
+    while (icp_pending()) {
+      mlo_align_job aj;
+      make_align_job(aj);
+      aj.slot = 0;
+      mlo_icp_result res;
+      be_.scanset_align(set_, 1, &aj, &res);
+      on_align_result(res);
+      if (needs_deskew()) deskew();
+    }
+    mlo_insert_job ij;
+    if (after_icp(ij)) {
+      ij.slot = 0;
+      mlo_map_counts cnt;
+      be_.scanset_insert(set_, 1, &ij, &cnt);
+      after_insert(cnt);
+    }
+    return finish_scan();
+  }
+  ScanOutput finish_dropped() { return ScanOutput{}; }
+
  private:
+  // layers are known (sizes + ICP-layer bounding box): max-range estimate, then first-scan seeding or ICP set-up
+  void on_layers(const mlo_scan_info& info) {
+    out_.n_map_layer = info.n_map;
+    out_.n_icp_layer = info.n_icp;
+    doUpdateEstimatedMaxSensorRange(info);  // :744-769 (first points layer of the observation = decimated_for_icp)
+    out_.est_max_range = est_max_range_.value_or(0.0);
+    first_scan_ = !map_ || map_points_ == 0;
+    if (first_scan_) {
+      // first point cloud: no ICP, seed the map at the origin (:817-839)
+      trajectory_.emplace_back(stamp_, last_lidar_pose_);
+      fuse_pose(stamp_, pose_identity());
+      return;
+    }
+    const bool hasMotionModel = motion_.has_value();
+    init_guess_ = hasMotionModel ? motion_->pose : last_lidar_pose_;  // :852-897 (prior term: see DESIGN.md, f2)
+    last_keyframe_pose_ = last_lidar_pose_;                           // :904
+    since_last_ = last_icp_time_ ? stamp_ - *last_icp_time_ : 0.0;
+    last_icp_time_ = stamp_;
+    ip_ = icp_.params;
+    remaining_ = ip_.maxIterations;
+    total_iterations_ = 0;
+    hook_ = IterationHook{};
+    hook_.enabled = params_.optimize_twist;
+    hook_.min_trans = params_.optimize_twist_rerun_min_trans;
+    hook_.min_rot_rad = params_.optimize_twist_rerun_min_rot_deg * M_PI / 180.0;
+    current_solution_ = init_guess_;
+    icp_pending_ = true;
+  }
+
   struct NavState {
     Pose pose;
     std::array<double, 6> twist;
@@ -623,10 +724,6 @@ class LidarOdometryT {
     ns.pose = pose_compose(b.second, d);
     return ns;
   }
-  void apply_deskew() {
-    be_.deskew(map_skewed_.data(), map_skewed_.size() / 4, twist_.data(), map_layer_);
-    be_.deskew(icp_skewed_.data(), icp_skewed_.size() / 4, twist_.data(), icp_layer_);
-  }
   void fuse_pose(double stamp, const Pose& p) {
     fused_.emplace_back(stamp, p);
     if (fused_.size() > 8) fused_.erase(fused_.begin());
@@ -651,9 +748,10 @@ class LidarOdometryT {
     const double a[3] = {mn[0], mn[1], mn[2]}, b[3] = {mx[0], mx[1], mx[2]};
     return std::max(norm3(a), norm3(b));
   }
-  void doUpdateEstimatedMaxSensorRange() {  // :1515-1546
-    if (!est_max_range_ || icp_layer_.empty()) return;
-    const double radius = std::max(bbox_radius(icp_layer_.data(), 3, icp_layer_.size() / 3), params_.absolute_minimum_sensor_range);
+  void doUpdateEstimatedMaxSensorRange(const mlo_scan_info& info) {  // :1515-1546
+    if (!est_max_range_ || info.n_icp == 0) return;
+    const double a3[3] = {info.icp_min[0], info.icp_min[1], info.icp_min[2]}, b3[3] = {info.icp_max[0], info.icp_max[1], info.icp_max[2]};
+    const double radius = std::max(std::max(norm3(a3), norm3(b3)), params_.absolute_minimum_sensor_range);
     inst_max_range_ = radius;
     const double a = params_.max_sensor_range_filter_coefficient;
     est_max_range_ = *est_max_range_ * a + radius * (1.0 - a);
@@ -728,7 +826,19 @@ class LidarOdometryT {
   void* map_ = nullptr;
   uint64_t map_points_ = 0;
   float cull_dist_ = 0;
-  std::vector<float> map_layer_, icp_layer_, map_skewed_, icp_skewed_, adj_t_;
+  typename Backend::ScanSet* set_ = nullptr;  // one-slot set of the stand-alone onLidar() path
+  std::vector<float> adj_t_;
+  // per-scan transient state between the phases
+  ScanOutput out_;
+  std::optional<NavState> motion_;
+  double stamp_ = 0, since_last_ = 0;
+  bool do_deskew_ = false, needs_deskew_ = false, first_deskew_ = false, first_scan_ = false, icp_pending_ = false,
+       insert_pending_ = false;
+  Pose init_guess_ = pose_identity(), last_keyframe_pose_ = pose_identity(), current_solution_ = pose_identity();
+  Parameters ip_;
+  IterationHook hook_;
+  Results result_;
+  uint32_t remaining_ = 0, total_iterations_ = 0;
   std::vector<std::pair<double, Pose>> trajectory_, fused_;
   std::vector<Pose> keyframes_;
   Pose last_lidar_pose_ = pose_identity();
@@ -738,6 +848,121 @@ class LidarOdometryT {
   bool last_icp_was_good_ = true;
   double last_icp_quality_ = 0;
   uint32_t removal_counter_ = 0;
+};
+
+// A fleet of independent LidarOdometry instances (one sequence each: the reference runs them as separate processes,
+// eval/cli_kitti.sh:23) advanced in lock step on one device: every phase of onLidar() is issued ONCE for all
+// sequences (one filter pass, one align pass over per-sequence local maps, one insert pass), which is what fills
+// a B200 when a single 64-beam scan cannot.  Results are those of the stand-alone instances.
+template <class Backend>
+class LidarOdometryFleetT {
+ public:
+  LidarOdometryFleetT(Backend& be, uint32_t n_sequences) : be_(be) {
+    for (uint32_t i = 0; i < n_sequences; i++) seq_.push_back(std::make_unique<LidarOdometryT<Backend>>(be));
+    set_ = be_.scanset_create(n_sequences);
+  }
+  ~LidarOdometryFleetT() {
+    seq_.clear();
+    if (set_) be_.scanset_destroy(set_);
+  }
+  uint32_t size() const { return uint32_t(seq_.size()); }
+  LidarOdometryT<Backend>& sequence(uint32_t i) { return *seq_.at(i); }
+  void initialize(const YamlNode& cfg) {
+    for (auto& s : seq_) s->initialize(cfg);
+  }
+  // One lock step: cloud i (pts[i] with n[i] points, stamp stamps[i], optional per-point times t[i]) goes to
+  // sequence i; pts[i] == nullptr leaves sequence i idle.  out[i] is what onLidar() would have returned.
+  // host wall time [ms] spent per phase since the last reset: 0 begin (host), 1 filter, 2 deskew, 3 align, 4 host logic
+  // after ICP, 5 insert, 6 lock steps counted
+  std::array<double, 8> phase_ms{};
+  void onLidarBatch(const float* const* pts, uint32_t stride, const uint64_t* n, const double* stamps, const float* const* t,
+                    ScanOutput* out) {
+    using clk = std::chrono::steady_clock;
+    auto t_last = clk::now();
+    auto lap = [&](int k) {
+      const auto now = clk::now();
+      phase_ms[k] += std::chrono::duration<double, std::milli>(now - t_last).count();
+      t_last = now;
+    };
+    phase_ms[6] += 1.0;
+    const uint32_t S = size();
+    std::vector<uint32_t> live;  // sequences with an accepted observation this step
+    std::vector<mlo_scan_job> fjobs;
+    for (uint32_t i = 0; i < S; i++) {
+      out[i] = ScanOutput{};
+      if (!pts[i] && n[i]) continue;
+      if (!pts[i]) continue;
+      mlo_scan_job j;
+      if (!seq_[i]->begin_scan(pts[i], stride, n[i], stamps[i], t ? t[i] : nullptr, j)) continue;
+      j.slot = i;
+      fjobs.push_back(j);
+      live.push_back(i);
+    }
+    if (live.empty()) return;
+    lap(0);
+    std::vector<mlo_scan_info> info(live.size());
+    be_.scanset_filter(set_, uint32_t(fjobs.size()), fjobs.data(), stride, info.data());
+    lap(1);
+    for (size_t k = 0; k < live.size(); k++) seq_[live[k]]->after_filter(info[k]);
+    run_deskews(live);
+    lap(2);
+    for (;;) {
+      std::vector<uint32_t> who;
+      std::vector<mlo_align_job> ajobs;
+      for (uint32_t i : live)
+        if (seq_[i]->icp_pending()) {
+          mlo_align_job a;
+          seq_[i]->make_align_job(a);
+          a.slot = i;
+          ajobs.push_back(a);
+          who.push_back(i);
+        }
+      if (who.empty()) break;
+      std::vector<mlo_icp_result> res(who.size());
+      be_.scanset_align(set_, uint32_t(ajobs.size()), ajobs.data(), res.data());
+      lap(3);
+      for (size_t k = 0; k < who.size(); k++) seq_[who[k]]->on_align_result(res[k]);
+      run_deskews(who);
+      lap(2);
+    }
+    std::vector<uint32_t> ins;
+    std::vector<mlo_insert_job> ijobs;
+    for (uint32_t i : live) {
+      mlo_insert_job j;
+      if (seq_[i]->after_icp(j)) {
+        j.slot = i;
+        ijobs.push_back(j);
+        ins.push_back(i);
+      }
+    }
+    lap(4);
+    if (!ins.empty()) {
+      std::vector<mlo_map_counts> cnt(ins.size());
+      be_.scanset_insert(set_, uint32_t(ijobs.size()), ijobs.data(), cnt.data());
+      for (size_t k = 0; k < ins.size(); k++) seq_[ins[k]]->after_insert(cnt[k]);
+    }
+    lap(5);
+    for (uint32_t i : live) out[i] = seq_[i]->finish_scan();
+  }
+
+ private:
+  void run_deskews(const std::vector<uint32_t>& among) {
+    std::vector<uint32_t> slots;
+    std::vector<double> tw;
+    for (uint32_t i : among)
+      if (seq_[i]->needs_deskew()) {
+        slots.push_back(i);
+        const auto& w = seq_[i]->deskew_twist();
+        tw.insert(tw.end(), w.begin(), w.end());
+      }
+    if (slots.empty()) return;
+    std::vector<mlo_scan_info> info(slots.size());
+    be_.scanset_deskew(set_, uint32_t(slots.size()), slots.data(), tw.data(), info.data());
+    for (size_t k = 0; k < slots.size(); k++) seq_[slots[k]]->after_deskew(info[k]);
+  }
+  Backend& be_;
+  std::vector<std::unique_ptr<LidarOdometryT<Backend>>> seq_;
+  typename Backend::ScanSet* set_ = nullptr;
 };
 
 }  // namespace mlo_host

@@ -32,6 +32,12 @@ HOST_SIGNATURES = {
     "mlo_lo_on_lidar_t": (C.c_int, [_vp, _vp, _u32, _vp, _u64, C.c_double, C.POINTER(ScanOutput)]),
     "mlo_lo_trajectory": (C.c_int, [_vp, _vp, _vp, _u64, C.POINTER(_u64)]),
     "mlo_lo_reset": (C.c_int, [_vp]),
+    "mlo_fleet_create": (C.c_int, [_vp, C.c_char_p, C.c_int, _u32, C.POINTER(_vp)]),
+    "mlo_fleet_destroy": (None, [_vp]),
+    "mlo_fleet_last_error": (C.c_char_p, [_vp]),
+    "mlo_fleet_on_lidar": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, C.POINTER(ScanOutput)]),
+    "mlo_fleet_phase_times": (C.c_int, [_vp, _vp, C.c_int]),
+    "mlo_fleet_trajectory": (C.c_int, [_vp, _u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "mlo_host_last_error": (C.c_char_p, []),
     "mlo_host_icp_tables": (C.c_int, [C.c_char_p, C.c_double, _u32, _vp, _vp, _vp, C.POINTER(capi.IcpParams)]),
     "mlo_host_filter1": (C.c_int, [C.c_char_p, C.c_double, C.c_double, C.POINTER(capi.Filter1Params)]),
@@ -124,4 +130,70 @@ class LidarOdometry:
         lib().mlo_lo_trajectory(self.h, None, None, 0, C.byref(n))
         st, ps = np.zeros(n.value), np.zeros((n.value, 3, 4))
         lib().mlo_lo_trajectory(self.h, st.ctypes.data, ps.ctypes.data, n.value, C.byref(n))
+        return st, ps
+
+
+def _fleet_args(clouds, stamps, ts, as_pts):
+    """ctypes argument arrays of one lock step; a cloud of None leaves that sequence idle."""
+    S = len(clouds)
+    keep = [None if c is None else as_pts(c) for c in clouds]
+    stride = next((c.shape[1] for c in keep if c is not None), 3)
+    assert all(c is None or c.shape[1] == stride for c in keep)
+    pts = (_vp * S)(*[None if c is None else c.ctypes.data for c in keep])
+    n = (_u64 * S)(*[0 if c is None else len(c) for c in keep])
+    st = (C.c_double * S)(*[float(x) for x in stamps])
+    tp = None
+    if ts is not None:
+        tk = [None if t is None else np.ascontiguousarray(t, dtype=np.float32) for t in ts]
+        keep.append(tk)
+        tp = (_vp * S)(*[None if t is None else t.ctypes.data for t in tk])
+    return keep, stride, pts, n, st, tp
+
+
+class LidarOdometryFleet:
+    """n independent mola::LidarOdometry instances advanced in lock step on one GPU context (mlo_fleet_*): one filter
+    pass, one align pass over per-sequence local maps and one insert pass per step."""
+
+    def __init__(self, ctx: Context, yaml_path_or_text, n_sequences: int, is_text: bool = False):
+        self.ctx, self.n = ctx, n_sequences
+        h = _vp()
+        rc = lib().mlo_fleet_create(ctx.h, str(yaml_path_or_text).encode(), int(is_text), n_sequences, C.byref(h))
+        if rc != 0:
+            raise MloError(rc, lib().mlo_fleet_last_error(None).decode())
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None) and self.ctx.h:
+            lib().mlo_fleet_destroy(self.h)
+        self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def on_lidar(self, clouds, stamps, ts=None):
+        """clouds[i] -> sequence i (None = idle).  Returns a list of ScanOutput."""
+        assert len(clouds) == self.n and len(stamps) == self.n
+        keep, stride, pts, n, st, tp = _fleet_args(clouds, stamps, ts, _pts)
+        out = (ScanOutput * self.n)()
+        rc = lib().mlo_fleet_on_lidar(self.h, pts, stride, n, st, tp, out)
+        if rc != 0:
+            raise MloError(rc, lib().mlo_fleet_last_error(self.h).decode())
+        del keep
+        return list(out)
+
+    def phase_times(self, reset: bool = True) -> dict:
+        a = np.zeros(8)
+        lib().mlo_fleet_phase_times(self.h, a.ctypes.data, int(reset))
+        steps = max(a[6], 1.0)
+        names = ["host_before_filter", "filter", "deskew", "align", "host_after_icp", "insert"]
+        return {k + "_ms_per_step": float(a[i] / steps) for i, k in enumerate(names)}
+
+    def trajectory(self, sequence: int):
+        n = _u64()
+        lib().mlo_fleet_trajectory(self.h, sequence, None, None, 0, C.byref(n))
+        st, ps = np.zeros(n.value), np.zeros((n.value, 3, 4))
+        lib().mlo_fleet_trajectory(self.h, sequence, st.ctypes.data, ps.ctypes.data, n.value, C.byref(n))
         return st, ps

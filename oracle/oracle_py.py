@@ -274,3 +274,35 @@ class OracleLidarOdometry:
         if rc != 0:
             raise RuntimeError("orc_lo_on_lidar failed")
         return out
+
+
+class OracleLidarOdometryFleet:
+    """The product's fleet orchestrator (LidarOdometryFleetT) over the CPU oracle: checks on the CPU that lock-step
+    batching does not change any per-sequence result."""
+
+    def __init__(self, yaml_path_or_text, n_sequences: int, is_text: bool = False):
+        from mola_lidar_odometry_b200.host_api import ScanOutput
+        L = lib()
+        L.orc_fleet_create.restype = _vp
+        L.orc_fleet_create.argtypes = [C.c_char_p, C.c_int, _u32]
+        L.orc_fleet_destroy.argtypes = [_vp]
+        L.orc_fleet_on_lidar.restype = C.c_int
+        L.orc_fleet_on_lidar.argtypes = [_vp, _vp, _u32, _vp, _vp, _vp, C.POINTER(ScanOutput)]
+        self._out_t, self.n = ScanOutput, n_sequences
+        self.h = L.orc_fleet_create(str(yaml_path_or_text).encode(), int(is_text), n_sequences)
+        if not self.h:
+            raise RuntimeError("orc_fleet_create failed")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_fleet_destroy(self.h)
+            self.h = None
+
+    def on_lidar(self, clouds, stamps, ts=None):
+        from mola_lidar_odometry_b200.host_api import _fleet_args
+        keep, stride, pts, n, st, tp = _fleet_args(clouds, stamps, ts, _f32)
+        out = (self._out_t * self.n)()
+        if lib().orc_fleet_on_lidar(self.h, pts, stride, n, st, tp, out) != 0:
+            raise RuntimeError("orc_fleet_on_lidar failed")
+        del keep
+        return list(out)

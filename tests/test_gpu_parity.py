@@ -74,6 +74,40 @@ def test_map_cull_bit_exact(ctx, world):
     _assert_maps_equal(g, o)
 
 
+def test_map_cull_in_place_reuses_rows_bit_exact(ctx, world):
+    """Repeated insert + cull along a drive: culled voxel ids go through the free stack and are reused; the map content
+    stays bit-identical to the oracle's erase-voxels loop, with a capacity that is only enough when rows are reused."""
+    frames = world["frames"]
+    o = O.OracleMap(1.0, 20, 0.0)
+    peak = created = prev = 0
+    for fr in frames:
+        o.insert(fr["map_layer"], fr["gt"])
+        nv = o.stats()[0]
+        peak, created = max(peak, nv), created + nv - prev
+        o.cull(fr["gt"][:, 3], 25.0)
+        prev = o.stats()[0]
+    from mola_lidar_odometry_b200.api import LocalMap
+    cap = int(peak * 1.05)
+    assert created > 3 * cap, "the drive must create more voxels than the capacity holds unless culled rows are reused"
+    g = LocalMap(ctx, 1.0, 20, 0.0, cap)
+    o = O.OracleMap(1.0, 20, 0.0)
+    for i, fr in enumerate(frames):
+        g.insert(fr["map_layer"], fr["gt"])
+        o.insert(fr["map_layer"], fr["gt"])
+        g.cull(fr["gt"][:, 3], 25.0)
+        o.cull(fr["gt"][:, 3], 25.0)
+        assert g.stats() == o.stats(), i
+        if i % 6 == 5:
+            _assert_maps_equal(g, o)
+    _assert_maps_equal(g, o)
+    # NN over the culled + refilled map (dead column buckets stay on the probe chains)
+    q = frames[-1]["icp_layer"]
+    qg = (frames[-1]["gt"][:, :3] @ q.T).T + frames[-1]["gt"][:, 3]
+    gx, gd, gf = g.nn_single(qg.astype(np.float32))
+    ox, od, of, _ = o.nn_single(qg.astype(np.float32))
+    assert np.array_equal(gf, of) and np.array_equal(gd.view(np.uint32), od.view(np.uint32)) and gf.mean() > 0.3
+
+
 def test_map_clear_and_empty_inputs(ctx, world):
     g, o = _mk_maps(ctx)
     g.insert(np.zeros((0, 3), np.float32), np.eye(4)[:3])
@@ -391,3 +425,70 @@ def test_deskew_and_xyzt_filter_bit_exact(ctx, world):
     big[:, 3] = 1.0
     assert np.allclose(ctx.deskew(big, [1, 2, 3, 0.3, -0.4, 1.2]), O.deskew(big, [1, 2, 3, 0.3, -0.4, 1.2]), atol=1e-5)
     assert len(ctx.deskew(np.zeros((0, 4), np.float32), [0] * 6)) == 0
+
+
+# ------------------------------------------------------------------------------------------------ scan sets
+def test_scanset_layers_align_insert_parity(ctx, world):
+    """mlo_scanset_*: three scans filtered in one pass, layers bit-exact vs the oracle; one align pass against THREE
+    different local maps; one insert pass (+ cull); a ragged job list (empty cloud)."""
+    from mola_lidar_odometry_b200.api import LocalMap, ScanSet
+    frames, fp = world["frames"], world["fp"]
+    S = 3
+    gm = [LocalMap(ctx, 1.0, 20, 0.0, 1 << 16) for _ in range(S)]
+    om = [O.OracleMap(1.0, 20, 0.0) for _ in range(S)]
+    for s in range(S):                      # map s holds frames s .. s+5
+        for fr in frames[s:s + 6]:
+            gm[s].insert(fr["map_layer"], fr["gt"])
+            om[s].insert(fr["map_layer"], fr["gt"])
+    ks = [7, 9, 11]
+    raws = [frames[k]["raw"] for k in ks]
+    sset = ScanSet(ctx, S + 1)
+    info = sset.filter([0, 1, 2, 3], raws + [np.zeros((0, raws[0].shape[1]), np.float32)], [fp] * 4)
+    for s in range(S):
+        assert (info[s].n_map, info[s].n_icp) == (len(frames[ks[s]]["map_layer"]), len(frames[ks[s]]["icp_layer"]))
+        assert np.array_equal(sset.download(s, 0), frames[ks[s]]["map_layer"])
+        assert np.array_equal(sset.download(s, 1), frames[ks[s]]["icp_layer"])
+        assert np.array_equal(np.array(info[s].icp_min[:], np.float32), frames[ks[s]]["icp_layer"].min(axis=0))
+        assert np.array_equal(np.array(info[s].icp_max[:], np.float32), frames[ks[s]]["icp_layer"].max(axis=0))
+    assert (info[3].n_map, info[3].n_icp) == (0, 0)
+    rng = np.random.default_rng(5)
+    inits = np.stack([synth.perturb(frames[k]["gt"], rng, 0.3, 1.0) for k in ks] + [np.eye(4)[:3]])
+    owners = [capi.IcpParamsOwner(sigma=float(rng.uniform(1.5, 2.5))) for _ in range(S + 1)]
+    res = sset.align([0, 1, 2, 3], gm + [gm[0]], inits, [w.p for w in owners])
+    for s in range(S):
+        _check_result(res[s], O.icp_align(om[s], frames[ks[s]]["icp_layer"], inits[s], owners[s].p))
+        single = ctx.icp_align(frames[ks[s]]["icp_layer"], gm[s], inits[s], owners[s].p)
+        assert np.allclose(res[s].pose, single.pose, rtol=0, atol=1e-9) and res[s].n_iterations == single.n_iterations
+    assert res[3].termination == 1           # NoPairings for the empty scan
+    counts = sset.insert([0, 1, 2], gm, np.stack([r.pose for r in res[:S]]), cull=[0.0, 40.0, 40.0])
+    for s in range(S):
+        om[s].insert(frames[ks[s]]["map_layer"], np.array(res[s].pose))
+        if s > 0:
+            om[s].cull(np.array(res[s].pose)[:, 3], 40.0)
+        assert counts[s] == gm[s].stats()
+    # poses agree to ~1e-13 only, so a point within that distance of a voxel face may land next door: compare sizes
+    for s in range(S):
+        gv, ov = gm[s].stats(), om[s].stats()
+        assert abs(gv[0] - ov[0]) <= max(2, ov[0] // 1000) and abs(gv[1] - ov[1]) <= max(4, ov[1] // 1000)
+    sset.close()
+
+
+def test_scanset_deskew_bit_exact(ctx, world, scene, traj):
+    from mola_lidar_odometry_b200.api import ScanSet
+    tw = synth.body_twists(traj)
+    fp = world["fp"]
+    raws, ts = zip(*[synth.scan_skewed(scene, traj[k], tw[k], scan_seed=1000 + k) for k in (3, 4)])
+    ts = [t - 0.5 * (t.min() + t.max()) for t in ts]
+    sset = ScanSet(ctx, 2)
+    info = sset.filter([1, 0], list(raws), [fp, fp], ts=list(ts))
+    with pytest.raises(Exception):
+        sset.download(0, 1)                   # skewed layers: deskew first
+    twists = np.stack([tw[3], tw[4]])
+    info2 = sset.deskew([1, 0], twists)
+    for j, slot in enumerate([1, 0]):
+        a, b = O.filter_1st_pass_xyzt(raws[j], ts[j], fp)
+        assert (info[j].n_map, info[j].n_icp) == (len(a), len(b)) == (info2[j].n_map, info2[j].n_icp)
+        assert np.array_equal(sset.download(slot, 0).view(np.uint32), O.deskew(a, twists[j]).view(np.uint32))
+        assert np.array_equal(sset.download(slot, 1).view(np.uint32), O.deskew(b, twists[j]).view(np.uint32))
+        assert np.array_equal(np.array(info2[j].icp_max[:], np.float32), O.deskew(b, twists[j]).max(axis=0))
+    sset.close()

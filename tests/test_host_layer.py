@@ -26,7 +26,7 @@ def _bench_env(monkeypatch):
 def test_host_header_symbols_exported(built):
     from mola_lidar_odometry_b200 import host_api
     txt = re.sub(r"/\*.*?\*/", "", (ROOT / "include" / "mlo_b200_host.h").read_text(), flags=re.S)
-    names = sorted(set(re.findall(r"\b(mlo_(?:lo|host)_[a-z0-9_]+)\s*\(", txt)))
+    names = sorted(set(re.findall(r"\b(mlo_(?:lo|host|fleet)_[a-z0-9_]+)\s*\(", txt)))
     lib = ctypes.CDLL(str(capi.LIB_PATH))
     assert names and not [n for n in names if not hasattr(lib, n)]
     assert set(names) == set(host_api.HOST_SIGNATURES)
@@ -211,3 +211,130 @@ def test_deskew_requires_timestamps_when_not_ignored(built, scene, traj, monkeyp
     raw = scene.scan(traj[0], scan_seed=1000)
     with pytest.raises(RuntimeError):                       # the reference's rosbag2 test fails the same way
         lo.on_lidar(raw, 0.0)                               # (test_lidar_odometry_rosbag2.cpp, MOLA_IGNORE_NO_POINT_STAMPS=false)
+
+
+# ------------------------------------------------------------------------------------------------ fleets (lock step)
+def _fleet_inputs(scene, n_seq, n_scans, skew=False):
+    """n_seq different drives through the same scene; sequence s starts 2 scans later than s-1 (idle slots first)."""
+    trajs = [synth.trajectory_T00(n_scans + 4, seed=7 + s) for s in range(n_seq)]
+    tws = [synth.body_twists(tr) for tr in trajs]
+    steps = []
+    for k in range(n_scans):
+        clouds, ts = [], []
+        for s in range(n_seq):
+            kk = k - 2 * s
+            if kk < 0:
+                clouds.append(None)
+                ts.append(None)
+            elif skew:
+                raw, t = synth.scan_skewed(scene, trajs[s][kk], tws[s][kk], scan_seed=(7 + s) * 1000 + kk)
+                clouds.append(raw)
+                ts.append(t)
+            else:
+                clouds.append(scene.scan(trajs[s][kk], scan_seed=(7 + s) * 1000 + kk))
+                ts.append(None)
+        steps.append((clouds, [0.1 * k] * n_seq, ts if skew else None))
+    return steps
+
+
+def _same_output(a, b, exact):
+    assert (a.processed, a.icp_ran, a.icp_good, a.map_updated, a.icp_runs) == (b.processed, b.icp_ran, b.icp_good, b.map_updated, b.icp_runs)
+    assert (a.n_map_layer, a.n_icp_layer) == (b.n_map_layer, b.n_icp_layer)
+    if exact:
+        assert np.array_equal(a.pose, b.pose) and a.sigma == b.sigma and a.quality == b.quality
+        assert (a.icp_iterations, a.termination) == (b.icp_iterations, b.termination)
+
+
+def test_fleet_on_oracle_equals_independent_sequences(built, scene):
+    """LidarOdometryFleetT only regroups calls: over the oracle backend its per-sequence outputs are bit-identical to
+    stand-alone LidarOdometry instances (idle slots, staggered starts, first-scan seeding, keyframes)."""
+    from oracle import oracle_py as O
+    S, N = 3, 9
+    steps = _fleet_inputs(scene, S, N)
+    fleet = O.OracleLidarOdometryFleet(DEFAULT_YAML, S)
+    solo = [O.OracleLidarOdometry(DEFAULT_YAML) for _ in range(S)]
+    for clouds, stamps, _ in steps:
+        outs = fleet.on_lidar(clouds, stamps)
+        for s in range(S):
+            if clouds[s] is None:
+                assert not outs[s].processed
+                continue
+            _same_output(outs[s], solo[s].on_lidar(clouds[s], stamps[s]), exact=True)
+    assert outs[0].icp_ran and outs[S - 1].icp_ran
+
+
+def test_fleet_on_oracle_deskew_twist_loop(built, scene, monkeypatch):
+    """The hook re-run / re-deskew loop (LidarOdometry.cpp:954-1007) regrouped across sequences: still bit-identical."""
+    from oracle import oracle_py as O
+    monkeypatch.setenv("MOLA_OPTIMIZE_TWIST", "true")
+    monkeypatch.setenv("MOLA_SKIP_DESKEW", "false")
+    S, N = 2, 7
+    steps = _fleet_inputs(scene, S, N, skew=True)
+    fleet = O.OracleLidarOdometryFleet(DEFAULT_YAML, S)
+    solo = [O.OracleLidarOdometry(DEFAULT_YAML) for _ in range(S)]
+    for clouds, stamps, ts in steps:
+        outs = fleet.on_lidar(clouds, stamps, ts)
+        for s in range(S):
+            if clouds[s] is not None:
+                _same_output(outs[s], solo[s].on_lidar(clouds[s], stamps[s], ts[s]), exact=True)
+
+
+@pytest.mark.gpu
+def test_fleet_gpu_matches_oracle_sequences(ctx, scene):
+    """One device pass per phase over 4 sequences with their own local maps == 4 oracle sequences (1 mm / 0.01 deg)."""
+    from mola_lidar_odometry_b200.host_api import LidarOdometryFleet
+    from oracle import oracle_py as O
+    S, N = 4, 16
+    steps = _fleet_inputs(scene, S, N)
+    fleet = LidarOdometryFleet(ctx, DEFAULT_YAML, S)
+    solo = [O.OracleLidarOdometry(DEFAULT_YAML) for _ in range(S)]
+    worst = (0.0, 0.0)
+    for clouds, stamps, _ in steps:
+        outs = fleet.on_lidar(clouds, stamps)
+        for s in range(S):
+            if clouds[s] is None:
+                assert not outs[s].processed
+                continue
+            b = solo[s].on_lidar(clouds[s], stamps[s])
+            _same_output(outs[s], b, exact=False)
+            et, er = O.pose_error(outs[s].pose, b.pose)
+            worst = max(worst, (et, er))
+            assert et <= 1e-3 and er <= 1e-2, (s, et, er)
+            assert outs[s].sigma == pytest.approx(b.sigma, abs=1e-6)
+    st, ps = fleet.trajectory(S - 1)
+    assert len(st) == N - 2 * (S - 1) and np.allclose(ps[-1], outs[S - 1].pose)
+    print("worst fleet-vs-oracle delta (m, deg):", worst)
+    fleet.close()
+
+
+@pytest.mark.gpu
+def test_fleet_gpu_deskew_and_ndt(ctx, scene, monkeypatch):
+    """Fleet over lidar3d-ndt.yaml, and over the default pipeline with deskew + twist loop on, vs oracle sequences."""
+    from mola_lidar_odometry_b200.host_api import LidarOdometryFleet
+    from oracle import oracle_py as O
+    S, N = 2, 8
+    steps = _fleet_inputs(scene, S, N)
+    fleet = LidarOdometryFleet(ctx, NDT_YAML, S)
+    solo = [O.OracleLidarOdometry(NDT_YAML) for _ in range(S)]
+    for clouds, stamps, _ in steps:
+        outs = fleet.on_lidar(clouds, stamps)
+        for s in range(S):
+            if clouds[s] is not None:
+                b = solo[s].on_lidar(clouds[s], stamps[s])
+                et, er = O.pose_error(outs[s].pose, b.pose)
+                assert et <= 1e-3 and er <= 1e-2 and (outs[s].icp_good, outs[s].map_updated) == (b.icp_good, b.map_updated)
+    fleet.close()
+    monkeypatch.setenv("MOLA_OPTIMIZE_TWIST", "true")
+    monkeypatch.setenv("MOLA_SKIP_DESKEW", "false")
+    steps = _fleet_inputs(scene, S, N, skew=True)
+    fleet = LidarOdometryFleet(ctx, DEFAULT_YAML, S)
+    solo = [O.OracleLidarOdometry(DEFAULT_YAML) for _ in range(S)]
+    for clouds, stamps, ts in steps:
+        outs = fleet.on_lidar(clouds, stamps, ts)
+        for s in range(S):
+            if clouds[s] is not None:
+                b = solo[s].on_lidar(clouds[s], stamps[s], ts[s])
+                _same_output(outs[s], b, exact=False)
+                et, er = O.pose_error(outs[s].pose, b.pose)
+                assert et <= 1e-3 and er <= 1e-2, (s, et, er)
+    fleet.close()
