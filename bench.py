@@ -426,6 +426,8 @@ def run_sequences(args, rank, local_rank, world):
             ctx.profile_get(True)
         t0 = time.perf_counter()
         for k in range(N):
+            if k + 1 < N and not args.no_prefetch:   # upload of step k+1 overlaps the ICP of step k
+                fleet.prefetch([views[s][k + 1] for s in range(S)])
             outs = fleet.on_lidar([views[s][k] for s in range(S)], [0.1 * k] * S)
             for s in range(S):
                 poses[s].append(outs[s].pose.copy())
@@ -503,6 +505,7 @@ def main():
                     help="config1 = the headline (default); sequence = BASELINE configs[2]/[4] full odometry loop; "
                          "ndt = configs[3] (lidar3d-ndt.yaml, O128 sensor)")
     ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (sequence/ndt workloads)")
+    ap.add_argument("--no-prefetch", action="store_true", help="sequence workloads: no overlapped upload of the next step")
     ap.add_argument("--scans", type=int, default=120, help="scans per sequence (sequence/ndt workloads)")
     args = ap.parse_args()
 

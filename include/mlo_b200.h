@@ -316,6 +316,12 @@ void mlo_scanset_destroy(mlo_scanset* set);
  * mlo_scanset_deskew must run before align/insert.  info[j] describes job j. */
 int mlo_scanset_filter(mlo_scanset* set, uint32_t n_jobs, const mlo_scan_job* jobs, uint32_t stride_floats,
                        mlo_scan_info* info);
+/* Optional: announce the raw clouds of the NEXT mlo_scanset_filter call (same host pointers, sizes and order of the
+ * non-empty clouds).  Their host-to-device transfer is enqueued on the context's copy stream from inside the next
+ * compute call, so it overlaps that call's ICP loop; the buffers must stay valid and unchanged until that filter call
+ * (pinned memory recommended).  A filter call with other clouds simply ignores the announcement. */
+int mlo_scanset_prefetch(mlo_scanset* set, uint32_t n_clouds, const float* const* pts, const uint64_t* n,
+                         uint32_t stride_floats);
 /* FilterDeskew of the listed slots with one twist (vx vy vz wx wy wz) each; info[i] is refreshed for slots[i]. */
 int mlo_scanset_deskew(mlo_scanset* set, uint32_t n, const uint32_t* slots, const double* twists6, mlo_scan_info* info);
 /* ICP::align of the listed scans, each against its own map, in one device pass. */

@@ -45,6 +45,9 @@ const char* mlo_fleet_last_error(const mlo_fleet* f);
 /* One lock step: cloud i -> sequence i (pts[i] == NULL leaves sequence i idle; t may be NULL, or hold NULL entries). */
 int mlo_fleet_on_lidar(mlo_fleet* f, const float* const* pts, uint32_t stride_floats, const uint64_t* n, const double* stamps_s,
                        const float* const* t, mlo_lo_scan_output* out);
+/* Optional: announce the clouds of the NEXT mlo_fleet_on_lidar call (same pointers / sizes); their host-to-device
+ * transfer then overlaps the ICP of the call made in between (mlo_scanset_prefetch).  Buffers must stay valid. */
+int mlo_fleet_prefetch(mlo_fleet* f, const float* const* pts, uint32_t stride_floats, const uint64_t* n);
 /* Host wall time [ms] per phase accumulated since the last reset: [0] per-scan host logic before the filter,
  * [1] filter pass, [2] deskew passes, [3] align passes, [4] host logic after ICP, [5] insert pass, [6] lock steps. */
 int mlo_fleet_phase_times(mlo_fleet* f, double out_ms[8], int reset);

@@ -212,6 +212,7 @@ _SIGNATURES = {
     "mlo_scanset_create": (C.c_int, [_vp, C.c_uint32, C.POINTER(_vp)]),
     "mlo_scanset_destroy": (None, [_vp]),
     "mlo_scanset_filter": (C.c_int, [_vp, C.c_uint32, C.POINTER(ScanJob), C.c_uint32, C.POINTER(ScanInfo)]),
+    "mlo_scanset_prefetch": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.c_uint32]),
     "mlo_scanset_deskew": (C.c_int, [_vp, C.c_uint32, _vp, _vp, C.POINTER(ScanInfo)]),
     "mlo_scanset_align": (C.c_int, [_vp, C.c_uint32, C.POINTER(AlignJob), C.POINTER(IcpResult)]),
     "mlo_scanset_insert": (C.c_int, [_vp, C.c_uint32, C.POINTER(InsertJob), C.POINTER(MapCounts)]),

@@ -703,37 +703,66 @@ MLO_D void finish_iteration(const IcpProblem& P, IcpState& S, double* T, double*
   }
 }
 
-// The solve step, executed by ONE warp: ordered sum of the problem's block partials (lane k owns element k,
-// read through L2), then lane 0 applies the prior, solves the 6x6 system, retracts and does the
-// end-of-iteration bookkeeping.  Returns (on every lane) 0 = problem finished, 1 = another inner GN
-// iteration is pending, 2 = next ICP iteration.
-__device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const double* partials, const uint32_t* part_cnt, int after_match,
-                                       uint32_t nblk_match) {
+// Sum of a problem's block partials by a whole thread block (SOLVE_WARPS warps): warp w adds the partials
+// b = w, w + SOLVE_WARPS, ... in ascending order (lane k owns element k, eight L2 loads in flight), then the warp
+// sums are combined in warp order.  The order is fixed by (nblk, SOLVE_WARPS) alone, so a run is reproducible.
+// Every thread of the block must call this (it contains a barrier); the totals land in s_tot / s_cnt.
+constexpr uint32_t SOLVE_WARPS = ICP_BLOCK / 32;
+struct SolveScratch {
+  double tot[NACC];
+  uint32_t cnt[2];
+  double part[SOLVE_WARPS][NACC];
+  uint32_t pcnt[SOLVE_WARPS][2];
+};
+MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const uint32_t* part_cnt, uint32_t nblk,
+                              SolveScratch& sc) {
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  if (warp < SOLVE_WARPS) {
+    if (lane < NACC) {
+      double acc = 0.0;
+      const double* base = partials + size_t(P.part_begin) * NACC + lane;
+      uint32_t b = warp;
+      for (; b + 7 * SOLVE_WARPS < nblk; b += 8 * SOLVE_WARPS) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) v[u] = __ldcg(base + size_t(b + u * SOLVE_WARPS) * NACC);
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u];
+      }
+      for (; b < nblk; b += SOLVE_WARPS) acc += __ldcg(base + size_t(b) * NACC);
+      sc.part[warp][lane] = acc;
+    } else if (lane < NACC + 2) {
+      uint32_t cnt = 0;
+      for (uint32_t b = warp; b < nblk; b += SOLVE_WARPS) cnt += __ldcg(&part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)]);
+      sc.pcnt[warp][lane - NACC] = cnt;
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double t = sc.part[0][threadIdx.x];
+#pragma unroll
+    for (uint32_t w = 1; w < SOLVE_WARPS; w++) t += sc.part[w][threadIdx.x];
+    sc.tot[threadIdx.x] = t;
+  } else if (threadIdx.x < NACC + 2) {
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < SOLVE_WARPS; w++) t += sc.pcnt[w][threadIdx.x - NACC];
+    sc.cnt[threadIdx.x - NACC] = t;
+  }
+  __syncthreads();
+}
+
+// The solve step, executed by ONE warp after sum_partials_block: lane 0 applies the prior, solves the 6x6 system,
+// retracts and does the end-of-iteration bookkeeping.  Returns (on every lane) 0 = problem finished, 1 = another
+// inner GN iteration is pending, 2 = next ICP iteration.
+__device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const SolveScratch& sc, int after_match) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u;
-  double acc = 0.0;
-  uint32_t cnt = 0;
-  const uint32_t nblk = after_match ? nblk_match : P.n_blocks_acc;
-  if (lane < NACC) {
-    // sequential (deterministic) order, eight L2 loads in flight at a time
-    const double* base = partials + size_t(P.part_begin) * NACC + lane;
-    uint32_t b = 0;
-    for (; b + 8 <= nblk; b += 8) {
-      double v[8];
-#pragma unroll
-      for (int u = 0; u < 8; u++) v[u] = __ldcg(base + size_t(b + u) * NACC);
-#pragma unroll
-      for (int u = 0; u < 8; u++) acc += v[u];
-    }
-    for (; b < nblk; b++) acc += __ldcg(base + size_t(b) * NACC);
-  } else if (lane < NACC + 2) {
-    for (uint32_t b = 0; b < nblk; b++) cnt += __ldcg(&part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)]);
-  }
   double a[NACC];
 #pragma unroll
-  for (int k = 0; k < int(NACC); k++) a[k] = __shfl_sync(FULL, acc, k);
-  const uint32_t npairs = __shfl_sync(FULL, cnt, NACC);
-  const uint32_t ncand = __shfl_sync(FULL, cnt, NACC + 1);
+  for (int k = 0; k < int(NACC); k++) a[k] = sc.tot[k];
+  const uint32_t npairs = sc.cnt[0];
+  const uint32_t ncand = sc.cnt[1];
   // stage T / prev / prev2 (36 contiguous doubles of the state) in shared memory: one coalesced read and one
   // coalesced write-back by the whole warp instead of ~100 serial global accesses by lane 0
   __shared__ double s_pose[36];
@@ -924,15 +953,18 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   chunk_accumulate(P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
-// one warp per problem. `after_match` = 1 when the partials come from the match phase (inner 0).
-__global__ void __launch_bounds__(32)
+// one block per problem. `after_match` = 1 when the partials come from the match phase (inner 0).
+__global__ void __launch_bounds__(ICP_BLOCK)
     k_solve(const IcpProblem* __restrict__ probs, IcpState* __restrict__ states, const double* partials,
             const uint32_t* part_cnt, int after_match, uint32_t* __restrict__ n_active) {
   const IcpProblem& P = probs[blockIdx.x];
   IcpState& S = states[blockIdx.x];
   if (S.done) return;
   if (!after_match && !S.inner_pending) return;
-  const int next = solve_step(P, S, partials, part_cnt, after_match, P.n_blocks);
+  __shared__ SolveScratch sc;
+  sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc);
+  if (threadIdx.x >= 32) return;
+  const int next = solve_step(P, S, sc, after_match);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -1055,6 +1087,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
                      const float4* __restrict__ local, float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt,
                      IcpQueue q, uint32_t qpw) {
   __shared__ MapDev sMap;
+  __shared__ SolveScratch s_solve;
   __shared__ uint32_t s_item;
   __shared__ int s_last;
   __shared__ double sT[12];
@@ -1109,10 +1142,12 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
       if (s_last) atomicExch(&q.phase_cnt[prob], 0u);
     }
     __syncthreads();
+    if (s_last) {
+      __threadfence();  // acquire: the other blocks' partials (read through L2) and the problem state
+      sum_partials_block(P, partials, part_cnt, phase == 0 ? P.n_blocks_pers : P.n_blocks_acc, s_solve);
+    }
     if (s_last && threadIdx.x < 32) {
-      if (threadIdx.x == 0) __threadfence();  // acquire: lane 0 reads the problem state with plain loads
-      __syncwarp();
-      const int next = solve_step(P, S, partials, part_cnt, phase == 0, P.n_blocks_pers);
+      const int next = solve_step(P, S, s_solve, phase == 0);
       if (threadIdx.x == 0) __threadfence();  // state of the problem visible before its next items
       __syncwarp();
       if (next == 1) {

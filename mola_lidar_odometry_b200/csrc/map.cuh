@@ -223,11 +223,9 @@ MLO_D void voxel_stats(const MapDev& m, uint32_t vid, uint32_t n) {
 //           appends the pending points in index order (cap and min-distance tests as upstream).
 constexpr uint32_t PSLOT_NONE = 0xFFFFFFFFu;
 
-__global__ void k_insert_link(MapDev m, const float* __restrict__ src, uint32_t stride, uint32_t n, Pose34 T,
-                              float4* __restrict__ g_out, uint32_t* __restrict__ pslot, int32_t* head,
-                              int32_t* __restrict__ next) {
-  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
+MLO_D void insert_link_point(const MapDev& m, const float* __restrict__ src, uint32_t stride, uint32_t i, const Pose34& T,
+                             float4* __restrict__ g_out, uint32_t* __restrict__ pslot, int32_t* head,
+                             int32_t* __restrict__ next) {
   const float* p = src + size_t(i) * stride;
   float gx, gy, gz;
   compose_point_f(T.m, p[0], p[1], p[2], gx, gy, gz);
@@ -248,10 +246,16 @@ __global__ void k_insert_link(MapDev m, const float* __restrict__ src, uint32_t 
   next[i] = atomicExch(&head[c], int32_t(i));
 }
 
-__global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__ g, const uint32_t* __restrict__ pslot,
-                                int32_t* head, const int32_t* __restrict__ next) {
+__global__ void k_insert_link(MapDev m, const float* __restrict__ src, uint32_t stride, uint32_t n, Pose34 T,
+                              float4* __restrict__ g_out, uint32_t* __restrict__ pslot, int32_t* head,
+                              int32_t* __restrict__ next) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  insert_link_point(m, src, stride, i, T, g_out, pslot, head, next);
+}
+
+MLO_D void insert_commit_point(const MapDev& m, uint32_t i, const float4* __restrict__ g, const uint32_t* __restrict__ pslot,
+                               int32_t* head, const int32_t* __restrict__ next) {
   const uint32_t c = pslot[i];
   if (c == PSLOT_NONE) return;
   // owner = smallest index on the list
@@ -293,6 +297,39 @@ __global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__
   head[c] = -1;  // leave the scratch list heads clean for the next insert
 }
 
+__global__ void k_insert_commit(MapDev m, uint32_t n, const float4* __restrict__ g, const uint32_t* __restrict__ pslot,
+                                int32_t* head, const int32_t* __restrict__ next) {
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  insert_commit_point(m, i, g, pslot, head, next);
+}
+
+// Batched forms for a lock step of a fleet: job blockIdx.y = one (map, cloud, pose) triple; the three passes of all
+// jobs run as three launches instead of three per map.
+struct InsertJobDev {
+  MapDev m;
+  const float* src;  // float4 points of the map layer
+  uint32_t n;
+  Pose34 T;
+  float4* g;         // scratch, n entries each
+  uint32_t* pslot;
+  int32_t* next;
+  int32_t* head;     // the map's per-cell list heads
+  int32_t sx, sy, sz, d;  // cull: sensor cell and distance in cells (d < 0: no cull)
+};
+__global__ void k_insert_link_batch(const InsertJobDev* __restrict__ jobs) {
+  const InsertJobDev& j = jobs[blockIdx.y];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  insert_link_point(j.m, j.src, 4, i, j.T, j.g, j.pslot, j.head, j.next);
+}
+__global__ void k_insert_commit_batch(const InsertJobDev* __restrict__ jobs) {
+  const InsertJobDev& j = jobs[blockIdx.y];
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= j.n) return;
+  insert_commit_point(j.m, i, j.g, j.pslot, j.head, j.next);
+}
+
 // ------------------------------------------------------------------ cull (filtered rebuild)
 // insertOpts.remove_voxels_farther_than (default.yaml:238): keep voxels whose per-axis cell distance
 // to the sensor's cell is <= ceil(dist * voxel_size_inv); survivors are re-hashed into `dst`.
@@ -332,8 +369,7 @@ __global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_buckets, int32_t sx
 
 // In-place cull: one thread per voxel id below the high-water mark.  An out-of-range voxel loses its cell word
 // (the column bucket stays claimed), its id goes on the free stack and its points leave the statistics.
-__global__ void k_cull_inplace(MapDev m, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
-  const uint32_t v = blockIdx.x * blockDim.x + threadIdx.x;
+MLO_D void cull_voxel(const MapDev& m, uint32_t v, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
   const uint32_t hwm = min(*reinterpret_cast<volatile uint32_t*>(&m.counters[0]), m.capacity_voxels);
   if (v >= hwm) return;
   const unsigned long long key = m.vkey[v];
@@ -358,6 +394,14 @@ __global__ void k_cull_inplace(MapDev m, int32_t sx, int32_t sy, int32_t sz, int
   atomicAdd(&m.counters[5], 1u);
   const int slot = atomicAdd(reinterpret_cast<int*>(&m.counters[3]), 1);
   m.free_ids[slot] = v;
+}
+__global__ void k_cull_inplace(MapDev m, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
+  cull_voxel(m, blockIdx.x * blockDim.x + threadIdx.x, sx, sy, sz, d);
+}
+__global__ void k_cull_inplace_batch(const InsertJobDev* __restrict__ jobs) {
+  const InsertJobDev& j = jobs[blockIdx.y];
+  if (j.d < 0) return;
+  cull_voxel(j.m, blockIdx.x * blockDim.x + threadIdx.x, j.sx, j.sy, j.sz, j.d);
 }
 
 // ------------------------------------------------------------------ nearest neighbour

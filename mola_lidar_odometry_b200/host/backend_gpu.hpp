@@ -38,6 +38,9 @@ struct BackendGpu {
   void scanset_filter(ScanSet* s, uint32_t n, const mlo_scan_job* jobs, uint32_t stride, mlo_scan_info* info) {
     check(mlo_scanset_filter(s, n, jobs, stride, info));
   }
+  void scanset_prefetch(ScanSet* s, uint32_t n, const float* const* pts, const uint64_t* np, uint32_t stride) {
+    check(mlo_scanset_prefetch(s, n, pts, np, stride));
+  }
   void scanset_deskew(ScanSet* s, uint32_t n, const uint32_t* slots, const double* twists6, mlo_scan_info* info) {
     check(mlo_scanset_deskew(s, n, slots, twists6, info));
   }

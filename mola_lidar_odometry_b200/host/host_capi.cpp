@@ -133,6 +133,17 @@ int mlo_fleet_on_lidar(mlo_fleet* f, const float* const* pts, uint32_t stride, c
   }
 }
 
+int mlo_fleet_prefetch(mlo_fleet* f, const float* const* pts, uint32_t stride, const uint64_t* n) {
+  if (!f || !pts || !n || (stride != 3 && stride != 4)) return MLO_ERR_INVALID_ARG;
+  try {
+    f->fleet.prefetch(pts, stride, n);
+    return MLO_OK;
+  } catch (const std::exception& e) {
+    f->err = e.what();
+    return MLO_ERR_CUDA;
+  }
+}
+
 int mlo_fleet_phase_times(mlo_fleet* f, double out_ms[8], int reset) {
   if (!f || !out_ms) return MLO_ERR_INVALID_ARG;
   for (int k = 0; k < 8; k++) out_ms[k] = f->fleet.phase_ms[k];

@@ -201,14 +201,16 @@ class ICP {
     t1_.assign(len, 0.0);
     t2_.assign(len, 0.0);
     t3_.assign(len, 1.0);
-    const double saved_it = source->has("ICP_ITERATION") ? source->get("ICP_ITERATION") : 0.0;
+    if (!source->has("ICP_ITERATION")) source->updateVariable("ICP_ITERATION", 0.0);
+    const int it_slot = source->slot("ICP_ITERATION");
+    const double saved_it = source->at(it_slot);
     for (uint32_t it = 0; it < len; it++) {
-      source->updateVariable("ICP_ITERATION", double(it));
+      source->set(it_slot, double(it));
       if (m_pt2pt) t1_[it] = m_pt2pt->threshold.eval(*source);
       if (m_pt2pl) t2_[it] = m_pt2pl->distanceThreshold.eval(*source);
       if (gn) t3_[it] = gn->robustKernelParam.eval(*source);
     }
-    source->updateVariable("ICP_ITERATION", saved_it);
+    source->set(it_slot, saved_it);
     q.table_len = len;
     q.pt2pt_threshold_by_iter = t1_.data();
     q.pt2pl_threshold_by_iter = t2_.data();
@@ -870,6 +872,8 @@ class LidarOdometryFleetT {
   void initialize(const YamlNode& cfg) {
     for (auto& s : seq_) s->initialize(cfg);
   }
+  // Optional: the clouds of the NEXT onLidarBatch call; their upload overlaps the ICP of the call made in between.
+  void prefetch(const float* const* pts, uint32_t stride, const uint64_t* n) { be_.scanset_prefetch(set_, size(), pts, n, stride); }
   // One lock step: cloud i (pts[i] with n[i] points, stamp stamps[i], optional per-point times t[i]) goes to
   // sequence i; pts[i] == nullptr leaves sequence i idle.  out[i] is what onLidar() would have returned.
   // host wall time [ms] spent per phase since the last reset: 0 begin (host), 1 filter, 2 deskew, 3 align, 4 host logic

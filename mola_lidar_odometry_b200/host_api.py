@@ -36,6 +36,7 @@ HOST_SIGNATURES = {
     "mlo_fleet_destroy": (None, [_vp]),
     "mlo_fleet_last_error": (C.c_char_p, [_vp]),
     "mlo_fleet_on_lidar": (C.c_int, [_vp, _vp, _u32, _vp, _vp, _vp, C.POINTER(ScanOutput)]),
+    "mlo_fleet_prefetch": (C.c_int, [_vp, _vp, _u32, _vp]),
     "mlo_fleet_phase_times": (C.c_int, [_vp, _vp, C.c_int]),
     "mlo_fleet_trajectory": (C.c_int, [_vp, _u32, _vp, _vp, _u64, C.POINTER(_u64)]),
     "mlo_host_last_error": (C.c_char_p, []),
@@ -183,6 +184,14 @@ class LidarOdometryFleet:
             raise MloError(rc, lib().mlo_fleet_last_error(self.h).decode())
         del keep
         return list(out)
+
+    def prefetch(self, clouds):
+        """Announce the clouds of the NEXT on_lidar call (the same array objects must be passed then)."""
+        keep, stride, pts, n, _, _ = _fleet_args(clouds, [0.0] * self.n, None, _pts)
+        self._prefetched = keep
+        rc = lib().mlo_fleet_prefetch(self.h, pts, stride, n)
+        if rc != 0:
+            raise MloError(rc, lib().mlo_fleet_last_error(self.h).decode())
 
     def phase_times(self, reset: bool = True) -> dict:
         a = np.zeros(8)

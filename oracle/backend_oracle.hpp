@@ -86,6 +86,7 @@ struct BackendOracle {
       }
     }
   }
+  void scanset_prefetch(ScanSet*, uint32_t, const float* const*, const uint64_t*, uint32_t) {}  // nothing to overlap on the CPU
   void scanset_deskew(ScanSet* s, uint32_t n, const uint32_t* slots, const double* twists6, mlo_scan_info* info) {
     for (uint32_t i = 0; i < n; i++) {
       auto& sl = s->slots.at(slots[i]);
