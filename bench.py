@@ -444,11 +444,16 @@ def run_sequences(args, rank, local_rank, world):
         return wall, [(wall, np.stack(poses[s]), its[s]) for s in range(S)], prof, host_phases
     run_fleet()                               # warm-up pass (allocations, first-touch)
     l0 = ctx.launch_count
+    cuprof = os.environ.get("MLO_BENCH_CUPROF") == "1"   # ncu --profile-from-start off: capture the timed pass only
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
     wall, res, _, host_phases = run_fleet()
     torch.cuda.synchronize()
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = ctx.launch_count - l0
     t = torch.tensor([wall], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -504,7 +509,7 @@ def main():
     ap.add_argument("--workload", default="config1", choices=["config1", "sequence", "ndt"],
                     help="config1 = the headline (default); sequence = BASELINE configs[2]/[4] full odometry loop; "
                          "ndt = configs[3] (lidar3d-ndt.yaml, O128 sensor)")
-    ap.add_argument("--sequences", type=int, default=8, help="independent sequences per GPU (sequence/ndt workloads)")
+    ap.add_argument("--sequences", type=int, default=32, help="independent sequences per GPU (sequence/ndt workloads)")
     ap.add_argument("--no-prefetch", action="store_true", help="sequence workloads: no overlapped upload of the next step")
     ap.add_argument("--scans", type=int, default=120, help="scans per sequence (sequence/ndt workloads)")
     args = ap.parse_args()
@@ -602,7 +607,12 @@ def main():
     sampler = ClockSampler(local_rank)
     sampler.start()
     l0 = ctx.launch_count
+    cuprof = os.environ.get("MLO_BENCH_CUPROF") == "1"   # ncu --profile-from-start off: capture the timed region only
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStart()
     ms_dev, ms_wall = timed(step_resident, args.steps, 0)
+    if cuprof:
+        torch.cuda.cudart().cudaProfilerStop()
     launches = ctx.launch_count - l0
     clocks = sampler.stop()
     # ---- roofline pass: the same K steps again with per-kernel CUDA events inside the library (on its stream).

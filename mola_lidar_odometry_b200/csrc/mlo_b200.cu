@@ -141,6 +141,7 @@ struct mlo_map {
   uint64_t table_size = 0;  // number of 32-byte buckets
   int32_t* head = nullptr;  // per-cell (4 per bucket) scratch list heads for insert
   uint64_t n_voxels = 0, n_points = 0;  // as of the last digest of the device counters
+  uint64_t hwm = 0;                     // voxel ids handed out so far (counters[0]) as of the last digest
 };
 
 struct mlo_dcloud {
@@ -314,6 +315,7 @@ int digest_map_counters(mlo_map* m, const uint32_t* h) {
                                          std::to_string(m->dev.capacity_voxels) + ")");
   m->n_voxels = uint64_t(h[0]) - uint64_t(h[3]);
   m->n_points = h[1];
+  m->hwm = h[0];
   if (uint64_t(h[4]) * 2 > m->table_size) return map_rebuild(m, false, 0, 0, 0, 0);
   return MLO_OK;
 }
@@ -346,10 +348,13 @@ int map_insert_device(mlo_map* m, const float* d_pts, uint32_t stride, uint64_t 
 }
 
 // in-place cull (no host synchronisation): thread per voxel id, early exit above the device-side high-water mark
-int map_cull_device(mlo_map* m, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
+// `new_since_digest` = upper bound of the voxel ids handed out since the counters were last read by the host
+int map_cull_device(mlo_map* m, int32_t sx, int32_t sy, int32_t sz, int32_t d, uint64_t new_since_digest) {
   mlo_ctx* c = m->ctx;
   CU(c, cudaMemsetAsync(m->dev.counters + 5, 0, sizeof(uint32_t), c->stream));
-  LAUNCH(c, k_cull_inplace, uint32_t((uint64_t(m->dev.capacity_voxels) + 255) / 256), 256, m->dev, sx, sy, sz, d);
+  const uint64_t bound = std::min<uint64_t>(m->dev.capacity_voxels, m->hwm + new_since_digest);
+  if (bound == 0) return MLO_OK;
+  LAUNCH(c, k_cull_inplace, uint32_t((bound + 255) / 256), 256, m->dev, sx, sy, sz, d);
   CU(c, cudaGetLastError());
   return MLO_OK;
 }
@@ -1057,6 +1062,7 @@ void mlo_map_destroy(mlo_map* m) {
 int mlo_map_clear(mlo_map* m) {
   if (!m) return MLO_ERR_INVALID_ARG;
   DeviceGuard g(m->ctx->device);
+  m->hwm = m->n_voxels = m->n_points = 0;
   return clear_map_buffers(m->ctx, m->dev, m->table_size);
 }
 
@@ -1103,7 +1109,7 @@ int mlo_map_cull(mlo_map* m, const double sensor[3], float dist) {
                 sz = voxel_index_map(float(sensor[2]), inv);
   const int32_t d = int32_t(std::ceil(dist * inv));
   const size_t e0 = prof_begin(c);
-  int rc = map_cull_device(m, sx, sy, sz, d);
+  int rc = map_cull_device(m, sx, sy, sz, d, 0);
   prof_end(c, 2, e0);
   if (rc != MLO_OK) return rc;
   rc = check_map_errors(m);
@@ -1550,7 +1556,7 @@ int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t strid
       const double s[3] = {out->pose_3x4[3], out->pose_3x4[7], out->pose_3x4[11]};
       const float inv = map->dev.inv_voxel;
       rc = map_cull_device(map, voxel_index_map(float(s[0]), inv), voxel_index_map(float(s[1]), inv),
-                           voxel_index_map(float(s[2]), inv), int32_t(std::ceil(cull_farther_than * inv)));
+                           voxel_index_map(float(s[2]), inv), int32_t(std::ceil(cull_farther_than * inv)), nmap[0]);
       if (rc != MLO_OK) return rc;
     }
     prof_end(c, 2, e0);
@@ -1855,8 +1861,8 @@ int mlo_scanset_insert(mlo_scanset* set, uint32_t n_jobs, const mlo_insert_job* 
       d.sy = voxel_index_map(float(jobs[j].pose_3x4[7]), inv);
       d.sz = voxel_index_map(float(jobs[j].pose_3x4[11]), inv);
       d.d = int32_t(std::ceil(jobs[j].cull_farther_than * inv));
-      any_cull = true;
-      max_cap = std::max(max_cap, m->dev.capacity_voxels);
+      any_cull = true;  // the cull pass only has to visit voxel ids below the high-water mark after this insert
+      max_cap = std::max<uint32_t>(max_cap, uint32_t(std::min<uint64_t>(m->dev.capacity_voxels, m->hwm + sl.n_map)));
     }
     off += sl.n_map;
     max_n = std::max(max_n, sl.n_map);

@@ -1,14 +1,10 @@
 #!/bin/bash
 run() { # S extra-env extra-args
   echo "== S=$1 $2 $3"
-  env $2 timeout 300 python bench.py --workload sequence --sequences $1 --scans 60 --no-cpu-baseline $3 2>/dev/null | python -c "
+  env $2 timeout 300 python bench.py --sequences $1 --no-cpu-baseline $3 2>/dev/null | python -c "
 import json,sys
 d=json.loads(sys.stdin.read()); print(round(d['value'],1),'scans/s', {k:round(v,3) for k,v in d['phases']['host_wall_timed_pass'].items()}, {k:round(v,3) for k,v in d['phases']['device_events_pass'].items()})"
 }
-run 1 X=1
-run 8 X=1
-run 8 X=1 --no-prefetch
-run 32 X=1
-run 32 X=1 --no-prefetch
-run 32 MLO_PERSISTENT=2
-run 64 X=1
+run 32 X=1 "--workload sequence --scans 60"
+run 64 X=1 "--workload sequence --scans 60"
+run 8 X=1 "--workload ndt --scans 40"
