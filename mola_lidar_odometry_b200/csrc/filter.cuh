@@ -63,37 +63,52 @@ MLO_D bool predicate_keep(const DecimJob& j, float x, float y, float z) {
   return true;
 }
 
+// Neighbouring returns of a sweep mostly fall into the same voxel, so the lanes of a warp first agree on their distinct
+// keys (MATCH.ANY): only the lowest lane of each group — the smallest input index of the group — probes the table and does
+// the atomicMin; the others take its slot.  Same table contents as one atomic per point, several times fewer atomics.
 __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_hash(const DecimJob* __restrict__ jobs) {
   const DecimJob& j = jobs[blockIdx.y];
   const uint32_t n = job_n(j);
+  if (blockIdx.x * DECIM_BLOCK >= n) return;  // whole block beyond the cloud (uniform)
   const uint32_t i = blockIdx.x * DECIM_BLOCK + threadIdx.x;
-  bool pred = false;
+  const uint32_t lane = threadIdx.x & 31u;
+  bool pred = false, valid = false;
+  uint64_t key = 0;
+  uint32_t h = 0;
   if (i < n) {
     const float4 p = load_point(j.in, j.in_stride, i);
     pred = predicate_keep(j, p.x, p.y, p.z);
-    uint32_t slot = SLOT_NONE;
     if (pred) {
       const int32_t kx = voxel_index_filter(p.x, j.resolution), ky = voxel_index_filter(p.y, j.resolution),
                     kz = voxel_index_filter(p.z, j.resolution);
       if (key_in_range(kx) && key_in_range(ky) && key_in_range(kz)) {
-        const uint64_t key = pack_key(kx, ky, kz);
-        uint32_t h = hash_cell(kx, ky, kz) & j.tab_mask;
-        for (;;) {
-          unsigned long long* kp = reinterpret_cast<unsigned long long*>(&j.tab_keys[h]);
-          unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-          if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-          if (cur == KEY_EMPTY || cur == key) break;
-          h = (h + 1) & j.tab_mask;
-        }
-        atomicMin(&j.tab_first[h], i);
-        slot = h;
+        key = pack_key(kx, ky, kz);
+        h = hash_cell(kx, ky, kz) & j.tab_mask;
+        valid = true;
       } else {
         atomicOr(j.err, ERR_KEY_RANGE);
         pred = false;
       }
     }
-    j.pslot[i] = slot;
   }
+  // packed keys use 63 bits: the top bit marks lanes without a key (each its own group)
+  const uint64_t mkey = valid ? key : (0x8000000000000000ull | lane);
+  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, mkey);
+  const int leader = __ffs(peers) - 1;
+  uint32_t slot = SLOT_NONE;
+  if (valid && int(lane) == leader) {
+    for (;;) {
+      unsigned long long* kp = reinterpret_cast<unsigned long long*>(&j.tab_keys[h]);
+      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+      if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+      if (cur == KEY_EMPTY || cur == key) break;
+      h = (h + 1) & j.tab_mask;
+    }
+    atomicMin(&j.tab_first[h], i);
+    slot = h;
+  }
+  slot = __shfl_sync(0xFFFFFFFFu, slot, leader);
+  if (i < n) j.pslot[i] = valid ? slot : SLOT_NONE;
   const uint32_t c = __syncthreads_count(pred);
   if (threadIdx.x == 0 && c) atomicAdd(j.npred, c);
 }

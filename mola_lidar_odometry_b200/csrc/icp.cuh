@@ -863,6 +863,7 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const S
     if (lane == 0) step_measure(sT, sPrev, dt, dr);
     if (lane == 1 && has2) step_measure(sT, sPrev2, dt, dr);
     const double dt1 = __shfl_sync(FULL, dt, 1), dr1 = __shfl_sync(FULL, dr, 1);
+    __syncwarp();  // lane 1 has read prev2 before lane 0 overwrites it below
     if (lane == 0) {
       finish_iteration(P, S, sT, sPrev, sPrev2, fmin(dt, dt1), fmin(dr, dr1));
       next = S.done ? 0 : 2;
