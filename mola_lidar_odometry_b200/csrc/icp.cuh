@@ -380,47 +380,77 @@ struct WarpScratch {
   uint16_t list[WL_CAP];
 };
 
-MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
-  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
-  for (uint32_t base = 0; base < n; base += 16) {
-    float4 p[4];
-    uint32_t meta[4];  // (valid << 31) | (order << 5) | q, order = e*32 + slot; q is shared by the 8 lanes of a segment
+// one batch of the drain: 4 segments per lane group (16 per warp); issue the loads of [base, base + 16)
+MLO_D void wl_issue(const MapDev& map, const WarpScratch& ws, uint32_t n, uint32_t base, uint32_t grp, uint32_t sub, float4 (&p)[4],
+                    uint32_t (&meta)[4]) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const uint32_t idx = base + u * 4 + grp;
-      meta[u] = 0;
-      if (idx < n) {
-        const uint32_t it = ws.list[idx];
-        const uint32_t q = it & 31u, e = (it >> 5) & 31u, slot = (it >> 10) * 8u + sub;
-        const uint32_t w = ws.words[e][q];
-        meta[u] = q;
-        if (slot < cell_cnt(w)) {
-          p[u] = __ldg(map.pts + size_t(cell_vid(w)) * map.row + slot);
-          meta[u] = 0x80000000u | ((e * 32u + slot) << 5) | q;
-        }
+  for (int u = 0; u < 4; u++) {
+    const uint32_t idx = base + u * 4 + grp;
+    meta[u] = 0;  // (valid << 31) | (order << 5) | q, order = e*32 + slot; q is shared by the 8 lanes of a segment
+    if (idx < n) {
+      const uint32_t it = ws.list[idx];
+      const uint32_t q = it & 31u, e = (it >> 5) & 31u, slot = (it >> 10) * 8u + sub;
+      const uint32_t w = ws.words[e][q];
+      meta[u] = q;
+      if (slot < cell_cnt(w)) {
+        p[u] = __ldg(map.pts + size_t(cell_vid(w)) * map.row + slot);
+        meta[u] = 0x80000000u | ((e * 32u + slot) << 5) | q;
       }
     }
+  }
+}
+MLO_D void wl_consume(WarpScratch& ws, uint32_t sub, const float4 (&p)[4], const uint32_t (&meta)[4]) {
 #pragma unroll
-    for (int u = 0; u < 4; u++) {
-      unsigned long long key = ~0ull;
-      const uint32_t q = meta[u] & 31u;
-      if (meta[u] & 0x80000000u) {
-        const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]);
-        key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu);
-      }
+  for (int u = 0; u < 4; u++) {
+    unsigned long long key = ~0ull;
+    const uint32_t q = meta[u] & 31u;
+    if (meta[u] & 0x80000000u) {
+      const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]);
+      key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu);
+    }
 #pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {  // segmented min over the 8 lanes of the segment (uniform control flow)
-        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
-        key = other < key ? other : key;
+    for (int o = 1; o < 8; o <<= 1) {  // segmented min over the 8 lanes of the segment (uniform control flow)
+      const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+      key = other < key ? other : key;
+    }
+    if (sub == 0 && key != ~0ull) atomicMin(&ws.best[q], key);
+  }
+}
+
+// PIPE = false: issue 16 segments, wait, reduce, repeat.  PIPE = true: the loads of the next 16 segments are issued
+// before the current 16 are reduced (two batches of registers), so a warp always has 4-8 row loads in flight.
+template <bool PIPE>
+MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  if constexpr (!PIPE) {
+    for (uint32_t base = 0; base < n; base += 16) {
+      float4 p[4];
+      uint32_t meta[4];
+      wl_issue(map, ws, n, base, grp, sub, p, meta);
+      wl_consume(ws, sub, p, meta);
+    }
+  } else {
+    float4 p[4], pn[4];
+    uint32_t meta[4], mn[4];
+    if (n) wl_issue(map, ws, n, 0, grp, sub, p, meta);
+    for (uint32_t base = 0; base < n; base += 16) {
+      const bool more = base + 16 < n;
+      if (more) wl_issue(map, ws, n, base + 16, grp, sub, pn, mn);
+      wl_consume(ws, sub, p, meta);
+      if (more) {
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+          p[u] = pn[u];
+          meta[u] = mn[u];
+        }
       }
-      if (sub == 0 && key != ~0ull) atomicMin(&ws.best[q], key);
     }
   }
   __syncwarp();
 }
 
 constexpr uint32_t WL_BLOCK = 32;  // the work-list kernel runs one warp per block: a chunk is 32 queries
-template <int NWARPS>
+template <int NWARPS, bool PIPE = false>
 MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
@@ -489,7 +519,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       uint32_t off = incl - np;
       for (uint32_t k = 0; k < np; k++) ws.list[off + k] = uint16_t((k << 10) | (13u << 5) | lane);
       __syncwarp();
-      wl_process(map, ws, total);
+      wl_process<PIPE>(map, ws, total);
     }
     // ---- phase 3: per query, the neighbour cells that can still beat the bound from the own cell
     uint32_t visit = 0, my_items = 0;
@@ -532,7 +562,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
         }
       }
       __syncwarp();
-      wl_process(map, ws, total);
+      wl_process<PIPE>(map, ws, total);
       start = end;
     }
     // ---- result per query
@@ -908,8 +938,8 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
 }
 
 // four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
-template <bool MULTI>
-__global__ void __launch_bounds__(ICP_BLOCK, 8)
+template <bool MULTI, bool PIPE = false, int MINB = 8>
+__global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_match_accumulate_wl4(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
                            const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,
                            float4* __restrict__ pairB, double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
@@ -922,8 +952,8 @@ __global__ void __launch_bounds__(ICP_BLOCK, 8)
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
   if (MULTI) stage_map(sMap, maps, P.map_idx);
   __syncthreads();
-  if constexpr (MULTI) chunk_match_wl<4>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
-  else chunk_match_wl<4>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  if constexpr (MULTI) chunk_match_wl<4, PIPE>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  else chunk_match_wl<4, PIPE>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
 template <int MIN_BLOCKS>

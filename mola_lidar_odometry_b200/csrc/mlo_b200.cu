@@ -98,6 +98,9 @@ struct mlo_ctx {
   int tpq_min_queries_per_sm = 512;  // MLO_TPQ_MIN: below this many queries per SM the warp-per-query chunks win
                                      // (S=8 fleet, 56 k queries: align 1.40 ms warp vs 2.15 ms thread-per-query)
   int wl_min_blocks = 32;  // MLO_WL_MIN_BLOCKS (one-warp blocks per SM)
+  int wl_variant = 3;      // MLO_WL_VARIANT (A/B at B=512, scans/s): 0 = 8 blocks/SM, 64 registers: 25.7k; 1 = drain loop software-
+                           // pipelined at 8 blocks/SM: 23.8k; 2 = pipelined at 6 blocks/SM: 25.3k; 3 = 6 blocks/SM, 80 registers,
+                           // fewer spills: 26.1k (default)
   int wl_warps = 4;        // MLO_WL_WARPS: 4 = four-warp blocks (default), 1 = one-warp blocks (A/B: slower)
   int table_factor = 8;    // MLO_TABLE_FACTOR: hash buckets per voxel of capacity (load factor ~0.08: fewer re-probes): occupancy target of the work-list kernel (register budget), experiments
   bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
@@ -814,9 +817,17 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
 #define MLO_WL_LAUNCH(MB)                                                                                              \
   LAUNCH_ON(c, sg, k_match_accumulate_wl<MB>, grid_g, WL_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),   \
             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
-        if (c->wl_warps == 4)
-          LAUNCH_ON(c, sg, k_match_accumulate_wl4<false>, grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,
-                    c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
+#define MLO_WL4_LAUNCH(PIPE, MB)                                                                                            \
+  LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, PIPE, MB>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,           \
+            c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
+        if (c->wl_warps == 4) {
+          switch (c->wl_variant) {  // MLO_WL_VARIANT: A/B of the drain loop (profiles/README.md)
+            case 1: MLO_WL4_LAUNCH(true, 8); break;
+            case 2: MLO_WL4_LAUNCH(true, 6); break;
+            case 3: MLO_WL4_LAUNCH(false, 6); break;
+            default: MLO_WL4_LAUNCH(false, 8); break;
+          }
+        }
         else switch (c->wl_min_blocks) {
           case 16: MLO_WL_LAUNCH(16); break;
           case 24: MLO_WL_LAUNCH(24); break;
@@ -940,6 +951,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* wb = getenv("MLO_WL_MIN_BLOCKS")) c->wl_min_blocks = atoi(wb);
   if (const char* tq = getenv("MLO_TPQ_MIN")) c->tpq_min_queries_per_sm = std::max(1, atoi(tq));
   if (const char* ww = getenv("MLO_WL_WARPS")) c->wl_warps = atoi(ww);
+  if (const char* wv = getenv("MLO_WL_VARIANT")) c->wl_variant = atoi(wv);
   if (const char* tf = getenv("MLO_TABLE_FACTOR")) c->table_factor = std::max(1, atoi(tf));
   if (const char* sg = getenv("MLO_STREAM_GROUPS")) c->stream_groups = std::min(int(mlo_ctx::MAX_GROUPS), std::max(1, atoi(sg)));
   if (const char* pk = getenv("MLO_PERSISTENT")) {

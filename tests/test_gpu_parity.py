@@ -492,3 +492,39 @@ def test_scanset_deskew_bit_exact(ctx, world, scene, traj):
         assert np.array_equal(sset.download(slot, 1).view(np.uint32), O.deskew(b, twists[j]).view(np.uint32))
         assert np.array_equal(np.array(info2[j].icp_max[:], np.float32), O.deskew(b, twists[j]).max(axis=0))
     sset.close()
+
+
+def test_scanset_prefetch_is_transparent(ctx, world):
+    """mlo_scanset_prefetch only moves the upload of the NEXT filter call onto the copy stream: announced, ignored
+    (other clouds) and matched calls all give the layers and ICP results of the plain path."""
+    from mola_lidar_odometry_b200.api import ScanSet
+    import ctypes as C
+    frames, fp = world["frames"], world["fp"]
+    g, o = _build_pair(ctx, world)
+    raws = [np.ascontiguousarray(frames[k]["raw"], dtype=np.float32) for k in (12, 13, 14, 15)]
+
+    def announce(sset, clouds):
+        pts = (C.c_void_p * len(clouds))(*[c.ctypes.data for c in clouds])
+        n = (C.c_uint64 * len(clouds))(*[len(c) for c in clouds])
+        ctx.check(ctx.lib.mlo_scanset_prefetch(sset.h, len(clouds), pts, n, clouds[0].shape[1]))
+
+    sset = ScanSet(ctx, 2)
+    rng = np.random.default_rng(3)
+    ip = capi.IcpParamsOwner(sigma=2.0)
+    announce(sset, raws[2:4])                         # for the call AFTER the next one
+    info = sset.filter([0, 1], raws[0:2], [fp, fp])   # not the announced clouds: plain upload, announcement kept
+    assert [i.n_icp for i in info] == [len(frames[12]["icp_layer"]), len(frames[13]["icp_layer"])]
+    inits = np.stack([synth.perturb(frames[k]["gt"], rng, 0.3, 1.0) for k in (12, 13)])
+    r0 = sset.align([0, 1], [g, g], inits, [ip.p, ip.p])   # the announced transfer is enqueued inside this call
+    info = sset.filter([0, 1], raws[2:4], [fp, fp])   # matched: consumes the prefetched buffer
+    for s, k in enumerate((14, 15)):
+        assert np.array_equal(sset.download(s, 0), frames[k]["map_layer"])
+        assert np.array_equal(sset.download(s, 1), frames[k]["icp_layer"])
+    inits2 = np.stack([synth.perturb(frames[k]["gt"], rng, 0.3, 1.0) for k in (14, 15)])
+    r1 = sset.align([0, 1], [g, g], inits2, [ip.p, ip.p])
+    for s, k in enumerate((14, 15)):
+        _check_result(r1[s], O.icp_align(o, frames[k]["icp_layer"], inits2[s], ip.p))
+    announce(sset, raws[0:2])                         # announced and consumed with no compute call in between
+    info = sset.filter([1, 0], raws[0:2], [fp, fp])
+    assert np.array_equal(sset.download(1, 1), frames[12]["icp_layer"]) and np.array_equal(sset.download(0, 1), frames[13]["icp_layer"])
+    sset.close()
