@@ -6,12 +6,13 @@ is missing or unloadable — there is no CPU fallback on the product path.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 import numpy as np
 
 PKG = Path(__file__).resolve().parent
-LIB_PATH = PKG / "libmlo_b200.so"
+LIB_PATH = Path(os.environ["MLO_B200_LIB"]) if os.environ.get("MLO_B200_LIB") else PKG / "libmlo_b200.so"  # (override: scratch builds)
 
 MLO_OK = 0
 TERM_NAMES = {0: "Undefined", 1: "NoPairings", 2: "SolverError", 3: "MaxIterations", 4: "Stalled", 5: "HookRequest"}

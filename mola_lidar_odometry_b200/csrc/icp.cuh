@@ -785,7 +785,7 @@ MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const
 // The solve step, executed by ONE warp after sum_partials_block: lane 0 applies the prior, solves the 6x6 system,
 // retracts and does the end-of-iteration bookkeeping.  Returns (on every lane) 0 = problem finished, 1 = another
 // inner GN iteration is pending, 2 = next ICP iteration.
-__device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const SolveScratch& sc, int after_match) {
+__device__ __noinline__ int solve_step(const IcpProblem& Pg, IcpState& Sg, const SolveScratch& sc, int after_match) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u;
   double a[NACC];
@@ -793,14 +793,25 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const S
   for (int k = 0; k < int(NACC); k++) a[k] = sc.tot[k];
   const uint32_t npairs = sc.cnt[0];
   const uint32_t ncand = sc.cnt[1];
-  // stage T / prev / prev2 (36 contiguous doubles of the state) in shared memory: one coalesced read and one
-  // coalesced write-back by the whole warp instead of ~100 serial global accesses by lane 0
-  __shared__ double s_pose[36];
-  for (uint32_t i = lane; i < 36; i += 32) s_pose[i] = __ldcg(&S.T[0] + i);
+  // Stage the problem description and its state in shared memory: two coalesced reads and one coalesced write-back by
+  // the whole warp instead of ~150 serial, mostly dependent global accesses by lane 0 (each an L2 round trip).
+  __shared__ IcpProblem sP;
+  __shared__ IcpState sS;
+  static_assert(sizeof(IcpProblem) % 4 == 0 && sizeof(IcpState) % 4 == 0, "copied word by word");
+  {
+    const uint32_t* gp = reinterpret_cast<const uint32_t*>(&Pg);
+    const uint32_t* gs = reinterpret_cast<const uint32_t*>(&Sg);
+    uint32_t* dp = reinterpret_cast<uint32_t*>(&sP);
+    uint32_t* ds = reinterpret_cast<uint32_t*>(&sS);
+    for (uint32_t i = lane; i < sizeof(IcpProblem) / 4; i += 32) dp[i] = __ldg(gp + i);
+    for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) ds[i] = __ldcg(gs + i);
+  }
   __syncwarp();
-  double* const sT = s_pose;
-  double* const sPrev = s_pose + 12;
-  double* const sPrev2 = s_pose + 24;
+  const IcpProblem& P = sP;
+  IcpState& S = sS;
+  double* const sT = S.T;
+  double* const sPrev = S.prev;
+  double* const sPrev2 = S.prev2;
   int next = 0;
   if (lane == 0) {
     bool finished = false;
@@ -900,8 +911,85 @@ __device__ __noinline__ int solve_step(const IcpProblem& P, IcpState& S, const S
     }
   }
   __syncwarp();
-  for (uint32_t i = lane; i < 36; i += 32) (&S.T[0])[i] = s_pose[i];
+  {
+    uint32_t* gs = reinterpret_cast<uint32_t*>(&Sg);
+    const uint32_t* ds = reinterpret_cast<const uint32_t*>(&sS);
+    for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) gs[i] = ds[i];
+  }
   return __shfl_sync(FULL, next, 0);
+}
+
+// Inner Gauss-Newton iterations >= 1 inside the block that just solved (small problems): the block re-linearises ALL
+// stored pairings of the problem at the updated pose (thread-strided, then the warp butterfly + ordered cross-warp sum
+// of block_reduce_store, into shared memory), and its first warp solves again - no queue round trip, no partials in
+// global memory, no other block involved.  Returns the same codes as solve_step (never 1).
+constexpr uint32_t FUSE_MAX_Q = 16384;  // <= 128 pairings per thread
+MLO_D void block_reduce_to(double* a, uint32_t npairs, SolveScratch& sc) {
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) {
+    double v = a[k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+    if (lane == 0) sc.part[warp][k] = v;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xFFFFFFFFu, npairs, o);
+  if (lane == 0) sc.pcnt[warp][0] = npairs;
+  __syncthreads();
+  if (threadIdx.x < NACC) {
+    double t = sc.part[0][threadIdx.x];
+#pragma unroll
+    for (uint32_t w = 1; w < SOLVE_WARPS; w++) t += sc.part[w][threadIdx.x];
+    sc.tot[threadIdx.x] = t;
+  } else if (threadIdx.x == NACC) {
+    uint32_t t = 0;
+#pragma unroll
+    for (uint32_t w = 0; w < SOLVE_WARPS; w++) t += sc.pcnt[w][0];
+    sc.cnt[0] = t;
+    sc.cnt[1] = 0;
+  }
+  __syncthreads();
+}
+// every thread of the (ICP_BLOCK-wide) block calls this with the block-uniform `next` of the preceding solve
+MLO_D int fused_inner_iterations(const IcpProblem& P, IcpState& S, SolveScratch& sc, int next, uint32_t it, const float4* __restrict__ local,
+                                 const float4* pairA, const float4* pairB) {
+  __shared__ double f_T[12];
+  __shared__ int f_next;
+  while (next == 1) {
+    // the pose was written to the problem state by this block's first warp (solve_step): fence + barrier, then read it
+    // back through L2
+    if (threadIdx.x < 32) __threadfence();
+    __syncthreads();
+    if (threadIdx.x < 12) f_T[threadIdx.x] = __ldcg(&S.T[threadIdx.x]);
+    __syncthreads();
+    const double kc = table_at(P.kparam, P.table_len, it);
+    double a[NACC];
+#pragma unroll
+    for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
+    uint32_t npairs = 0;
+    for (uint32_t q = threadIdx.x; q < P.n_q; q += ICP_BLOCK) {
+      const float4 pa = __ldcg(&pairA[P.q_begin + q]);
+      if (pa.w == 0.f) continue;
+      const float4 l = __ldg(&local[P.q_begin + q]);
+      if (pa.w == 1.f) {
+        contrib_pt2pt(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
+      } else {
+        const float4 nb = __ldcg(&pairB[P.q_begin + q]);
+        contrib_pt2pl(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, nb.x, nb.y, nb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+      }
+      npairs++;
+    }
+    block_reduce_to(a, npairs, sc);
+    if (threadIdx.x < 32) {
+      const int n = solve_step(P, S, sc, 0);
+      if (threadIdx.x == 0) f_next = n;
+    }
+    __syncthreads();
+    next = f_next;
+    __syncthreads();
+  }
+  return next;
 }
 
 // ------------------------------------------------------------------ one kernel per phase (launch sequence)
@@ -984,18 +1072,28 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   chunk_accumulate(P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
-// one block per problem. `after_match` = 1 when the partials come from the match phase (inner 0).
+// one block per problem. `after_match` = 1 when the partials come from the match phase (inner 0).  With `fuse` the
+// block also runs the remaining inner Gauss-Newton iterations of the problem itself (problems up to FUSE_MAX_Q
+// queries), so an ICP iteration of the launch sequence is two launches: match, solve.
 __global__ void __launch_bounds__(ICP_BLOCK)
     k_solve(const IcpProblem* __restrict__ probs, IcpState* __restrict__ states, const double* partials,
-            const uint32_t* part_cnt, int after_match, uint32_t* __restrict__ n_active) {
+            const uint32_t* part_cnt, int after_match, uint32_t* __restrict__ n_active, int fuse,
+            const float4* __restrict__ local, const float4* pairA, const float4* pairB) {
   const IcpProblem& P = probs[blockIdx.x];
   IcpState& S = states[blockIdx.x];
   if (S.done) return;
   if (!after_match && !S.inner_pending) return;
   __shared__ SolveScratch sc;
+  __shared__ int s_next;
+  const uint32_t it = S.it;  // (the match phase of this iteration used the same index; read before the solve bumps it)
   sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc);
-  if (threadIdx.x >= 32) return;
-  const int next = solve_step(P, S, sc, after_match);
+  if (threadIdx.x < 32) {
+    const int n = solve_step(P, S, sc, after_match);
+    if (threadIdx.x == 0) s_next = n;
+  }
+  __syncthreads();
+  int next = s_next;
+  if (fuse && P.n_q <= FUSE_MAX_Q) next = fused_inner_iterations(P, S, sc, next, it, local, pairA, pairB);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -1028,6 +1126,22 @@ __global__ void k_init_states(const IcpProblem* __restrict__ probs, IcpState* __
     atomicAdd(n_active, 1u);
   }
 }
+
+#ifdef MLO_TRACE
+// Timeline of problem 0 inside the persistent kernel (scratch builds only: scratch/trace_persistent.py).
+__device__ unsigned long long g_trace[16384];
+__device__ unsigned int g_trace_n;
+MLO_D void trace_event(uint32_t prob, uint32_t code) {
+  if (prob != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned int i = atomicAdd(&g_trace_n, 1u);
+  if (i < 16384) g_trace[i] = (t << 8) | code;
+}
+#define MLO_TRACE_EVENT(prob, code) do { if (threadIdx.x == 0) trace_event(prob, code); } while (0)
+#else
+#define MLO_TRACE_EVENT(prob, code) do { } while (0)
+#endif
 
 // ------------------------------------------------------------------ persistent, queue-driven align
 // One launch runs the whole ICP::align loop of a batch.  Work items = (problem, phase, chunk); a bounded
@@ -1116,9 +1230,10 @@ template <bool TPQ, bool MULTI>
 __global__ void __launch_bounds__(ICP_BLOCK, 4)
     k_icp_persistent(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs, IcpState* states,
                      const float4* __restrict__ local, float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt,
-                     IcpQueue q, uint32_t qpw) {
+                     IcpQueue q, uint32_t qpw, int fuse) {
   __shared__ MapDev sMap;
   __shared__ SolveScratch s_solve;
+  __shared__ int s_nx;
   __shared__ uint32_t s_item;
   __shared__ int s_last;
   __shared__ double sT[12];
@@ -1149,6 +1264,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
     const uint32_t item = s_item;
     if (item == ITEM_EXIT) return;
     const uint32_t prob = item >> 16, chunk = (item >> 1) & 0x7FFFu, phase = item & 1u;
+    if (chunk == 0) MLO_TRACE_EVENT(prob, 1 + phase);  // 1: first match chunk popped, 2: first accumulate chunk popped
     const IcpProblem& P = probs[prob];
     IcpState& S = states[prob];
     if (threadIdx.x < 12) sT[threadIdx.x] = __ldcg(&S.T[threadIdx.x]);
@@ -1173,18 +1289,35 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
       if (s_last) atomicExch(&q.phase_cnt[prob], 0u);
     }
     __syncthreads();
+    if (chunk == 0) MLO_TRACE_EVENT(prob, 3);  // chunk 0 of the phase finished
     if (s_last) {
+      MLO_TRACE_EVENT(prob, 4);  // last chunk of the phase finished
       __threadfence();  // acquire: the other blocks' partials (read through L2) and the problem state
       sum_partials_block(P, partials, part_cnt, phase == 0 ? P.n_blocks_pers : P.n_blocks_acc, s_solve);
+      MLO_TRACE_EVENT(prob, 5);  // partials summed
+    }
+    if (s_last) {
+      if (threadIdx.x < 32) {
+        const int n = solve_step(P, S, s_solve, phase == 0);
+        if (threadIdx.x == 0) s_nx = n;
+      }
+      __syncthreads();
+      MLO_TRACE_EVENT(prob, 6);  // first solve done
+      int nx = s_nx;
+      if (fuse && P.n_q <= FUSE_MAX_Q) nx = fused_inner_iterations(P, S, s_solve, nx, s_it, local, pairA, pairB);
+      if (threadIdx.x == 0) s_nx = nx;
+      __syncthreads();
+      MLO_TRACE_EVENT(prob, 7);  // fused inner iterations done
     }
     if (s_last && threadIdx.x < 32) {
-      const int next = solve_step(P, S, s_solve, phase == 0);
+      const int next = s_nx;
       if (threadIdx.x == 0) __threadfence();  // state of the problem visible before its next items
       __syncwarp();
       if (next == 1) {
         queue_push(q, prob, 1u, P.n_blocks_acc);
       } else if (next == 2) {
         queue_push(q, prob, 0u, P.n_blocks_pers);
+        MLO_TRACE_EVENT(prob, 8);  // next match phase published
       } else if (threadIdx.x == 0) {
         if (atomicSub(&q.ctrl[2], 1u) == 1u) atomicExch(&q.ctrl[3], 1u);
       }

@@ -103,6 +103,8 @@ struct mlo_ctx {
                            // fewer spills: 26.1k (default)
   int wl_warps = 4;        // MLO_WL_WARPS: 4 = four-warp blocks (default), 1 = one-warp blocks (A/B: slower)
   int table_factor = 8;    // MLO_TABLE_FACTOR: hash buckets per voxel of capacity (load factor ~0.08: fewer re-probes): occupancy target of the work-list kernel (register budget), experiments
+  int qpw_floor = 4;         // MLO_QPW_FLOOR: fewest queries a warp handles per chunk in the warp-per-query kernels
+  bool fuse_inner = true;    // MLO_FUSE_INNER=0: inner GN iterations as separate accumulate + solve launches (A/B)
   bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
   int consuming_slot = -1;  // staging slot read by the compute call in progress
   // transfers registered by a prefetch call and enqueued from inside the next compute call, right after that call's
@@ -594,7 +596,7 @@ void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const Ma
                        const IcpProblem* dP, IcpState* dS, const float4* d_local, const IcpQueue& q, uint32_t qpw) {
 #define MLO_PERS(T, M, QPW)                                                                                              \
   LAUNCH(c, (k_icp_persistent<T, M>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),            \
-         c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW)
+         c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW, c->fuse_inner ? 1 : 0)
   if (tpq && multi) MLO_PERS(true, true, 0u);
   else if (tpq) MLO_PERS(true, false, 0u);
   else if (multi) MLO_PERS(false, true, qpw);
@@ -642,7 +644,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     return off;
   };
   std::vector<size_t> toff(3 * size_t(B));
-  uint32_t part_total = 0, max_blocks = 0, max_blocks_acc = 0, max_it = 0, max_inner = 1;
+  uint32_t part_total = 0, max_blocks = 0, max_blocks_acc = 0, max_it = 0, max_inner = 1, max_nq = 0;
   // queries per warp: 32 when the batch alone fills the machine, fewer for latency-bound small batches
   uint64_t total_queries = 0, q_end = 0;
   for (uint32_t b = 0; b < B; b++) {
@@ -650,7 +652,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     q_end = std::max(q_end, q_begin[b] + n_q[b]);
   }
   uint32_t qpw = 32;
-  const uint32_t qpw_floor = total_queries >= 256 ? 4u : 1u;  // below 4 the per-block reduction dominates the chunk
+  const uint32_t qpw_floor = total_queries >= 256 ? uint32_t(c->qpw_floor) : 1u;  // (MLO_QPW_FLOOR)
   while (qpw > qpw_floor && total_queries / qpw < uint64_t(c->sm_count) * 32) qpw >>= 1;
   // large batches: thread-per-query kernel (hundreds of queries in flight per SM); small: warp-per-query
   const bool use_tpq = c->force_kernel == 1 || c->force_kernel == 3 ||
@@ -700,6 +702,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     P.part_begin = part_total;
     part_total += std::max(std::max(P.n_blocks, P.n_blocks_pers), P.n_blocks_acc);
     max_blocks = std::max(max_blocks, P.n_blocks);
+    max_nq = std::max(max_nq, P.n_q);
     max_blocks_acc = std::max(max_blocks_acc, P.n_blocks_acc);
     max_it = std::max(max_it, P.max_iterations);
     if (P.solver == MLO_SOLVER_GAUSS_NEWTON) max_inner = std::max(max_inner, P.gn_max_iterations);
@@ -840,11 +843,15 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
         LAUNCH_ON(c, sg, k_match_accumulate<false>, grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,
                   c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
       if (g == 0) prof_end(c, 3, e_nn);
-      LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active);
-      for (uint32_t inner = 1; inner < max_inner; inner++) {
+      // problems up to FUSE_MAX_Q queries run their inner Gauss-Newton iterations inside the solve block
+      const int fuse = (c->fuse_inner && max_nq <= FUSE_MAX_Q) ? 1 : 0;
+      LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active, fuse,
+                d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
+      for (uint32_t inner = 1; inner < max_inner && !fuse; inner++) {
         LAUNCH_ON(c, sg, k_accumulate, grid_acc_g, ICP_BLOCK, gP, gS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
                   c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
-        LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active);
+        LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active, 0,
+                  d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
       }
     }
     if (((it % check_every) == check_every - 1 || it + 1 == max_it) && n_groups > 1)
@@ -948,6 +955,8 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->dev_name = prop.name;
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
   if (const char* th = getenv("MLO_TAIL_HANDOVER")) c->tail_handover = atoi(th) != 0;
+  if (const char* fi = getenv("MLO_FUSE_INNER")) c->fuse_inner = atoi(fi) != 0;
+  if (const char* qf = getenv("MLO_QPW_FLOOR")) c->qpw_floor = std::min(32, std::max(1, atoi(qf)));
   if (const char* wb = getenv("MLO_WL_MIN_BLOCKS")) c->wl_min_blocks = atoi(wb);
   if (const char* tq = getenv("MLO_TPQ_MIN")) c->tpq_min_queries_per_sm = std::max(1, atoi(tq));
   if (const char* ww = getenv("MLO_WL_WARPS")) c->wl_warps = atoi(ww);
@@ -1919,6 +1928,21 @@ int mlo_scanset_download(mlo_scanset* set, uint32_t slot, int layer, float* out_
   if (set->skewed && !set->deskewed) return fail(c, MLO_ERR_INVALID_ARG, "skewed layers: call mlo_scanset_deskew first");
   return download_xyz(c, (layer == 0 ? set->map_layer() : set->icp_layer()) + sl.off, *n, out_xyz);
 }
+
+#ifdef MLO_TRACE
+// scratch builds only: copy out and reset the persistent-kernel timeline of problem 0
+int mlo_debug_trace_read(unsigned long long* out, unsigned int max_n, unsigned int* n) {
+  unsigned int cnt = 0;
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(&cnt, g_trace_n, sizeof(cnt));
+  *n = cnt < 16384 ? cnt : 16384;
+  if (*n > max_n) *n = max_n;
+  if (*n) cudaMemcpyFromSymbol(out, g_trace, size_t(*n) * sizeof(unsigned long long));
+  cnt = 0;
+  cudaMemcpyToSymbol(g_trace_n, &cnt, sizeof(cnt));
+  return MLO_OK;
+}
+#endif
 
 // ------------------------------------------------------------------ profiling
 int mlo_profile_enable(mlo_ctx* c, int enabled) {
