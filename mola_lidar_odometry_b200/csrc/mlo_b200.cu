@@ -15,29 +15,38 @@
 using namespace mlo;
 
 // ------------------------------------------------------------------ small host utilities
-struct DBuf {  // grow-only device buffer
+struct DBuf {  // grow-only device buffer, backed by the device's stream-ordered pool (release threshold unlimited, see
+               // mlo_create): a scan set or context that is destroyed and re-created gets its buffers back without a
+               // driver allocation.  Allocation and release are ordered on the null stream and completed before use.
   void* p = nullptr;
   size_t cap = 0;
+  static cudaError_t pool_alloc(void** out, size_t bytes) {
+    cudaError_t e = cudaMallocAsync(out, bytes, nullptr);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(nullptr);
+    return e;
+  }
   cudaError_t ensure(size_t bytes) {
     if (bytes <= cap) return cudaSuccess;
-    if (p) cudaFree(p);
-    p = nullptr;
-    cap = 0;
+    release();
     // geometric growth: batch sizes creep up by a few points from step to step, and every re-allocation is a
     // device-wide synchronisation
     size_t want = std::max(bytes + bytes / 4, size_t(1) << 16);
     want = (want + 255) & ~size_t(255);
-    cudaError_t e = cudaMalloc(&p, want);
+    cudaError_t e = pool_alloc(&p, want);
     if (e != cudaSuccess && want > bytes) {  // tight on memory: retry with the exact size
       cudaGetLastError();
       want = (bytes + 255) & ~size_t(255);
-      e = cudaMalloc(&p, want);
+      e = pool_alloc(&p, want);
     }
     if (e == cudaSuccess) cap = want;
+    else p = nullptr;
     return e;
   }
   void release() {
-    if (p) cudaFree(p);
+    if (p) {
+      cudaDeviceSynchronize();  // (work on any stream may still read the buffer; growth and teardown are rare)
+      cudaFreeAsync(p, nullptr);
+    }
     p = nullptr;
     cap = 0;
   }

@@ -528,3 +528,30 @@ def test_scanset_prefetch_is_transparent(ctx, world):
     info = sset.filter([1, 0], raws[0:2], [fp, fp])
     assert np.array_equal(sset.download(1, 1), frames[12]["icp_layer"]) and np.array_equal(sset.download(0, 1), frames[13]["icp_layer"])
     sset.close()
+
+
+def test_scanset_argument_errors(ctx, world):
+    """Bad jobs are refused with MLO_ERR_INVALID_ARG (the adapter turns that into the exception the reference's worker
+    latches, LidarOdometry.cpp:614-619) and leave the set usable."""
+    from mola_lidar_odometry_b200.api import LocalMap, MloError, ScanSet
+    frames, fp = world["frames"], world["fp"]
+    raw = frames[3]["raw"]
+    sset = ScanSet(ctx, 2)
+    with pytest.raises(MloError):
+        sset.filter([2], [raw], [fp])                       # slot out of range
+    with pytest.raises(MloError):
+        sset.filter([0, 0], [raw, raw], [fp, fp])           # two jobs for one slot
+    g = LocalMap(ctx, 1.0, 20, 0.0, 1 << 14)
+    ip = capi.IcpParamsOwner(sigma=2.0)
+    sset.filter([1], [raw], [fp])
+    with pytest.raises(MloError):
+        sset.align([0], [g], np.eye(4)[None, :3], [ip.p])   # slot 0 holds no scan
+    with pytest.raises(MloError):
+        sset.insert([1, 1], [g, g], np.stack([np.eye(4)[:3]] * 2))   # two insert jobs for one map
+    with pytest.raises(MloError):
+        sset.deskew([1], np.zeros((1, 6)))                  # no skewed layers: the filter ran without timestamps
+    res = sset.align([1], [g], np.eye(4)[None, :3], [ip.p])  # empty map: the matcher pairs nothing
+    assert res[0].termination == 1 and res[0].n_pairings == 0
+    assert sset.insert([1], [g], np.eye(4)[None, :3])[0][1] == len(frames[3]["map_layer"])
+    sset.close()
+    g.close()
