@@ -745,10 +745,15 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   IcpState* dS = c->d_states.as<IcpState>();
   LAUNCH(c, k_init_states, (B + 127) / 128, 128, dP, dS, c->d_init.as<double>(), B, d_active);
 
-  {  // all small uploads of this call are enqueued: now start the deferred transfer of the next staged batch
-    int rc = issue_deferred_uploads(c, c->consuming_slot);
-    if (rc != MLO_OK) return rc;
-  }
+  // The deferred transfer of the next staged batch is enqueued once ALL host-to-device uploads of this call are in
+  // the queue (the work-queue upload of the persistent path included): the copy engine serves transfers in submission
+  // order, and a 64 MB batch in front of a 4 KB queue upload would hold the ICP kernel back by milliseconds.
+  bool deferred_issued = false;
+  auto issue_deferred_once = [&]() -> int {
+    if (deferred_issued) return MLO_OK;
+    deferred_issued = true;
+    return issue_deferred_uploads(c, c->consuming_slot);
+  };
   const size_t e_icp = prof_begin(c);
   const dim3 grid(std::max(max_blocks, 1u), B);
   const dim3 grid_acc(std::max(max_blocks_acc, 1u), B);
@@ -796,10 +801,18 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
       const size_t e_nn = prof_begin(c);
       launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
       prof_end(c, 3, e_nn);
+      {
+        int rc = issue_deferred_once();
+        if (rc != MLO_OK) return rc;
+      }
       CU(c, cudaMemcpyAsync(h_active, q.ctrl + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
       CU(c, cudaStreamSynchronize(c->stream));
       if (*h_active != 0) return fail(c, MLO_ERR_CUDA, "persistent ICP kernel timed out waiting on its work queue");
     }
+  }
+  {  // launch-sequence path (or nothing to run): no further uploads follow
+    int rc = issue_deferred_once();
+    if (rc != MLO_OK) return rc;
   }
   // stream groups: contiguous slices of the batch, each with its own launch sequence (group 0 on the context stream)
   // (per-kernel timing needs the kernel alone on the device: one group while profiling)
@@ -1653,9 +1666,9 @@ static int scanset_issue_prefetch(mlo_scanset* set) {
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, set->raw_next.ensure(bytes));
   }
-  // raw_next was the raw buffer of the step before the current one: order the copy after whatever still reads it
-  CU(c, cudaEventRecord(set->staged_ready, c->stream));
-  CU(c, cudaStreamWaitEvent(c->copy_stream, set->staged_ready, 0));
+  // raw_next was the raw buffer of an EARLIER filter call, and every filter call ends with a synchronisation of the
+  // context stream (it returns the layer sizes): nothing in flight reads raw_next, so the copy needs no ordering
+  // against the context stream - in particular it must not wait for the ICP kernel it is meant to overlap.
   uint64_t off = 0;
   for (const auto& st : set->pend.clouds) {
     CU(c, cudaMemcpyAsync(set->raw_next.as<float>() + off * stride, st.src, st.n * stride * sizeof(float), cudaMemcpyHostToDevice,
