@@ -1226,8 +1226,8 @@ __global__ void k_queue_build(const IcpProblem* __restrict__ probs, const IcpSta
   atomicAdd(&q.ctrl[2], 1u);
 }
 
-template <bool TPQ, bool MULTI>
-__global__ void __launch_bounds__(ICP_BLOCK, 4)
+template <bool TPQ, bool MULTI, int MINB = 4>
+__global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_icp_persistent(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs, IcpState* states,
                      const float4* __restrict__ local, float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt,
                      IcpQueue q, uint32_t qpw, int fuse) {
@@ -1272,13 +1272,13 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
     if (MULTI && phase == 0) stage_map(sMap, maps, P.map_idx);
     __syncthreads();
     if (phase == 0) {
-      constexpr int TAG = (TPQ ? 2 : 0) + (MULTI ? 1 : 0);  // one out-of-line copy per kernel instance
+      constexpr int TAG = (TPQ ? 2 : 0) + (MULTI ? 1 : 0) + (MINB == 4 ? 0 : 4);  // one out-of-line copy per kernel instance
       if constexpr (TPQ && MULTI) chunk_match_tpq_ool<TAG>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
       else if constexpr (TPQ) chunk_match_tpq_ool<TAG>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
       else if constexpr (MULTI) chunk_match_warp_ool<TAG>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
       else chunk_match_warp_ool<TAG>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
     } else {
-      chunk_accumulate_ool<(TPQ ? 2 : 0) + (MULTI ? 1 : 0)>(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+      chunk_accumulate_ool<(TPQ ? 2 : 0) + (MULTI ? 1 : 0) + (MINB == 4 ? 0 : 4)>(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

@@ -112,6 +112,10 @@ struct mlo_ctx {
                            // fewer spills: 26.1k (default)
   int wl_warps = 4;        // MLO_WL_WARPS: 4 = four-warp blocks (default), 1 = one-warp blocks (A/B: slower)
   int table_factor = 8;    // MLO_TABLE_FACTOR: hash buckets per voxel of capacity (load factor ~0.08: fewer re-probes): occupancy target of the work-list kernel (register budget), experiments
+  int pers_minb = 0;         // MLO_PERS_MINB: resident blocks per SM the persistent kernel is compiled for (4: 128 registers,
+                             // 2: 255 registers - the solve step keeps more of its 6x6 arrays in registers); 0 = auto: 2 for a
+                             // single problem (align 0.926 vs 0.978 ms per scan), 4 otherwise (32 sequences: 1.72 vs 2.01 ms)
+  int pers_minb_now = 4;     // the choice for the align call in progress
   int qpw_floor = 4;         // MLO_QPW_FLOOR: fewest queries a warp handles per chunk in the warp-per-query kernels
   bool fuse_inner = true;    // MLO_FUSE_INNER=0: inner GN iterations as separate accumulate + solve launches (A/B)
   bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
@@ -604,8 +608,16 @@ int issue_deferred_uploads(mlo_ctx* c, int except_slot) {
 void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const MapDev& map, const MapDev* d_maps,
                        const IcpProblem* dP, IcpState* dS, const float4* d_local, const IcpQueue& q, uint32_t qpw) {
 #define MLO_PERS(T, M, QPW)                                                                                              \
-  LAUNCH(c, (k_icp_persistent<T, M>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),            \
-         c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW, c->fuse_inner ? 1 : 0)
+  do {                                                                                                                   \
+    if (c->pers_minb_now == 2)                                                                                           \
+      LAUNCH(c, (k_icp_persistent<T, M, 2>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),     \
+             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW,                   \
+             c->fuse_inner ? 1 : 0);                                                                                     \
+    else                                                                                                                 \
+      LAUNCH(c, (k_icp_persistent<T, M, 4>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),     \
+             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW,                   \
+             c->fuse_inner ? 1 : 0);                                                                                     \
+  } while (0)
   if (tpq && multi) MLO_PERS(true, true, 0u);
   else if (tpq) MLO_PERS(true, false, 0u);
   else if (multi) MLO_PERS(false, true, qpw);
@@ -797,7 +809,9 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
         CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true, true>, ICP_BLOCK, 0));
         c->persistent_blocks = std::max(1, per_sm) * c->sm_count;
       }
-      const uint32_t nblk = std::min<uint32_t>(uint32_t(c->persistent_blocks), std::max<uint32_t>(part_total, 1u));
+      c->pers_minb_now = c->pers_minb ? c->pers_minb : (B == 1 ? 2 : 4);
+      const uint32_t resident = c->pers_minb_now == 2 ? uint32_t(2 * c->sm_count) : uint32_t(c->persistent_blocks);
+      const uint32_t nblk = std::min<uint32_t>(resident, std::max<uint32_t>(part_total, 1u));
       const size_t e_nn = prof_begin(c);
       launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
       prof_end(c, 3, e_nn);
@@ -906,7 +920,9 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
           CU(c, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_icp_persistent<true, true>, ICP_BLOCK, 0));
           c->persistent_blocks = std::max(1, per_sm) * c->sm_count;
         }
-        const uint32_t nblk = std::min<uint32_t>(uint32_t(c->persistent_blocks), std::max<uint32_t>(part_total, 1u));
+        c->pers_minb_now = c->pers_minb == 2 ? 2 : 4;  // (a tail of a large batch: several problems)
+        const uint32_t resident = c->pers_minb_now == 2 ? uint32_t(2 * c->sm_count) : uint32_t(c->persistent_blocks);
+        const uint32_t nblk = std::min<uint32_t>(resident, std::max<uint32_t>(part_total, 1u));
         const size_t e_nn = prof_begin(c);
         launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
         prof_end(c, 3, e_nn);
@@ -978,6 +994,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
   if (const char* th = getenv("MLO_TAIL_HANDOVER")) c->tail_handover = atoi(th) != 0;
   if (const char* fi = getenv("MLO_FUSE_INNER")) c->fuse_inner = atoi(fi) != 0;
+  if (const char* pm = getenv("MLO_PERS_MINB")) c->pers_minb = atoi(pm) == 2 ? 2 : (atoi(pm) == 4 ? 4 : 0);
   if (const char* qf = getenv("MLO_QPW_FLOOR")) c->qpw_floor = std::min(32, std::max(1, atoi(qf)));
   if (const char* wb = getenv("MLO_WL_MIN_BLOCKS")) c->wl_min_blocks = atoi(wb);
   if (const char* tq = getenv("MLO_TPQ_MIN")) c->tpq_min_queries_per_sm = std::max(1, atoi(tq));
