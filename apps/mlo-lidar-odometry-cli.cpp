@@ -8,6 +8,9 @@
 //   --output-tum-path <file>               estimated trajectory in TUM format (apps/...cli.cpp:524-531)
 //   --only-first-n <N> / --skip-first-n <N>
 //   --lidar-hz <Hz>                        (extension) scan rate used to stamp .bin files (default 10)
+// Several inputs separated by commas (--input-kitti-seq 00,02,05 or --input-bin-dir a,b) run as a FLEET: independent
+// LidarOdometry instances advancing in lock step on one GPU (mlo_fleet_*), the one-GPU counterpart of the reference's
+// `parallel -j` over sequences (eval/cli_kitti.sh:23); the trajectory of input <name> goes to <output>_<name>.<ext>.
 // Loop shape = cli.cpp:469-522: read observation i, onNewObservation, wait until processed.  rawlog / rosbag2 /
 // MulRan / KITTI-360 / Paris-Luco readers, simplemap output and plugin loading are out of scope.
 #include <algorithm>
@@ -27,7 +30,7 @@ namespace fs = std::filesystem;
 
 static void usage() {
   std::fprintf(stderr,
-               "USAGE: mlo-lidar-odometry-cli -c <pipeline.yaml> (--input-kitti-seq <NN> | --input-bin-dir <dir>)\n"
+               "USAGE: mlo-lidar-odometry-cli -c <pipeline.yaml> (--input-kitti-seq <NN>[,<NN>...] | --input-bin-dir <dir>[,<dir>...])\n"
                "         [--output-tum-path <file>] [--only-first-n N] [--skip-first-n N] [--kitti-correction-angle-deg D]\n"
                "         [--lidar-hz HZ] [--cuda-device ID]\n");
 }
@@ -69,80 +72,123 @@ int main(int argc, char** argv) {
     else { std::fprintf(stderr, "unknown argument '%s'\n", a.c_str()); usage(); return 2; }
   }
   if (yaml.empty() || (kitti_seq.empty() && bin_dir.empty())) { usage(); return 2; }
+  auto split = [](const std::string& v) {
+    std::vector<std::string> out;
+    size_t b = 0;
+    while (b <= v.size()) {
+      const size_t e = v.find(',', b);
+      const std::string tok = v.substr(b, e == std::string::npos ? std::string::npos : e - b);
+      if (!tok.empty()) out.push_back(tok);
+      if (e == std::string::npos) break;
+      b = e + 1;
+    }
+    return out;
+  };
   bool is_kitti = false;
+  std::vector<std::string> dirs, names;
   if (bin_dir.empty()) {
     const char* base = std::getenv("KITTI_BASE_DIR");
     if (!base) { std::fprintf(stderr, "KITTI_BASE_DIR is not set (needed by --input-kitti-seq)\n"); return 2; }
-    bin_dir = std::string(base) + "/sequences/" + kitti_seq + "/velodyne";
+    for (const std::string& sq : split(kitti_seq)) {
+      dirs.push_back(std::string(base) + "/sequences/" + sq + "/velodyne");
+      names.push_back(sq);
+    }
     is_kitti = true;
+  } else {
+    dirs = split(bin_dir);
+    for (size_t i = 0; i < dirs.size(); i++) names.push_back(fs::path(dirs[i]).filename().string().empty() ? std::to_string(i) : fs::path(dirs[i]).filename().string());
   }
-  std::vector<fs::path> files;
-  std::error_code ec;
-  for (auto& e : fs::directory_iterator(bin_dir, ec))
-    if (e.path().extension() == ".bin") files.push_back(e.path());
-  if (ec || files.empty()) { std::fprintf(stderr, "no *.bin clouds under '%s'\n", bin_dir.c_str()); return 2; }
-  std::sort(files.begin(), files.end());
+  const uint32_t S = uint32_t(dirs.size());
+  std::vector<std::vector<fs::path>> files(S);
+  size_t longest = 0;
+  for (uint32_t q = 0; q < S; q++) {
+    std::error_code ec;
+    for (auto& e : fs::directory_iterator(dirs[q], ec))
+      if (e.path().extension() == ".bin") files[q].push_back(e.path());
+    if (ec || files[q].empty()) { std::fprintf(stderr, "no *.bin clouds under '%s'\n", dirs[q].c_str()); return 2; }
+    std::sort(files[q].begin(), files[q].end());
+    longest = std::max(longest, files[q].size());
+  }
 
   mlo_ctx* ctx = nullptr;
   if (mlo_create(device, &ctx) != MLO_OK) { std::fprintf(stderr, "mlo_create failed: no sm_100 device (there is no CPU fallback)\n"); return 3; }
-  mlo_lo* lo = nullptr;
-  if (mlo_lo_create(ctx, yaml.c_str(), 0, &lo) != MLO_OK) {
-    std::fprintf(stderr, "cannot initialise from '%s': %s\n", yaml.c_str(), mlo_lo_last_error(nullptr));
+  mlo_fleet* fleet = nullptr;
+  if (mlo_fleet_create(ctx, yaml.c_str(), 0, S, &fleet) != MLO_OK) {
+    std::fprintf(stderr, "cannot initialise from '%s': %s\n", yaml.c_str(), mlo_fleet_last_error(nullptr));
     mlo_destroy(ctx);
     return 2;
   }
   const double corr = (is_kitti || angle_given) ? angle_deg * M_PI / 180.0 : 0.0;
-  std::vector<float> cloud;
-  size_t n_done = 0;
+  std::vector<std::vector<float>> cloud(S);
+  std::vector<const float*> pts(S);
+  std::vector<uint64_t> npts(S);
+  std::vector<double> stamps(S);
+  std::vector<mlo_lo_scan_output> outs(S);
+  size_t n_done = 0, n_steps = 0;
   const auto t0 = std::chrono::steady_clock::now();
-  for (size_t i = size_t(std::max(0L, skip_n)); i < files.size(); i++) {
-    if (first_n > 0 && long(n_done) >= first_n) break;
-    std::ifstream f(files[i], std::ios::binary | std::ios::ate);
-    const std::streamsize bytes = f.tellg();
-    f.seekg(0);
-    cloud.resize(size_t(bytes) / sizeof(float));
-    f.read(reinterpret_cast<char*>(cloud.data()), bytes);
-    const uint64_t n = cloud.size() / 4;
-    if (corr != 0.0) {  // Deschaud 2018: rotate every point by `corr` about the axis (p x z)
-      for (uint64_t k = 0; k < n; k++) {
-        float* p = &cloud[4 * k];
-        const double ax = p[1], ay = -p[0];  // p x (0,0,1)
-        const double an = std::sqrt(ax * ax + ay * ay);
-        if (an < 1e-9) continue;
-        const double ux = ax / an, uy = ay / an, c = std::cos(corr), s = std::sin(corr);
-        const double x = p[0], y = p[1], z = p[2], d = ux * x + uy * y;
-        p[0] = float(x * c + (uy * z) * s + ux * d * (1 - c));
-        p[1] = float(y * c + (-ux * z) * s + uy * d * (1 - c));
-        p[2] = float(z * c + (ux * y - uy * x) * s);
+  for (size_t i = size_t(std::max(0L, skip_n)); i < longest; i++) {
+    if (first_n > 0 && long(n_steps) >= first_n) break;
+    for (uint32_t q = 0; q < S; q++) {
+      pts[q] = nullptr;
+      npts[q] = 0;
+      stamps[q] = double(i) / hz;
+      if (i >= files[q].size()) continue;  // this sequence has ended: its slot stays idle
+      std::ifstream f(files[q][i], std::ios::binary | std::ios::ate);
+      const std::streamsize bytes = f.tellg();
+      f.seekg(0);
+      cloud[q].resize(size_t(bytes) / sizeof(float));
+      f.read(reinterpret_cast<char*>(cloud[q].data()), bytes);
+      const uint64_t n = cloud[q].size() / 4;
+      if (corr != 0.0) {  // Deschaud 2018: rotate every point by `corr` about the axis (p x z)
+        for (uint64_t k = 0; k < n; k++) {
+          float* p = &cloud[q][4 * k];
+          const double ax = p[1], ay = -p[0];  // p x (0,0,1)
+          const double an = std::sqrt(ax * ax + ay * ay);
+          if (an < 1e-9) continue;
+          const double ux = ax / an, uy = ay / an, c = std::cos(corr), s = std::sin(corr);
+          const double x = p[0], y = p[1], z = p[2], d = ux * x + uy * y;
+          p[0] = float(x * c + (uy * z) * s + ux * d * (1 - c));
+          p[1] = float(y * c + (-ux * z) * s + uy * d * (1 - c));
+          p[2] = float(z * c + (ux * y - uy * x) * s);
+        }
       }
+      pts[q] = cloud[q].data();
+      npts[q] = n;
+      n_done++;
     }
-    mlo_lo_scan_output out;
-    if (mlo_lo_on_lidar(lo, cloud.data(), 4, n, double(i) / hz, &out) != MLO_OK) {
-      std::fprintf(stderr, "fatal error at scan %zu: %s\n", i, mlo_lo_last_error(lo));  // LidarOdometry.cpp:614-619
-      mlo_lo_destroy(lo);
+    if (mlo_fleet_on_lidar(fleet, pts.data(), 4, npts.data(), stamps.data(), nullptr, outs.data()) != MLO_OK) {
+      std::fprintf(stderr, "fatal error at scan %zu: %s\n", i, mlo_fleet_last_error(fleet));  // LidarOdometry.cpp:614-619
+      mlo_fleet_destroy(fleet);
       mlo_destroy(ctx);
       return 1;
     }
-    n_done++;
-    if (n_done % 100 == 0) std::fprintf(stderr, "[cli] %zu scans, quality %.2f, sigma %.2f\n", n_done, out.quality, out.sigma);
+    n_steps++;
+    if (n_steps % 100 == 0) std::fprintf(stderr, "[cli] %zu steps, quality %.2f, sigma %.2f\n", n_steps, outs[0].quality, outs[0].sigma);
   }
   const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
-  std::fprintf(stderr, "[cli] %zu scans in %.2f s (%.1f scans/s)\n", n_done, secs, n_done / std::max(secs, 1e-9));
+  std::fprintf(stderr, "[cli] %zu scans of %u sequence(s) in %.2f s (%.1f scans/s)\n", n_done, S, secs, n_done / std::max(secs, 1e-9));
   if (!out_tum.empty()) {
-    uint64_t n = 0;
-    mlo_lo_trajectory(lo, nullptr, nullptr, 0, &n);
-    std::vector<double> st(n), ps(12 * n);
-    mlo_lo_trajectory(lo, st.data(), ps.data(), n, &n);
-    std::FILE* fo = std::fopen(out_tum.c_str(), "w");
-    if (!fo) { std::fprintf(stderr, "cannot write '%s'\n", out_tum.c_str()); return 1; }
-    for (uint64_t k = 0; k < n; k++) {
-      double q[4];
-      quat_of(&ps[12 * k], q);
-      std::fprintf(fo, "%.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f\n", st[k], ps[12 * k + 3], ps[12 * k + 7], ps[12 * k + 11], q[0], q[1], q[2], q[3]);
+    for (uint32_t q = 0; q < S; q++) {
+      std::string path = out_tum;
+      if (S > 1) {  // <stem>_<name><ext>
+        const fs::path p(out_tum);
+        path = (p.parent_path() / (p.stem().string() + "_" + names[q] + p.extension().string())).string();
+      }
+      uint64_t n = 0;
+      mlo_fleet_trajectory(fleet, q, nullptr, nullptr, 0, &n);
+      std::vector<double> st(n), ps(12 * n);
+      mlo_fleet_trajectory(fleet, q, st.data(), ps.data(), n, &n);
+      std::FILE* fo = std::fopen(path.c_str(), "w");
+      if (!fo) { std::fprintf(stderr, "cannot write '%s'\n", path.c_str()); return 1; }
+      for (uint64_t k = 0; k < n; k++) {
+        double qt[4];
+        quat_of(&ps[12 * k], qt);
+        std::fprintf(fo, "%.6f %.6f %.6f %.6f %.6f %.6f %.6f %.6f\n", st[k], ps[12 * k + 3], ps[12 * k + 7], ps[12 * k + 11], qt[0], qt[1], qt[2], qt[3]);
+      }
+      std::fclose(fo);
     }
-    std::fclose(fo);
   }
-  mlo_lo_destroy(lo);
+  mlo_fleet_destroy(fleet);
   mlo_destroy(ctx);
   return 0;
 }

@@ -49,3 +49,30 @@ def test_cli_matches_library_trajectory(ctx, scene, traj, tmp_path, monkeypatch)
                         "--only-first-n", "5"], capture_output=True, text=True, env=env)
     assert r.returncode == 0 and len(np.loadtxt(out)) == 5
     lo.close()
+
+
+@pytest.mark.gpu
+def test_cli_fleet_of_two_inputs(ctx, scene, tmp_path):
+    """Comma-separated inputs run as a lock-step fleet on one GPU (the counterpart of `parallel -j` in eval/cli_kitti.sh):
+    each trajectory equals the one of a stand-alone run; a shorter input simply ends earlier."""
+    import os
+    from mola_lidar_odometry_b200 import synth
+    env = dict(os.environ, MOLA_OPTIMIZE_TWIST="false", MOLA_INITIAL_VX="8.0")
+    lens = {"a": 8, "b": 6}
+    for name, seed in (("a", 7), ("b", 8)):
+        tr = synth.trajectory_T00(12, seed=seed)
+        (tmp_path / name).mkdir()
+        for k in range(lens[name]):
+            scene.scan(tr[k], scan_seed=seed * 1000 + k).tofile(tmp_path / name / f"{k:06d}.bin")
+    out = tmp_path / "fleet.tum"
+    r = subprocess.run([str(CLI), "-c", str(YAML), "--input-bin-dir", f"{tmp_path / 'a'},{tmp_path / 'b'}", "--output-tum-path",
+                        str(out)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    for name in ("a", "b"):
+        solo = tmp_path / f"solo_{name}.tum"
+        r = subprocess.run([str(CLI), "-c", str(YAML), "--input-bin-dir", str(tmp_path / name), "--output-tum-path", str(solo)],
+                           capture_output=True, text=True, env=env)
+        assert r.returncode == 0, r.stderr
+        f, s1 = np.loadtxt(tmp_path / f"fleet_{name}.tum"), np.loadtxt(solo)
+        assert f.shape == s1.shape == (lens[name], 8)
+        assert np.allclose(f, s1, atol=2e-6)
