@@ -13,6 +13,9 @@ One "step" = one batch of B scans through filter_1st_pass -> ICP align (no map i
   cpu_baseline  the CPU oracle (our restatement of mp2p_icp/mola_metric_maps — NOT the upstream binary) timed on
                 this box's host cores on a bounded sample of the same scans
   --impl reference  times only that CPU path (the reference's own binary cannot be built: DESIGN.md)
+
+  --workload sequence|ndt  (not the bench line) BASELINE configs[2]/[3]/[4]: whole sequences through the C++ host
+                orchestrator; the --sequences S sequences of a GPU advance in lock step as one fleet (mlo_fleet_*).
 """
 from __future__ import annotations
 

@@ -338,3 +338,25 @@ def test_fleet_gpu_deskew_and_ndt(ctx, scene, monkeypatch):
                 et, er = O.pose_error(outs[s].pose, b.pose)
                 assert et <= 1e-3 and er <= 1e-2, (s, et, er)
     fleet.close()
+
+
+def test_compiled_formulas_edge_cases(built):
+    """Formulas are compiled once into postfix programs (host/formula.hpp): precedence, associativity, nesting, unary signs,
+    booleans, errors at evaluation time, and re-evaluation with changed variables."""
+    from mola_lidar_odometry_b200 import host_api as H
+    from mola_lidar_odometry_b200.api import MloError
+    assert H.eval_formula("2+3*4^2/8-1") == 2 + 3 * 16 / 8 - 1
+    assert H.eval_formula("(-2)^2") == 4 and H.eval_formula("2^-1") == 0.5 and H.eval_formula("-(2^2)") == -4
+    assert H.eval_formula("--3") == 3 and H.eval_formula("+3-+2") == 1
+    assert H.eval_formula("max(min(5, 3), abs(-2)) + sqrt(16)") == 7
+    assert H.eval_formula("max(0.20, 0.0055*R)", R=100.0) == pytest.approx(0.55)
+    assert H.eval_formula("true + false*3") == 1
+    assert H.eval_formula(" 1e-3*x + .5 ", x=2000.0) == 2.5
+    deep = "(" * 30 + "1" + ")" * 30
+    assert H.eval_formula(deep) == 1
+    for bad in ("1 +", "max(1)", "foo(2)", "2 $ 3", "(1", "1 2"):
+        with pytest.raises(MloError):
+            H.eval_formula(bad)
+    # the per-iteration tables re-evaluate the same compiled formulas with ICP_ITERATION changing
+    thr, _, kp, _ = H.icp_tables(DEFAULT_YAML.read_text(), 1.0, 64)
+    assert thr[0] == 4.0 and thr[63] == 2.0 and np.all(np.diff(thr) <= 0) and np.allclose(kp, thr / 4.0)
