@@ -360,3 +360,22 @@ def test_compiled_formulas_edge_cases(built):
     # the per-iteration tables re-evaluate the same compiled formulas with ICP_ITERATION changing
     thr, _, kp, _ = H.icp_tables(DEFAULT_YAML.read_text(), 1.0, 64)
     assert thr[0] == 4.0 and thr[63] == 2.0 and np.all(np.diff(thr) <= 0) and np.allclose(kp, thr / 4.0)
+
+
+def test_fleet_time_gate_and_ragged_steps(built, scene):
+    """A scan that arrives too early for ITS sequence (min_time_between_scans, LidarOdometry.cpp:643-657) is dropped for
+    that sequence only; the others advance.  Per-sequence stamps differ inside one lock step."""
+    from oracle import oracle_py as O
+    S = 2
+    trajs = [synth.trajectory_T00(8, seed=7 + s) for s in range(S)]
+    fleet = O.OracleLidarOdometryFleet(DEFAULT_YAML, S)
+    solo = [O.OracleLidarOdometry(DEFAULT_YAML) for _ in range(S)]
+    for k in range(5):
+        clouds = [scene.scan(trajs[s][k], scan_seed=(7 + s) * 1000 + k) for s in range(S)]
+        # sequence 1 repeats its previous stamp at step 2 (dropped) and runs on a different clock otherwise
+        stamps = [0.1 * k, 100.0 + 0.1 * (k if k != 2 else 1) + (0.0004 if k == 2 else 0.0)]
+        outs = fleet.on_lidar(clouds, stamps)
+        for s in range(S):
+            b = solo[s].on_lidar(clouds[s], stamps[s])
+            _same_output(outs[s], b, exact=True)
+        assert outs[0].processed and outs[1].processed == (k != 2)
