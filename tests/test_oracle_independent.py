@@ -59,3 +59,97 @@ def test_nn_matches_brute_force_lidar_frame(world):
     bd2, bf = _brute(pts, q, 1.0, 20)
     assert np.array_equal(f, bf) and np.array_equal(d2[f].view(np.uint32), bd2[bf].view(np.uint32))
     assert ncand > 0
+
+
+def test_gauss_newton_step_matches_independent_numpy(built):
+    """ONE Gauss-Newton step of Solver_GaussNewton written independently in numpy/scipy (dense 4x4 matrix exponential,
+    explicit 3x6 Jacobians J = [R | -R [l]x], Geman-McClure weight w = c^4 / (c^2 + e^2)^2, brute-force nearest
+    neighbour) against the oracle's align with maxIterations = 1 and one inner iteration: pins the Jacobian convention,
+    the tangent order (x y z rx ry rz), the right-multiplicative retraction and the robust weight of the oracle."""
+    import scipy.linalg
+    from mola_lidar_odometry_b200 import capi, synth
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(11)
+    world = rng.uniform(-8.0, 8.0, (400, 3)).astype(np.float32)
+    world = world[np.min(np.abs(world - np.round(world)), axis=1) > 0.05]          # keep away from voxel faces
+    m = O.OracleMap(1.0, 20)
+    I34 = np.eye(4)[:3]
+    m.insert(world, I34)
+    T_true = synth.pose34(0.12, -0.08, 0.05, np.deg2rad(1.5), np.deg2rad(-0.8), np.deg2rad(0.6))
+    Ti = np.linalg.inv(synth.to44(T_true))
+    local = (world.astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3] + rng.normal(0, 0.01, world.shape)).astype(np.float32)
+    T0 = synth.pose34(0.02, 0.01, -0.01, np.deg2rad(0.2))
+    sigma = 1.0
+    ip = capi.IcpParamsOwner(sigma=sigma, max_iterations=1)
+    ip.p.gn_max_iterations = 1
+    res = O.icp_align(m, local, T0, ip.p)
+    # ---- independent evaluation
+    thr, c = 4.0 * sigma, 1.0 * sigma                     # default.yaml:190,198 at ICP_ITERATION = 0
+    R0, t0 = T0[:, :3], T0[:, 3]
+    g = (local.astype(np.float64) @ R0.T + t0).astype(np.float32)                  # matcher works on float32 points
+    d2 = ((g[:, None, :].astype(np.float64) - world[None, :, :].astype(np.float64)) ** 2).sum(axis=2)
+    nn = d2.argmin(axis=1)
+    keep = d2[np.arange(len(g)), nn].astype(np.float32) < np.float32(thr * thr)
+    assert keep.sum() == res.n_pairings > 200
+    H, b = np.zeros((6, 6)), np.zeros(6)
+    for l, q in zip(local[keep].astype(np.float64), world[nn[keep]].astype(np.float64)):
+        r = R0 @ l + t0 - q
+        w = c ** 4 / (c ** 2 + r @ r) ** 2
+        lx = np.array([[0, -l[2], l[1]], [l[2], 0, -l[0]], [-l[1], l[0], 0]])
+        J = np.hstack([R0, -R0 @ lx])
+        H += w * J.T @ J
+        b += w * J.T @ r
+    delta = -np.linalg.solve(H, b)
+    xi = np.zeros((4, 4))
+    xi[:3, :3] = np.array([[0, -delta[5], delta[4]], [delta[5], 0, -delta[3]], [-delta[4], delta[3], 0]])
+    xi[:3, 3] = delta[:3]
+    T1 = (synth.to44(T0) @ scipy.linalg.expm(xi))[:3]
+    assert np.allclose(np.asarray(res.pose), T1, rtol=0, atol=1e-10)
+    et0, _ = O.pose_error(T0, T_true)
+    et1, _ = O.pose_error(T1, T_true)
+    assert et1 < 0.2 * et0                                # and the step goes the right way
+
+
+def test_map_insert_cull_and_decimation_match_independent_python(world):
+    """The local-map update (insert with cap + min distance, then voxel cull) and FirstPoint decimation written
+    independently with Python dicts over a synthetic LiDAR drive, against the oracle's export / kept indices."""
+    from mola_lidar_odometry_b200 import capi
+    voxel, cap, min_d = 1.0, 20, 0.2
+    inv = np.float32(1.0) / np.float32(voxel)
+    ref = {}                                                  # (kx,ky,kz) -> list of float32 points, stored order
+    o = O.OracleMap(voxel, cap, min_d)
+    for fr in world["frames"][:5]:
+        T = fr["gt"]
+        o.insert(fr["map_layer"], T)
+        R, t = T[:, :3], T[:, 3]
+        for p in fr["map_layer"].astype(np.float64):
+            g = (R @ p + t).astype(np.float32)                # pose * point in double, stored as float32
+            k = tuple((g * inv).astype(np.int32))             # truncation toward zero
+            cell = ref.setdefault(k, [])
+            if len(cell) >= cap:
+                continue
+            if any(np.float32(((q - g) ** 2).sum(dtype=np.float32)) < np.float32(min_d * min_d) for q in cell):
+                continue
+            cell.append(g)
+        s = T[:, 3].astype(np.float32)
+        dist = 30.0
+        o.cull(T[:, 3], dist)
+        ks = tuple((s * inv).astype(np.int32))
+        d = int(np.ceil(np.float32(dist) * inv))
+        ref = {k: v for k, v in ref.items() if max(abs(k[0] - ks[0]), abs(k[1] - ks[1]), abs(k[2] - ks[2])) <= d}
+    keys, cnt, xyz = o.export()                               # sorted by (kx, ky, kz), points in stored order
+    rk = sorted(k for k, v in ref.items() if v)
+    assert [tuple(k) for k in keys] == rk
+    assert list(cnt) == [len(ref[k]) for k in rk]
+    assert np.array_equal(xyz.view(np.uint32), np.concatenate([np.stack(ref[k]) for k in rk]).view(np.uint32))
+    # FirstPoint decimation: first point (input order) of every occupied voxel, resolution 0.55
+    raw = world["frames"][2]["raw"][:, :3]
+    res = np.float32(0.55)
+    seen, first = set(), []
+    for i, p in enumerate(raw):
+        k = tuple((p / res).astype(np.int32))
+        if k not in seen:
+            seen.add(k)
+            first.append(i)
+    got = O.decimate_first(raw, capi.decimate_params(0.55, 10))
+    assert np.array_equal(np.sort(got), np.array(first))
