@@ -153,3 +153,83 @@ def test_map_insert_cull_and_decimation_match_independent_python(world):
             first.append(i)
     got = O.decimate_first(raw, capi.decimate_params(0.55, 10))
     assert np.array_equal(np.sort(got), np.array(first))
+
+
+def test_align_loop_matches_independent_numpy(built):
+    """The whole ICP::align loop (SURVEY.md A.1) written independently: per-iteration threshold / kernel-parameter
+    formulas of lidar3d-default.yaml, matcher, two inner Gauss-Newton iterations on fixed pairings, stall test on
+    log(prev^-1 T) against the previous and the one-before-previous solution, iteration accounting."""
+    import scipy.linalg
+    from mola_lidar_odometry_b200 import capi, synth
+    from oracle import oracle_py as O
+    rng = np.random.default_rng(5)
+    world = rng.uniform(-8.0, 8.0, (500, 3)).astype(np.float32)
+    world = world[np.min(np.abs(world - np.round(world)), axis=1) > 0.08]
+    m = O.OracleMap(1.0, 20)
+    m.insert(world, I34)
+    T_true = synth.pose34(0.25, -0.15, 0.1, np.deg2rad(2.0), np.deg2rad(-1.0), np.deg2rad(1.0))
+    Ti = np.linalg.inv(synth.to44(T_true))
+    local = (world.astype(np.float64) @ Ti[:3, :3].T + Ti[:3, 3] + rng.normal(0, 0.02, world.shape)).astype(np.float32)
+    sigma = 0.6
+    ip = capi.IcpParamsOwner(sigma=sigma, max_iterations=40)
+    res = O.icp_align(m, local, I34, ip.p)
+
+    def hat(w):
+        return np.array([[0, -w[2], w[1]], [w[2], 0, -w[0]], [-w[1], w[0], 0]])
+
+    def exp6(d):
+        xi = np.zeros((4, 4))
+        xi[:3, :3] = hat(d[3:])
+        xi[:3, 3] = d[:3]
+        return scipy.linalg.expm(xi)
+
+    def log6(T):
+        L = np.real(scipy.linalg.logm(T))
+        return np.array([L[0, 3], L[1, 3], L[2, 3], L[2, 1], L[0, 2], L[1, 0]])
+
+    T = np.eye(4)
+    prev, prev2 = T.copy(), None
+    it, term = 0, None
+    W = world.astype(np.float64)
+    while term is None:
+        base = max(sigma, 2.0 * sigma - 1.5 * sigma * it / 30.0)
+        thr, c = 2.0 * base, 0.5 * base
+        g = (local.astype(np.float64) @ T[:3, :3].T + T[:3, 3]).astype(np.float32)
+        d2 = ((g[:, None, :].astype(np.float64) - W[None]) ** 2).sum(axis=2)
+        nn = d2.argmin(axis=1)
+        keep = d2[np.arange(len(g)), nn].astype(np.float32) < np.float32(thr * thr)
+        if not keep.any():
+            term = 1
+            break
+        L, Q = local[keep].astype(np.float64), W[nn[keep]]
+        for inner in range(2):
+            R0, t0 = T[:3, :3], T[:3, 3]
+            H, b = np.zeros((6, 6)), np.zeros(6)
+            for l, q in zip(L, Q):
+                r = R0 @ l + t0 - q
+                w = c ** 4 / (c ** 2 + r @ r) ** 2
+                J = np.hstack([R0, -R0 @ hat(l)])
+                H += w * J.T @ J
+                b += w * J.T @ r
+            delta = -np.linalg.solve(H, b)
+            T = T @ exp6(delta)
+            if np.linalg.norm(delta) < 1e-7:
+                break
+        stalled = False
+        for ref in (prev, prev2):
+            if ref is None:
+                continue
+            d = log6(np.linalg.inv(ref) @ T)
+            stalled = stalled or (np.linalg.norm(d[:3]) < 1e-4 and np.linalg.norm(d[3:]) < 5e-5)
+        prev2, prev = prev, T.copy()
+        if stalled:
+            term = 4
+            break
+        it += 1
+        if it >= 40:
+            term = 3
+    assert (term, it) == (res.termination, res.n_iterations)
+    assert np.allclose(np.asarray(res.pose), T[:3], rtol=0, atol=1e-9)
+    assert int(keep.sum()) == res.n_pairings
+    et, er = O.pose_error(T[:3], T_true)
+    assert et < 0.01 and er < 0.05
