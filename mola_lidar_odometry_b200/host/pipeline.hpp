@@ -403,8 +403,15 @@ class LidarOdometryT {
         else if (m == "TimestampAdjustMethod::EarliestIsZero") params_.timestamps_middle_is_zero = false;
         else throw std::runtime_error("FilterAdjustTimestamps: unsupported method '" + m + "'");
       }
-    icp_.initialize(cfg.at("icp_settings_with_vel"));
+    icp_.initialize(cfg.at("icp_settings_with_vel"));  // AlignKind::RegularOdometry (LidarOdometry.cpp:340-341)
     icp_.attachToParameterSource(parameter_source);
+    // AlignKind::NoMotionModel: optional, defaults to the regular set (LidarOdometry.cpp:343-349, default.yaml:154)
+    has_icp_no_vel_ = cfg.has("icp_settings_without_vel");
+    icp_no_vel_ = ICP<Backend>();
+    if (has_icp_no_vel_) {
+      icp_no_vel_.initialize(cfg["icp_settings_without_vel"]);
+      icp_no_vel_.attachToParameterSource(parameter_source);
+    }
     filter1_.initialize(cfg.at("observations_filter_1st_pass"));
     bool found = false;
     for (const YamlNode& g : cfg.at("localmap_generator").seq)
@@ -509,13 +516,14 @@ class LidarOdometryT {
   bool icp_pending() const { return icp_pending_; }
   // Phase D: one ICP::align call of the do/while at :954-1007
   void make_align_job(mlo_align_job& job) {
+    ICP<Backend>& icp = *icp_case_;
     ip_.maxIterations = remaining_;
     hook_.checkpoint = current_solution_;
-    icp_.setIterationHook(hook_);
+    icp.setIterationHook(hook_);
     std::memset(&job, 0, sizeof(job));
     job.map = static_cast<const mlo_map*>(map_);
     std::memcpy(job.init_pose_3x4, current_solution_.data(), sizeof(job.init_pose_3x4));
-    icp_.make_params(ip_, std::nullopt, job.params);
+    icp.make_params(ip_, std::nullopt, job.params);
   }
   void on_align_result(const mlo_icp_result& res) {
     Results& r = result_;
@@ -677,7 +685,9 @@ class LidarOdometryT {
     last_keyframe_pose_ = last_lidar_pose_;                           // :904
     since_last_ = last_icp_time_ ? stamp_ - *last_icp_time_ : 0.0;
     last_icp_time_ = stamp_;
-    ip_ = icp_.params;
+    // without a valid twist estimate the NoMotionModel ICP set applies, if the pipeline defines one (:899-903)
+    icp_case_ = (hasMotionModel || !has_icp_no_vel_) ? &icp_ : &icp_no_vel_;
+    ip_ = icp_case_->params;
     remaining_ = ip_.maxIterations;
     total_iterations_ = 0;
     hook_ = IterationHook{};
@@ -822,7 +832,9 @@ class LidarOdometryT {
   }
 
   Backend& be_;
-  ICP<Backend> icp_;
+  ICP<Backend> icp_, icp_no_vel_;
+  ICP<Backend>* icp_case_ = &icp_;
+  bool has_icp_no_vel_ = false;
   FilterPipeline1st filter1_;
   LocalMapDefinition mapdef_;
   void* map_ = nullptr;

@@ -379,3 +379,22 @@ def test_fleet_time_gate_and_ragged_steps(built, scene):
             b = solo[s].on_lidar(clouds[s], stamps[s])
             _same_output(outs[s], b, exact=True)
         assert outs[0].processed and outs[1].processed == (k != 2)
+
+
+def test_icp_settings_without_vel_is_used_without_motion_model(built, scene, traj, monkeypatch):
+    """AlignKind::NoMotionModel (LidarOdometry.cpp:343-349,899-903): when the pipeline defines `icp_settings_without_vel`
+    it is the ICP set of every scan that has no twist estimate; otherwise the regular set serves both cases."""
+    from oracle import oracle_py as O
+    monkeypatch.setenv("MOLA_INITIAL_VX", "0.0")              # no initial twist: scan 1 has no motion model
+    text = DEFAULT_YAML.read_text()
+    a = text.index("icp_settings_with_vel:")
+    b = text.index("localmap_generator:")
+    block = text[a:b].replace("icp_settings_with_vel:", "icp_settings_without_vel:").replace("maxIterations: 300", "maxIterations: 2")
+    assert "maxIterations: 2\n" in block
+    lo2 = O.OracleLidarOdometry(text + "\n" + block, is_text=True)
+    lo1 = O.OracleLidarOdometry(text, is_text=True)
+    outs2 = _run(lo2, scene, traj, 4)
+    outs1 = _run(lo1, scene, traj, 4)
+    assert outs2[1].icp_ran and outs2[1].icp_iterations == 2 and outs2[1].termination == 3      # MaxIterations of the no-vel set
+    assert outs1[1].icp_iterations > 2 and outs1[1].termination == 4                            # regular set: runs until stalled
+    assert outs2[2].icp_iterations > 2                                                          # motion model available again
