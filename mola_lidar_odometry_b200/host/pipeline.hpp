@@ -328,6 +328,10 @@ struct LidarOdometryParams {  // the subset of LidarOdometry::Parameters around 
   bool local_map_updates_enabled = true;
   Formula min_translation_between_keyframes{"1.0"}, min_rotation_between_keyframes{"30"}, max_distance_to_keep_keyframes{"0"};
   uint32_t check_for_removal_every_n = 100;
+  bool measure_from_last_kf_only = false;  // local_map_updates.measure_from_last_kf_only (LidarOdometry.cpp:188,1066-1068)
+  // observation_validity_checks (default.yaml:118-121, LidarOdometry.cpp:749-755,1548-1569); only the 'raw' layer is known here
+  bool obs_validity_enabled = false;
+  uint64_t obs_validity_min_points = 1000;
   double min_icp_goodness = 0.25;
   bool adaptive_enabled = true;
   double initial_sigma = 2.0, min_motion = 0.1, maximum_sigma = 3.0, kp = 2.0, alpha = 0.9;
@@ -375,6 +379,15 @@ class LidarOdometryT {
     params_.min_rotation_between_keyframes = Formula(lm.at("min_rotation_between_keyframes").str());
     if (lm.has("max_distance_to_keep_keyframes")) params_.max_distance_to_keep_keyframes = Formula(lm["max_distance_to_keep_keyframes"].str());
     params_.check_for_removal_every_n = uint32_t(lm["check_for_removal_every_n"].num(100));
+    params_.measure_from_last_kf_only = lm["measure_from_last_kf_only"].boolean(false);
+    if (p.has("observation_validity_checks")) {
+      const YamlNode& ov = p["observation_validity_checks"];
+      params_.obs_validity_enabled = ov["enabled"].boolean(false);
+      params_.obs_validity_min_points = uint64_t(ov["minimum_point_count"].num(1000));
+      const std::string layer = ov["check_layer_name"].str_or("raw");
+      if (params_.obs_validity_enabled && layer != "raw")
+        throw std::runtime_error("observation_validity_checks: only check_layer_name 'raw' is supported, got '" + layer + "'");
+    }
     params_.min_icp_goodness = p["min_icp_goodness"].num(0.25);
     const YamlNode& at = p["adaptive_threshold"];
     params_.adaptive_enabled = at["enabled"].boolean(true);
@@ -435,6 +448,9 @@ class LidarOdometryT {
     est_max_range_.reset();
     inst_max_range_.reset();
     last_obs_time_.reset();
+    last_icp_time_.reset();
+    first_ever_time_.reset();
+    last_motion_model_output_.reset();
     last_icp_was_good_ = true;
     last_icp_quality_ = 0.0;
     removal_counter_ = 0;
@@ -460,16 +476,22 @@ class LidarOdometryT {
     icp_pending_ = false;
     needs_deskew_ = false;
     insert_pending_ = false;
+    dropped_ = false;
     if (last_obs_time_ && stamp - *last_obs_time_ < params_.min_time_between_scans) return false;  // :643-657
-    last_obs_time_ = stamp;
+    prev_obs_time_ = last_obs_time_;
+    last_obs_time_ = stamp;  // (:763; taken back in on_layers if the observation turns out to be invalid, :749-755)
+    n_raw_ = n;
     stamp_ = stamp;
     out_.processed = true;
     if (!est_max_range_) {  // doInitializeEstimatedMaxSensorRange, :1487-1513
       const double r = std::max(bbox_radius(pts, stride, n), params_.absolute_minimum_sensor_range);
       if (n) est_max_range_ = r;
     }
-    motion_ = estimated_navstate(stamp);      // :808-815
-    updatePipelineDynamicVariables(motion_);  // :692
+    // :692 runs BEFORE the motion model is queried for this scan (:808-815): the twist variables seen by the filters (and,
+    // unless the hook re-estimates them, by the keyframe formulas) are those of the PREVIOUS scan's motion-model output
+    updatePipelineDynamicVariables(last_motion_model_output_);
+    motion_ = estimated_navstate(stamp);      // :808-815 (pure query; stored as last_motion_model_output once the
+                                              // observation has passed the validity check, on_layers)
     // 1st-pass filter (:732-735); the 2nd pass is the identity with deskew skipped (:737-741)
     std::memset(&job, 0, sizeof(job));
     job.fp = filter1_.realize(parameter_source);
@@ -548,6 +570,7 @@ class LidarOdometryT {
   }
   // Phase E: gating, adaptive sigma, keyframe decision (:1011-1158).  Returns true when a map insert must follow.
   bool after_icp(mlo_insert_job& job) {
+    if (dropped_) return false;
     bool updateLocalMap = first_scan_;
     const bool hasMotionModel = motion_.has_value();
     if (!first_scan_) {
@@ -567,6 +590,8 @@ class LidarOdometryT {
       } else {
         fused_.clear();  // navstate_fuse.reset()
       }
+      parameter_source.updateVariable("icp_iterations", double(r.nIterations));  // :1046-1048
+      parameter_source.updateVariable("twistCorrectionCount", double(out_.icp_runs > 0 ? out_.icp_runs - 1 : 0));
       if (params_.adaptive_enabled) doUpdateAdaptiveThreshold(pose_minus(r.optimal_tf_mean, init_guess_), motion_);  // :1052-1063
       // keyframe decision (:1066-1115)
       double dist = 0, rot = 0;
@@ -626,6 +651,7 @@ class LidarOdometryT {
     insert_pending_ = false;
   }
   ScanOutput finish_scan() {
+    if (dropped_) return ScanOutput{};
     out_.pose = last_lidar_pose_;
     out_.sigma = sigma_;
     return out_;
@@ -673,6 +699,14 @@ class LidarOdometryT {
     out_.n_icp_layer = info.n_icp;
     doUpdateEstimatedMaxSensorRange(info);  // :744-769 (first points layer of the observation = decimated_for_icp)
     out_.est_max_range = est_max_range_.value_or(0.0);
+    if (params_.obs_validity_enabled && !(n_raw_ > params_.obs_validity_min_points)) {  // :749-755: discarded, nothing stored
+      last_obs_time_ = prev_obs_time_;
+      dropped_ = true;
+      out_ = ScanOutput{};
+      return;
+    }
+    if (!first_ever_time_) first_ever_time_ = stamp_;  // :766-767
+    last_motion_model_output_ = motion_;                // :811
     first_scan_ = !map_ || map_points_ == 0;
     if (first_scan_) {
       // first point cloud: no ICP, seed the map at the origin (:817-839)
@@ -805,6 +839,8 @@ class LidarOdometryT {
       if (!parameter_source.has(v)) parameter_source.updateVariable(v, 0);
     if (est_max_range_) parameter_source.updateVariable("ESTIMATED_SENSOR_MAX_RANGE", *est_max_range_);
     parameter_source.updateVariable("INSTANTANEOUS_SENSOR_MAX_RANGE", inst_max_range_ ? *inst_max_range_ : 20.0);
+    if (last_obs_time_ && first_ever_time_)  // :1626-1630
+      parameter_source.updateVariable("current_relative_timestamp", *last_obs_time_ - *first_ever_time_);
   }
   // mola::SearchablePoseList::check: distance to the closest stored keyframe; true when the list is empty
   bool closest_keyframe(const Pose& p, double& dist, double& rot) {
@@ -814,7 +850,9 @@ class LidarOdometryT {
     }
     double best = 1e300;
     const Pose* bk = nullptr;
+    if (params_.measure_from_last_kf_only) bk = &keyframes_.back();
     for (const Pose& k : keyframes_) {
+      if (params_.measure_from_last_kf_only) break;
       const double d[3] = {k[3] - p[3], k[7] - p[7], k[11] - p[11]};
       const double n = norm3(d);
       if (n < best) {
@@ -858,7 +896,10 @@ class LidarOdometryT {
   Pose last_lidar_pose_ = pose_identity();
   std::array<double, 6> twist_{};
   double sigma_ = 0;
-  std::optional<double> est_max_range_, inst_max_range_, last_obs_time_, last_icp_time_;
+  std::optional<double> est_max_range_, inst_max_range_, last_obs_time_, prev_obs_time_, first_ever_time_, last_icp_time_;
+  std::optional<NavState> last_motion_model_output_;  // state_.last_motion_model_output: assigned at :811, read at :692
+  uint64_t n_raw_ = 0;
+  bool dropped_ = false;
   bool last_icp_was_good_ = true;
   double last_icp_quality_ = 0;
   uint32_t removal_counter_ = 0;

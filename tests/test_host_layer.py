@@ -398,3 +398,42 @@ def test_icp_settings_without_vel_is_used_without_motion_model(built, scene, tra
     assert outs2[1].icp_ran and outs2[1].icp_iterations == 2 and outs2[1].termination == 3      # MaxIterations of the no-vel set
     assert outs1[1].icp_iterations > 2 and outs1[1].termination == 4                            # regular set: runs until stalled
     assert outs2[2].icp_iterations > 2                                                          # motion model available again
+
+
+def test_observation_validity_check_discards_small_clouds(built, scene, traj, monkeypatch):
+    """observation_validity_checks (default.yaml:118-121, LidarOdometry.cpp:749-755): an observation whose 'raw' layer does
+    not have MORE than minimum_point_count points is discarded after the filters ran - no pose, no map update, and its stamp
+    is not remembered by the min_time_between_scans gate."""
+    from oracle import oracle_py as O
+    monkeypatch.setenv("MOLA_ENABLE_OBS_VALIDITY_FILTER", "true")
+    monkeypatch.setenv("MOLA_OBS_VALIDITY_MIN_POINTS", "5000")
+    lo = O.OracleLidarOdometry(DEFAULT_YAML)
+    raw0 = scene.scan(traj[0], scan_seed=1000)
+    assert lo.on_lidar(raw0, 0.0).processed
+    small = scene.scan(traj[1], scan_seed=1001)[:5000]           # exactly the minimum: not "more than"
+    o = lo.on_lidar(small, 0.1)
+    assert not o.processed and not o.icp_ran and not o.map_updated
+    # the discarded stamp was not stored: a valid cloud 0.5 ms later is NOT dropped by the time gate (it would be otherwise)
+    o = lo.on_lidar(scene.scan(traj[1], scan_seed=1001), 0.1005)
+    assert o.processed and o.icp_ran
+    ref = O.OracleLidarOdometry(DEFAULT_YAML)
+    ref.on_lidar(raw0, 0.0)
+    b = ref.on_lidar(scene.scan(traj[1], scan_seed=1001), 0.1005)
+    # same registration up to the max-range low-pass, which the discarded cloud DID feed (:744 runs before the check :749)
+    et, er = O.pose_error(o.pose, b.pose)
+    assert et < 0.05 and er < 0.1 and o.est_max_range != b.est_max_range
+    monkeypatch.setenv("MOLA_ENABLE_OBS_VALIDITY_FILTER", "false")
+    lo2 = O.OracleLidarOdometry(DEFAULT_YAML)
+    lo2.on_lidar(raw0, 0.0)
+    assert lo2.on_lidar(small, 0.1).processed                    # check disabled (the default): processed
+
+
+def test_twist_variables_at_scan_start_are_the_previous_motion_model_output(built, scene, traj):
+    """LidarOdometry.cpp:692 refreshes the pipeline variables BEFORE the motion model is queried for the new scan (:808-815):
+    the keyframe formulas of default.yaml:44-45 therefore see the previous scan's twist.  With a constant initial twist and
+    no rotation the thresholds are the same either way; what must hold is that scan 1 (whose 'previous' output does not
+    exist) evaluates them with a zero twist: min_translation = 0.001 * R < the 0.8 m step, so scan 1 is a keyframe."""
+    from oracle import oracle_py as O
+    lo = O.OracleLidarOdometry(DEFAULT_YAML)
+    outs = _run(lo, scene, traj, 3)
+    assert outs[1].icp_good and outs[1].map_updated
