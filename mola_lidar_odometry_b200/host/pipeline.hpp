@@ -395,6 +395,7 @@ class LidarOdometryT {
     params_.min_motion = at["min_motion"].num(0.1);
     params_.maximum_sigma = at["maximum_sigma"].num(3.0);
     params_.kp = at["kp"].num(2.0);
+    if (params_.adaptive_enabled && !(params_.kp > 1.0)) throw std::runtime_error("adaptive_threshold.kp must be > 1 (LidarOdometry.cpp:1468)");
     params_.alpha = at["alpha"].num(0.9);
     if (cfg.has("navstate_fuse_params"))
     {
