@@ -592,7 +592,9 @@ class LidarOdometryT {
         fused_.clear();  // navstate_fuse.reset()
       }
       parameter_source.updateVariable("icp_iterations", double(r.nIterations));  // :1046-1048
-      parameter_source.updateVariable("twistCorrectionCount", double(out_.icp_runs > 0 ? out_.icp_runs - 1 : 0));
+      // (the reference's local counter is never incremented - :926,939 bump the PARAMETER instead - so the variable stays
+      // 0 and optimize_twist_max_corrections never limits the re-runs; reproduced as is)
+      parameter_source.updateVariable("twistCorrectionCount", 0.0);
       if (params_.adaptive_enabled) doUpdateAdaptiveThreshold(pose_minus(r.optimal_tf_mean, init_guess_), motion_);  // :1052-1063
       // keyframe decision (:1066-1115)
       double dist = 0, rot = 0;
