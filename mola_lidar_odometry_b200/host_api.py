@@ -134,21 +134,48 @@ class LidarOdometry:
         return st, ps
 
 
+# numpy view of an array of ScanOutput (same layout as the C struct): lets a driver read S results without S x 13
+# ctypes attribute accesses
+SCAN_OUTPUT_DTYPE = np.dtype({"names": [f[0] for f in ScanOutput._fields_],
+                              "formats": [np.int32, np.int32, np.int32, np.int32, (np.float64, (3, 4)), np.float64, np.float64,
+                                          np.float64, np.uint32, np.uint32, np.int32, np.uint64, np.uint64],
+                              "offsets": [getattr(ScanOutput, f[0]).offset for f in ScanOutput._fields_],
+                              "itemsize": C.sizeof(ScanOutput)})
+
+
+def _addr(a: np.ndarray) -> int:
+    return a.__array_interface__["data"][0]
+
+
+def _as_cloud(c, as_pts):
+    if type(c) is np.ndarray and c.dtype == np.float32 and c.ndim == 2 and c.shape[1] in (3, 4) and c.flags.c_contiguous:
+        return c
+    return as_pts(c)
+
+
 def _fleet_args(clouds, stamps, ts, as_pts):
     """ctypes argument arrays of one lock step; a cloud of None leaves that sequence idle."""
     S = len(clouds)
-    keep = [None if c is None else as_pts(c) for c in clouds]
+    keep = [None if c is None else _as_cloud(c, as_pts) for c in clouds]
     stride = next((c.shape[1] for c in keep if c is not None), 3)
     assert all(c is None or c.shape[1] == stride for c in keep)
-    pts = (_vp * S)(*[None if c is None else c.ctypes.data for c in keep])
-    n = (_u64 * S)(*[0 if c is None else len(c) for c in keep])
-    st = (C.c_double * S)(*[float(x) for x in stamps])
+    pts = (_vp * S)(*[None if c is None else _addr(c) for c in keep])
+    n = (_u64 * S)(*[0 if c is None else c.shape[0] for c in keep])
+    st = (C.c_double * S)(*stamps)
     tp = None
     if ts is not None:
         tk = [None if t is None else np.ascontiguousarray(t, dtype=np.float32) for t in ts]
         keep.append(tk)
-        tp = (_vp * S)(*[None if t is None else t.ctypes.data for t in tk])
+        tp = (_vp * S)(*[None if t is None else _addr(t) for t in tk])
     return keep, stride, pts, n, st, tp
+
+
+def _fleet_outputs(out, n, as_arrays):
+    """The ScanOutput array of one lock step as a list of structs, or (as_arrays) as ONE numpy structured array
+    (fields as in ScanOutput; `pose_3x4` is [n, 3, 4])."""
+    if not as_arrays:
+        return list(out)
+    return np.frombuffer(out, dtype=SCAN_OUTPUT_DTYPE, count=n).copy()
 
 
 class LidarOdometryFleet:
@@ -157,6 +184,7 @@ class LidarOdometryFleet:
 
     def __init__(self, ctx: Context, yaml_path_or_text, n_sequences: int, is_text: bool = False):
         self.ctx, self.n = ctx, n_sequences
+        self._arg_cache = {}
         h = _vp()
         rc = lib().mlo_fleet_create(ctx.h, str(yaml_path_or_text).encode(), int(is_text), n_sequences, C.byref(h))
         if rc != 0:
@@ -174,21 +202,34 @@ class LidarOdometryFleet:
         except Exception:
             pass
 
-    def on_lidar(self, clouds, stamps, ts=None):
-        """clouds[i] -> sequence i (None = idle).  Returns a list of ScanOutput."""
+    def on_lidar(self, clouds, stamps, ts=None, as_arrays: bool = False):
+        """clouds[i] -> sequence i (None = idle).  Returns a list of ScanOutput, or with as_arrays one numpy structured
+        array of dtype SCAN_OUTPUT_DTYPE."""
         assert len(clouds) == self.n and len(stamps) == self.n
-        keep, stride, pts, n, st, tp = _fleet_args(clouds, stamps, ts, _pts)
+        cached = self._arg_cache.pop(tuple(map(id, clouds)), None) if ts is None else None
+        if cached is not None:
+            keep, stride, pts, n = cached             # the argument arrays built by prefetch() for these very objects
+            st, tp = (C.c_double * self.n)(*stamps), None
+        else:
+            keep, stride, pts, n, st, tp = _fleet_args(clouds, stamps, ts, _pts)
         out = (ScanOutput * self.n)()
         rc = lib().mlo_fleet_on_lidar(self.h, pts, stride, n, st, tp, out)
         if rc != 0:
             raise MloError(rc, lib().mlo_fleet_last_error(self.h).decode())
         del keep
-        return list(out)
+        return _fleet_outputs(out, self.n, as_arrays)
 
     def prefetch(self, clouds):
         """Announce the clouds of the NEXT on_lidar call (the same array objects must be passed then)."""
-        keep, stride, pts, n, _, _ = _fleet_args(clouds, [0.0] * self.n, None, _pts)
-        self._prefetched = keep
+        keep, stride, pts, n, _, _ = _fleet_args(clouds, (0.0,) * self.n, None, _pts)
+        # Reusable by on_lidar only when the caller's own arrays are the ones pointed to (no conversion copy was made):
+        # the cache then holds references to exactly those objects, so their ids cannot be recycled meanwhile.
+        same = all(k is c for k, c in zip(keep, clouds))
+        self._prefetched = keep                       # (the announced buffers must stay alive until they are consumed)
+        if same:
+            if len(self._arg_cache) >= 2:             # the announcement for step k+1 is made before step k runs: keep two
+                self._arg_cache.pop(next(iter(self._arg_cache)))
+            self._arg_cache[tuple(map(id, clouds))] = (keep, stride, pts, n)
         rc = lib().mlo_fleet_prefetch(self.h, pts, stride, n)
         if rc != 0:
             raise MloError(rc, lib().mlo_fleet_last_error(self.h).decode())

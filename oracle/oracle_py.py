@@ -298,11 +298,11 @@ class OracleLidarOdometryFleet:
             lib().orc_fleet_destroy(self.h)
             self.h = None
 
-    def on_lidar(self, clouds, stamps, ts=None):
-        from mola_lidar_odometry_b200.host_api import _fleet_args
+    def on_lidar(self, clouds, stamps, ts=None, as_arrays: bool = False):
+        from mola_lidar_odometry_b200.host_api import _fleet_args, _fleet_outputs
         keep, stride, pts, n, st, tp = _fleet_args(clouds, stamps, ts, _f32)
         out = (self._out_t * self.n)()
         if lib().orc_fleet_on_lidar(self.h, pts, stride, n, st, tp, out) != 0:
             raise RuntimeError("orc_fleet_on_lidar failed")
         del keep
-        return list(out)
+        return _fleet_outputs(out, self.n, as_arrays)

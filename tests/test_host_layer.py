@@ -261,6 +261,16 @@ def test_fleet_on_oracle_equals_independent_sequences(built, scene):
                 continue
             _same_output(outs[s], solo[s].on_lidar(clouds[s], stamps[s]), exact=True)
     assert outs[0].icp_ran and outs[S - 1].icp_ran
+    # the structured-array form of the outputs (one numpy array for all sequences) carries the same values
+    from mola_lidar_odometry_b200.host_api import SCAN_OUTPUT_DTYPE
+    fleet2 = O.OracleLidarOdometryFleet(DEFAULT_YAML, S)
+    for clouds, stamps, _ in steps:
+        arr = fleet2.on_lidar(clouds, stamps, as_arrays=True)
+    assert arr.dtype == SCAN_OUTPUT_DTYPE and arr["pose_3x4"].shape == (S, 3, 4)
+    for s in range(S):
+        assert np.array_equal(arr["pose_3x4"][s], outs[s].pose) and arr["icp_iterations"][s] == outs[s].icp_iterations
+        assert (arr["processed"][s], arr["map_updated"][s], arr["n_icp_layer"][s]) == (outs[s].processed, outs[s].map_updated, outs[s].n_icp_layer)
+        assert arr["sigma"][s] == outs[s].sigma and arr["quality"][s] == outs[s].quality
 
 
 def test_fleet_on_oracle_deskew_twist_loop(built, scene, monkeypatch):
@@ -437,3 +447,63 @@ def test_twist_variables_at_scan_start_are_the_previous_motion_model_output(buil
     lo = O.OracleLidarOdometry(DEFAULT_YAML)
     outs = _run(lo, scene, traj, 3)
     assert outs[1].icp_good and outs[1].map_updated
+
+
+def test_fleet_python_wrapper_argument_reuse(monkeypatch):
+    """LidarOdometryFleet (the GPU-side ctypes wrapper) against a stand-in library: the pointers handed to
+    mlo_fleet_on_lidar are the callers' arrays; the argument arrays built by prefetch() are reused by the on_lidar() call
+    for the same array objects, and never when a conversion copy had to be made."""
+    import ctypes as C
+    from mola_lidar_odometry_b200 import host_api as H
+
+    class FakeLib:
+        def __init__(self):
+            self.calls = []
+
+        def mlo_fleet_create(self, ctx, yaml, is_text, n, out):
+            C.cast(out, C.POINTER(C.c_void_p))[0] = 1234
+            return 0
+
+        def mlo_fleet_destroy(self, h):
+            pass
+
+        def mlo_fleet_last_error(self, h):
+            return b""
+
+        def _ptrs(self, pts, n, S):
+            return [(pts[i], n[i]) for i in range(S)]
+
+        def mlo_fleet_prefetch(self, h, pts, stride, n):
+            self.calls.append(("prefetch", stride, self._ptrs(pts, n, 2), id(pts)))
+            return 0
+
+        def mlo_fleet_on_lidar(self, h, pts, stride, n, st, tp, out):
+            self.calls.append(("on_lidar", stride, self._ptrs(pts, n, 2), id(pts), [st[0], st[1]], tp))
+            out[1].icp_iterations = 5
+            return 0
+
+    fake = FakeLib()
+    monkeypatch.setattr(H, "lib", lambda: fake)
+
+    class Ctx:
+        h = 1
+
+    fleet = H.LidarOdometryFleet(Ctx(), "unused.yaml", 2)
+    a, b = np.zeros((10, 4), np.float32), np.ones((7, 4), np.float32)
+    addr = lambda x: x.__array_interface__["data"][0]
+    clouds, other = [a, b], [b, a]
+    fleet.prefetch(clouds)
+    fleet.prefetch(other)                                      # the announcement for the step after next comes first
+    out = fleet.on_lidar(clouds, [0.5, 0.6], as_arrays=True)
+    pre, onl = fake.calls[0], fake.calls[2]
+    del fake.calls[1]
+    assert pre[2] == onl[2] == [(addr(a), 10), (addr(b), 7)] and pre[1] == onl[1] == 4
+    assert pre[3] == onl[3]                                    # the very same ctypes pointer array was reused
+    assert onl[4] == [0.5, 0.6] and onl[5] is None and out["icp_iterations"][1] == 5
+    out = fleet.on_lidar([b, None], [0.7, 0.7])                # other objects: fresh arguments, idle slot = NULL / 0
+    assert fake.calls[2][2] == [(addr(b), 7), (None, 0)] and fake.calls[2][3] != pre[3] and len(out) == 2
+    d = np.zeros((5, 3), np.float64)                           # needs a float32 copy: never served from the cache
+    fleet.prefetch([d, d])
+    fleet.on_lidar([d, d], [0.8, 0.8])
+    assert fake.calls[3][2][0][0] != addr(d) and fake.calls[4][3] != fake.calls[3][3] and fake.calls[4][1] == 3
+    fleet.h = None
