@@ -111,7 +111,7 @@ struct mlo_ctx {
                            // pipelined at 8 blocks/SM: 23.8k; 2 = pipelined at 6 blocks/SM: 25.3k; 3 = 6 blocks/SM, 80 registers,
                            // fewer spills: 26.1k (default)
   int wl_warps = 4;        // MLO_WL_WARPS: 4 = four-warp blocks (default), 1 = one-warp blocks (A/B: slower)
-  int table_factor = 8;    // MLO_TABLE_FACTOR: hash buckets per voxel of capacity (load factor ~0.08: fewer re-probes): occupancy target of the work-list kernel (register budget), experiments
+  int table_factor = 8;    // MLO_TABLE_FACTOR: hash buckets per voxel of capacity (load factor ~0.08: fewer re-probes)
   int pers_minb = 0;         // MLO_PERS_MINB: resident blocks per SM the persistent kernel is compiled for (4: 128 registers,
                              // 2: 255 registers - the solve step keeps more of its 6x6 arrays in registers); 0 = auto: 2 for a
                              // single problem (align 0.926 vs 0.978 ms per scan), 4 otherwise (32 sequences: 1.72 vs 2.01 ms)
