@@ -507,3 +507,21 @@ def test_fleet_python_wrapper_argument_reuse(monkeypatch):
     fleet.on_lidar([d, d], [0.8, 0.8])
     assert fake.calls[3][2][0][0] != addr(d) and fake.calls[4][3] != fake.calls[3][3] and fake.calls[4][1] == 3
     fleet.h = None
+
+
+REF_PIPELINES = Path("/root/reference/pipelines")
+
+
+@pytest.mark.skipif(not REF_PIPELINES.exists(), reason="the reference tree only exists in the build container")
+@pytest.mark.parametrize("name", ["lidar3d-default.yaml", "lidar3d-ndt.yaml"])
+def test_reference_pipeline_files_load_unmodified_and_agree(built, scene, traj, name):
+    """The YAML surface is the reference's: its OWN pipeline files (full of GUI / IO / ROS blocks this path ignores) are
+    parsed unmodified by the host layer and drive the odometry to bit-identical results as this repo's trimmed copies."""
+    from oracle import oracle_py as O
+    ref = O.OracleLidarOdometry(REF_PIPELINES / name)
+    own = O.OracleLidarOdometry(ROOT / "pipelines" / name)
+    for k in range(6):
+        raw = scene.scan(traj[k], scan_seed=1000 + k)
+        a, b = ref.on_lidar(raw, 0.1 * k), own.on_lidar(raw, 0.1 * k)
+        _same_output(a, b, exact=True)
+    assert a.icp_ran and a.icp_good
