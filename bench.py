@@ -267,65 +267,95 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------- CPU arm
-def cpu_scans_per_sec(omap, scans, inits, fp, n_threads: int, budget_s: float, max_scans: int):
-    """filter_1st_pass + align with the CPU oracle, `n_threads` independent scans in flight (process-per-sequence
-    is the reference's own parallelism, eval/cli_kitti.sh:23).  Bounded by `budget_s` / `max_scans`."""
+def cpu_scans_per_sec(omap, scans, inits, fp, n_threads: int, budget_s: float, max_scans: int, warm_scans: int = 0,
+                      order=None):
+    """filter_1st_pass + align with the CPU oracle: ONE persistent pool of `n_threads` workers pulling scans off one queue
+    (process-per-sequence is the reference's own parallelism, eval/cli_kitti.sh:23) - no per-step join, thread start-up
+    outside the timed region, `warm_scans` untimed scans first (>= 3).  Bounded by `budget_s` /
+    `max_scans`.  Returns (scans/s, scans done, seconds, mean per-bucket ms, median-of-5-segments scans/s)."""
     from oracle import oracle_py as O
-    ips = [capi.IcpParamsOwner(sigma=SIGMA) for _ in scans]
-    done = []
-    t0 = time.perf_counter()
+    ips = [capi.IcpParamsOwner(sigma=SIGMA) for _ in range(n_threads)]
+    order = list(range(len(scans))) if order is None else list(order)
+    todo = order[:max_scans]
     lock = threading.Lock()
-    nxt = [0]
+    state = {"next": 0, "t0": None, "go": False}
+    done = []
+    ready = threading.Barrier(n_threads + 1)
 
-    def worker():
+    def worker(tid):
+        for w in range(warm_scans // n_threads + (1 if tid < warm_scans % n_threads else 0)):   # untimed warm-up
+            i = todo[(tid + w * n_threads) % len(todo)]
+            O.scan_register(omap, scans[i], fp, inits[i], ips[tid].p)
+        ready.wait()      # every worker is warm: the main thread starts the clock
+        ready.wait()
         while True:
             with lock:
-                i = nxt[0]
-                if i >= min(len(scans), max_scans) or time.perf_counter() - t0 > budget_s:
+                k = state["next"]
+                if k >= len(todo) or time.perf_counter() - state["t0"] > budget_s:
                     return
-                nxt[0] += 1
-            res, ms = O.scan_register(omap, scans[i], fp, inits[i], ips[i].p)
+                state["next"] += 1
+            i = todo[k]
+            res, ms = O.scan_register(omap, scans[i], fp, inits[i], ips[tid].p)
+            t = time.perf_counter()
             with lock:
-                done.append((i, res.n_iterations, ms))
+                done.append((t, i, res.n_iterations, ms))
 
-    th = [threading.Thread(target=worker) for _ in range(n_threads)]
+    th = [threading.Thread(target=worker, args=(t,)) for t in range(n_threads)]
     for t in th:
         t.start()
+    ready.wait()
+    state["t0"] = time.perf_counter()
+    ready.wait()
     for t in th:
         t.join()
-    dt = time.perf_counter() - t0
-    ms = np.array([d[2] for d in done])
-    return len(done) / dt, len(done), dt, ms.mean(0) if len(done) else np.zeros(3)
+    t_end = max([d[0] for d in done], default=state["t0"])
+    dt = t_end - state["t0"]
+    ms = np.array([d[3] for d in done])
+    # median of 5 consecutive segments of the run (by completion time)
+    seg = None
+    if len(done) >= 10:
+        ts = np.sort(np.array([d[0] for d in done])) - state["t0"]
+        edges = [0.0] + [float(ts[(j + 1) * len(ts) // 5 - 1]) for j in range(5)]
+        counts = [(j + 1) * len(ts) // 5 - j * len(ts) // 5 for j in range(5)]
+        seg = float(np.median([c / max(e1 - e0, 1e-9) for c, e0, e1 in zip(counts, edges[:-1], edges[1:])]))
+    return len(done) / max(dt, 1e-9), len(done), dt, (ms.mean(0) if len(done) else np.zeros(3)), seg
+
+
+def config_dict(B, scans, map_stats, world):
+    """The `config` of the bench line: identical for the GPU arm and the --impl reference arm."""
+    return {"workload": WORKLOAD, "scans_per_step_per_gpu": B, "points_per_scan": int(np.mean([len(s) for s in scans])),
+            "map_voxels": int(map_stats[0]), "map_points": int(map_stats[1]),
+            "l2_policy": "inputs larger than L2: 4 rotating windows of B raw scans + 400 MB map working set",
+            "parallelism": f"replicas x{world} (one rank per GPU, map replicated, scans sharded)"}
+
+
+N_WINDOWS = 4
 
 
 def run_reference(args, rank: int):
-    """--impl reference: the CPU path only (oracle port; the upstream binary cannot be built here)."""
+    """--impl reference: the reference's CPU path alone (oracle port: the upstream binary cannot be built here)
+    on the SAME workload, config and step size as the GPU arm: steps x B scans stream through one persistent pool of all
+    host cores (no per-step join); K steps are timed after W warm-up steps' worth of scans (capped at 4 per core)."""
     if rank != 0:
         return
     cores = os.cpu_count() or 1
-    wl = Workload(max(args.batch, 32), seed=args.seed, threads=cores)
+    B = args.batch
+    wl = Workload(B * N_WINDOWS, seed=args.seed, threads=cores)
     omap, layers = plan_map_layers(wl)
     scans, gts, inits = wl.query_set(layers[-1][0])
-    per_step = max(cores, min(args.batch, 32))
-    times = []
-    total = args.steps + args.warmup
-    for s in range(total):
-        sel = [(s * per_step + j) % len(scans) for j in range(per_step)]
-        t0 = time.perf_counter()
-        v, n, dt, _ = cpu_scans_per_sec(omap, [scans[i] for i in sel], inits[sel], wl.fp, cores, 1e9, per_step)
-        if s >= args.warmup:
-            times.append((n, dt))
-    n = sum(t[0] for t in times)
-    dt = sum(t[1] for t in times)
-    value = n / dt
+    order = [(s * B + j) % len(scans) for s in range(args.steps) for j in range(B)]
+    warm = min(args.warmup * B, 4 * cores)
+    value, n, dt, _, seg = cpu_scans_per_sec(omap, scans, inits, wl.fp, cores, 1e9, len(order), warm_scans=max(3, warm), order=order)
     line = {"metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": 1e3 * dt / max(1, args.steps), "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 distances / f64 normal equations", "data": "synthetic",
             "impl": "reference",
-            "config": {"workload": WORKLOAD, "scans_per_step": per_step, "map_voxels": TARGET_VOXELS,
-                       "note": "CPU oracle port of mp2p_icp/mola_metric_maps (upstream binary not buildable here)"},
+            "config": config_dict(B, scans, omap.stats(), args.gpus),
             "cpu_baseline": {"value": value, "unit": "scans/s", "cores": cores, "kind": "port",
-                             "sample": f"{n} scans, {per_step} per step, {cores} independent scans in flight"},
+                             "sample": f"{n} scans = {args.steps} steps x {B}, one persistent pool of {cores} workers "
+                                       f"(independent scans in flight, like eval/cli_kitti.sh), {max(3, warm)} warm-up scans",
+                             "median_of_5_segments": seg,
+                             "note": "CPU = our restatement of mp2p_icp/mola_metric_maps, not the upstream binary (unbuildable here)"},
             "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     emit(line)
@@ -499,6 +529,30 @@ def run_sequences(args, rank, local_rank, world):
         c.close()
 
 
+def bind_near_gpu(idx: int):
+    """Run this rank on the CPUs next to its GPU (sysfs local_cpulist of the GPU's PCI function) so that the pinned
+    staging buffers it allocates are NUMA-local to the GPU's root port.  Returns a short description or None."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(idx)
+        bdf = f"{pr.pci_domain_id:04x}:{pr.pci_bus_id:02x}:{pr.pci_device_id:02x}.0"
+        base = Path("/sys/bus/pci/devices") / bdf
+        cpus = set()
+        for part in (base / "local_cpulist").read_text().strip().split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        node = (base / "numa_node").read_text().strip()
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return {"pci": bdf, "numa_node": int(node), "cpus": len(cpus)}
+    except Exception as e:  # sysfs layout differs / not permitted: run unbound
+        return {"error": str(e)[:80]}
+
+
 # ---------------------------------------------------------------------------------------------- GPU arm
 def main():
     ap = argparse.ArgumentParser()
@@ -536,15 +590,16 @@ def main():
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: the product path has no CPU fallback")
     torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank)   # before any pinned allocation: first touch places the staging buffers
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
 
     cores = os.cpu_count() or 1
-    threads = max(1, cores // max(1, world))
+    threads = max(1, min(len(os.sched_getaffinity(0)), cores // max(1, world)))
     ctx = Context(local_rank)
     B = args.batch
-    n_windows = 4
+    n_windows = N_WINDOWS
     wl = Workload(B * n_windows, seed=args.seed + rank, threads=threads)
     gmap, layers = build_gpu_map(ctx, wl, TARGET_VOXELS, rank, world)
     scans, gts, inits = wl.query_set(layers[-1][0])
@@ -553,10 +608,11 @@ def main():
     params = [o.p for o in owners]
     windows = [list(range(w * B, (w + 1) * B)) for w in range(n_windows)]
     resident = [ctx.upload_batch([scans[i] for i in win]) for win in windows]
-    # pinned host copies for the e2e leg
+    # pinned host copies for the e2e leg: x, y, z packed (12 B per point).  The path reads no other channel (the 4th lane of
+    # a KITTI .bin is intensity), and packed xyz is also what an MRPT caller holds (CPointsMap keeps x / y / z vectors).
     host = []
     for win in windows:
-        flat, offs, stride = Context._concat([scans[i] for i in win])
+        flat, offs, stride = Context._concat([np.ascontiguousarray(scans[i][:, :3]) for i in win])
         t = torch.from_numpy(flat).pin_memory()
         host.append((t, offs, stride, t.numpy()))
     ext = torch.cuda.ExternalStream(ctx.stream, device=torch.device("cuda", local_rank))
@@ -643,6 +699,7 @@ def main():
     ms_dev2, ms_wall2 = timed(step_e2e, args.steps, args.warmup)
     ms_step2 = max(ms_dev2, ms_wall2) / args.steps
     e2e_value = world * B / (ms_step2 * 1e-3)
+    res_e2e, win_e2e = last["res"], windows[last["w"]]
     h2d = int(np.mean([h[0].numel() * 4 for h in host]))  # bytes of one step's raw clouds
     d2h = int(B * C.sizeof(capi.IcpResult))
 
@@ -677,23 +734,36 @@ def main():
                 "ms_per_step_of_that_pass": max(ms_dev_prof, ms_wall_prof) / args.steps,
                 "candidates_per_query": P / max(1, qi)}
 
+    # ---- parity of the timed path (rank 0): EVERY scan of the last timed batch against the oracle, tolerance asserted
     # ---- CPU baseline (rank 0, N=1 only): bounded sample of the same scans with the oracle
     cpu = None
     parity = None
     if rank == 0 and not args.no_cpu_baseline:
         omap = build_oracle_map(wl, layers)
-        # parity spot check of the last GPU batch against the oracle (first 8 scans)
-        deltas = []
-        for r, i in list(zip(res, win))[:8]:
-            orr, _ = O.scan_register(omap, scans[i], wl.fp, inits[i], params[0])
-            deltas.append(O.pose_error(r.pose, orr.pose))
-        parity = {"scans": len(deltas), "max_trans_m": max(d[0] for d in deltas), "max_rot_deg": max(d[1] for d in deltas)}
+        ip_chk = [capi.IcpParamsOwner(sigma=SIGMA) for _ in range(cores)]
+
+        def chk(a):
+            j, (r, i) = a
+            orr, _ = O.scan_register(omap, scans[i], wl.fp, inits[i], ip_chk[j % cores].p)
+            return O.pose_error(r.pose, orr.pose) + (int(r.n_iterations) - int(orr.n_iterations), int(r.termination) - int(orr.termination))
+        parity = {"tolerance": "1e-3 m / 1e-2 deg per scan (north_star), asserted"}
+        with ThreadPoolExecutor(cores) as ex:
+            for leg, (rr, ww) in {"resident": (res, win), "e2e": (res_e2e, win_e2e)}.items():
+                deltas = list(ex.map(chk, enumerate(zip(rr, ww))))
+                parity[leg] = {"scans": len(deltas), "max_trans_m": max(d[0] for d in deltas),
+                               "max_rot_deg": max(d[1] for d in deltas),
+                               "iteration_count_differs": int(sum(1 for d in deltas if d[2] != 0)),
+                               "termination_differs": int(sum(1 for d in deltas if d[3] != 0))}
+                assert parity[leg]["max_trans_m"] <= 1e-3 and parity[leg]["max_rot_deg"] <= 1e-2, \
+                    f"GPU result ({leg} leg) differs from the oracle: {parity[leg]}"
         if world == 1:
-            v1, n1, dt1, ms3 = cpu_scans_per_sec(omap, scans, inits, wl.fp, 1, args.cpu_budget * 0.4, 64)
-            vN, nN, dtN, _ = cpu_scans_per_sec(omap, scans, inits, wl.fp, cores, args.cpu_budget * 0.6, len(scans))
+            v1, n1, dt1, ms3, _ = cpu_scans_per_sec(omap, scans, inits, wl.fp, 1, args.cpu_budget * 0.4, 64, warm_scans=3)
+            vN, nN, dtN, _, segN = cpu_scans_per_sec(omap, scans, inits, wl.fp, cores, args.cpu_budget * 0.6, len(scans),
+                                                     warm_scans=max(3, 2 * cores))
             cpu = {"value": vN, "unit": "scans/s", "cores": cores, "kind": "port",
-                   "sample": f"{nN} scans of this workload in {dtN:.1f}s, {cores} independent scans in flight "
-                             f"(process-per-sequence like eval/cli_kitti.sh)",
+                   "sample": f"{nN} scans of this workload in {dtN:.1f}s, one persistent pool of {cores} workers "
+                             f"(independent scans in flight, like eval/cli_kitti.sh), warm-up scans untimed",
+                   "median_of_5_segments": segN,
                    "single_thread": {"value": v1, "scans": n1,
                                      "ms_filter_1st/run_icp/update_local_map": [float(x) for x in ms3]},
                    "note": "CPU = our restatement of mp2p_icp/mola_metric_maps, not the upstream binary"}
@@ -702,12 +772,10 @@ def main():
         line = {"metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32 distances / f64 normal equations", "data": "synthetic",
-                "config": {"workload": WORKLOAD, "scans_per_step_per_gpu": B, "points_per_scan": int(np.mean([len(s) for s in scans])),
-                           "map_voxels": gmap.stats()[0], "map_points": gmap.stats()[1],
-                           "l2_policy": "inputs larger than L2: 4 rotating windows of B raw scans + 400 MB map working set",
-                           "parallelism": f"replicas x{world} (one rank per GPU, map replicated, scans sharded)"},
+                "config": config_dict(B, scans, gmap.stats(), world),
                 "e2e": {"value": e2e_value, "unit": "scans/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "ms_per_step": ms_step2},
+                        "ms_per_step": ms_step2, "host_layout": "x,y,z float32 packed (12 B/pt), pinned, NUMA-local to the GPU",
+                        "host_link_GBps": h2d / (ms_step2 * 1e-3) / 1e9, "numa": numa},
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "quality": {"mean_iterations": float(np.mean(iters)), "max_err_vs_gt_m": max(e[0] for e in err_gt),
                             "median_err_vs_gt_m": float(np.median([e[0] for e in err_gt])), "parity_vs_oracle": parity},

@@ -85,6 +85,13 @@ int mlo_device_info(const mlo_ctx* ctx, char* name, uint32_t name_len, int* sm_c
 void* mlo_stream(const mlo_ctx* ctx);
 /* Count of kernels this context has launched since creation (bench.py "gpu_launches"). */
 uint64_t mlo_launch_count(const mlo_ctx* ctx);
+/* Launch-policy knobs of this context (never change results beyond summation order; for A/B runs and for tests that must
+ * exercise one specific device path).  Names: "align_path" (0 auto, 1 one kernel per phase = the large-batch launch
+ * sequence, 2 queue-driven persistent kernel, 3 one thread block per problem), "large_batch_queries" (total queries at
+ * which auto picks the launch sequence; 0 = SM count x 1024), "tail_handover", "tail_path", "stream_groups",
+ * "fuse_inner", "block_threads", "force_kernel", "wl_variant", "wl_warps", "pers_minb".  Unknown name: MLO_ERR_INVALID_ARG. */
+int mlo_set_option(mlo_ctx* ctx, const char* name, int64_t value);
+int mlo_get_option(const mlo_ctx* ctx, const char* name, int64_t* value);
 
 /* ------------------------------------------------------------------ local map
  * Replaces mola::HashedVoxelPointCloud / mola::NDT behind

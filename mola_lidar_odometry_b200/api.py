@@ -71,6 +71,15 @@ class Context:
         self.check(self.lib.mlo_device_info(self.h, name, 128, C.byref(sm), C.byref(ma), C.byref(mi)))
         return name.value.decode(), sm.value, (ma.value, mi.value)
 
+    def set_option(self, name: str, value: int):
+        """Launch-policy knob (include/mlo_b200.h mlo_set_option): e.g. align_path = 1 forces the large-batch launch sequence."""
+        self.check(self.lib.mlo_set_option(self.h, name.encode(), int(value)))
+
+    def get_option(self, name: str) -> int:
+        v = C.c_int64()
+        self.check(self.lib.mlo_get_option(self.h, name.encode(), C.byref(v)))
+        return int(v.value)
+
     def profile_enable(self, on: bool = True):
         self.check(self.lib.mlo_profile_enable(self.h, int(on)))
 

@@ -175,6 +175,8 @@ _SIGNATURES = {
     "mlo_device_info": (C.c_int, [_vp, C.c_char_p, _u32, C.POINTER(C.c_int), C.POINTER(C.c_int), C.POINTER(C.c_int)]),
     "mlo_stream": (_vp, [_vp]),
     "mlo_launch_count": (_u64, [_vp]),
+    "mlo_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "mlo_get_option": (C.c_int, [_vp, C.c_char_p, C.POINTER(C.c_int64)]),
     "mlo_map_create": (C.c_int, [_vp, C.POINTER(MapParams), C.POINTER(_vp)]),
     "mlo_map_destroy": (None, [_vp]),
     "mlo_map_clear": (C.c_int, [_vp]),

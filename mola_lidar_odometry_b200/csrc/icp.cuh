@@ -690,48 +690,8 @@ MLO_D bool horn_from_sums(const double* a, double n, double* T) {
   return true;
 }
 
-// End-of-iteration bookkeeping of mp2p_icp::ICP::align: step measure against prev and
-// prev-prev, hook-as-data, stall test, iteration counter, MaxIterations.
-// step measure of the new pose against a reference pose: norms of the two halves of log_SE3(ref^-1 T)
-MLO_D void step_measure(const double* T, const double* ref, double& dt, double& dr) {
-  double D[12], d[6];
-  pose_minus(T, ref, D);
-  se3_log(D, d);
-  dt = nrm3(d);
-  dr = nrm3(d + 3);
-}
-
-// executed by lane 0 after the step measures (vs prev on lane 0, vs prev-prev on lane 1) have been combined
-MLO_D void finish_iteration(const IcpProblem& P, IcpState& S, double* T, double* prev, double* prev2, double dt, double dr) {
-#pragma unroll
-  for (int k = 0; k < 12; k++) {
-    prev2[k] = prev[k];
-    prev[k] = T[k];
-  }
-  S.has_prev2 = 1;
-  S.inner_pending = 0;
-  if (P.hook_enabled) {
-    double D[12], w[3];
-    pose_minus(T, P.hook_checkpoint, D);
-    so3_log_of_pose(D, w);
-    const double tt[3] = {D[3], D[7], D[11]};
-    if (nrm3(tt) > P.hook_min_trans || nrm3(w) > P.hook_min_rot) {
-      S.term = MLO_TERM_HOOK_REQUEST;
-      S.done = 1;
-      return;
-    }
-  }
-  if (fabs(dt) < P.min_abs_step_trans && fabs(dr) < P.min_abs_step_rot) {
-    S.term = MLO_TERM_STALLED;
-    S.done = 1;
-    return;
-  }
-  S.it++;
-  if (S.it >= P.max_iterations) {
-    S.term = MLO_TERM_MAX_ITERATIONS;
-    S.done = 1;
-  }
-}
+// End-of-iteration bookkeeping of mp2p_icp::ICP::align — step measure against prev and prev-prev,
+// hook-as-data, stall test, iteration counter, MaxIterations — lives in solve_core below.
 
 // Sum of a problem's block partials by a whole thread block (SOLVE_WARPS warps): warp w adds the partials
 // b = w, w + SOLVE_WARPS, ... in ascending order (lane k owns element k, eight L2 loads in flight), then the warp
@@ -782,19 +742,186 @@ MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const
   __syncthreads();
 }
 
-// The solve step, executed by ONE warp after sum_partials_block: lane 0 applies the prior, solves the 6x6 system,
-// retracts and does the end-of-iteration bookkeeping.  Returns (on every lane) 0 = problem finished, 1 = another
-// inner GN iteration is pending, 2 = next ICP iteration.
-__device__ __noinline__ int solve_step(const IcpProblem& Pg, IcpState& Sg, const SolveScratch& sc, int after_match) {
+// ---- the solve step (one warp; problem and state in SHARED memory) --------------------------------------------
+// Prior term of Solver_GaussNewton (LidarOdometry.cpp:854-877): e = log(prior^-1 T), J = d log(D exp(eps))/d eps;
+// g += J^T L e ; H += J^T L J.  Out of line (rare, loop-heavy): keeps the common path's arrays in registers.
+__device__ __noinline__ void prior_add(const IcpProblem& P, const double* T, double* H, double* g) {
+  double D[12], e[6], J[36], LJ[36], Le[6];
+  pose_minus(T, P.prior_pose, D);
+  se3_log(D, e);
+  se3_right_jacobian_inv(e, J);
+  for (int i = 0; i < 6; i++) {
+    double s = 0;
+    for (int m = 0; m < 6; m++) s += P.prior_info[6 * i + m] * e[m];
+    Le[i] = s;
+    for (int j = 0; j < 6; j++) {
+      double t = 0;
+      for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * J[6 * m + j];
+      LJ[6 * i + j] = t;
+    }
+  }
+  for (int i = 0; i < 6; i++) {
+    for (int m = 0; m < 6; m++) g[i] += J[6 * m + i] * Le[m];
+    for (int j = 0; j < 6; j++)
+      for (int m = 0; m < 6; m++) H[6 * i + j] += J[6 * m + i] * LJ[6 * m + j];
+  }
+}
+__device__ __noinline__ bool horn_from_sums_ool(const double* a, double n, double* T) { return horn_from_sums(a, n, T); }
+
+// Measures of T against a reference pose, one lane each: D = ref^-1 T; dt, dr = norms of the two halves of
+// log_SE3(D) (the stall / oscillation test of ICP::align); tD = |D.t|, wD = |log_SO3(D.R)| (the twist hook of
+// LidarOdometry.cpp:930-940).  The three references of an iteration (prev, prev-prev, hook checkpoint) run on
+// three lanes through this ONE code path, i.e. concurrently.
+MLO_D void pose_measures(const double* T, const double* ref, double& dt, double& dr, double& tD, double& wD) {
+  double D[12], d[6];
+  pose_minus(T, ref, D);
+  se3_log(D, d);
+  dt = nrm3(d);
+  dr = nrm3(d + 3);
+  const double tt[3] = {D[3], D[7], D[11]};
+  tD = nrm3(tt);
+  wD = dr;  // se3_log's rotation half IS so3_log_of_pose(D)
+}
+
+// Executed by ONE warp once the 27 sums (+ counts) of the current linearisation sit in sc.tot / sc.cnt.
+// P and S live in shared memory.  Returns (on every lane) 0 = problem finished, 1 = another inner GN iteration is
+// pending, 2 = next ICP iteration.
+MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int after_match) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u;
-  double a[NACC];
-#pragma unroll
-  for (int k = 0; k < int(NACC); k++) a[k] = sc.tot[k];
   const uint32_t npairs = sc.cnt[0];
   const uint32_t ncand = sc.cnt[1];
-  // Stage the problem description and its state in shared memory: two coalesced reads and one coalesced write-back by
-  // the whole warp instead of ~150 serial, mostly dependent global accesses by lane 0 (each an L2 round trip).
+  double* const sT = S.T;
+  int next = 0;
+  bool finished = false;
+  if (after_match) {
+    if (lane == 0) {
+      S.n_pairs = npairs;
+      uint64_t pot = 0;
+      if (P.matcher_mask & MLO_MATCHER_PT2PL) pot += P.n_q;
+      if (P.matcher_mask & MLO_MATCHER_PT2PT) pot += P.n_q;
+      S.n_potential = pot;
+      S.n_query_it += P.n_q;
+      S.n_cand += ncand;
+      S.inner = 0;
+      if (npairs == 0) {
+        S.term = MLO_TERM_NO_PAIRINGS;
+        S.done = 1;
+      }
+    }
+    finished = npairs == 0;  // (warp-uniform)
+  }
+  if (!finished) {
+    if (P.solver == MLO_SOLVER_HORN) {
+      if (lane == 0) {
+        const bool ok = horn_from_sums_ool(sc.tot, double(npairs), sT);
+        if (!ok) {
+          S.term = MLO_TERM_SOLVER_ERROR;
+          S.done = 1;
+        } else {
+          next = 3;
+        }
+      }
+    } else {
+      // the symmetric 6x6 system is laid out in S.H by the whole warp (it is also the Hessian reported as covariance)
+      for (uint32_t idx = lane; idx < 36; idx += 32) {
+        const uint32_t i = idx / 6, j = idx % 6, r = i < j ? i : j, c = i < j ? j : i;
+        S.H[idx] = sc.tot[r * 6 - (r * (r - 1)) / 2 + (c - r)];
+      }
+      __syncwarp();
+      if (lane == 0) {
+        double g[6];
+#pragma unroll
+        for (int i = 0; i < 6; i++) g[i] = sc.tot[21 + i];
+        if (P.has_prior) {
+          double gs[6];
+#pragma unroll
+          for (int i = 0; i < 6; i++) gs[i] = g[i];
+          prior_add(P, sT, S.H, gs);
+#pragma unroll
+          for (int i = 0; i < 6; i++) g[i] = gs[i];
+        }
+        S.have_H = 1;
+        double H[36], mg[6], delta[6];
+#pragma unroll
+        for (int i = 0; i < 36; i++) H[i] = S.H[i];
+#pragma unroll
+        for (int i = 0; i < 6; i++) mg[i] = -g[i];
+        const bool ok = ldlt6(H, mg, delta);
+        if (!ok) {
+          S.term = MLO_TERM_SOLVER_ERROR;
+          S.done = 1;
+        } else {
+          double E[12], Tn[12];
+          se3_exp(delta, E);
+          pose_mul(sT, E, Tn);
+#pragma unroll
+          for (int i = 0; i < 12; i++) sT[i] = Tn[i];
+          double dn = 0;
+#pragma unroll
+          for (int i = 0; i < 6; i++) dn += delta[i] * delta[i];
+          S.inner++;
+          const bool last_inner = (sqrt(dn) < P.gn_min_delta) || (S.inner >= P.gn_max_iterations);
+          if (!last_inner) {
+            S.inner_pending = 1;
+            next = 1;
+          } else {
+            next = 3;  // retraction done, this was the last inner iteration: end-of-iteration bookkeeping follows
+          }
+        }
+      }
+    }
+  }
+  next = __shfl_sync(FULL, next, 0);
+  if (next == 3) {
+    __syncwarp();  // the new pose (written by lane 0) is visible to lanes 1 and 2
+    const int has2 = S.has_prev2;
+    double dt = 1e300, dr = 1e300, tD = 0.0, wD = 0.0;
+    const bool measure = lane == 0 || (lane == 1 && has2) || (lane == 2 && P.hook_enabled);
+    if (measure) {
+      const double* ref = lane == 0 ? S.prev : (lane == 1 ? S.prev2 : P.hook_checkpoint);
+      pose_measures(sT, ref, dt, dr, tD, wD);
+    }
+    const double dt1 = __shfl_sync(FULL, dt, 1), dr1 = __shfl_sync(FULL, dr, 1);
+    const double tH = __shfl_sync(FULL, tD, 2), wH = __shfl_sync(FULL, wD, 2);
+    __syncwarp();  // lane 1 has read prev2 before lane 0 overwrites it below
+    if (lane == 0) {
+      double* prev = S.prev;
+      double* prev2 = S.prev2;
+#pragma unroll
+      for (int k = 0; k < 12; k++) {
+        prev2[k] = prev[k];
+        prev[k] = sT[k];
+      }
+      S.has_prev2 = 1;
+      S.inner_pending = 0;
+      dt = fmin(dt, dt1);
+      dr = fmin(dr, dr1);
+      if (P.hook_enabled && (tH > P.hook_min_trans || wH > P.hook_min_rot)) {
+        S.term = MLO_TERM_HOOK_REQUEST;
+        S.done = 1;
+      } else if (fabs(dt) < P.min_abs_step_trans && fabs(dr) < P.min_abs_step_rot) {
+        S.term = MLO_TERM_STALLED;
+        S.done = 1;
+      } else {
+        S.it++;
+        if (S.it >= P.max_iterations) {
+          S.term = MLO_TERM_MAX_ITERATIONS;
+          S.done = 1;
+        }
+      }
+      next = S.done ? 0 : 2;
+    }
+  }
+  __syncwarp();
+  return __shfl_sync(FULL, next, 0);
+}
+
+// solve_core for callers whose problem and state live in GLOBAL memory (launch sequence, queue-driven kernel):
+// stage both in shared memory (two coalesced reads, one coalesced write-back by the whole warp instead of ~150 serial,
+// mostly dependent global accesses by lane 0).
+__device__ __noinline__ int solve_step(const IcpProblem& Pg, IcpState& Sg, SolveScratch& sc, int after_match) {
+  const uint32_t lane = threadIdx.x & 31u;
   __shared__ IcpProblem sP;
   __shared__ IcpState sS;
   static_assert(sizeof(IcpProblem) % 4 == 0 && sizeof(IcpState) % 4 == 0, "copied word by word");
@@ -807,116 +934,14 @@ __device__ __noinline__ int solve_step(const IcpProblem& Pg, IcpState& Sg, const
     for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) ds[i] = __ldcg(gs + i);
   }
   __syncwarp();
-  const IcpProblem& P = sP;
-  IcpState& S = sS;
-  double* const sT = S.T;
-  double* const sPrev = S.prev;
-  double* const sPrev2 = S.prev2;
-  int next = 0;
-  if (lane == 0) {
-    bool finished = false;
-    if (after_match) {
-      S.n_pairs = npairs;
-      uint64_t pot = 0;
-      if (P.matcher_mask & MLO_MATCHER_PT2PL) pot += P.n_q;
-      if (P.matcher_mask & MLO_MATCHER_PT2PT) pot += P.n_q;
-      S.n_potential = pot;
-      S.n_query_it += P.n_q;
-      S.n_cand += ncand;
-      S.inner = 0;
-      if (npairs == 0) {
-        S.term = MLO_TERM_NO_PAIRINGS;
-        S.done = 1;
-        finished = true;
-      }
-    }
-    if (!finished) {
-      bool ok = true;
-      bool last_inner = true;
-      if (P.solver == MLO_SOLVER_HORN) {
-        ok = horn_from_sums(a, double(npairs), sT);
-      } else {
-        double H[36], g[6];
-        int k = 0;
-        for (int i = 0; i < 6; i++)
-          for (int j = i; j < 6; j++) {
-            H[6 * i + j] = a[k];
-            H[6 * j + i] = a[k];
-            k++;
-          }
-        for (int i = 0; i < 6; i++) g[i] = a[21 + i];
-        if (P.has_prior) {
-          // e = log(prior^-1 T), J = d log(D exp(eps))/d eps ; g += J^T L e ; H += J^T L J
-          double D[12], e[6], J[36], LJ[36], Le[6];
-          pose_minus(sT, P.prior_pose, D);
-          se3_log(D, e);
-          se3_right_jacobian_inv(e, J);
-          for (int i = 0; i < 6; i++) {
-            double s = 0;
-            for (int m = 0; m < 6; m++) s += P.prior_info[6 * i + m] * e[m];
-            Le[i] = s;
-            for (int j = 0; j < 6; j++) {
-              double t = 0;
-              for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * J[6 * m + j];
-              LJ[6 * i + j] = t;
-            }
-          }
-          for (int i = 0; i < 6; i++) {
-            for (int m = 0; m < 6; m++) g[i] += J[6 * m + i] * Le[m];
-            for (int j = 0; j < 6; j++)
-              for (int m = 0; m < 6; m++) H[6 * i + j] += J[6 * m + i] * LJ[6 * m + j];
-          }
-        }
-        for (int i = 0; i < 36; i++) S.H[i] = H[i];
-        S.have_H = 1;
-        double mg[6], delta[6];
-        for (int i = 0; i < 6; i++) mg[i] = -g[i];
-        ok = ldlt6(H, mg, delta);
-        if (ok) {
-          double E[12], Tn[12];
-          se3_exp(delta, E);
-          pose_mul(sT, E, Tn);
-#pragma unroll
-          for (int i = 0; i < 12; i++) sT[i] = Tn[i];
-          double dn = 0;
-          for (int i = 0; i < 6; i++) dn += delta[i] * delta[i];
-          S.inner++;
-          last_inner = (sqrt(dn) < P.gn_min_delta) || (S.inner >= P.gn_max_iterations);
-        }
-      }
-      if (!ok) {
-        S.term = MLO_TERM_SOLVER_ERROR;
-        S.done = 1;
-      } else if (!last_inner) {
-        S.inner_pending = 1;
-        next = 1;
-      } else {
-        next = 3;  // retraction done, this was the last inner iteration: end-of-iteration bookkeeping follows
-      }
-    }
-  }
-  next = __shfl_sync(FULL, next, 0);
-  if (next == 3) {
-    // lanes 0 and 1 evaluate the two SE(3) logs of the stall / oscillation test concurrently
-    __syncwarp();
-    const int has2 = __shfl_sync(FULL, lane == 0 ? S.has_prev2 : 0, 0);
-    double dt = 1e300, dr = 1e300;
-    if (lane == 0) step_measure(sT, sPrev, dt, dr);
-    if (lane == 1 && has2) step_measure(sT, sPrev2, dt, dr);
-    const double dt1 = __shfl_sync(FULL, dt, 1), dr1 = __shfl_sync(FULL, dr, 1);
-    __syncwarp();  // lane 1 has read prev2 before lane 0 overwrites it below
-    if (lane == 0) {
-      finish_iteration(P, S, sT, sPrev, sPrev2, fmin(dt, dt1), fmin(dr, dr1));
-      next = S.done ? 0 : 2;
-    }
-  }
+  const int next = solve_core(sP, sS, sc, after_match);
   __syncwarp();
   {
     uint32_t* gs = reinterpret_cast<uint32_t*>(&Sg);
     const uint32_t* ds = reinterpret_cast<const uint32_t*>(&sS);
     for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) gs[i] = ds[i];
   }
-  return __shfl_sync(FULL, next, 0);
+  return next;
 }
 
 // Inner Gauss-Newton iterations >= 1 inside the block that just solved (small problems): the block re-linearises ALL

@@ -562,16 +562,13 @@ MLO_D uint32_t probe_words(const MapDev& m, const int32_t kq[3], uint32_t* ws, u
 // (d2, canonical order) so the result equals the sequential first-minimum scan bit for bit.
 // `ws` points at this thread's column of a shared-memory scratch [27][wstride] holding the 27 packed cell
 // words (dynamic indexing without local memory; unaffected by the L1 invalidation of device-scope fences).
-MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz, uint32_t* ws, uint32_t wstride) {
+// Second half of nn_single_thread: the pruned scan over the 27 packed cell words already in ws[e * wstride].
+MLO_D NNHit nn_scan_words(const MapDev& m, float qx, float qy, float qz, const int32_t kq[3], const uint32_t* ws, uint32_t wstride) {
   NNHit r;
   r.x = r.y = r.z = 0.f;
   r.d2 = __int_as_float(0x7f800000);
   r.found = 0;
   r.ncand = 0;
-  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel),
-                         voxel_index_map(qz, m.inv_voxel)};
-  if (!(key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]))) return r;
-  r.ncand = probe_words(m, kq, ws, wstride);
   uint32_t border = 0xFFFFFFFFu;
   const float qv[3] = {qx, qy, qz};
   auto scan_cell = [&](uint32_t ww, uint32_t e) {
@@ -625,6 +622,23 @@ MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz, uint
     scan_cell(ws[e * wstride], uint32_t(e));
   }
   r.found = border != 0xFFFFFFFFu;
+  return r;
+}
+
+MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz, uint32_t* ws, uint32_t wstride) {
+  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel),
+                         voxel_index_map(qz, m.inv_voxel)};
+  if (!(key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]))) {
+    NNHit r;
+    r.x = r.y = r.z = 0.f;
+    r.d2 = __int_as_float(0x7f800000);
+    r.found = 0;
+    r.ncand = 0;
+    return r;
+  }
+  const uint32_t ncand = probe_words(m, kq, ws, wstride);
+  NNHit r = nn_scan_words(m, qx, qy, qz, kq, ws, wstride);
+  r.ncand = ncand;
   return r;
 }
 

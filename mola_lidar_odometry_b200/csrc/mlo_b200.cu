@@ -9,6 +9,7 @@
 
 #include "filter.cuh"
 #include "icp.cuh"
+#include "icp_block.cuh"
 #include "map.cuh"
 #include "se3.cuh"
 
@@ -104,6 +105,14 @@ struct mlo_ctx {
   } stage[2];
   bool use_persistent = true;  // MLO_PERSISTENT=0 selects the one-kernel-per-phase launch sequence
   bool persistent_forced = false;
+  // mlo_set_option("align_path") / MLO_ALIGN_PATH: 0 = auto (block kernel for small batches, launch sequence for large
+  // ones), 1 = launch sequence, 2 = queue-driven persistent kernel, 3 = one thread block per problem (k_icp_block)
+  int align_path = 0;
+  int tail_path = 3;      // kernel that finishes the stragglers of a launch sequence: 3 = block, 2 = queue
+  int block_threads = 0;  // threads per block of k_icp_block: 0 = auto, else 128 / 256 / 512
+  bool block_attr_set[6] = {false, false, false, false, false, false};
+  int last_align_path = 0, last_stream_groups = 0, last_tail_handover = 0;  // what the last align call did (tests)
+  uint64_t large_batch_queries = 0;  // 0 = auto (sm_count * 1024): batches at or above it take the launch sequence
   int tpq_min_queries_per_sm = 512;  // MLO_TPQ_MIN: below this many queries per SM the warp-per-query chunks win
                                      // (S=8 fleet, 56 k queries: align 1.40 ms warp vs 2.15 ms thread-per-query)
   int wl_min_blocks = 32;  // MLO_WL_MIN_BLOCKS (one-warp blocks per SM)
@@ -625,6 +634,39 @@ void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const Ma
 #undef MLO_PERS
 }
 
+template <int NT, bool PLANES>
+int launch_block_nt(mlo_ctx* c, int slot, uint32_t B, const MapDev* d_maps, const IcpProblem* dP, IcpState* dS, const float4* d_local) {
+  const size_t smem = sizeof(BlockShared<NT>);
+  if (!c->block_attr_set[slot]) {
+    CU(c, cudaFuncSetAttribute(k_icp_block<NT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
+    c->block_attr_set[slot] = true;
+  }
+  k_icp_block<NT, PLANES><<<B, NT, smem, c->stream>>>(d_maps, dP, dS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
+  c->launches++;
+  CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+// One thread block per problem (icp_block.cuh).  Threads per block: as many as the largest problem has queries, up to
+// 512 (one block per SM at 128 registers); batches beyond one block per SM trade threads for resident blocks.
+int launch_block(mlo_ctx* c, uint32_t B, uint32_t max_nq, bool planes, const MapDev* d_maps, const IcpProblem* dP, IcpState* dS,
+                 const float4* d_local) {
+  int nt = c->block_threads;
+  if (nt != 128 && nt != 256 && nt != 512) {
+    nt = 512;
+    if (B > uint32_t(c->sm_count)) nt = 256;
+    if (B > 2u * uint32_t(c->sm_count)) nt = 128;
+    while (nt > 128 && max_nq <= uint32_t(nt / 2)) nt /= 2;
+  }
+  if (planes) {  // any problem of the batch runs Matcher_Point2Plane
+    if (nt == 512) return launch_block_nt<512, true>(c, 3, B, d_maps, dP, dS, d_local);
+    if (nt == 256) return launch_block_nt<256, true>(c, 4, B, d_maps, dP, dS, d_local);
+    return launch_block_nt<128, true>(c, 5, B, d_maps, dP, dS, d_local);
+  }
+  if (nt == 512) return launch_block_nt<512, false>(c, 0, B, d_maps, dP, dS, d_local);
+  if (nt == 256) return launch_block_nt<256, false>(c, 1, B, d_maps, dP, dS, d_local);
+  return launch_block_nt<128, false>(c, 2, B, d_maps, dP, dS, d_local);
+}
+
 // The batched align driver over device-resident float4 local points.  Problem b reads local points
 // [q_begin[b], q_begin[b] + n_q[b]) of d_local and matches against maps[b] (all equal: the read-only-map batch of
 // config[1]; different: a fleet of independent sequences advanced in lock step, one local map each).
@@ -644,7 +686,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   const bool multi = uniq.size() > 1;
   const mlo_map* map = uniq[0];
   const MapDev* d_maps = nullptr;
-  if (multi) {
+  {  // (always: the block kernel stages its map descriptor from this table, single map or not)
     std::vector<MapDev> hm(uniq.size());
     for (size_t k = 0; k < uniq.size(); k++) hm[k] = uniq[k]->dev;
     CU(c, c->d_maps.ensure(hm.size() * sizeof(MapDev)));
@@ -666,6 +708,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   };
   std::vector<size_t> toff(3 * size_t(B));
   uint32_t part_total = 0, max_blocks = 0, max_blocks_acc = 0, max_it = 0, max_inner = 1, max_nq = 0;
+  bool any_planes = false;
   // queries per warp: 32 when the batch alone fills the machine, fewer for latency-bound small batches
   uint64_t total_queries = 0, q_end = 0;
   for (uint32_t b = 0; b < B; b++) {
@@ -699,6 +742,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     P.gn_min_delta = p.gn_min_delta;
     P.robust_kernel = p.robust_kernel;
     P.matcher_mask = p.matcher_mask;
+    any_planes = any_planes || (p.matcher_mask & MLO_MATCHER_PT2PL);
     P.table_len = p.table_len;
     toff[3 * b] = put(p.pt2pt_threshold_by_iter, p.table_len);
     toff[3 * b + 1] = put(p.pt2pl_threshold_by_iter, p.table_len);
@@ -772,8 +816,28 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   const uint32_t check_every = 4;
   // the queue-driven kernel wins while a launch sequence would be latency/launch-bound (small batches);
   // for large batches one kernel per phase streams better (profiles/README.md)
-  bool persistent = c->use_persistent && (c->persistent_forced || total_queries < uint64_t(c->sm_count) * 1024) && B < 65536 &&
-                    max_blocks < 32768 && max_blocks_acc < 32768;  // (chunk counts of the persistent geometry are <= these)
+  const uint64_t large_at = c->large_batch_queries ? c->large_batch_queries : uint64_t(c->sm_count) * 1024;
+  const bool queue_ok = B < 65536 && max_blocks < 32768 && max_blocks_acc < 32768;  // (chunk counts of the queue geometry)
+  int path = c->align_path;
+  if (path == 0) {
+    if (!c->use_persistent) path = 1;
+    else if (c->persistent_forced) path = 2;
+    else path = total_queries < large_at ? 3 : 1;
+  }
+  if (path == 2 && !queue_ok) path = 1;
+  const bool persistent = path == 2;
+  c->last_align_path = path;
+  c->last_stream_groups = 1;
+  c->last_tail_handover = 0;
+  if (path == 3) {
+    // ---- one thread block per problem runs the whole align loop (icp_block.cuh)
+    const size_t e_nn = prof_begin(c);
+    int rc = launch_block(c, B, max_nq, any_planes, d_maps, dP, dS, d_local);
+    prof_end(c, 3, e_nn);
+    if (rc != MLO_OK) return rc;
+    rc = issue_deferred_once();
+    if (rc != MLO_OK) return rc;
+  }
   if (persistent) {
     // ---- one launch for the whole align loop: queue of (problem, phase, chunk) items
     std::vector<uint32_t> items;
@@ -830,13 +894,14 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   }
   // stream groups: contiguous slices of the batch, each with its own launch sequence (group 0 on the context stream)
   // (per-kernel timing needs the kernel alone on the device: one group while profiling)
-  const uint32_t n_groups = (!persistent && use_tpq && B >= 64 && !c->prof_on) ? uint32_t(c->stream_groups) : 1u;
+  const uint32_t n_groups = (path == 1 && use_tpq && B >= 64 && !c->prof_on) ? uint32_t(c->stream_groups) : 1u;
+  if (path == 1) c->last_stream_groups = int(n_groups);
   auto group_stream = [&](uint32_t g) { return g == 0 ? c->stream : c->aux_stream[g - 1]; };
   if (n_groups > 1) {
     CU(c, cudaEventRecord(c->ev_fork, c->stream));
     for (uint32_t g = 1; g < n_groups; g++) CU(c, cudaStreamWaitEvent(c->aux_stream[g - 1], c->ev_fork, 0));
   }
-  for (uint32_t it = 0; !persistent && it < max_it; it++) {
+  for (uint32_t it = 0; path == 1 && it < max_it; it++) {
     for (uint32_t g = 0; g < n_groups; g++) {
       const uint32_t g0 = uint32_t(uint64_t(B) * g / n_groups), g1 = uint32_t(uint64_t(B) * (g + 1) / n_groups);
       const uint32_t Bg = g1 - g0;
@@ -902,8 +967,16 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
       // Tail hand-over: once few problems remain, a launch sequence is latency-bound (each iteration still costs
       // four launches); the queue-driven kernel finishes the stragglers in one launch.
       const uint64_t avg_q = total_queries / std::max<uint32_t>(B, 1);
+      if (c->tail_handover && c->tail_path == 3 && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * 512) {
+        const size_t e_nn = prof_begin(c);
+        int rc = launch_block(c, B, max_nq, any_planes, d_maps, dP, dS, d_local);  // (finished problems leave at once)
+        c->last_tail_handover = 3;
+        prof_end(c, 3, e_nn);
+        if (rc != MLO_OK) return rc;
+        break;
+      }
       if (c->use_persistent && c->tail_handover && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * 512 &&
-          B < 65536 && max_blocks < 32768 && max_blocks_acc < 32768) {
+          queue_ok) {
         const uint32_t qcap = uint32_t(next_pow2(std::max<uint64_t>(2ull * part_total, 1024)));
         CU(c, c->d_queue.ensure((2ull * qcap + 8 + B) * sizeof(uint32_t)));
         uint32_t* dq = c->d_queue.as<uint32_t>();
@@ -913,6 +986,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
         q.ctrl = dq + 2ull * qcap;
         q.phase_cnt = dq + 2ull * qcap + 8;
         q.mask = qcap - 1;
+        c->last_tail_handover = 2;
         LAUNCH(c, k_queue_reset, (std::max(qcap, B) + 255) / 256, 256, q, B);
         LAUNCH(c, k_queue_build, (B + 127) / 128, 128, dP, dS, q, B);
         if (c->persistent_blocks == 0) {
@@ -1002,6 +1076,9 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* wv = getenv("MLO_WL_VARIANT")) c->wl_variant = atoi(wv);
   if (const char* tf = getenv("MLO_TABLE_FACTOR")) c->table_factor = std::max(1, atoi(tf));
   if (const char* sg = getenv("MLO_STREAM_GROUPS")) c->stream_groups = std::min(int(mlo_ctx::MAX_GROUPS), std::max(1, atoi(sg)));
+  if (const char* ap = getenv("MLO_ALIGN_PATH")) c->align_path = std::min(3, std::max(0, atoi(ap)));
+  if (const char* tp = getenv("MLO_TAIL_PATH")) c->tail_path = atoi(tp) == 2 ? 2 : 3;
+  if (const char* bt = getenv("MLO_BLOCK_THREADS")) c->block_threads = atoi(bt);
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
@@ -1074,6 +1151,44 @@ int mlo_device_info(const mlo_ctx* c, char* name, uint32_t name_len, int* sm_cou
   return MLO_OK;
 }
 void* mlo_stream(const mlo_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
+  if (!c || !name) return MLO_ERR_INVALID_ARG;
+  const std::string n(name);
+  if (n == "align_path") c->align_path = int(std::min<int64_t>(3, std::max<int64_t>(0, v)));
+  else if (n == "tail_path") c->tail_path = v == 2 ? 2 : 3;
+  else if (n == "tail_handover") c->tail_handover = v != 0;
+  else if (n == "block_threads") c->block_threads = int(v);
+  else if (n == "stream_groups") c->stream_groups = int(std::min<int64_t>(mlo_ctx::MAX_GROUPS, std::max<int64_t>(1, v)));
+  else if (n == "fuse_inner") c->fuse_inner = v != 0;
+  else if (n == "force_kernel") c->force_kernel = int(v);
+  else if (n == "wl_variant") c->wl_variant = int(v);
+  else if (n == "wl_warps") c->wl_warps = int(v);
+  else if (n == "large_batch_queries") c->large_batch_queries = uint64_t(std::max<int64_t>(0, v));
+  else if (n == "pers_minb") c->pers_minb = v == 2 ? 2 : (v == 4 ? 4 : 0);
+  else return fail(c, MLO_ERR_INVALID_ARG, "unknown option: " + n);
+  return MLO_OK;
+}
+int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
+  if (!c || !name || !out) return MLO_ERR_INVALID_ARG;
+  const std::string n(name);
+  if (n == "align_path") *out = c->align_path;
+  else if (n == "tail_path") *out = c->tail_path;
+  else if (n == "tail_handover") *out = c->tail_handover;
+  else if (n == "block_threads") *out = c->block_threads;
+  else if (n == "stream_groups") *out = c->stream_groups;
+  else if (n == "fuse_inner") *out = c->fuse_inner;
+  else if (n == "force_kernel") *out = c->force_kernel;
+  else if (n == "wl_variant") *out = c->wl_variant;
+  else if (n == "wl_warps") *out = c->wl_warps;
+  else if (n == "large_batch_queries") *out = int64_t(c->large_batch_queries);
+  else if (n == "pers_minb") *out = c->pers_minb;
+  else if (n == "last_align_path") *out = c->last_align_path;
+  else if (n == "last_stream_groups") *out = c->last_stream_groups;
+  else if (n == "last_tail_handover") *out = c->last_tail_handover;
+  else return MLO_ERR_INVALID_ARG;
+  return MLO_OK;
+}
 uint64_t mlo_launch_count(const mlo_ctx* c) { return c ? c->launches : 0; }
 
 int32_t mlo_voxel_index(float coord, float voxel_size) { return voxel_index_map(coord, 1.0f / voxel_size); }

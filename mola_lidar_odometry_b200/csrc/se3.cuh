@@ -8,7 +8,9 @@
 namespace mlo {
 
 MLO_HD void mat3_mul(const double* A, const double* B, double* C) {
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) C[3 * i + j] = A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
 }
 MLO_HD void hat(const double* w, double* W) {
@@ -25,14 +27,19 @@ MLO_HD double nrm3(const double* a) { return sqrt(a[0] * a[0] + a[1] * a[1] + a[
 
 // C = A * B for 3x4 poses
 MLO_HD void pose_mul(const double* A, const double* B, double* C) {
+  #pragma unroll
   for (int r = 0; r < 3; r++) {
+    #pragma unroll
     for (int c = 0; c < 3; c++) C[4 * r + c] = A[4 * r] * B[c] + A[4 * r + 1] * B[4 + c] + A[4 * r + 2] * B[8 + c];
     C[4 * r + 3] = A[4 * r] * B[3] + A[4 * r + 1] * B[7] + A[4 * r + 2] * B[11] + A[4 * r + 3];
   }
 }
 MLO_HD void pose_inv(const double* A, double* C) {
+  #pragma unroll
   for (int r = 0; r < 3; r++)
+    #pragma unroll
     for (int c = 0; c < 3; c++) C[4 * r + c] = A[4 * c + r];
+  #pragma unroll
   for (int r = 0; r < 3; r++) C[4 * r + 3] = -(C[4 * r] * A[3] + C[4 * r + 1] * A[7] + C[4 * r + 2] * A[11]);
 }
 // B^-1 * A  ("A - B" in MRPT notation, LidarOdometry.cpp:930-931)
@@ -65,11 +72,15 @@ MLO_HD void se3_exp(const double* xi, double* T) {
   double W[9], W2[9];
   hat(phi, W);
   mat3_mul(W, W, W2);
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) T[4 * i + j] = (i == j ? 1.0 : 0.0) + a * W[3 * i + j] + b * W2[3 * i + j];
   // t = (I + b W + c W^2) rho
+  #pragma unroll
   for (int i = 0; i < 3; i++) {
     double s = rho[i];
+    #pragma unroll
     for (int j = 0; j < 3; j++) s += (b * W[3 * i + j] + c * W2[3 * i + j]) * rho[j];
     T[4 * i + 3] = s;
   }
@@ -120,6 +131,7 @@ MLO_HD void se3_log(const double* T, double* xi) {
   double a[3], b[3];
   cross3(phi, tt, a);
   cross3(phi, a, b);
+  #pragma unroll
   for (int i = 0; i < 3; i++) rho[i] = tt[i] - 0.5 * a[i] + d * b[i];
 }
 
@@ -150,6 +162,7 @@ MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
     c3 = (2.0 * t - 3.0 * s + t * c) / (2.0 * t2 * t2 * t);
   }
   double A[9];
+  #pragma unroll
   for (int i = 0; i < 9; i++) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * F[i] + k * FF[i];
   // Q = P/2 + c1 (FP + PF + FPF) + c2 (FFP + PFF - 3 FPF) + c3 (FPFF + FFPF)
   double FP[9], PF[9], FPF[9], FFP[9], PFF[9], FPFF[9], FFPF[9];
@@ -161,12 +174,15 @@ MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
   mat3_mul(FPF, F, FPFF);
   mat3_mul(F, FPF, FFPF);
   double Q[9];
+  #pragma unroll
   for (int i = 0; i < 9; i++)
     Q[i] = 0.5 * P[i] + c1 * (FP[i] + PF[i] + FPF[i]) + c2 * (FFP[i] + PFF[i] - 3.0 * FPF[i]) + c3 * (FPFF[i] + FFPF[i]);
   double AQ[9], AQA[9];
   mat3_mul(A, Q, AQ);
   mat3_mul(AQ, A, AQA);
+  #pragma unroll
   for (int i = 0; i < 3; i++)
+    #pragma unroll
     for (int j = 0; j < 3; j++) {
       J[6 * i + j] = A[3 * i + j];
       J[6 * i + 3 + j] = -AQA[3 * i + j];
@@ -220,10 +236,12 @@ MLO_HD bool ldlt6(const double* H, const double* b, double* x) {
 }
 
 MLO_HD bool spd6_inverse(const double* H, double* inv) {
+  #pragma unroll
   for (int c = 0; c < 6; c++) {
     double e[6] = {0, 0, 0, 0, 0, 0}, x[6];
     e[c] = 1.0;
     if (!ldlt6(H, e, x)) return false;
+    #pragma unroll
     for (int r = 0; r < 6; r++) inv[6 * r + c] = x[r];
   }
   return true;

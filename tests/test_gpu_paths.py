@@ -1,0 +1,227 @@
+"""GPU parity of EVERY device path of ICP::align (module/src/LidarOdometry.cpp:961-962) against the CPU oracle.
+
+The library picks one of three device paths by batch size (include/mlo_b200.h mlo_set_option "align_path"):
+  1  one kernel per phase (k_match_accumulate_wl4 -> k_solve [-> k_accumulate -> k_solve]) over stream groups, with a
+     hand-over of the stragglers to a single-launch kernel: the LARGE-batch path the headline and the roofline are
+     quoted on (>= 148 x 1024 total queries),
+  2  the queue-driven persistent kernel (k_icp_persistent),
+  3  one thread block per problem (k_icp_block): small batches, single sequences, fleets.
+Each is forced here and compared with the oracle for EVERY problem of the batch: pose (1 mm / 0.01 deg, north_star),
+termination reason, iteration count, pairings, potential pairings, candidate counts, quality.
+"""
+from concurrent.futures import ThreadPoolExecutor
+import os
+
+import numpy as np
+import pytest
+
+from mola_lidar_odometry_b200 import capi, synth
+from oracle import oracle_py as O
+
+pytestmark = pytest.mark.gpu
+
+TOL_TRANS_M = 1e-3   # BASELINE.json north_star: <= 1 mm / 0.01 deg per scan
+TOL_ROT_DEG = 1e-2
+
+
+def _check(gr, orr, it_slack=0):
+    et, er = O.pose_error(gr.pose, orr.pose)
+    assert et <= TOL_TRANS_M and er <= TOL_ROT_DEG, f"pose differs: {et} m, {er} deg"
+    assert gr.termination == orr.termination
+    assert abs(int(gr.n_iterations) - int(orr.n_iterations)) <= it_slack
+    if int(gr.n_iterations) == int(orr.n_iterations):
+        assert gr.n_pairings == orr.n_pairings
+        assert gr.n_potential_pairings == orr.n_potential_pairings
+        assert gr.n_candidate_points == orr.n_candidate_points
+        assert gr.n_query_iterations == orr.n_query_iterations
+        assert abs(gr.quality - orr.quality) < 1e-12
+
+
+class _Options:
+    """Set launch-policy knobs on the (session-scoped) context and put them back afterwards."""
+
+    def __init__(self, ctx, **kw):
+        self.ctx, self.kw, self.old = ctx, kw, {}
+
+    def __enter__(self):
+        for k, v in self.kw.items():
+            self.old[k] = self.ctx.get_option(k)
+            self.ctx.set_option(k, v)
+        return self
+
+    def __exit__(self, *a):
+        for k, v in self.old.items():
+            self.ctx.set_option(k, v)
+
+
+# ------------------------------------------------------------------ small batch, every path, every solver feature
+@pytest.fixture(scope="module")
+def small_case(ctx, world):
+    from mola_lidar_odometry_b200.api import LocalMap
+    g, o = LocalMap(ctx, 1.0, 20, 0.0, 1 << 16), O.OracleMap(1.0, 20, 0.0)
+    for fr in world["frames"][:12]:
+        g.insert(fr["map_layer"], fr["gt"])
+        o.insert(fr["map_layer"], fr["gt"])
+    rng = np.random.default_rng(21)
+    locals_, inits, owners = [], [], []
+    for j, k in enumerate((12, 13, 14, 15, 16, 17, 18, 19, 20, 21)):
+        fr = world["frames"][k]
+        init = synth.perturb(fr["gt"], rng, 0.3, 1.0)
+        ip = capi.IcpParamsOwner(sigma=2.0 if j % 2 == 0 else 1.0)
+        if j == 1:
+            ip.p.robust_kernel = capi.KERNEL_CAUCHY
+        if j == 2:
+            ip.p.robust_kernel = capi.KERNEL_NONE
+        if j == 3:
+            info = np.diag([50.0, 50.0, 50.0, 2000.0, 2000.0, 2000.0])
+            info[0, 1] = info[1, 0] = 5.0
+            ip.set_prior(init, info)
+        if j == 4:
+            init = synth.compose(fr["gt"], synth.pose34(0.6, 0.1, 0, 0.01))
+            ip.set_hook(init, 0.15, 0.75)
+        if j == 5:
+            ip = capi.IcpParamsOwner(sigma=2.0, max_iterations=3)
+        if j == 6:
+            init = synth.compose(fr["gt"], synth.pose34(5000, 0, 0, 0))   # NoPairings
+        if j == 7:
+            ip.p.gn_max_iterations = 1
+        locals_.append(fr["icp_layer"])
+        inits.append(init)
+        owners.append(ip)
+    refs = [O.icp_align(o, l, i, ip.p) for l, i, ip in zip(locals_, inits, owners)]
+    return dict(g=g, locals=locals_, inits=np.stack(inits), owners=owners, refs=refs)
+
+
+@pytest.mark.parametrize("path", [1, 2, 3])
+@pytest.mark.parametrize("fuse", [1, 0])
+def test_every_align_path_matches_the_oracle(ctx, small_case, path, fuse):
+    c = small_case
+    with _Options(ctx, align_path=path, fuse_inner=fuse):
+        res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        assert ctx.get_option("last_align_path") == path
+    terms = set()
+    for gr, orr in zip(res, c["refs"]):
+        _check(gr, orr)
+        terms.add(int(gr.termination))
+    assert {1, 3, 4, 5} <= terms   # NoPairings, MaxIterations, Stalled, HookRequest all occur in this batch
+
+
+@pytest.mark.parametrize("threads", [128, 256, 512])
+def test_block_kernel_thread_counts(ctx, small_case, threads):
+    c = small_case
+    with _Options(ctx, align_path=3, block_threads=threads):
+        res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+    for gr, orr in zip(res, c["refs"]):
+        _check(gr, orr)
+
+
+def test_block_kernel_single_problem_and_horn(ctx, small_case, world):
+    c = small_case
+    for j in (0, 3, 4):
+        with _Options(ctx, align_path=3):
+            gr = ctx.icp_align(c["locals"][j], c["g"], c["inits"][j], c["owners"][j].p)
+        _check(gr, c["refs"][j])
+    ip = capi.IcpParamsOwner(sigma=1.0, max_iterations=40)
+    ip.p.solver = capi.SOLVER_HORN
+    o = O.OracleMap(1.0, 20, 0.0)
+    for fr in world["frames"][:12]:
+        o.insert(fr["map_layer"], fr["gt"])
+    orr = O.icp_align(o, c["locals"][0], c["inits"][0], ip.p)
+    for path in (1, 2, 3):
+        with _Options(ctx, align_path=path):
+            gr = ctx.icp_align(c["locals"][0], c["g"], c["inits"][0], ip.p)
+        _check(gr, orr, it_slack=1)
+
+
+def test_block_kernel_ndt_point_to_plane(ctx, world):
+    from mola_lidar_odometry_b200.api import LocalMap
+    g = LocalMap(ctx, 1.0, 32, 0.2, 1 << 16, kind=capi.MAP_NDT)
+    o = O.OracleMap(1.0, 32, 0.2, kind=capi.MAP_NDT)
+    for fr in world["frames"][:12]:
+        g.insert(fr["map_layer"], fr["gt"])
+        o.insert(fr["map_layer"], fr["gt"])
+    rng = np.random.default_rng(3)
+    locals_, inits, owners = [], [], []
+    for k in (12, 14, 16, 18):
+        fr = world["frames"][k]
+        locals_.append(fr["icp_layer"])
+        inits.append(synth.perturb(fr["gt"], rng, 0.2, 0.5))
+        owners.append(capi.IcpParamsOwner(sigma=1.0, pipeline="ndt"))
+    refs = [O.icp_align(o, l, i, ip.p) for l, i, ip in zip(locals_, inits, owners)]
+    for path in (1, 2, 3):
+        with _Options(ctx, align_path=path):
+            res = ctx.icp_align_batch(locals_, g, np.stack(inits), [ip.p for ip in owners])
+        for gr, orr in zip(res, refs):
+            _check(gr, orr)
+            assert gr.n_pairings > 0
+
+
+# ------------------------------------------------------------------ the LARGE-batch launch sequence (config[1]-shaped)
+N_LARGE = 128
+
+
+@pytest.fixture(scope="module")
+def large_case(ctx, scene):
+    """128 K64 scans against a 0.5 m / cap-20 map of >= 2^18 voxels (BASELINE.json configs[1] shape):
+    >= 148 x 1024 total queries, so the library's own policy takes the one-kernel-per-phase launch sequence."""
+    from mola_lidar_odometry_b200.api import LocalMap
+    threads = os.cpu_count() or 4
+    traj = synth.trajectory_T00(2000, seed=7)
+    T0 = traj[0]
+    fp = capi.filter1_default(100.0)
+    g, o = LocalMap(ctx, 0.5, 20, 0.0, 1 << 19), O.OracleMap(0.5, 20, 0.0)
+    ks = list(range(0, 2000, 5))
+    with ThreadPoolExecutor(threads) as ex:
+        for c0 in range(0, len(ks), 32):
+            part = ks[c0:c0 + 32]
+            layers = list(ex.map(lambda k: O.filter_1st_pass(scene.scan(traj[k], scan_seed=1000 + k), fp)[0], part))
+            for k, a in zip(part, layers):
+                T = synth.relative(T0, traj[k])
+                g.insert(a, T)
+                o.insert(a, T)
+            if o.stats()[0] >= (1 << 18):
+                last = part[-1]
+                break
+        else:
+            raise RuntimeError("trajectory exhausted before 2^18 voxels")
+        assert g.stats() == o.stats() and g.stats()[0] >= (1 << 18)
+        rng = np.random.default_rng(5)
+        poses, inits = [], []
+        for i, k in enumerate(rng.integers(0, last, N_LARGE)):
+            Tw = synth.compose(traj[k], synth.pose34(0, 0, 0, np.deg2rad(3.0 * i)))
+            poses.append(Tw)
+            inits.append(synth.perturb(synth.relative(T0, Tw), rng, 0.3, 1.0))
+        locals_ = list(ex.map(lambda a: O.filter_1st_pass(scene.scan(a[1], scan_seed=700000 + a[0]), fp)[1], enumerate(poses)))
+        owners = [capi.IcpParamsOwner(sigma=2.0) for _ in range(N_LARGE)]
+        refs = list(ex.map(lambda a: O.icp_align(o, a[0], a[1], a[2].p), zip(locals_, inits, owners)))
+    total_q = sum(len(l) for l in locals_)
+    assert total_q >= 148 * 1024, total_q
+    return dict(g=g, locals=locals_, inits=np.stack(inits), owners=owners, refs=refs, total_q=total_q)
+
+
+@pytest.mark.parametrize("groups,tail,tail_path,fuse", [(3, 1, 3, 1), (1, 0, 3, 1), (3, 1, 2, 0), (2, 1, 3, 0), (1, 1, 3, 1)])
+def test_large_batch_launch_sequence_matches_the_oracle(ctx, large_case, groups, tail, tail_path, fuse):
+    c = large_case
+    l0 = ctx.launch_count
+    with _Options(ctx, stream_groups=groups, tail_handover=tail, tail_path=tail_path, fuse_inner=fuse):
+        res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        assert ctx.get_option("align_path") == 0           # the library's own policy ...
+        assert ctx.get_option("last_align_path") == 1      # ... took the launch sequence
+        assert ctx.get_option("last_stream_groups") == groups
+        assert ctx.get_option("last_tail_handover") == (tail_path if tail else 0)
+    assert ctx.launch_count - l0 >= 2 * min(int(r.n_iterations) for r in res)   # (several launches per ICP iteration)
+    worst = (0.0, 0.0)
+    for gr, orr in zip(res, c["refs"]):
+        _check(gr, orr)
+        worst = max(worst, O.pose_error(gr.pose, orr.pose))
+    print(f"large batch ({c['total_q']} queries): worst GPU-vs-oracle pose delta {worst}")
+
+
+def test_large_batch_other_paths_agree(ctx, large_case):
+    """The same 128 problems through the queue-driven kernel and the block kernel (two blocks per SM at this size)."""
+    c = large_case
+    for path in (2, 3):
+        with _Options(ctx, align_path=path):
+            res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        for gr, orr in zip(res, c["refs"]):
+            _check(gr, orr)
