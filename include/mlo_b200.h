@@ -89,7 +89,10 @@ uint64_t mlo_launch_count(const mlo_ctx* ctx);
  * exercise one specific device path).  Names: "align_path" (0 auto, 1 one kernel per phase = the large-batch launch
  * sequence, 2 queue-driven persistent kernel, 3 one thread block per problem), "large_batch_queries" (total queries at
  * which auto picks the launch sequence; 0 = SM count x 1024), "tail_handover", "tail_path", "stream_groups",
- * "fuse_inner", "block_threads", "force_kernel", "wl_variant", "wl_warps", "pers_minb".  Unknown name: MLO_ERR_INVALID_ARG. */
+ * "fuse_inner", "block_threads" (256 / 512), "block_cluster" (thread blocks per problem: 1 / 2 / 4 / 8), "filter_group_mb",
+ * "force_kernel", "wl_variant", "wl_warps", "pers_minb"; read-only "last_align_path", "last_stream_groups",
+ * "last_tail_handover", "last_block_cluster", "last_block_threads" describe the last align call.
+ * Unknown name: MLO_ERR_INVALID_ARG. */
 int mlo_set_option(mlo_ctx* ctx, const char* name, int64_t value);
 int mlo_get_option(const mlo_ctx* ctx, const char* name, int64_t* value);
 

@@ -3,40 +3,53 @@
 // (:297-302) and FilterBoundingBox "outside" (:305-310) predicates fused in front of the 2nd decimation.
 //
 // FirstPoint on a GPU: every point hashes its voxel into a scratch table and does atomicMin(first, i);
-// the survivors are the points with first[voxel] == i, compacted in input order by a block scan.
-// One launch handles a batch: blockIdx.y selects the job (one cloud each).
+// the survivors are the points with first[voxel] == i, compacted in input order (k_decim_claim / k_decim_finalize).
+// One launch handles a group of clouds: blockIdx.y selects the job (one cloud each).
 #pragma once
 #include "common.cuh"
 
 namespace mlo {
 
-struct DecimJob {
-  const float* in;         // first input point
-  const float* in_t;       // optional per-point channel carried in .w (timestamps for FilterDeskew), else nullptr
-  int32_t keep_w;          // carry .w of the input (stride 4) through to the outputs
-  uint32_t in_stride;      // floats per point (3 or 4)
-  uint32_t n_in_static;    // input size when n_in_dev == nullptr
-  const uint32_t* n_in_dev;  // input size produced on device by the previous stage
-  float resolution;
-  uint32_t min_pts;
+// Predicates fused with a decimation: FilterByRange (keep rmin <= |p| <= rmax) and FilterBoundingBox "outside".
+struct PointPred {
   int32_t use_range;
   float rmin2, rmax2;
   int32_t use_bbox;
   float bmin[3], bmax[3];
-  uint64_t* tab_keys;  // scratch hash: keys (0xFF.. = empty) and first index (0xFFFFFFFF)
-  uint32_t* tab_first;
+};
+
+// One 16-byte table entry = half a DRAM sector: voxel key and the smallest input index seen in that voxel sit in the
+// same sector, so the claim (CAS on the key) and the atomicMin that follows touch one L2 line.
+struct __align__(16) DecimEntry {
+  unsigned long long key;  // KEY_EMPTY = free
+  uint32_t first;          // smallest input index that fell into this voxel
+  uint32_t pad;
+};
+static_assert(sizeof(DecimEntry) == 16, "entry layout");
+
+struct DecimJob {
+  const float* in;         // first input point
+  const float* in_t;       // optional per-point channel carried in .w (timestamps for FilterDeskew), else nullptr
+  int32_t keep_w;          // carry .w of the input (stride 4) through to the output
+  uint32_t in_stride;      // floats per point (3 or 4)
+  uint32_t n_in_static;    // input size when n_in_dev == nullptr
+  const uint32_t* n_in_dev;  // input size produced on device by the previous stage
+  float resolution;
+  uint32_t min_pts;        // minimum_input_points_to_filter: below it the cloud passes through undecimated
+  PointPred pre;           // applied BEFORE the decimation (mlo_voxel_decimate_first with range / bbox)
+  PointPred post;          // applied to the decimated points (the 1st-pass pipeline: by-range and bbox sit AFTER the
+                           // first FilterDecimateVoxels, pipelines/lidar3d-default.yaml:285-310)
+  DecimEntry* tab;         // scratch hash (all bytes 0xFF = empty)
   uint32_t tab_mask;
-  uint32_t* pslot;     // per input point: its table slot (or NONE)
-  uint8_t* flags;      // per input point: bit0 keepA (predicate), bit1 keepB (predicate && first-in-voxel)
-  uint32_t* blockcnt;  // [nblocks][2]
-  uint32_t* blockoff;  // [nblocks][2]
-  uint32_t* npred;     // number of predicate survivors
-  uint32_t* err;       // error bits (ERR_KEY_RANGE)
-  float4* outA;        // predicate survivors ("decimated_for_map_skewed"), may be null
-  uint32_t* nA;
-  float4* outB;        // decimated survivors
-  uint32_t* nB;
-  uint32_t* outB_idx;  // optional: input indices of outB
+  float4* cand_pt;         // per block of DECIM_BLOCK inputs: the block's candidate points, in input order ...
+  uint2* cand_meta;        // ... with (table slot, input index)
+  uint32_t* blockcnt;      // candidates per block
+  unsigned long long* status;  // decoupled look-back: (flag << 32) | count per block; 0 = not yet published
+  uint32_t* npred;         // number of points that passed `pre`
+  uint32_t* err;           // error bits (ERR_KEY_RANGE, ERR_CAPACITY = scratch table exhausted)
+  float4* out;             // decimated (and post-filtered) points, input order
+  uint32_t* n_out;
+  uint32_t* out_idx;       // optional: input indices of `out`
 };
 
 constexpr uint32_t DECIM_BLOCK = 256;
@@ -50,7 +63,7 @@ MLO_D float4 load_point(const float* base, uint32_t stride, uint32_t i) {
   return make_float4(__ldg(p), __ldg(p + 1), __ldg(p + 2), 0.f);
 }
 
-MLO_D bool predicate_keep(const DecimJob& j, float x, float y, float z) {
+MLO_D bool predicate_keep(const PointPred& j, float x, float y, float z) {
   if (j.use_range) {
     const float n2 = x * x + y * y + z * z;
     if (!(n2 >= j.rmin2 && n2 <= j.rmax2)) return false;
@@ -63,21 +76,38 @@ MLO_D bool predicate_keep(const DecimJob& j, float x, float y, float z) {
   return true;
 }
 
-// Neighbouring returns of a sweep mostly fall into the same voxel, so the lanes of a warp first agree on their distinct
-// keys (MATCH.ANY): only the lowest lane of each group — the smallest input index of the group — probes the table and does
-// the atomicMin; the others take its slot.  Same table contents as one atomic per point, several times fewer atomics.
-__global__ void __launch_bounds__(DECIM_BLOCK) k_decim_hash(const DecimJob* __restrict__ jobs) {
+// FirstPoint decimation in two passes that read the cloud ONCE:
+//
+//  k_decim_claim     thread per input point: predicate, voxel key, then the lanes of a warp agree on their distinct keys
+//                    (MATCH.ANY: neighbouring returns of a sweep share voxels) and the lowest lane of each group - the
+//                    smallest input index of the group - claims the voxel's table entry and does atomicMin(first, i).
+//                    A point whose atomicMin did not lower the entry is already beaten and is dropped here; the others
+//                    are CANDIDATES (about one per output point): the block writes them, in input order, with their
+//                    coordinates into its own slice of the candidate buffers.
+//  k_decim_finalize  thread per candidate: winner iff first[slot] is still its index; `post` predicates; ordered
+//                    compaction across the blocks of a cloud by a decoupled look-back (each block publishes its count,
+//                    a warp sums its predecessors' counts 32 at a time); winners go out in input order.
+//
+// The raw cloud, the per-point slot array and the flag array of a hash / flag / scan / scatter chain are never re-read:
+// the second pass touches candidates only.  One launch handles a group of clouds (blockIdx.y); the caller sizes groups so
+// that their tables stay resident in the 126 MB L2 between the memset that clears them and the last read.
+__global__ void __launch_bounds__(DECIM_BLOCK) k_decim_claim(const DecimJob* __restrict__ jobs) {
   const DecimJob& j = jobs[blockIdx.y];
   const uint32_t n = job_n(j);
   if (blockIdx.x * DECIM_BLOCK >= n) return;  // whole block beyond the cloud (uniform)
   const uint32_t i = blockIdx.x * DECIM_BLOCK + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31u;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool has_pre = j.pre.use_range || j.pre.use_bbox;
+  const bool pass_all = n < j.min_pts;  // fewer inputs than minimum_input_points_to_filter: certain pass-through
   bool pred = false, valid = false;
   uint64_t key = 0;
   uint32_t h = 0;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
   if (i < n) {
-    const float4 p = load_point(j.in, j.in_stride, i);
-    pred = predicate_keep(j, p.x, p.y, p.z);
+    p = load_point(j.in, j.in_stride, i);
+    if (j.in_t) p.w = __ldg(j.in_t + i);
+    else if (!j.keep_w) p.w = 0.f;
+    pred = predicate_keep(j.pre, p.x, p.y, p.z);
     if (pred) {
       const int32_t kx = voxel_index_filter(p.x, j.resolution), ky = voxel_index_filter(p.y, j.resolution),
                     kz = voxel_index_filter(p.z, j.resolution);
@@ -91,142 +121,137 @@ __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_hash(const DecimJob* __re
       }
     }
   }
-  // packed keys use 63 bits: the top bit marks lanes without a key (each its own group)
-  const uint64_t mkey = valid ? key : (0x8000000000000000ull | lane);
-  const uint32_t peers = __match_any_sync(0xFFFFFFFFu, mkey);
-  const int leader = __ffs(peers) - 1;
+  bool cand = false;
   uint32_t slot = SLOT_NONE;
-  if (valid && int(lane) == leader) {
-    for (;;) {
-      unsigned long long* kp = reinterpret_cast<unsigned long long*>(&j.tab_keys[h]);
-      unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-      if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-      if (cur == KEY_EMPTY || cur == key) break;
-      h = (h + 1) & j.tab_mask;
-    }
-    atomicMin(&j.tab_first[h], i);
-    slot = h;
-  }
-  slot = __shfl_sync(0xFFFFFFFFu, slot, leader);
-  if (i < n) j.pslot[i] = valid ? slot : SLOT_NONE;
-  const uint32_t c = __syncthreads_count(pred);
-  if (threadIdx.x == 0 && c) atomicAdd(j.npred, c);
-}
-
-__global__ void __launch_bounds__(DECIM_BLOCK) k_decim_flag(const DecimJob* __restrict__ jobs) {
-  const DecimJob& j = jobs[blockIdx.y];
-  const uint32_t n = job_n(j);
-  const uint32_t i = blockIdx.x * DECIM_BLOCK + threadIdx.x;
-  if (blockIdx.x * DECIM_BLOCK >= n) return;  // whole block beyond the cloud (uniform)
-  bool a = false, b = false;
-  if (i < n) {
-    const uint32_t s = j.pslot[i];
-    a = (s != SLOT_NONE);
-    // minimum_input_points_to_filter: below it the layer passes through undecimated
-    b = a && (*j.npred < j.min_pts || j.tab_first[s] == i);
-    j.flags[i] = uint8_t((a ? 1 : 0) | (b ? 2 : 0));
-  }
-  const uint32_t ca = __syncthreads_count(a), cb = __syncthreads_count(b);
-  if (threadIdx.x == 0) {
-    j.blockcnt[2 * blockIdx.x] = ca;
-    j.blockcnt[2 * blockIdx.x + 1] = cb;
-  }
-}
-
-// one block per job: exclusive scan of the per-block counts -> block offsets and totals
-__global__ void __launch_bounds__(512) k_decim_scan(const DecimJob* __restrict__ jobs) {
-  const DecimJob& j = jobs[blockIdx.x];
-  const uint32_t n = job_n(j);
-  const uint32_t nblk = (n + DECIM_BLOCK - 1) / DECIM_BLOCK;
-  __shared__ uint32_t wsum[2][16];
-  __shared__ uint32_t carry[2];
-  if (threadIdx.x < 2) carry[threadIdx.x] = 0;
-  __syncthreads();
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (uint32_t base = 0; base < nblk; base += 512) {
-    const uint32_t b = base + threadIdx.x;
-    uint32_t v[2] = {0, 0}, inc[2];
-    if (b < nblk) {
-      v[0] = j.blockcnt[2 * b];
-      v[1] = j.blockcnt[2 * b + 1];
-    }
-#pragma unroll
-    for (int k = 0; k < 2; k++) {
-      uint32_t x = v[k];
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-        if (lane >= o) x += y;
-      }
-      inc[k] = x;
-      if (lane == 31) wsum[k][warp] = x;
-    }
-    __syncthreads();
-    if (warp == 0) {
-#pragma unroll
-      for (int k = 0; k < 2; k++) {
-        uint32_t x = (lane < 16) ? wsum[k][lane] : 0;
-#pragma unroll
-        for (int o = 1; o < 16; o <<= 1) {
-          const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, x, o);
-          if (lane >= o) x += y;
+  if (pass_all) {
+    cand = valid;
+  } else {
+    // packed keys use 63 bits: the top bit marks lanes without a key (each its own group)
+    const uint64_t mkey = valid ? key : (0x8000000000000000ull | lane);
+    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, mkey);
+    const int leader = __ffs(peers) - 1;
+    bool lowered = false;
+    if (valid && int(lane) == leader) {
+      uint32_t probes = 0;
+      for (;;) {
+        unsigned long long* kp = &j.tab[h].key;
+        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
+        if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
+        if (cur == KEY_EMPTY || cur == key) break;
+        h = (h + 1) & j.tab_mask;
+        if (++probes > j.tab_mask) {  // scratch table exhausted (the caller retries with a larger one)
+          atomicOr(j.err, ERR_CAPACITY);
+          h = SLOT_NONE;
+          break;
         }
-        if (lane < 16) wsum[k][lane] = x;  // inclusive over warps
       }
+      if (h != SLOT_NONE) lowered = atomicMin(&j.tab[h].first, i) > i;
+      slot = h;
     }
-    __syncthreads();
+    slot = __shfl_sync(0xFFFFFFFFu, slot, leader);
+    // with `pre` predicates the pass-through rule depends on the number of survivors, known only after this pass:
+    // every survivor stays a candidate and k_decim_finalize applies whichever rule holds
+    cand = valid && (lowered || has_pre);
+    if (!valid) slot = SLOT_NONE;
+  }
+  // ---- block-ordered compaction of the candidates into this block's slice
+  __shared__ uint32_t wcnt[DECIM_BLOCK / 32];
+  __shared__ uint32_t wpred[DECIM_BLOCK / 32];
+  const uint32_t bc = __ballot_sync(0xFFFFFFFFu, cand), bp = __ballot_sync(0xFFFFFFFFu, pred);
+  if (lane == 0) {
+    wcnt[warp] = __popc(bc);
+    wpred[warp] = __popc(bp);
+  }
+  __syncthreads();
+  uint32_t off = 0, total = 0, tp = 0;
 #pragma unroll
-    for (int k = 0; k < 2; k++) {
-      const uint32_t wprev = warp ? wsum[k][warp - 1] : 0;
-      if (b < nblk) j.blockoff[2 * b + k] = carry[k] + wprev + inc[k] - v[k];
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      carry[0] += wsum[0][15];
-      carry[1] += wsum[1][15];
-    }
-    __syncthreads();
+  for (uint32_t w = 0; w < DECIM_BLOCK / 32; w++) {
+    if (w < warp) off += wcnt[w];
+    total += wcnt[w];
+    tp += wpred[w];
+  }
+  if (cand) {
+    const size_t o = size_t(blockIdx.x) * DECIM_BLOCK + off + __popc(bc & ((1u << lane) - 1u));
+    j.cand_pt[o] = p;
+    j.cand_meta[o] = make_uint2(slot, i);
   }
   if (threadIdx.x == 0) {
-    if (j.nA) *j.nA = carry[0];
-    *j.nB = carry[1];
+    j.blockcnt[blockIdx.x] = total;
+    if (tp) atomicAdd(j.npred, tp);
   }
 }
 
-__global__ void __launch_bounds__(DECIM_BLOCK) k_decim_scatter(const DecimJob* __restrict__ jobs) {
+// Exclusive prefix of `count` over the blocks [0, b) of one cloud (decoupled look-back), called by warp 0 of block b.
+// status[k] = (flag << 32) | value with flag 1 = the block's own count, 2 = inclusive prefix up to and including it.
+// Blocks of a cloud are dispatched in ascending blockIdx.x, so every predecessor is running or done: no deadlock.
+MLO_D uint32_t lookback_exclusive(unsigned long long* status, uint32_t b, uint32_t count) {
+  const uint32_t FULL = 0xFFFFFFFFu, lane = threadIdx.x & 31u;
+  volatile unsigned long long* st = status;
+  if (lane == 0) st[b] = ((b == 0 ? 2ull : 1ull) << 32) | count;
+  if (b == 0) return 0u;
+  uint32_t excl = 0;
+  int32_t idx = int32_t(b) - 1 - int32_t(lane);
+  for (;;) {
+    unsigned long long s = idx >= 0 ? st[idx] : (2ull << 32);
+    while (__any_sync(FULL, (s >> 32) == 0ull)) {
+      if ((s >> 32) == 0ull) s = st[idx];
+    }
+    const uint32_t pm = __ballot_sync(FULL, (s >> 32) == 2ull);
+    const uint32_t upto = pm ? uint32_t(__ffs(pm) - 1) : 31u;  // nearest predecessor holding an inclusive prefix
+    uint32_t v = lane <= upto ? uint32_t(s & 0xFFFFFFFFull) : 0u;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    excl += v;
+    if (pm) break;
+    idx -= 32;
+  }
+  if (lane == 0) st[b] = (2ull << 32) | (excl + count);
+  return excl;
+}
+
+__global__ void __launch_bounds__(DECIM_BLOCK) k_decim_finalize(const DecimJob* __restrict__ jobs) {
   const DecimJob& j = jobs[blockIdx.y];
   const uint32_t n = job_n(j);
   if (blockIdx.x * DECIM_BLOCK >= n) return;
-  const uint32_t i = blockIdx.x * DECIM_BLOCK + threadIdx.x;
-  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  uint32_t f = 0;
-  float4 p = make_float4(0, 0, 0, 0);
-  if (i < n) {
-    f = j.flags[i];
-    if (f) {
-      p = load_point(j.in, j.in_stride, i);
-      if (j.in_t) p.w = __ldg(j.in_t + i);
-      else if (!j.keep_w) p.w = 0.f;
+  const uint32_t nblk = (n + DECIM_BLOCK - 1) / DECIM_BLOCK;
+  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const uint32_t c = j.blockcnt[blockIdx.x];
+  const bool has_pre = j.pre.use_range || j.pre.use_bbox;
+  const bool pass_all = n < j.min_pts || (has_pre && *j.npred < j.min_pts);
+  bool keep = false;
+  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
+  uint32_t idx = 0;
+  if (threadIdx.x < c) {
+    const size_t o = size_t(blockIdx.x) * DECIM_BLOCK + threadIdx.x;
+    const uint2 m = j.cand_meta[o];
+    p = j.cand_pt[o];
+    idx = m.y;
+    const bool win = pass_all || (m.x != SLOT_NONE && j.tab[m.x].first == m.y);
+    keep = win && predicate_keep(j.post, p.x, p.y, p.z);
+  }
+  __shared__ uint32_t wcnt[DECIM_BLOCK / 32];
+  __shared__ uint32_t s_excl;
+  const uint32_t bk = __ballot_sync(0xFFFFFFFFu, keep);
+  if (lane == 0) wcnt[warp] = __popc(bk);
+  __syncthreads();
+  uint32_t off = 0, total = 0;
+#pragma unroll
+  for (uint32_t w = 0; w < DECIM_BLOCK / 32; w++) {
+    if (w < warp) off += wcnt[w];
+    total += wcnt[w];
+  }
+  if (warp == 0) {
+    const uint32_t e = lookback_exclusive(j.status, blockIdx.x, total);
+    if (lane == 0) {
+      s_excl = e;
+      if (blockIdx.x == nblk - 1) *j.n_out = e + total;
     }
   }
-  __shared__ uint32_t wcnt[2][DECIM_BLOCK / 32];
-  const uint32_t ba = __ballot_sync(0xFFFFFFFFu, f & 1u), bb = __ballot_sync(0xFFFFFFFFu, f & 2u);
-  if (lane == 0) {
-    wcnt[0][warp] = __popc(ba);
-    wcnt[1][warp] = __popc(bb);
-  }
   __syncthreads();
-  uint32_t offA = j.blockoff[2 * blockIdx.x], offB = j.blockoff[2 * blockIdx.x + 1];
-  for (uint32_t w = 0; w < warp; w++) {
-    offA += wcnt[0][w];
-    offB += wcnt[1][w];
-  }
-  const uint32_t lt = (1u << lane) - 1u;
-  if ((f & 1u) && j.outA) j.outA[offA + __popc(ba & lt)] = p;
-  if (f & 2u) {
-    const uint32_t o = offB + __popc(bb & lt);
-    j.outB[o] = p;
-    if (j.outB_idx) j.outB_idx[o] = i;
+  if (keep) {
+    const uint32_t o = s_excl + off + __popc(bk & ((1u << lane) - 1u));
+    j.out[o] = p;
+    if (j.out_idx) j.out_idx[o] = idx;
   }
 }
 

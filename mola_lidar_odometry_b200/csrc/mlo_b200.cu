@@ -109,8 +109,11 @@ struct mlo_ctx {
   // ones), 1 = launch sequence, 2 = queue-driven persistent kernel, 3 = one thread block per problem (k_icp_block)
   int align_path = 0;
   int tail_path = 3;      // kernel that finishes the stragglers of a launch sequence: 3 = block, 2 = queue
-  int block_threads = 0;  // threads per block of k_icp_block: 0 = auto, else 128 / 256 / 512
+  int block_threads = 0;  // threads per block of k_icp_block: 0 = auto, else 256 / 512
+  int block_cluster = 0;  // thread blocks per problem (cluster size) of k_icp_block: 0 = auto, else 1 / 2 / 4 / 8
+  int last_block_cluster = 0, last_block_threads = 0;
   bool block_attr_set[6] = {false, false, false, false, false, false};
+  int filter_group_mb = 72;  // mlo_set_option("filter_group_mb"): scratch bytes per group of clouds in the 1st-pass filter (L2-resident)
   int last_align_path = 0, last_stream_groups = 0, last_tail_handover = 0;  // what the last align call did (tests)
   uint64_t large_batch_queries = 0;  // 0 = auto (sm_count * 1024): batches at or above it take the launch sequence
   int tpq_min_queries_per_sm = 512;  // MLO_TPQ_MIN: below this many queries per SM the warp-per-query chunks win
@@ -144,7 +147,7 @@ struct mlo_ctx {
   std::string dev_name;
   // scratch
   DBuf d_in, d_local, d_pairA, d_pairB, d_partials, d_partcnt, d_probs, d_states, d_tables, d_init, d_misc;
-  DBuf d_f_tab, d_f_pslot, d_f_flags, d_f_blk, d_f_jobs, d_f_cnt, d_f_stage1, d_f_map, d_f_icp;
+  DBuf d_f_tab, d_f_pslot, d_f_flags, d_f_blk, d_f_jobs, d_f_cnt, d_f_map, d_f_icp;
   DBuf d_ins_g, d_ins_slot, d_ins_next, d_ins_jobs, d_queue, d_tchan, d_maps;
   HBuf h_misc, h_states, h_stage;
   // profiling
@@ -403,24 +406,27 @@ int map_rebuild(mlo_map* m, bool use_filter, int32_t sx, int32_t sy, int32_t sz,
   return MLO_OK;
 }
 
-void fill_decim(DecimJob& j, const mlo_decimate_params& p, bool with_predicates) {
-  j.resolution = p.voxel_filter_resolution;
-  j.min_pts = p.minimum_input_points_to_filter;
-  j.use_range = with_predicates && p.use_range;
-  j.rmin2 = p.range_min * p.range_min;
-  j.rmax2 = p.range_max * p.range_max;
-  j.use_bbox = with_predicates && p.use_bbox_outside;
+void fill_pred(PointPred& q, const mlo_decimate_params& p, bool on) {
+  q.use_range = on && p.use_range;
+  q.rmin2 = p.range_min * p.range_min;
+  q.rmax2 = p.range_max * p.range_max;
+  q.use_bbox = on && p.use_bbox_outside;
   for (int k = 0; k < 3; k++) {
-    j.bmin[k] = p.bbox_min[k];
-    j.bmax[k] = p.bbox_max[k];
+    q.bmin[k] = p.bbox_min[k];
+    q.bmax[k] = p.bbox_max[k];
   }
 }
 
-// Device filter pipeline over a batch of raw clouds resident on the device.
-//   stage 1: decimate(raw, for_map.resolution)                  -> s1 (float4)
-//   stage 2: range/bbox predicates -> map layer ; decimate(.., for_icp.resolution) -> icp layer
+// Device filter pipeline over a batch of raw clouds resident on the device (filter.cuh):
+//   stage 1: decimate(raw, for_map.resolution), then the by-range / bbox predicates   -> map layer
+//   stage 2: decimate(map layer, for_icp.resolution)                                   -> icp layer
+// (the predicates sit between the two FilterDecimateVoxels of pipelines/lidar3d-default.yaml:285-319: applying them
+// to the winners of stage 1 and decimating the survivors is the same computation).
 // Outputs per cloud b live at [out_off[b], ...) of d_f_map / d_f_icp with device counts in d_f_cnt
-// (layout per cloud: [n_s1, n_map, n_icp, npred1, npred2, err]).
+// (layout per cloud: [n_single, n_map, n_icp, npred1, npred2, err]).
+// Clouds are processed in GROUPS whose scratch (hash tables + candidate slices) fits the L2 with room to spare: the
+// memset that clears a group's tables, the claims, and the winner tests all hit L2-resident lines, and the next group
+// reuses the same addresses.  DRAM sees the raw clouds once and the two layers once.
 struct FilterBatch {
   uint32_t n_clouds = 0;
   std::vector<uint64_t> out_off;  // per-cloud output offset (== raw offset: outputs never exceed inputs)
@@ -429,98 +435,186 @@ struct FilterBatch {
   DBuf* out_map = nullptr;
   DBuf* out_icp = nullptr;
   DBuf* out_cnt = nullptr;
+  // what was run (a retry with conservative table sizes repeats exactly this)
+  const float* d_raw = nullptr;
+  uint32_t stride = 0;
+  const mlo_filter1_params* fps = nullptr;
+  bool single = false;
+  uint32_t* d_idx_out = nullptr;
+  const float* d_t = nullptr;
 };
 constexpr uint32_t CNT_STRIDE = 8;
 
 int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n_clouds, const uint64_t* offsets,
                      const mlo_filter1_params* fps, bool single_decimate_idx, uint32_t* d_idx_out, FilterBatch& fb,
-                     const float* d_t = nullptr) {
+                     const float* d_t = nullptr, bool conservative = false) {
   fb.n_clouds = n_clouds;
   fb.out_off.assign(offsets, offsets + n_clouds + 1);
+  fb.d_raw = d_raw;
+  fb.stride = stride;
+  fb.fps = fps;
+  fb.single = single_decimate_idx;
+  fb.d_idx_out = d_idx_out;
+  fb.d_t = d_t;
   const uint64_t total = offsets[n_clouds];
   uint32_t max_n = 0;
   for (uint32_t b = 0; b < n_clouds; b++) max_n = std::max<uint32_t>(max_n, uint32_t(offsets[b + 1] - offsets[b]));
   fb.max_n = max_n;
-  if (total == 0 || max_n == 0) return MLO_OK;
-  // scratch hash tables: one per cloud per stage, sized 2x the cloud (power of two)
-  std::vector<uint64_t> tab_off(n_clouds + 1, 0);
-  for (uint32_t b = 0; b < n_clouds; b++)
-    tab_off[b + 1] = tab_off[b] + next_pow2(std::max<uint64_t>(2 * (offsets[b + 1] - offsets[b]), 1024));
-  const uint64_t tab_total = tab_off[n_clouds];
-  const uint32_t nblk_max = (max_n + DECIM_BLOCK - 1) / DECIM_BLOCK;
-  std::vector<uint64_t> blk_off(n_clouds + 1, 0);
-  for (uint32_t b = 0; b < n_clouds; b++)
-    blk_off[b + 1] = blk_off[b] + (offsets[b + 1] - offsets[b] + DECIM_BLOCK - 1) / DECIM_BLOCK;
-  const uint64_t blk_total = blk_off[n_clouds];
-
-  CU(c, c->d_f_tab.ensure(2 * tab_total * (sizeof(uint64_t) + sizeof(uint32_t))));
-  CU(c, c->d_f_pslot.ensure(2 * total * sizeof(uint32_t)));
-  CU(c, c->d_f_flags.ensure(2 * total));
-  CU(c, c->d_f_blk.ensure(2 * blk_total * 4 * sizeof(uint32_t)));
   DBuf& b_map = fb.out_map ? *fb.out_map : c->d_f_map;
   DBuf& b_icp = fb.out_icp ? *fb.out_icp : c->d_f_icp;
   DBuf& b_cnt = fb.out_cnt ? *fb.out_cnt : c->d_f_cnt;
-  CU(c, b_cnt.ensure(size_t(n_clouds) * CNT_STRIDE * sizeof(uint32_t)));
-  CU(c, c->d_f_stage1.ensure(total * sizeof(float4)));
+  CU(c, b_cnt.ensure(std::max<size_t>(size_t(n_clouds), 1) * CNT_STRIDE * sizeof(uint32_t)));
+  uint32_t* cnt = b_cnt.as<uint32_t>();
+  CU(c, cudaMemsetAsync(cnt, 0, std::max<size_t>(size_t(n_clouds), 1) * CNT_STRIDE * sizeof(uint32_t), c->stream));
+  if (total == 0 || max_n == 0) return MLO_OK;
+  // ---- per-cloud scratch geometry and the groups
+  // stage-1 table: one entry per input point at most (load factor <= 1, ~0.3 on lidar sweeps); stage-2 table: its input
+  // is the map layer, typically a third of the cloud or less: a quarter of the cloud unless `conservative` (the retry
+  // after a table-exhausted error)
+  struct Geo {
+    uint64_t tab1, tab2, nblk, pts;
+  };
+  std::vector<Geo> geo(n_clouds);
+  for (uint32_t b = 0; b < n_clouds; b++) {
+    const uint64_t n = offsets[b + 1] - offsets[b];
+    geo[b].pts = n;
+    geo[b].nblk = (n + DECIM_BLOCK - 1) / DECIM_BLOCK;
+    geo[b].tab1 = next_pow2(std::max<uint64_t>(n, 1024));
+    geo[b].tab2 = single_decimate_idx ? 0 : next_pow2(std::max<uint64_t>(conservative ? n : n / 4, 1024));
+  }
+  const uint64_t budget = uint64_t(std::max(1, c->filter_group_mb)) << 20;
+  std::vector<uint32_t> group_begin{0};
+  uint64_t g_tab = 0, g_pts = 0, g_blk = 0, max_tab = 0, max_pts = 0, max_blk = 0, acc = 0;
+  for (uint32_t b = 0; b < n_clouds; b++) {
+    const uint64_t bytes = (geo[b].tab1 + geo[b].tab2) * sizeof(DecimEntry) + geo[b].pts * (sizeof(float4) + sizeof(uint2));
+    if (b > group_begin.back() && acc + bytes > budget) {
+      group_begin.push_back(b);
+      acc = g_tab = g_pts = g_blk = 0;
+    }
+    acc += bytes;
+    g_tab += geo[b].tab1 + geo[b].tab2;
+    g_pts += geo[b].pts;
+    g_blk += geo[b].nblk;
+    max_tab = std::max(max_tab, g_tab);
+    max_pts = std::max(max_pts, g_pts);
+    max_blk = std::max(max_blk, g_blk);
+  }
+  group_begin.push_back(n_clouds);
+  CU(c, c->d_f_tab.ensure(max_tab * sizeof(DecimEntry)));
+  CU(c, c->d_f_pslot.ensure(max_pts * sizeof(float4)));   // candidate points
+  CU(c, c->d_f_flags.ensure(max_pts * sizeof(uint2)));    // candidate (slot, index)
+  CU(c, c->d_f_blk.ensure(max_blk * (2 * sizeof(unsigned long long) + sizeof(uint32_t))));  // status x2 stages + blockcnt
   CU(c, b_map.ensure(total * sizeof(float4)));
   CU(c, b_icp.ensure(total * sizeof(float4)));
   CU(c, c->d_f_jobs.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
   CU(c, c->h_stage.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
 
-  uint64_t* keys = c->d_f_tab.as<uint64_t>();
-  uint32_t* firsts = reinterpret_cast<uint32_t*>(keys + 2 * tab_total);
-  uint32_t* cnt = b_cnt.as<uint32_t>();
+  DecimEntry* tab = c->d_f_tab.as<DecimEntry>();
+  float4* cand_pt = c->d_f_pslot.as<float4>();
+  uint2* cand_meta = c->d_f_flags.as<uint2>();
+  unsigned long long* status = c->d_f_blk.as<unsigned long long>();
+  uint32_t* blockcnt = reinterpret_cast<uint32_t*>(status + 2 * max_blk);
   DecimJob* hj = c->h_stage.as<DecimJob>();
-  for (uint32_t b = 0; b < n_clouds; b++) {
-    const uint32_t n = uint32_t(offsets[b + 1] - offsets[b]);
-    for (int s = 0; s < 2; s++) {
-      DecimJob& j = hj[s * n_clouds + b];
-      std::memset(&j, 0, sizeof(j));
-      const uint64_t t0 = s * tab_total + tab_off[b];
-      j.tab_keys = keys + t0;
-      j.tab_first = firsts + t0;
-      j.tab_mask = uint32_t(tab_off[b + 1] - tab_off[b]) - 1;
-      j.pslot = c->d_f_pslot.as<uint32_t>() + s * total + offsets[b];
-      j.flags = c->d_f_flags.as<uint8_t>() + s * total + offsets[b];
-      j.blockcnt = c->d_f_blk.as<uint32_t>() + (s * blk_total + blk_off[b]) * 2;
-      j.blockoff = c->d_f_blk.as<uint32_t>() + 2 * blk_total * 2 + (s * blk_total + blk_off[b]) * 2;
-      j.err = cnt + b * CNT_STRIDE + 5;
+  struct GroupPlan {
+    uint32_t b0, b1, nblk_max;
+    uint64_t tab_entries, blocks;
+  };
+  std::vector<GroupPlan> plan;
+  for (size_t g = 0; g + 1 < group_begin.size(); g++) {
+    const uint32_t b0 = group_begin[g], b1 = group_begin[g + 1];
+    uint64_t t_off = 0, p_off = 0, k_off = 0;
+    uint32_t nblk_max = 0;
+    for (uint32_t b = b0; b < b1; b++) {
+      const uint32_t n = uint32_t(geo[b].pts);
+      DecimJob& j1 = hj[b];
+      DecimJob& j2 = hj[n_clouds + b];
+      std::memset(&j1, 0, sizeof(j1));
+      std::memset(&j2, 0, sizeof(j2));
+      // scratch shared by the two stages of a cloud (stage 2 starts when stage 1 has finished): candidate slices and
+      // block counts; own tables and own look-back words (both are cleared once per group)
+      j1.cand_pt = j2.cand_pt = cand_pt + p_off;
+      j1.cand_meta = j2.cand_meta = cand_meta + p_off;
+      j1.blockcnt = j2.blockcnt = blockcnt + k_off;
+      j1.status = status + k_off;
+      j2.status = status + max_blk + k_off;
+      j1.tab = tab + t_off;
+      j1.tab_mask = uint32_t(geo[b].tab1 - 1);
+      j2.tab = tab + t_off + geo[b].tab1;
+      j2.tab_mask = geo[b].tab2 ? uint32_t(geo[b].tab2 - 1) : 0u;
+      j1.err = j2.err = cnt + b * CNT_STRIDE + 5;
+      j1.in = d_raw + offsets[b] * stride;
+      j1.in_t = d_t ? d_t + offsets[b] : nullptr;
+      j1.in_stride = stride;
+      j1.n_in_static = n;
+      j1.resolution = fps[b].for_map.voxel_filter_resolution;
+      j1.min_pts = fps[b].for_map.minimum_input_points_to_filter;
+      j1.npred = cnt + b * CNT_STRIDE + 3;
+      if (single_decimate_idx) {  // mlo_voxel_decimate_first: predicates in front of ONE decimation, indices out
+        fill_pred(j1.pre, fps[b].for_map, true);
+        j1.out = b_map.as<float4>() + offsets[b];
+        j1.n_out = cnt + b * CNT_STRIDE + 0;
+        j1.out_idx = d_idx_out + offsets[b];
+      } else {
+        fill_pred(j1.post, fps[b].for_icp, true);
+        j1.out = b_map.as<float4>() + offsets[b];
+        j1.n_out = cnt + b * CNT_STRIDE + 1;
+        j2.in = reinterpret_cast<const float*>(b_map.as<float4>() + offsets[b]);
+        j2.in_stride = 4;
+        j2.keep_w = d_t ? 1 : 0;
+        j2.n_in_dev = cnt + b * CNT_STRIDE + 1;
+        j2.resolution = fps[b].for_icp.voxel_filter_resolution;
+        j2.min_pts = fps[b].for_icp.minimum_input_points_to_filter;
+        j2.npred = cnt + b * CNT_STRIDE + 4;
+        j2.out = b_icp.as<float4>() + offsets[b];
+        j2.n_out = cnt + b * CNT_STRIDE + 2;
+      }
+      t_off += geo[b].tab1 + geo[b].tab2;
+      p_off += geo[b].pts;
+      k_off += geo[b].nblk;
+      nblk_max = std::max<uint32_t>(nblk_max, uint32_t(geo[b].nblk));
     }
-    DecimJob& j1 = hj[b];
-    j1.in = d_raw + offsets[b] * stride;
-    j1.in_t = d_t ? d_t + offsets[b] : nullptr;
-    j1.in_stride = stride;
-    j1.n_in_static = n;
-    fill_decim(j1, fps[b].for_map, single_decimate_idx);
-    j1.npred = cnt + b * CNT_STRIDE + 3;
-    j1.outB = c->d_f_stage1.as<float4>() + offsets[b];
-    j1.nB = cnt + b * CNT_STRIDE + 0;
-    j1.outB_idx = single_decimate_idx ? d_idx_out + offsets[b] : nullptr;
-    DecimJob& j2 = hj[n_clouds + b];
-    j2.in = reinterpret_cast<const float*>(c->d_f_stage1.as<float4>() + offsets[b]);
-    j2.in_stride = 4;
-    j2.keep_w = d_t ? 1 : 0;
-    j2.n_in_dev = cnt + b * CNT_STRIDE + 0;
-    fill_decim(j2, fps[b].for_icp, true);
-    j2.npred = cnt + b * CNT_STRIDE + 4;
-    j2.outA = b_map.as<float4>() + offsets[b];
-    j2.nA = cnt + b * CNT_STRIDE + 1;
-    j2.outB = b_icp.as<float4>() + offsets[b];
-    j2.nB = cnt + b * CNT_STRIDE + 2;
+    plan.push_back({b0, b1, nblk_max, t_off, k_off});
   }
-  const int n_stages = single_decimate_idx ? 1 : 2;
   CU(c, cudaMemcpyAsync(c->d_f_jobs.p, hj, 2 * size_t(n_clouds) * sizeof(DecimJob), cudaMemcpyHostToDevice, c->stream));
-  CU(c, cudaMemsetAsync(c->d_f_tab.p, 0xFF, 2 * tab_total * (sizeof(uint64_t) + sizeof(uint32_t)), c->stream));
-  CU(c, cudaMemsetAsync(cnt, 0, size_t(n_clouds) * CNT_STRIDE * sizeof(uint32_t), c->stream));
-  const dim3 grid(nblk_max, n_clouds);
-  for (int s = 0; s < n_stages; s++) {
-    const DecimJob* dj = c->d_f_jobs.as<DecimJob>() + s * n_clouds;
-    LAUNCH(c, k_decim_hash, grid, DECIM_BLOCK, dj);
-    LAUNCH(c, k_decim_flag, grid, DECIM_BLOCK, dj);
-    LAUNCH(c, k_decim_scan, n_clouds, 512, dj);
-    LAUNCH(c, k_decim_scatter, grid, DECIM_BLOCK, dj);
+  const DecimJob* dj1 = c->d_f_jobs.as<DecimJob>();
+  const DecimJob* dj2 = dj1 + n_clouds;
+  for (const GroupPlan& g : plan) {
+    if (g.nblk_max == 0) continue;
+    CU(c, cudaMemsetAsync(tab, 0xFF, g.tab_entries * sizeof(DecimEntry), c->stream));
+    CU(c, cudaMemsetAsync(status, 0, g.blocks * sizeof(unsigned long long), c->stream));
+    if (!single_decimate_idx) CU(c, cudaMemsetAsync(status + max_blk, 0, g.blocks * sizeof(unsigned long long), c->stream));
+    const dim3 grid(g.nblk_max, g.b1 - g.b0);
+    LAUNCH(c, k_decim_claim, grid, DECIM_BLOCK, dj1 + g.b0);
+    LAUNCH(c, k_decim_finalize, grid, DECIM_BLOCK, dj1 + g.b0);
+    if (!single_decimate_idx) {
+      LAUNCH(c, k_decim_claim, grid, DECIM_BLOCK, dj2 + g.b0);
+      LAUNCH(c, k_decim_finalize, grid, DECIM_BLOCK, dj2 + g.b0);
+    }
   }
   CU(c, cudaGetLastError());
+  return MLO_OK;
+}
+
+// Copy the per-cloud counters of a filter batch back (one synchronisation) and check its error bits.  A scratch hash
+// table that ran full (a cloud whose first decimation keeps more than a quarter of its points) is not an error of the
+// caller: the batch is run again with tables sized for the worst case.
+int filter_counts(mlo_ctx* c, FilterBatch& fb, std::vector<uint32_t>& h) {
+  const DBuf& b_cnt = fb.out_cnt ? *fb.out_cnt : c->d_f_cnt;
+  h.assign(std::max<size_t>(fb.n_clouds, 1) * CNT_STRIDE, 0u);
+  for (int attempt = 0; attempt < 2; attempt++) {
+    CU(c, cudaMemcpyAsync(h.data(), b_cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
+    CU(c, cudaStreamSynchronize(c->stream));
+    bool full = false;
+    for (uint32_t b = 0; b < fb.n_clouds; b++) {
+      if (h[b * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+      full = full || (h[b * CNT_STRIDE + 5] & ERR_CAPACITY);
+    }
+    if (!full) return MLO_OK;
+    if (attempt == 1) return fail(c, MLO_ERR_CAPACITY, "decimation scratch table exhausted");
+    std::vector<uint64_t> offs = fb.out_off;
+    int rc = run_filter_batch(c, fb.d_raw, fb.stride, fb.n_clouds, offs.data(), fb.fps, fb.single, fb.d_idx_out, fb, fb.d_t, true);
+    if (rc != MLO_OK) return rc;
+  }
   return MLO_OK;
 }
 
@@ -635,36 +729,52 @@ void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const Ma
 }
 
 template <int NT, bool PLANES>
-int launch_block_nt(mlo_ctx* c, int slot, uint32_t B, const MapDev* d_maps, const IcpProblem* dP, IcpState* dS, const float4* d_local) {
+int launch_block_nt(mlo_ctx* c, int slot, uint32_t B, uint32_t cl, const MapDev* d_maps, const IcpProblem* dP, IcpState* dS,
+                    const float4* d_local) {
   const size_t smem = sizeof(BlockShared<NT>);
   if (!c->block_attr_set[slot]) {
     CU(c, cudaFuncSetAttribute(k_icp_block<NT, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(smem)));
     c->block_attr_set[slot] = true;
   }
-  k_icp_block<NT, PLANES><<<B, NT, smem, c->stream>>>(d_maps, dP, dS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B * cl);
+  cfg.blockDim = dim3(NT);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = c->stream;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeClusterDimension;
+  at[0].val.clusterDim.x = cl;
+  at[0].val.clusterDim.y = 1;
+  at[0].val.clusterDim.z = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  float4* pa = c->d_pairA.as<float4>();
+  float4* pb = c->d_pairB.as<float4>();
+  CU(c, cudaLaunchKernelEx(&cfg, k_icp_block<NT, PLANES>, d_maps, dP, dS, d_local, pa, pb));
   c->launches++;
-  CU(c, cudaGetLastError());
   return MLO_OK;
 }
-// One thread block per problem (icp_block.cuh).  Threads per block: as many as the largest problem has queries, up to
-// 512 (one block per SM at 128 registers); batches beyond one block per SM trade threads for resident blocks.
+// One thread-block cluster per problem (icp_block.cuh).  Blocks per cluster: as many as fit one block per SM for the
+// whole batch (a single sequence gets 8 SMs, a fleet of 32 gets 4 each), but at least 64 queries per block; 512 threads
+// per block (one block per SM at 128 registers) while the batch fits the machine, 256 (two per SM) beyond that.
 int launch_block(mlo_ctx* c, uint32_t B, uint32_t max_nq, bool planes, const MapDev* d_maps, const IcpProblem* dP, IcpState* dS,
                  const float4* d_local) {
+  uint32_t cl = uint32_t(c->block_cluster);
+  if (cl != 1 && cl != 2 && cl != 4 && cl != 8) {
+    cl = 8;
+    while (cl > 1 && B * cl > uint32_t(c->sm_count)) cl >>= 1;
+    while (cl > 1 && max_nq / cl < 64) cl >>= 1;
+  }
   int nt = c->block_threads;
-  if (nt != 128 && nt != 256 && nt != 512) {
-    nt = 512;
-    if (B > uint32_t(c->sm_count)) nt = 256;
-    if (B > 2u * uint32_t(c->sm_count)) nt = 128;
-    while (nt > 128 && max_nq <= uint32_t(nt / 2)) nt /= 2;
-  }
+  if (nt != 256 && nt != 512) nt = (B * cl <= uint32_t(c->sm_count) && max_nq > 128 * cl) ? 512 : 256;
+  c->last_block_cluster = int(cl);
+  c->last_block_threads = nt;
   if (planes) {  // any problem of the batch runs Matcher_Point2Plane
-    if (nt == 512) return launch_block_nt<512, true>(c, 3, B, d_maps, dP, dS, d_local);
-    if (nt == 256) return launch_block_nt<256, true>(c, 4, B, d_maps, dP, dS, d_local);
-    return launch_block_nt<128, true>(c, 5, B, d_maps, dP, dS, d_local);
+    if (nt == 512) return launch_block_nt<512, true>(c, 0, B, cl, d_maps, dP, dS, d_local);
+    return launch_block_nt<256, true>(c, 1, B, cl, d_maps, dP, dS, d_local);
   }
-  if (nt == 512) return launch_block_nt<512, false>(c, 0, B, d_maps, dP, dS, d_local);
-  if (nt == 256) return launch_block_nt<256, false>(c, 1, B, d_maps, dP, dS, d_local);
-  return launch_block_nt<128, false>(c, 2, B, d_maps, dP, dS, d_local);
+  if (nt == 512) return launch_block_nt<512, false>(c, 2, B, cl, d_maps, dP, dS, d_local);
+  return launch_block_nt<256, false>(c, 3, B, cl, d_maps, dP, dS, d_local);
 }
 
 // The batched align driver over device-resident float4 local points.  Problem b reads local points
@@ -1079,6 +1189,8 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* ap = getenv("MLO_ALIGN_PATH")) c->align_path = std::min(3, std::max(0, atoi(ap)));
   if (const char* tp = getenv("MLO_TAIL_PATH")) c->tail_path = atoi(tp) == 2 ? 2 : 3;
   if (const char* bt = getenv("MLO_BLOCK_THREADS")) c->block_threads = atoi(bt);
+  if (const char* bc = getenv("MLO_BLOCK_CLUSTER")) c->block_cluster = atoi(bc);
+  if (const char* fg = getenv("MLO_FILTER_GROUP_MB")) c->filter_group_mb = std::max(1, atoi(fg));
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
@@ -1116,7 +1228,7 @@ void mlo_destroy(mlo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DBuf* b : {&c->d_in, &c->d_local, &c->d_pairA, &c->d_pairB, &c->d_partials, &c->d_partcnt, &c->d_probs, &c->d_states,
                   &c->d_tables, &c->d_init, &c->d_misc, &c->d_f_tab, &c->d_f_pslot, &c->d_f_flags, &c->d_f_blk, &c->d_f_jobs,
-                  &c->d_f_cnt, &c->d_f_stage1, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan, &c->d_maps, &c->d_ins_jobs})
+                  &c->d_f_cnt, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan, &c->d_maps, &c->d_ins_jobs})
     b->release();
   c->h_misc.release();
   c->h_states.release();
@@ -1159,6 +1271,7 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "tail_path") c->tail_path = v == 2 ? 2 : 3;
   else if (n == "tail_handover") c->tail_handover = v != 0;
   else if (n == "block_threads") c->block_threads = int(v);
+  else if (n == "block_cluster") c->block_cluster = int(v);
   else if (n == "stream_groups") c->stream_groups = int(std::min<int64_t>(mlo_ctx::MAX_GROUPS, std::max<int64_t>(1, v)));
   else if (n == "fuse_inner") c->fuse_inner = v != 0;
   else if (n == "force_kernel") c->force_kernel = int(v);
@@ -1166,6 +1279,7 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "wl_warps") c->wl_warps = int(v);
   else if (n == "large_batch_queries") c->large_batch_queries = uint64_t(std::max<int64_t>(0, v));
   else if (n == "pers_minb") c->pers_minb = v == 2 ? 2 : (v == 4 ? 4 : 0);
+  else if (n == "filter_group_mb") c->filter_group_mb = int(std::max<int64_t>(1, v));
   else return fail(c, MLO_ERR_INVALID_ARG, "unknown option: " + n);
   return MLO_OK;
 }
@@ -1176,6 +1290,9 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   else if (n == "tail_path") *out = c->tail_path;
   else if (n == "tail_handover") *out = c->tail_handover;
   else if (n == "block_threads") *out = c->block_threads;
+  else if (n == "block_cluster") *out = c->block_cluster;
+  else if (n == "last_block_cluster") *out = c->last_block_cluster;
+  else if (n == "last_block_threads") *out = c->last_block_threads;
   else if (n == "stream_groups") *out = c->stream_groups;
   else if (n == "fuse_inner") *out = c->fuse_inner;
   else if (n == "force_kernel") *out = c->force_kernel;
@@ -1183,6 +1300,7 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   else if (n == "wl_warps") *out = c->wl_warps;
   else if (n == "large_batch_queries") *out = int64_t(c->large_batch_queries);
   else if (n == "pers_minb") *out = c->pers_minb;
+  else if (n == "filter_group_mb") *out = c->filter_group_mb;
   else if (n == "last_align_path") *out = c->last_align_path;
   else if (n == "last_stream_groups") *out = c->last_stream_groups;
   else if (n == "last_tail_handover") *out = c->last_tail_handover;
@@ -1428,10 +1546,9 @@ int mlo_voxel_decimate_first(mlo_ctx* c, const float* pts, uint32_t stride, uint
   rc = run_filter_batch(c, c->d_in.as<float>(), stride, 1, offs, &fp, true, c->d_local.as<uint32_t>(), fb);
   prof_end(c, 0, e0);
   if (rc != MLO_OK) return rc;
-  uint32_t h[CNT_STRIDE];
-  CU(c, cudaMemcpyAsync(h, c->d_f_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  if (h[5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  std::vector<uint32_t> h;
+  rc = filter_counts(c, fb, h);
+  if (rc != MLO_OK) return rc;
   *out_n = h[0];
   CU(c, cudaMemcpyAsync(out_idx, c->d_local.p, size_t(h[0]) * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   CU(c, cudaStreamSynchronize(c->stream));
@@ -1466,10 +1583,9 @@ int mlo_filter_1st_pass(mlo_ctx* c, const float* pts, uint32_t stride, uint64_t 
   rc = run_filter_batch(c, c->d_in.as<float>(), stride, 1, offs, p, false, nullptr, fb);
   prof_end(c, 0, e0);
   if (rc != MLO_OK) return rc;
-  uint32_t h[CNT_STRIDE];
-  CU(c, cudaMemcpyAsync(h, c->d_f_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  if (h[5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  std::vector<uint32_t> h;
+  rc = filter_counts(c, fb, h);
+  if (rc != MLO_OK) return rc;
   *out_map_n = h[1];
   *out_icp_n = h[2];
   if (out_map_xyz) {
@@ -1505,10 +1621,9 @@ int mlo_filter_1st_pass_xyzt(mlo_ctx* c, const float* pts, uint32_t stride, cons
   rc = run_filter_batch(c, c->d_in.as<float>(), stride, 1, offs, p, false, nullptr, fb, d_t);
   prof_end(c, 0, e0);
   if (rc != MLO_OK) return rc;
-  uint32_t h[CNT_STRIDE];
-  CU(c, cudaMemcpyAsync(h, c->d_f_cnt.p, sizeof(h), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
-  if (h[5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
+  std::vector<uint32_t> h;
+  rc = filter_counts(c, fb, h);
+  if (rc != MLO_OK) return rc;
   *out_map_n = h[1];
   *out_icp_n = h[2];
   if (out_map_xyzt && h[1])
@@ -1644,15 +1759,14 @@ static int scan_register_device(mlo_ctx* c, const mlo_map* map, uint32_t B, cons
   prof_end(c, 0, e0);
   if (rc != MLO_OK) return rc;
   // the ICP grid depends on the decimated sizes: one small D2H of the device counters
-  std::vector<uint32_t> h(size_t(B) * CNT_STRIDE);
-  CU(c, cudaMemcpyAsync(h.data(), c->d_f_cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-  CU(c, cudaStreamSynchronize(c->stream));
+  std::vector<uint32_t> h;
+  rc = filter_counts(c, fb, h);
+  if (rc != MLO_OK) return rc;
   // the ICP layers stay where the filter wrote them (at the raw offsets): problem b = [offsets[b], offsets[b] + n_icp)
   std::vector<uint64_t> qb(offsets, offsets + B);
   std::vector<uint32_t> nq(B);
   std::vector<const mlo_map*> maps(B, map);
   for (uint32_t b = 0; b < B; b++) {
-    if (h[b * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
     nq[b] = h[b * CNT_STRIDE + 2];
     if (map_layer_n) (*map_layer_n)[b] = h[b * CNT_STRIDE + 1];
   }
@@ -1910,14 +2024,11 @@ int mlo_scanset_filter(mlo_scanset* set, uint32_t n_jobs, const mlo_scan_job* jo
   int rc = run_filter_batch(c, set->raw.as<float>(), stride, n_jobs, off.data(), fps.data(), false, nullptr, fb, d_t);
   prof_end(c, 0, e0);
   if (rc != MLO_OK) return rc;
-  std::vector<uint32_t> h(size_t(n_jobs) * CNT_STRIDE, 0u);
-  if (total) {
-    CU(c, cudaMemcpyAsync(h.data(), set->cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
-    CU(c, cudaStreamSynchronize(c->stream));
-  }
+  std::vector<uint32_t> h;
+  rc = filter_counts(c, fb, h);
+  if (rc != MLO_OK) return rc;
   std::vector<uint32_t> sl_idx(n_jobs);
   for (uint32_t j = 0; j < n_jobs; j++) {
-    if (h[j * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
     auto& sl = set->slots[jobs[j].slot];
     sl.off = off[j];
     sl.n_raw = uint32_t(jobs[j].n);

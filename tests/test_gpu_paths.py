@@ -106,11 +106,15 @@ def test_every_align_path_matches_the_oracle(ctx, small_case, path, fuse):
     assert {1, 3, 4, 5} <= terms   # NoPairings, MaxIterations, Stalled, HookRequest all occur in this batch
 
 
-@pytest.mark.parametrize("threads", [128, 256, 512])
-def test_block_kernel_thread_counts(ctx, small_case, threads):
+@pytest.mark.parametrize("threads", [256, 512])
+@pytest.mark.parametrize("cluster", [1, 2, 4, 8])
+def test_block_kernel_geometries(ctx, small_case, threads, cluster):
+    """k_icp_block with every cluster size (blocks per problem, reductions through distributed shared memory) and both
+    block sizes; with 256 threads and one block the ~1.5 k queries of a problem take several passes."""
     c = small_case
-    with _Options(ctx, align_path=3, block_threads=threads):
+    with _Options(ctx, align_path=3, block_threads=threads, block_cluster=cluster):
         res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        assert ctx.get_option("last_block_cluster") == cluster and ctx.get_option("last_block_threads") == threads
     for gr, orr in zip(res, c["refs"]):
         _check(gr, orr)
 
