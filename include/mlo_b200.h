@@ -39,7 +39,7 @@ typedef enum mlo_status {
   MLO_ERR_INVALID_ARG = -1,
   MLO_ERR_CUDA = -2,        /* a CUDA runtime call failed; see mlo_last_error */
   MLO_ERR_NO_DEVICE = -3,   /* no sm_100 device: the product path refuses to run elsewhere */
-  MLO_ERR_CAPACITY = -4,    /* map voxel capacity / hash table exhausted */
+  MLO_ERR_CAPACITY = -4,    /* the map would exceed 2^26 voxels, or device memory for its growth is exhausted */
   MLO_ERR_KEY_RANGE = -5,   /* a voxel index does not fit the packed 21-bit-per-axis key */
   MLO_ERR_UNSUPPORTED = -6
 } mlo_status;
@@ -107,7 +107,8 @@ typedef struct mlo_map_params {
   float min_distance_between_points; /* insertOpts.min_distance_between_points [m], 0 = off */
   float max_eigen_ratio_for_planes;  /* NDT insertOpts.max_eigen_ratio_for_planes */
   uint32_t min_points_for_plane;     /* NDT: voxel needs >= this many points to be a plane (default 5) */
-  uint64_t capacity_voxels;          /* upper bound of simultaneously occupied voxels */
+  uint64_t capacity_voxels;          /* INITIAL capacity in occupied voxels: inserts re-hash the map into larger buffers
+                                        on demand (upstream's map is unbounded); hard limit 2^26 */
 } mlo_map_params;
 
 int mlo_map_create(mlo_ctx* ctx, const mlo_map_params* p, mlo_map** out);

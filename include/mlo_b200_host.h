@@ -18,6 +18,9 @@ typedef struct mlo_lo_scan_output {
   uint32_t icp_iterations, icp_runs;
   int32_t termination;
   uint64_t n_map_layer, n_icp_layer;
+  int32_t icp_had_prior;     /* the motion model's information went to the solver as the prior (LidarOdometry.cpp:859-861) */
+  int32_t has_motion_model;  /* estimated_navstate() produced an estimate for this scan (LidarOdometry.cpp:808-815) */
+  double prior_info_trace;   /* trace of that 6x6 information matrix */
 } mlo_lo_scan_output;
 
 /* LidarOdometry::initialize(cfg) (LidarOdometry.cpp:246): yaml = file path (is_text == 0) or YAML text. */

@@ -78,106 +78,161 @@ MLO_D bool predicate_keep(const PointPred& j, float x, float y, float z) {
 
 // FirstPoint decimation in two passes that read the cloud ONCE:
 //
-//  k_decim_claim     thread per input point: predicate, voxel key, then the lanes of a warp agree on their distinct keys
-//                    (MATCH.ANY: neighbouring returns of a sweep share voxels) and the lowest lane of each group - the
-//                    smallest input index of the group - claims the voxel's table entry and does atomicMin(first, i).
-//                    A point whose atomicMin did not lower the entry is already beaten and is dropped here; the others
-//                    are CANDIDATES (about one per output point): the block writes them, in input order, with their
-//                    coordinates into its own slice of the candidate buffers.
-//  k_decim_finalize  thread per candidate: winner iff first[slot] is still its index; `post` predicates; ordered
+//  k_decim_claim     PPT input points per thread (all loads of a thread issued before the first use): predicate, voxel
+//                    key, then the lanes of a warp agree on their distinct keys (MATCH.ANY: neighbouring returns of a
+//                    sweep share voxels) and the lowest lane of each group - the smallest input index of the group -
+//                    claims the voxel's table entry (one optimistic CAS) and does atomicMin(first, i); the PPT claims
+//                    and the PPT atomicMins of a thread are in flight together.  A point whose atomicMin did not lower
+//                    the entry is already beaten and is dropped here; the others are CANDIDATES (about one per output
+//                    point): the block writes them, in input order, with their coordinates into its own slice of the
+//                    candidate buffers.
+//  k_decim_finalize  PPT candidates per thread: winner iff first[slot] is still its index; `post` predicates; ordered
 //                    compaction across the blocks of a cloud by a decoupled look-back (each block publishes its count,
 //                    a warp sums its predecessors' counts 32 at a time); winners go out in input order.
 //
 // The raw cloud, the per-point slot array and the flag array of a hash / flag / scan / scatter chain are never re-read:
-// the second pass touches candidates only.  One launch handles a group of clouds (blockIdx.y); the caller sizes groups so
-// that their tables stay resident in the 126 MB L2 between the memset that clears them and the last read.
+// the second pass touches candidates only.  One launch handles a group of clouds (blockIdx.y).
+template <int PPT>
 __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_claim(const DecimJob* __restrict__ jobs) {
+  static_assert(PPT * (DECIM_BLOCK / 32) <= 32, "one warp scans the per-(pass, warp) counts");
   const DecimJob& j = jobs[blockIdx.y];
   const uint32_t n = job_n(j);
-  if (blockIdx.x * DECIM_BLOCK >= n) return;  // whole block beyond the cloud (uniform)
-  const uint32_t i = blockIdx.x * DECIM_BLOCK + threadIdx.x;
+  constexpr uint32_t TILE = DECIM_BLOCK * PPT;
+  const uint32_t base = blockIdx.x * TILE;
+  if (base >= n) return;  // whole block beyond the cloud (uniform)
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const bool has_pre = j.pre.use_range || j.pre.use_bbox;
   const bool pass_all = n < j.min_pts;  // fewer inputs than minimum_input_points_to_filter: certain pass-through
-  bool pred = false, valid = false;
-  uint64_t key = 0;
-  uint32_t h = 0;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (i < n) {
-    p = load_point(j.in, j.in_stride, i);
-    if (j.in_t) p.w = __ldg(j.in_t + i);
-    else if (!j.keep_w) p.w = 0.f;
-    pred = predicate_keep(j.pre, p.x, p.y, p.z);
-    if (pred) {
-      const int32_t kx = voxel_index_filter(p.x, j.resolution), ky = voxel_index_filter(p.y, j.resolution),
-                    kz = voxel_index_filter(p.z, j.resolution);
-      if (key_in_range(kx) && key_in_range(ky) && key_in_range(kz)) {
-        key = pack_key(kx, ky, kz);
-        h = hash_cell(kx, ky, kz) & j.tab_mask;
-        valid = true;
-      } else {
-        atomicOr(j.err, ERR_KEY_RANGE);
-        pred = false;
-      }
+  float4 p[PPT];
+  bool pred[PPT], valid[PPT], cand[PPT];
+  uint64_t key[PPT];
+  uint32_t h[PPT], slot[PPT];
+#pragma unroll
+  for (int u = 0; u < PPT; u++) {
+    const uint32_t i = base + u * DECIM_BLOCK + threadIdx.x;
+    p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i < n) {
+      p[u] = load_point(j.in, j.in_stride, i);
+      if (j.in_t) p[u].w = __ldg(j.in_t + i);
+      else if (!j.keep_w) p[u].w = 0.f;
     }
   }
-  bool cand = false;
-  uint32_t slot = SLOT_NONE;
-  if (pass_all) {
-    cand = valid;
-  } else {
-    // packed keys use 63 bits: the top bit marks lanes without a key (each its own group)
-    const uint64_t mkey = valid ? key : (0x8000000000000000ull | lane);
-    const uint32_t peers = __match_any_sync(0xFFFFFFFFu, mkey);
-    const int leader = __ffs(peers) - 1;
-    bool lowered = false;
-    if (valid && int(lane) == leader) {
-      uint32_t probes = 0;
-      for (;;) {
-        unsigned long long* kp = &j.tab[h].key;
-        unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(kp);
-        if (cur == KEY_EMPTY) cur = atomicCAS(kp, (unsigned long long)KEY_EMPTY, (unsigned long long)key);
-        if (cur == KEY_EMPTY || cur == key) break;
-        h = (h + 1) & j.tab_mask;
-        if (++probes > j.tab_mask) {  // scratch table exhausted (the caller retries with a larger one)
-          atomicOr(j.err, ERR_CAPACITY);
-          h = SLOT_NONE;
-          break;
+#pragma unroll
+  for (int u = 0; u < PPT; u++) {
+    const uint32_t i = base + u * DECIM_BLOCK + threadIdx.x;
+    pred[u] = valid[u] = cand[u] = false;
+    key[u] = 0;
+    h[u] = 0;
+    slot[u] = SLOT_NONE;
+    if (i < n) {
+      pred[u] = predicate_keep(j.pre, p[u].x, p[u].y, p[u].z);
+      if (pred[u]) {
+        const int32_t kx = voxel_index_filter(p[u].x, j.resolution), ky = voxel_index_filter(p[u].y, j.resolution),
+                      kz = voxel_index_filter(p[u].z, j.resolution);
+        if (key_in_range(kx) && key_in_range(ky) && key_in_range(kz)) {
+          key[u] = pack_key(kx, ky, kz);
+          h[u] = hash_cell(kx, ky, kz) & j.tab_mask;
+          valid[u] = true;
+        } else {
+          atomicOr(j.err, ERR_KEY_RANGE);
+          pred[u] = false;
         }
       }
-      if (h != SLOT_NONE) lowered = atomicMin(&j.tab[h].first, i) > i;
-      slot = h;
     }
-    slot = __shfl_sync(0xFFFFFFFFu, slot, leader);
-    // with `pre` predicates the pass-through rule depends on the number of survivors, known only after this pass:
-    // every survivor stays a candidate and k_decim_finalize applies whichever rule holds
-    cand = valid && (lowered || has_pre);
-    if (!valid) slot = SLOT_NONE;
   }
-  // ---- block-ordered compaction of the candidates into this block's slice
-  __shared__ uint32_t wcnt[DECIM_BLOCK / 32];
-  __shared__ uint32_t wpred[DECIM_BLOCK / 32];
-  const uint32_t bc = __ballot_sync(0xFFFFFFFFu, cand), bp = __ballot_sync(0xFFFFFFFFu, pred);
-  if (lane == 0) {
-    wcnt[warp] = __popc(bc);
-    wpred[warp] = __popc(bp);
+  if (pass_all) {
+#pragma unroll
+    for (int u = 0; u < PPT; u++) cand[u] = valid[u];
+  } else {
+    int leader[PPT];
+    bool lead[PPT];
+    unsigned long long cur[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      // packed keys use 63 bits: the top bit marks lanes without a key (each its own group)
+      const uint64_t mkey = valid[u] ? key[u] : (0x8000000000000000ull | lane);
+      const uint32_t peers = __match_any_sync(0xFFFFFFFFu, mkey);
+      leader[u] = __ffs(peers) - 1;
+      lead[u] = valid[u] && int(lane) == leader[u];
+    }
+    // optimistic claim: one CAS per leader, all of a thread's in flight together
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      cur[u] = KEY_EMPTY;
+      if (lead[u]) cur[u] = atomicCAS(&j.tab[h[u]].key, (unsigned long long)KEY_EMPTY, (unsigned long long)key[u]);
+    }
+    // collisions (another voxel sits in the slot): linear probing
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      if (lead[u] && cur[u] != KEY_EMPTY && cur[u] != key[u]) {
+        uint32_t probes = 0;
+        for (;;) {
+          h[u] = (h[u] + 1) & j.tab_mask;
+          if (++probes > j.tab_mask) {  // scratch table exhausted (the caller retries with a larger one)
+            atomicOr(j.err, ERR_CAPACITY);
+            h[u] = SLOT_NONE;
+            break;
+          }
+          const unsigned long long c2 = atomicCAS(&j.tab[h[u]].key, (unsigned long long)KEY_EMPTY, (unsigned long long)key[u]);
+          if (c2 == KEY_EMPTY || c2 == key[u]) break;
+        }
+      }
+    }
+    uint32_t old[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      old[u] = 0;
+      if (lead[u] && h[u] != SLOT_NONE) old[u] = atomicMin(&j.tab[h[u]].first, base + u * DECIM_BLOCK + threadIdx.x);
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      const uint32_t i = base + u * DECIM_BLOCK + threadIdx.x;
+      const bool lowered = lead[u] && h[u] != SLOT_NONE && old[u] > i;
+      slot[u] = __shfl_sync(0xFFFFFFFFu, lead[u] ? h[u] : SLOT_NONE, leader[u]);
+      // with `pre` predicates the pass-through rule depends on the number of survivors, known only after this pass:
+      // every survivor stays a candidate and k_decim_finalize applies whichever rule holds
+      cand[u] = valid[u] && (lowered || has_pre);
+      if (!valid[u]) slot[u] = SLOT_NONE;
+    }
+  }
+  // ---- block-ordered compaction of the candidates into this block's slice (input order = pass-major)
+  constexpr int NW = DECIM_BLOCK / 32;
+  __shared__ uint32_t wcnt[PPT * NW];
+  __shared__ uint32_t s_total, s_pred;
+  uint32_t bc[PPT];
+  uint32_t np = 0;
+#pragma unroll
+  for (int u = 0; u < PPT; u++) {
+    bc[u] = __ballot_sync(0xFFFFFFFFu, cand[u]);
+    np += __popc(__ballot_sync(0xFFFFFFFFu, pred[u]));
+    if (lane == 0) wcnt[u * NW + warp] = __popc(bc[u]);
+  }
+  if (threadIdx.x == 0) s_pred = 0;
+  __syncthreads();
+  if (lane == 0 && np) atomicAdd(&s_pred, np);
+  if (warp == 0) {
+    const uint32_t v = lane < PPT * NW ? wcnt[lane] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= uint32_t(o)) incl += y;
+    }
+    if (lane < PPT * NW) wcnt[lane] = incl - v;
+    if (lane == 31) s_total = incl;
   }
   __syncthreads();
-  uint32_t off = 0, total = 0, tp = 0;
 #pragma unroll
-  for (uint32_t w = 0; w < DECIM_BLOCK / 32; w++) {
-    if (w < warp) off += wcnt[w];
-    total += wcnt[w];
-    tp += wpred[w];
-  }
-  if (cand) {
-    const size_t o = size_t(blockIdx.x) * DECIM_BLOCK + off + __popc(bc & ((1u << lane) - 1u));
-    j.cand_pt[o] = p;
-    j.cand_meta[o] = make_uint2(slot, i);
+  for (int u = 0; u < PPT; u++) {
+    if (cand[u]) {
+      const size_t o = size_t(base) + wcnt[u * NW + warp] + __popc(bc[u] & ((1u << lane) - 1u));
+      j.cand_pt[o] = p[u];
+      j.cand_meta[o] = make_uint2(slot[u], base + u * DECIM_BLOCK + threadIdx.x);
+    }
   }
   if (threadIdx.x == 0) {
-    j.blockcnt[blockIdx.x] = total;
-    if (tp) atomicAdd(j.npred, tp);
+    j.blockcnt[blockIdx.x] = s_total;
+    if (s_pred) atomicAdd(j.npred, s_pred);
   }
 }
 
@@ -209,49 +264,78 @@ MLO_D uint32_t lookback_exclusive(unsigned long long* status, uint32_t b, uint32
   return excl;
 }
 
+template <int PPT>
 __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_finalize(const DecimJob* __restrict__ jobs) {
   const DecimJob& j = jobs[blockIdx.y];
   const uint32_t n = job_n(j);
-  if (blockIdx.x * DECIM_BLOCK >= n) return;
-  const uint32_t nblk = (n + DECIM_BLOCK - 1) / DECIM_BLOCK;
+  constexpr uint32_t TILE = DECIM_BLOCK * PPT;
+  const uint32_t base = blockIdx.x * TILE;
+  if (base >= n) return;
+  const uint32_t nblk = (n + TILE - 1) / TILE;
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
   const uint32_t c = j.blockcnt[blockIdx.x];
   const bool has_pre = j.pre.use_range || j.pre.use_bbox;
   const bool pass_all = n < j.min_pts || (has_pre && *j.npred < j.min_pts);
-  bool keep = false;
-  float4 p = make_float4(0.f, 0.f, 0.f, 0.f);
-  uint32_t idx = 0;
-  if (threadIdx.x < c) {
-    const size_t o = size_t(blockIdx.x) * DECIM_BLOCK + threadIdx.x;
-    const uint2 m = j.cand_meta[o];
-    p = j.cand_pt[o];
-    idx = m.y;
-    const bool win = pass_all || (m.x != SLOT_NONE && j.tab[m.x].first == m.y);
-    keep = win && predicate_keep(j.post, p.x, p.y, p.z);
-  }
-  __shared__ uint32_t wcnt[DECIM_BLOCK / 32];
-  __shared__ uint32_t s_excl;
-  const uint32_t bk = __ballot_sync(0xFFFFFFFFu, keep);
-  if (lane == 0) wcnt[warp] = __popc(bk);
-  __syncthreads();
-  uint32_t off = 0, total = 0;
+  bool keep[PPT];
+  float4 p[PPT];
+  uint2 m[PPT];
 #pragma unroll
-  for (uint32_t w = 0; w < DECIM_BLOCK / 32; w++) {
-    if (w < warp) off += wcnt[w];
-    total += wcnt[w];
+  for (int u = 0; u < PPT; u++) {
+    const uint32_t k = u * DECIM_BLOCK + threadIdx.x;
+    keep[u] = false;
+    m[u] = make_uint2(SLOT_NONE, 0u);
+    p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (k < c) {
+      m[u] = j.cand_meta[size_t(base) + k];
+      p[u] = j.cand_pt[size_t(base) + k];
+    }
   }
+  uint32_t first[PPT];
+#pragma unroll
+  for (int u = 0; u < PPT; u++) {
+    first[u] = 0xFFFFFFFFu;
+    if (!pass_all && m[u].x != SLOT_NONE) first[u] = j.tab[m[u].x].first;
+  }
+  constexpr int NW = DECIM_BLOCK / 32;
+  __shared__ uint32_t wcnt[PPT * NW];
+  __shared__ uint32_t s_total, s_excl;
+  uint32_t bk[PPT];
+#pragma unroll
+  for (int u = 0; u < PPT; u++) {
+    const uint32_t k = u * DECIM_BLOCK + threadIdx.x;
+    if (k < c) {
+      const bool win = pass_all || (m[u].x != SLOT_NONE && first[u] == m[u].y);
+      keep[u] = win && predicate_keep(j.post, p[u].x, p[u].y, p[u].z);
+    }
+    bk[u] = __ballot_sync(0xFFFFFFFFu, keep[u]);
+    if (lane == 0) wcnt[u * NW + warp] = __popc(bk[u]);
+  }
+  __syncthreads();
   if (warp == 0) {
+    const uint32_t v = lane < PPT * NW ? wcnt[lane] : 0u;
+    uint32_t incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
+      if (lane >= uint32_t(o)) incl += y;
+    }
+    if (lane < PPT * NW) wcnt[lane] = incl - v;
+    const uint32_t total = __shfl_sync(0xFFFFFFFFu, incl, 31);
     const uint32_t e = lookback_exclusive(j.status, blockIdx.x, total);
     if (lane == 0) {
       s_excl = e;
+      s_total = total;
       if (blockIdx.x == nblk - 1) *j.n_out = e + total;
     }
   }
   __syncthreads();
-  if (keep) {
-    const uint32_t o = s_excl + off + __popc(bk & ((1u << lane) - 1u));
-    j.out[o] = p;
-    if (j.out_idx) j.out_idx[o] = idx;
+#pragma unroll
+  for (int u = 0; u < PPT; u++) {
+    if (keep[u]) {
+      const uint32_t o = s_excl + wcnt[u * NW + warp] + __popc(bk[u] & ((1u << lane) - 1u));
+      j.out[o] = p[u];
+      if (j.out_idx) j.out_idx[o] = m[u].y;
+    }
   }
 }
 

@@ -1164,7 +1164,9 @@ MLO_D void trace_event(uint32_t prob, uint32_t code) {
   if (i < 16384) g_trace[i] = (t << 8) | code;
 }
 #define MLO_TRACE_EVENT(prob, code) do { if (threadIdx.x == 0) trace_event(prob, code); } while (0)
+MLO_D void trace_event_any(uint32_t code) { trace_event(0u, code); }
 #else
+MLO_D void trace_event_any(uint32_t) {}
 #define MLO_TRACE_EVENT(prob, code) do { } while (0)
 #endif
 

@@ -257,12 +257,14 @@ __device__ __noinline__ uint32_t block_match(BlockShared<NT>& sh, const double* 
       want = (P.matcher_mask & MLO_MATCHER_PT2PT) && !paired;
       if (want) ncand += npts;
     }
+    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 21);  // probes done (this thread)
     // ---- phase 2: own cells
     {
       const uint32_t wh = want ? sh.words[13][tid] : CELL_ABSENT;
       const uint32_t np = (wh == CELL_ABSENT) ? 0u : (cell_cnt(wh) + 7u) >> 3;
       block_publish_and_drain<NT>(map, sh, np ? (1u << 13) : 0u, np);
     }
+    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 22);  // own cells drained
     // ---- phase 3: per query, the neighbour cells whose box can still beat the bound from the own cell (exact pruning)
     uint32_t visit = 0, my_items = 0;
     if (want) {
@@ -281,7 +283,9 @@ __device__ __noinline__ uint32_t block_match(BlockShared<NT>& sh, const double* 
         }
       }
     }
+    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 23);  // neighbour cells selected
     block_publish_and_drain<NT>(map, sh, visit, my_items);
+    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 24);  // neighbour cells drained
     // ---- result per query
     if (want) {
       const unsigned long long b = sh.best[tid];
@@ -339,14 +343,14 @@ __global__ void __launch_bounds__(NT, 512 / NT)
   for (;;) {
     const uint32_t it = sh.it;
     const double* sT = sh.T;
-    MLO_TRACE_EVENT(prob, 11);  // iteration starts
+    if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 11);  // iteration starts
     // ---------------- match: Matcher_Point2Plane, then Matcher_Points_DistanceThreshold on the still unpaired points
     const double thr = table_at(P.thr_pt2pt, P.table_len, it);
     const float thr2 = float(thr * thr);
     const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
     const double kc = table_at(P.kparam, P.table_len, it);
     uint32_t ncand = block_match<NT, PLANES>(sh, sT, thr2, thr_pl, q0, qstride, local, pairA, pairB);
-    MLO_TRACE_EVENT(prob, 12);  // matches done
+    if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 12);  // matches done
     // ---------------- Solver_GaussNewton inner iterations (or the one Horn step) over the stored pairings.
     // Every thread re-reads the records it wrote itself: no barrier between match and accumulate.
     int next;
@@ -374,6 +378,7 @@ __global__ void __launch_bounds__(NT, 512 / NT)
       const double mine = warp_reduce32_transpose(a);
       sh.wpart[warp][lane] = mine;
       __syncthreads();
+      if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 15);  // accumulated + warp-reduced
       if (warp == 0) {
         double t = sh.wpart[0][lane];
 #pragma unroll
@@ -382,7 +387,7 @@ __global__ void __launch_bounds__(NT, 512 / NT)
       }
       if (CL > 1) cluster.sync();
       else __syncthreads();
-      MLO_TRACE_EVENT(prob, 13);  // linearisation reduced to one partial per block
+      if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 13);  // linearisation reduced to one partial per block
       if (rank == 0 && warp == 0) {
         double t = sh.cpart[0][lane];
         for (uint32_t r = 1; r < CL; r++) t += sh.cpart[r][lane];
@@ -390,6 +395,7 @@ __global__ void __launch_bounds__(NT, 512 / NT)
         else if (lane < NACC + 2) sh.sc.cnt[lane - NACC] = uint32_t(t);
         __syncwarp();
         const int n = solve_core_ool(sh.P, sh.S, sh.sc, after_match);
+        if (blockIdx.x == 0 && lane == 0) trace_event_any(16);  // solve_core returned
         // hand the verdict, the iteration index and the new pose to every block of the cluster
         for (uint32_t r = 0; r < CL; r++) {
           BlockShared<NT>* dst = (CL > 1 && r > 0) ? cluster.map_shared_rank(&sh, r) : &sh;
@@ -400,7 +406,7 @@ __global__ void __launch_bounds__(NT, 512 / NT)
       }
       if (CL > 1) cluster.sync();
       else __syncthreads();
-      MLO_TRACE_EVENT(prob, 14);  // solved
+      if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 14);  // solved
       next = sh.next;
       after_match = 0;
       ncand = 0;

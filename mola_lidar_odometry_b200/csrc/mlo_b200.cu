@@ -108,12 +108,16 @@ struct mlo_ctx {
   // mlo_set_option("align_path") / MLO_ALIGN_PATH: 0 = auto (block kernel for small batches, launch sequence for large
   // ones), 1 = launch sequence, 2 = queue-driven persistent kernel, 3 = one thread block per problem (k_icp_block)
   int align_path = 0;
-  int tail_path = 3;      // kernel that finishes the stragglers of a launch sequence: 3 = block, 2 = queue
+  int tail_path = 2;      // kernel that finishes the stragglers of a launch sequence: 2 = queue (measured faster at B = 512), 3 = block
   int block_threads = 0;  // threads per block of k_icp_block: 0 = auto, else 256 / 512
   int block_cluster = 0;  // thread blocks per problem (cluster size) of k_icp_block: 0 = auto, else 1 / 2 / 4 / 8
   int last_block_cluster = 0, last_block_threads = 0;
   bool block_attr_set[6] = {false, false, false, false, false, false};
-  int filter_group_mb = 72;  // mlo_set_option("filter_group_mb"): scratch bytes per group of clouds in the 1st-pass filter (L2-resident)
+  // mlo_set_option("filter_group_mb"): scratch bytes per group of clouds in the 1st-pass filter.  Groups small enough to
+  // keep their tables in L2 (72 MB) measured SLOWER than one group for the whole batch (more, shorter launches:
+  // profiles/README.md), so the default is "everything in one group".
+  int filter_group_mb = 1 << 20;
+  int filter_ppt = 4;  // mlo_set_option("filter_ppt"): input points per thread of the decimation kernels (1 / 2 / 4)
   int last_align_path = 0, last_stream_groups = 0, last_tail_handover = 0;  // what the last align call did (tests)
   uint64_t large_batch_queries = 0;  // 0 = auto (sm_count * 1024): batches at or above it take the launch sequence
   int tpq_min_queries_per_sm = 512;  // MLO_TPQ_MIN: below this many queries per SM the warp-per-query chunks win
@@ -172,6 +176,8 @@ struct mlo_map {
   int32_t* head = nullptr;  // per-cell (4 per bucket) scratch list heads for insert
   uint64_t n_voxels = 0, n_points = 0;  // as of the last digest of the device counters
   uint64_t hwm = 0;                     // voxel ids handed out so far (counters[0]) as of the last digest
+  uint64_t n_free = 0;                  // reusable voxel ids on the free stack (counters[3]) as of the last digest
+  uint32_t n_grown = 0;                 // how many times the map was re-hashed into larger buffers
 };
 
 struct mlo_dcloud {
@@ -346,6 +352,7 @@ int digest_map_counters(mlo_map* m, const uint32_t* h) {
   m->n_voxels = uint64_t(h[0]) - uint64_t(h[3]);
   m->n_points = h[1];
   m->hwm = h[0];
+  m->n_free = h[3];
   if (uint64_t(h[4]) * 2 > m->table_size) return map_rebuild(m, false, 0, 0, 0, 0);
   return MLO_OK;
 }
@@ -403,6 +410,45 @@ int map_rebuild(mlo_map* m, bool use_filter, int32_t sx, int32_t sy, int32_t sz,
          use_filter ? 1 : 0);
   CU(c, cudaGetLastError());
   std::swap(m->dev, m->alt);
+  return MLO_OK;
+}
+
+// upstream's HashedVoxelPointCloud is unbounded; here `capacity_voxels` is only the INITIAL size of the voxel payload
+// and of the hash table.  Before an insert of n points (each can open at most one voxel) the map is re-hashed into
+// buffers of twice the size (or more) if the worst case would not fit: inserts never fail for lack of capacity, and a
+// map that stays small keeps its table small (fewer pages and cache lines under the random probes of the NN search).
+int map_ensure_capacity(mlo_map* m, uint64_t n_new_points) {
+  mlo_ctx* c = m->ctx;
+  const uint64_t worst = m->hwm - std::min(m->hwm, m->n_free) + n_new_points;
+  if (worst <= m->dev.capacity_voxels) return MLO_OK;
+  uint64_t cap = m->dev.capacity_voxels;
+  while (cap < worst + worst / 4) cap *= 2;
+  if (cap > (1ull << 26)) cap = 1ull << 26;
+  if (cap < worst) return fail(c, MLO_ERR_CAPACITY, "map would exceed 2^26 voxels");
+  mlo_map_params np = m->prm;
+  np.capacity_voxels = cap;
+  const uint64_t new_table = next_pow2(std::max<uint64_t>(uint64_t(c->table_factor) * cap, 1024));
+  if (m->alt_ready) {
+    free_map_buffers(c, m->alt);
+    m->alt_ready = false;
+  }
+  MapDev nd{};
+  int rc = alloc_map_buffers(c, np, new_table, nd);
+  if (rc == MLO_OK) rc = clear_map_buffers(c, nd, new_table);
+  if (rc != MLO_OK) return rc;
+  LAUNCH(c, k_rebuild, uint32_t((m->table_size + 255) / 256), 256, m->dev, nd, m->table_size, 0, 0, 0, 0, 0);
+  CU(c, cudaGetLastError());
+  free_map_buffers(c, m->dev);  // (stream-ordered: after the rebuild has read them)
+  if (m->head) cudaFreeAsync(m->head, c->stream);
+  m->head = nullptr;
+  CU(c, cudaMallocAsync(&m->head, 4 * new_table * sizeof(int32_t), c->stream));
+  CU(c, cudaMemsetAsync(m->head, 0xFF, 4 * new_table * sizeof(int32_t), c->stream));
+  m->dev = nd;
+  m->prm = np;
+  m->table_size = new_table;
+  m->hwm = m->hwm - std::min(m->hwm, m->n_free);  // ids are dense again: an upper bound of the new high-water mark
+  m->n_free = 0;
+  m->n_grown++;
   return MLO_OK;
 }
 
@@ -468,9 +514,12 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
   CU(c, cudaMemsetAsync(cnt, 0, std::max<size_t>(size_t(n_clouds), 1) * CNT_STRIDE * sizeof(uint32_t), c->stream));
   if (total == 0 || max_n == 0) return MLO_OK;
   // ---- per-cloud scratch geometry and the groups
-  // stage-1 table: one entry per input point at most (load factor <= 1, ~0.3 on lidar sweeps); stage-2 table: its input
-  // is the map layer, typically a third of the cloud or less: a quarter of the cloud unless `conservative` (the retry
-  // after a table-exhausted error)
+  // stage-1 table: half an entry per input point (a 0.5 m grid keeps a third of a 64-beam sweep at most: load factor
+  // <= 0.6); stage-2 table: an eighth (its input is the map layer, its output a few thousand points).  A cloud that
+  // overflows either (hardly decimated at all) raises ERR_CAPACITY and the batch is run again with `conservative`
+  // tables of one entry per input point (filter_counts).
+  const int ppt = (c->filter_ppt == 1 || c->filter_ppt == 2) ? c->filter_ppt : 4;
+  const uint64_t tile = uint64_t(DECIM_BLOCK) * ppt;
   struct Geo {
     uint64_t tab1, tab2, nblk, pts;
   };
@@ -478,9 +527,9 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
   for (uint32_t b = 0; b < n_clouds; b++) {
     const uint64_t n = offsets[b + 1] - offsets[b];
     geo[b].pts = n;
-    geo[b].nblk = (n + DECIM_BLOCK - 1) / DECIM_BLOCK;
-    geo[b].tab1 = next_pow2(std::max<uint64_t>(n, 1024));
-    geo[b].tab2 = single_decimate_idx ? 0 : next_pow2(std::max<uint64_t>(conservative ? n : n / 4, 1024));
+    geo[b].nblk = (n + tile - 1) / tile;
+    geo[b].tab1 = next_pow2(std::max<uint64_t>(conservative ? n : n / 2, 1024));
+    geo[b].tab2 = single_decimate_idx ? 0 : next_pow2(std::max<uint64_t>(conservative ? n : n / 8, 1024));
   }
   const uint64_t budget = uint64_t(std::max(1, c->filter_group_mb)) << 20;
   std::vector<uint32_t> group_begin{0};
@@ -584,12 +633,18 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
     CU(c, cudaMemsetAsync(status, 0, g.blocks * sizeof(unsigned long long), c->stream));
     if (!single_decimate_idx) CU(c, cudaMemsetAsync(status + max_blk, 0, g.blocks * sizeof(unsigned long long), c->stream));
     const dim3 grid(g.nblk_max, g.b1 - g.b0);
-    LAUNCH(c, k_decim_claim, grid, DECIM_BLOCK, dj1 + g.b0);
-    LAUNCH(c, k_decim_finalize, grid, DECIM_BLOCK, dj1 + g.b0);
-    if (!single_decimate_idx) {
-      LAUNCH(c, k_decim_claim, grid, DECIM_BLOCK, dj2 + g.b0);
-      LAUNCH(c, k_decim_finalize, grid, DECIM_BLOCK, dj2 + g.b0);
+#define MLO_DECIM_STAGE(PPT, JOBS)                                   \
+  do {                                                               \
+    LAUNCH(c, k_decim_claim<PPT>, grid, DECIM_BLOCK, (JOBS) + g.b0);    \
+    LAUNCH(c, k_decim_finalize<PPT>, grid, DECIM_BLOCK, (JOBS) + g.b0); \
+  } while (0)
+    for (int stage = 0; stage < (single_decimate_idx ? 1 : 2); stage++) {
+      const DecimJob* js = stage == 0 ? dj1 : dj2;
+      if (ppt == 1) MLO_DECIM_STAGE(1, js);
+      else if (ppt == 2) MLO_DECIM_STAGE(2, js);
+      else MLO_DECIM_STAGE(4, js);
     }
+#undef MLO_DECIM_STAGE
   }
   CU(c, cudaGetLastError());
   return MLO_OK;
@@ -1191,6 +1246,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* bt = getenv("MLO_BLOCK_THREADS")) c->block_threads = atoi(bt);
   if (const char* bc = getenv("MLO_BLOCK_CLUSTER")) c->block_cluster = atoi(bc);
   if (const char* fg = getenv("MLO_FILTER_GROUP_MB")) c->filter_group_mb = std::max(1, atoi(fg));
+  if (const char* fp = getenv("MLO_FILTER_PPT")) c->filter_ppt = atoi(fp);
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
@@ -1280,6 +1336,7 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "large_batch_queries") c->large_batch_queries = uint64_t(std::max<int64_t>(0, v));
   else if (n == "pers_minb") c->pers_minb = v == 2 ? 2 : (v == 4 ? 4 : 0);
   else if (n == "filter_group_mb") c->filter_group_mb = int(std::max<int64_t>(1, v));
+  else if (n == "filter_ppt") c->filter_ppt = int(v);
   else return fail(c, MLO_ERR_INVALID_ARG, "unknown option: " + n);
   return MLO_OK;
 }
@@ -1301,6 +1358,7 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   else if (n == "large_batch_queries") *out = int64_t(c->large_batch_queries);
   else if (n == "pers_minb") *out = c->pers_minb;
   else if (n == "filter_group_mb") *out = c->filter_group_mb;
+  else if (n == "filter_ppt") *out = c->filter_ppt;
   else if (n == "last_align_path") *out = c->last_align_path;
   else if (n == "last_stream_groups") *out = c->last_stream_groups;
   else if (n == "last_tail_handover") *out = c->last_tail_handover;
@@ -1355,7 +1413,7 @@ void mlo_map_destroy(mlo_map* m) {
 int mlo_map_clear(mlo_map* m) {
   if (!m) return MLO_ERR_INVALID_ARG;
   DeviceGuard g(m->ctx->device);
-  m->hwm = m->n_voxels = m->n_points = 0;
+  m->hwm = m->n_voxels = m->n_points = m->n_free = 0;
   return clear_map_buffers(m->ctx, m->dev, m->table_size);
 }
 
@@ -1365,6 +1423,8 @@ int mlo_map_insert(mlo_map* m, const float* pts, uint32_t stride, uint64_t n, co
   DeviceGuard g(c->device);
   const size_t e0 = prof_begin(c);
   int rc = upload_strided(c, pts, stride, n, c->d_in);
+  if (rc != MLO_OK) return rc;
+  rc = map_ensure_capacity(m, n);
   if (rc != MLO_OK) return rc;
   rc = map_insert_device(m, c->d_in.as<float>(), stride, n, pose);
   prof_end(c, 2, e0);
@@ -1387,7 +1447,9 @@ int mlo_map_insert_soa(mlo_map* m, const float* x, const float* y, const float* 
     CU(c, cudaMemcpyAsync(d + 2 * n, z, n * sizeof(float), cudaMemcpyHostToDevice, c->stream));
     LAUNCH(c, k_soa_to_float4, uint32_t((n + 255) / 256), 256, d, d + n, d + 2 * n, n, c->d_local.as<float4>());
   }
-  int rc = map_insert_device(m, c->d_local.as<float>(), 4, n, pose);
+  int rc = map_ensure_capacity(m, n);
+  if (rc != MLO_OK) return rc;
+  rc = map_insert_device(m, c->d_local.as<float>(), 4, n, pose);
   if (rc != MLO_OK) return rc;
   return check_map_errors(m);
 }
@@ -1839,6 +1901,8 @@ int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t strid
   if (rc != MLO_OK) return rc;
   if (insert_into_map) {
     const size_t e0 = prof_begin(c);
+    rc = map_ensure_capacity(map, nmap[0]);
+    if (rc != MLO_OK) return rc;
     rc = map_insert_device(map, reinterpret_cast<const float*>(c->d_f_map.as<float4>()), 4, nmap[0], out->pose_3x4);
     if (rc != MLO_OK) return rc;
     if (cull_farther_than > 0.f) {
@@ -2130,6 +2194,10 @@ int mlo_scanset_insert(mlo_scanset* set, uint32_t n_jobs, const mlo_insert_job* 
   for (uint32_t j = 0; j < n_jobs; j++) {
     mlo_map* m = jobs[j].map;
     const auto& sl = set->slots[jobs[j].slot];
+    {
+      int rc = map_ensure_capacity(m, sl.n_map);
+      if (rc != MLO_OK) return rc;
+    }
     InsertJobDev& d = dj[j];
     d.m = m->dev;
     d.src = reinterpret_cast<const float*>(set->map_layer() + sl.off);

@@ -41,6 +41,9 @@ void put_output(const ScanOutput& s, mlo_lo_scan_output* out) {
   out->termination = s.termination;
   out->n_map_layer = s.n_map_layer;
   out->n_icp_layer = s.n_icp_layer;
+  out->icp_had_prior = s.icp_had_prior;
+  out->has_motion_model = s.has_motion_model;
+  out->prior_info_trace = s.prior_info_trace;
 }
 thread_local std::string g_err;
 YamlNode load_cfg(const char* yaml, int is_text) { return is_text ? yaml_parse(yaml) : yaml_load_file(yaml); }

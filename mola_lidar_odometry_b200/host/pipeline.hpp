@@ -23,7 +23,10 @@
 #include <string>
 #include <vector>
 
+#include <cstdlib>
+
 #include "formula.hpp"
+#include "navstate_fuse.hpp"
 #include "mlo_b200.h"
 #include "yaml_lite.hpp"
 
@@ -303,7 +306,7 @@ struct LocalMapDefinition {
   Formula voxel_size{"1.0"}, remove_voxels_farther_than{"0"};
   uint32_t max_points_per_voxel = 20;
   double min_distance_between_points = 0, max_eigen_ratio_for_planes = 0.05;
-  uint64_t capacity_voxels = 1u << 20;
+  uint64_t capacity_voxels = 1u << 17;  // INITIAL device capacity: the map grows on demand (mlo_map_insert), as upstream's is unbounded
   void initialize(const YamlNode& def) {
     const std::string c = def.at("class").str();
     if (c == "mola::HashedVoxelPointCloud") kind = MLO_MAP_HASHED_VOXEL_POINTS;
@@ -335,8 +338,8 @@ struct LidarOdometryParams {  // the subset of LidarOdometry::Parameters around 
   double min_icp_goodness = 0.25;
   bool adaptive_enabled = true;
   double initial_sigma = 2.0, min_motion = 0.1, maximum_sigma = 3.0, kp = 2.0, alpha = 0.9;
-  double max_time_to_use_velocity_model = 0.75;
-  std::array<double, 6> initial_twist{};  // navstate_fuse_params.initial_twist (default.yaml:139): vx vy vz wx wy wz
+  NavStateFuseParams navstate;  // navstate_fuse_params (default.yaml:126-144)
+  bool icp_prior_enabled = true;  // MLO_ICP_PRIOR=0: never send the motion-model information to the solver (A/B, tests)
   // observations_filter_2nd_pass FilterDeskew (default.yaml:328-350) + FilterAdjustTimestamps (:267-275)
   bool skip_deskew = false, silently_ignore_no_timestamps = true;
   bool timestamps_middle_is_zero = true;  // TimestampAdjustMethod::MiddleIsZero (else EarliestIsZero)
@@ -349,6 +352,8 @@ struct ScanOutput {
   uint32_t icp_iterations = 0, icp_runs = 0;
   int termination = MLO_TERM_UNDEFINED;
   uint64_t n_map_layer = 0, n_icp_layer = 0;
+  bool icp_had_prior = false, has_motion_model = false;
+  double prior_info_trace = 0;
 };
 
 template <class Backend>
@@ -400,9 +405,17 @@ class LidarOdometryT {
     if (cfg.has("navstate_fuse_params"))
     {
       const YamlNode& nf = cfg["navstate_fuse_params"];
-      params_.max_time_to_use_velocity_model = nf["max_time_to_use_velocity_model"].num(0.75);
+      NavStateFuseParams& np = params_.navstate;
+      np.max_time_to_use_velocity_model = nf["max_time_to_use_velocity_model"].num(0.75);
+      np.sliding_window_length = nf["sliding_window_length"].num(0.5);
+      np.sigma_random_walk_acceleration_linear = nf["sigma_random_walk_acceleration_linear"].num(1.0);
+      np.sigma_random_walk_acceleration_angular = nf["sigma_random_walk_acceleration_angular"].num(10.0);
+      np.sigma_integrator_position = nf["sigma_integrator_position"].num(1.0);
+      np.sigma_integrator_orientation = nf["sigma_integrator_orientation"].num(1.0);
+      np.initial_twist_sigma_lin = nf["initial_twist_sigma_lin"].num(20.0);
+      np.initial_twist_sigma_ang = nf["initial_twist_sigma_ang"].num(3.0);
       if (nf["initial_twist"].isSeq())
-        for (size_t k = 0; k < 6 && k < nf["initial_twist"].seq.size(); k++) params_.initial_twist[k] = nf["initial_twist"].seq[k].num(0.0);
+        for (size_t k = 0; k < 6 && k < nf["initial_twist"].seq.size(); k++) np.initial_twist[k] = nf["initial_twist"].seq[k].num(0.0);
     }
     if (cfg.has("observations_filter_2nd_pass"))
       for (const YamlNode& f : cfg["observations_filter_2nd_pass"].seq)
@@ -434,6 +447,10 @@ class LidarOdometryT {
         found = true;
       }
     if (!found) throw std::runtime_error("localmap_generator: no metric_map_definition");
+    if (const char* e = std::getenv("MLO_ICP_PRIOR")) params_.icp_prior_enabled = std::atoi(e) != 0;
+    navstate_.params = params_.navstate;
+    navstate_.set_lie([this](const double* xi, double* T) { be_.se3_exp(xi, T); },
+                      [this](const double* T, double* xi) { be_.se3_log(T, xi); });
     reset_state();
   }
 
@@ -444,7 +461,7 @@ class LidarOdometryT {
     trajectory_.clear();
     keyframes_.clear();
     last_lidar_pose_ = pose_identity();
-    fused_.clear();
+    navstate_.reset();
     sigma_ = 0;
     est_max_range_.reset();
     inst_max_range_.reset();
@@ -546,7 +563,7 @@ class LidarOdometryT {
     std::memset(&job, 0, sizeof(job));
     job.map = static_cast<const mlo_map*>(map_);
     std::memcpy(job.init_pose_3x4, current_solution_.data(), sizeof(job.init_pose_3x4));
-    icp.make_params(ip_, std::nullopt, job.params);
+    icp.make_params(ip_, prior_, job.params);  // the same prior on every align call of the do/while (:961-962)
   }
   void on_align_result(const mlo_icp_result& res) {
     Results& r = result_;
@@ -586,10 +603,10 @@ class LidarOdometryT {
       out_.icp_good = icpIsGood;
       if (icpIsGood) {
         last_lidar_pose_ = r.optimal_tf_mean;
-        fuse_pose(stamp_, r.optimal_tf_mean);
+        fuse_pose(stamp_, r.optimal_tf_mean, r.optimal_tf_cov.data());  // :1035-1036 (covariance of the ICP result)
         trajectory_.emplace_back(stamp_, last_lidar_pose_);
       } else {
-        fused_.clear();  // navstate_fuse.reset()
+        navstate_.reset();  // navstate_fuse.reset() (:1039)
       }
       parameter_source.updateVariable("icp_iterations", double(r.nIterations));  // :1046-1048
       // (the reference's local counter is never incremented - :926,939 bump the PARAMETER instead - so the variable stays
@@ -718,7 +735,16 @@ class LidarOdometryT {
       return;
     }
     const bool hasMotionModel = motion_.has_value();
-    init_guess_ = hasMotionModel ? motion_->pose : last_lidar_pose_;  // :852-897 (prior term: see DESIGN.md, f2)
+    init_guess_ = hasMotionModel ? motion_->pose : last_lidar_pose_;  // :852-897
+    prior_.reset();
+    if (hasMotionModel && params_.icp_prior_enabled) {  // ICP prior term: any information != 0? (:859-861)
+      bool any = false;
+      for (double v : motion_->cov_inv) any = any || v != 0.0;
+      if (any) prior_ = Prior{motion_->pose, motion_->cov_inv};
+    }
+    out_.has_motion_model = hasMotionModel;
+    out_.icp_had_prior = prior_.has_value();
+    if (prior_) for (int k = 0; k < 6; k++) out_.prior_info_trace += prior_->cov_inv[7 * k];
     last_keyframe_pose_ = last_lidar_pose_;                           // :904
     since_last_ = last_icp_time_ ? stamp_ - *last_icp_time_ : 0.0;
     last_icp_time_ = stamp_;
@@ -735,48 +761,11 @@ class LidarOdometryT {
     icp_pending_ = true;
   }
 
-  struct NavState {
-    Pose pose;
-    std::array<double, 6> twist;
-  };
-  // Constant-velocity stand-in for mola::NavStateFuse (external, row f2): body-frame twist from the last two fused
-  // poses; valid while the newest fused pose is younger than max_time_to_use_velocity_model.
-  std::optional<NavState> estimated_navstate(double stamp) {
-    if (fused_.size() == 1) {  // only the initial pose is known: extrapolate with the configured initial twist, if any
-      bool any = false;
-      for (double v : params_.initial_twist) any = any || v != 0.0;
-      const double dt = stamp - fused_.back().first;
-      if (!any || dt > params_.max_time_to_use_velocity_model) return std::nullopt;
-      NavState ns;
-      ns.twist = params_.initial_twist;
-      double step[6];
-      for (int k = 0; k < 6; k++) step[k] = ns.twist[k] * dt;
-      Pose d;
-      be_.se3_exp(step, d.data());
-      ns.pose = pose_compose(fused_.back().second, d);
-      return ns;
-    }
-    if (fused_.size() < 2) return std::nullopt;
-    const auto& a = fused_[fused_.size() - 2];
-    const auto& b = fused_.back();
-    const double dt0 = b.first - a.first, dt = stamp - b.first;
-    if (dt0 <= 0 || dt > params_.max_time_to_use_velocity_model) return std::nullopt;
-    const Pose rel = pose_minus(b.second, a.second);
-    double xi[6];
-    be_.se3_log(rel.data(), xi);
-    NavState ns;
-    for (int k = 0; k < 6; k++) ns.twist[k] = xi[k] / dt0;
-    double step[6];
-    for (int k = 0; k < 6; k++) step[k] = ns.twist[k] * dt;
-    Pose d;
-    be_.se3_exp(step, d.data());
-    ns.pose = pose_compose(b.second, d);
-    return ns;
-  }
-  void fuse_pose(double stamp, const Pose& p) {
-    fused_.emplace_back(stamp, p);
-    if (fused_.size() > 8) fused_.erase(fused_.begin());
-  }
+  // mola::NavStateFuse (host/navstate_fuse.hpp): sliding-window constant-velocity model; pose = ICP initial guess,
+  // cov_inv = information of the GN prior (:854-877), twist = the vx..wz pipeline variables (:1581-1600)
+  using NavState = NavStateFuse::NavState;
+  std::optional<NavState> estimated_navstate(double stamp) { return navstate_.estimated_navstate(stamp); }
+  void fuse_pose(double stamp, const Pose& p, const double* cov = nullptr) { navstate_.fuse_pose(stamp, p, cov); }
   void rot_log(const Pose& p, double w[3]) {
     Pose r = p;
     r[3] = r[7] = r[11] = 0.0;
@@ -886,6 +875,7 @@ class LidarOdometryT {
   // per-scan transient state between the phases
   ScanOutput out_;
   std::optional<NavState> motion_;
+  std::optional<Prior> prior_;  // in.prior of :859-877
   double stamp_ = 0, since_last_ = 0;
   bool do_deskew_ = false, needs_deskew_ = false, first_deskew_ = false, first_scan_ = false, icp_pending_ = false,
        insert_pending_ = false;
@@ -894,7 +884,8 @@ class LidarOdometryT {
   IterationHook hook_;
   Results result_;
   uint32_t remaining_ = 0, total_iterations_ = 0;
-  std::vector<std::pair<double, Pose>> trajectory_, fused_;
+  std::vector<std::pair<double, Pose>> trajectory_;
+  NavStateFuse navstate_;
   std::vector<Pose> keyframes_;
   Pose last_lidar_pose_ = pose_identity();
   std::array<double, 6> twist_{};

@@ -16,7 +16,8 @@ class ScanOutput(C.Structure):
     _fields_ = [("processed", C.c_int32), ("icp_ran", C.c_int32), ("icp_good", C.c_int32), ("map_updated", C.c_int32),
                 ("pose_3x4", C.c_double * 12), ("quality", C.c_double), ("sigma", C.c_double),
                 ("est_max_range", C.c_double), ("icp_iterations", C.c_uint32), ("icp_runs", C.c_uint32),
-                ("termination", C.c_int32), ("n_map_layer", C.c_uint64), ("n_icp_layer", C.c_uint64)]
+                ("termination", C.c_int32), ("n_map_layer", C.c_uint64), ("n_icp_layer", C.c_uint64),
+                ("icp_had_prior", C.c_int32), ("has_motion_model", C.c_int32), ("prior_info_trace", C.c_double)]
 
     @property
     def pose(self):
@@ -138,7 +139,7 @@ class LidarOdometry:
 # ctypes attribute accesses
 SCAN_OUTPUT_DTYPE = np.dtype({"names": [f[0] for f in ScanOutput._fields_],
                               "formats": [np.int32, np.int32, np.int32, np.int32, (np.float64, (3, 4)), np.float64, np.float64,
-                                          np.float64, np.uint32, np.uint32, np.int32, np.uint64, np.uint64],
+                                          np.float64, np.uint32, np.uint32, np.int32, np.uint64, np.uint64, np.int32, np.int32, np.float64],
                               "offsets": [getattr(ScanOutput, f[0]).offset for f in ScanOutput._fields_],
                               "itemsize": C.sizeof(ScanOutput)})
 

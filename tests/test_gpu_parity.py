@@ -45,6 +45,26 @@ def test_map_insert_bit_exact(ctx, world, voxel, cap, min_dist):
     _assert_maps_equal(g, o)
 
 
+def test_map_grows_on_demand_bit_exact(ctx, world):
+    """capacity_voxels is only the initial size (upstream's HashedVoxelPointCloud is unbounded): inserts that would not
+    fit re-hash the map into larger buffers; contents stay bit-identical to the oracle's, culling and NN included."""
+    g, o = _mk_maps(ctx, 1.0, 20, 0.0, capacity=256)
+    for k, fr in enumerate(world["frames"][:10]):
+        g.insert(fr["map_layer"], fr["gt"])
+        o.insert(fr["map_layer"], fr["gt"])
+        assert g.stats() == o.stats()
+        if k == 5:
+            s = fr["gt"][:, 3]
+            g.cull(s, 40.0)
+            o.cull(s, 40.0)
+    assert g.stats()[0] > 10 * 256
+    _assert_maps_equal(g, o)
+    q = world["frames"][11]["icp_layer"]
+    gx, gd, gf = g.nn_single(q)
+    ox, od, of, _ = o.nn_single(q)
+    assert np.array_equal(gf, of) and np.array_equal(gd.view(np.uint32)[gf], od.view(np.uint32)[of])
+
+
 def test_map_insert_soa_and_stride4(ctx, world):
     g, o = _mk_maps(ctx)
     fr = world["frames"][0]

@@ -525,3 +525,70 @@ def test_reference_pipeline_files_load_unmodified_and_agree(built, scene, traj, 
         a, b = ref.on_lidar(raw, 0.1 * k), own.on_lidar(raw, 0.1 * k)
         _same_output(a, b, exact=True)
     assert a.icp_ran and a.icp_good
+
+
+# ------------------------------------------------------------------ row f2: motion model (NavStateFuse) and the ICP prior
+def test_motion_model_emits_the_icp_prior_on_every_scan(built, scene, traj, monkeypatch):
+    """LidarOdometry.cpp:808-815,854-877,1035-1039: from the second scan on estimated_navstate() yields pose + information,
+    and that information reaches the solver as the prior (checked here over the oracle backend)."""
+    from oracle import oracle_py as O
+    lo = O.OracleLidarOdometry(DEFAULT_YAML)
+    gts = [synth.relative(traj[0], traj[k]) for k in range(20)]
+    traces = []
+    for k in range(20):
+        out = lo.on_lidar(scene.scan(traj[k], scan_seed=1000 + k), 0.1 * k)
+        if k == 0:
+            assert not out.icp_ran and not out.icp_had_prior
+            continue
+        assert out.has_motion_model and out.icp_had_prior and out.prior_info_trace > 0, k
+        assert out.icp_good
+        assert O.pose_error(out.pose, gts[k])[0] < 0.3
+        traces.append(out.prior_info_trace)
+    # a single fused pose (scan 1) predicts with the YAML's initial-twist sigma (20 m/s): far less information than the
+    # window fit of the later scans
+    assert traces[0] < 0.1 * min(traces[3:])
+    # without the prior the trajectory differs (slightly): the term is really in the normal equations
+    monkeypatch.setenv("MLO_ICP_PRIOR", "0")
+    lo2 = O.OracleLidarOdometry(DEFAULT_YAML)
+    lo3 = O.OracleLidarOdometry(DEFAULT_YAML)
+    monkeypatch.delenv("MLO_ICP_PRIOR")
+    lo4 = O.OracleLidarOdometry(DEFAULT_YAML)
+    d_off, d_on = 0.0, 0.0
+    for k in range(8):
+        raw = scene.scan(traj[k], scan_seed=1000 + k)
+        a, b, c = lo2.on_lidar(raw, 0.1 * k), lo3.on_lidar(raw, 0.1 * k), lo4.on_lidar(raw, 0.1 * k)
+        assert not a.icp_had_prior and np.array_equal(a.pose, b.pose)          # deterministic
+        d_off = max(d_off, O.pose_error(a.pose, c.pose)[0])
+    assert 0.0 < d_off < 0.05
+
+
+def test_navstate_fuse_window_and_velocity_horizon(built, scene, traj, monkeypatch):
+    """navstate_fuse_params: a gap longer than max_time_to_use_velocity_model drops the motion model for that scan
+    (AlignKind::NoMotionModel, no prior, no map update: LidarOdometry.cpp:899-903,1088)."""
+    from oracle import oracle_py as O
+    lo = O.OracleLidarOdometry(DEFAULT_YAML)
+    stamps = [0.0, 0.1, 0.2, 0.3, 1.5, 1.6]
+    outs = [lo.on_lidar(scene.scan(traj[k], scan_seed=1000 + k), t) for k, t in enumerate(stamps)]
+    assert [bool(o.has_motion_model) for o in outs] == [False, True, True, True, False, True]
+    assert not outs[4].icp_had_prior and not outs[4].map_updated
+    assert outs[5].icp_had_prior
+
+
+@pytest.mark.gpu
+def test_lidar_odometry_gpu_trajectory_with_prior_on_every_scan(ctx, scene, traj):
+    """Row f2 on the device: 30 scans, the motion model's 6x6 information is the Gauss-Newton prior of EVERY align call
+    (has_prior = 1 in mlo_icp_params); GPU backend vs oracle backend, same orchestrator."""
+    from mola_lidar_odometry_b200.host_api import LidarOdometry
+    from oracle import oracle_py as O
+    g, o = LidarOdometry(ctx, DEFAULT_YAML), O.OracleLidarOdometry(DEFAULT_YAML)
+    n_prior = 0
+    for k in range(30):
+        raw = scene.scan(traj[k], scan_seed=1000 + k)
+        a, b = g.on_lidar(raw, 0.1 * k), o.on_lidar(raw, 0.1 * k)
+        et, er = O.pose_error(a.pose, b.pose)
+        assert et <= 1e-3 and er <= 1e-2, (k, et, er)
+        assert (a.icp_had_prior, a.has_motion_model, a.icp_good, a.map_updated) == (b.icp_had_prior, b.has_motion_model, b.icp_good, b.map_updated)
+        assert a.prior_info_trace == pytest.approx(b.prior_info_trace, rel=1e-4)
+        n_prior += int(a.icp_had_prior)
+    assert n_prior == 29
+    g.close()
