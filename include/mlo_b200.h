@@ -146,6 +146,10 @@ int32_t mlo_voxel_index(float coord, float voxel_size);
 void mlo_se3_exp(const double xi[6], double pose_3x4[12]);
 void mlo_se3_log(const double pose_3x4[12], double xi[6]);
 void mlo_se3_right_jacobian_inv(const double xi[6], double J_6x6[36]);
+/* mp2p_icp::Results::optimal_tf.cov lives in MRPT's (x y z yaw pitch roll) chart (it feeds NavStateFuse::fuse_pose at
+ * LidarOdometry.cpp:1035-1036); mlo_icp_result.cov_6x6 is in the tangent space of T <- T exp(eps).  First-order change of
+ * chart: cov_ypr = J cov J^T with J = d(x y z yaw pitch roll)/d eps at `pose` (R = Rz(yaw) Ry(pitch) Rx(roll)). */
+void mlo_cov_tangent_to_ypr(const double pose_3x4[12], const double cov_tangent_6x6[36], double cov_ypr_6x6[36]);
 
 /* ------------------------------------------------------------------ filters
  * Replaces mp2p_icp_filters::FilterDecimateVoxels, DecimateMethod::FirstPoint

@@ -191,6 +191,7 @@ _SIGNATURES = {
     "mlo_se3_exp": (None, [_vp, _vp]),
     "mlo_se3_log": (None, [_vp, _vp]),
     "mlo_se3_right_jacobian_inv": (None, [_vp, _vp]),
+    "mlo_cov_tangent_to_ypr": (None, [_vp, _vp, _vp]),
     "mlo_voxel_decimate_first": (C.c_int, [_vp, _vp, _u32, _u64, C.POINTER(DecimateParams), _vp, C.POINTER(_u64)]),
     "mlo_filter_1st_pass": (C.c_int, [_vp, _vp, _u32, _u64, C.POINTER(Filter1Params), _vp, C.POINTER(_u64), _vp,
                                       C.POINTER(_u64)]),

@@ -703,6 +703,8 @@ struct SolveScratch {
   uint32_t cnt[2];
   double part[SOLVE_WARPS][NACC];
   uint32_t pcnt[SOLVE_WARPS][2];
+  // prior term, spread over the warp (prior_add_warp)
+  double g[6], e[6], Le[6], J[36], LJ[36];
 };
 MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const uint32_t* part_cnt, uint32_t nblk,
                               SolveScratch& sc) {
@@ -744,27 +746,45 @@ MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const
 
 // ---- the solve step (one warp; problem and state in SHARED memory) --------------------------------------------
 // Prior term of Solver_GaussNewton (LidarOdometry.cpp:854-877): e = log(prior^-1 T), J = d log(D exp(eps))/d eps;
-// g += J^T L e ; H += J^T L J.  Out of line (rare, loop-heavy): keeps the common path's arrays in registers.
-__device__ __noinline__ void prior_add(const IcpProblem& P, const double* T, double* H, double* g) {
-  double D[12], e[6], J[36], LJ[36], Le[6];
+// g += J^T L e ; H += J^T L J.  Lane 0 evaluates e and J (out of line: loop-heavy, keeps the common path's arrays in
+// registers); the 6x6 products are spread over the warp, one output entry per lane, each entry summed in the same order
+// (m = 0..5 onto the running value) as a single-thread loop would: same bits, a third of the time.
+__device__ __noinline__ void prior_e_and_J(const IcpProblem& P, const double* T, double* e_out, double* J_out) {
+  double D[12], e[6], J[36];
   pose_minus(T, P.prior_pose, D);
   se3_log(D, e);
   se3_right_jacobian_inv(e, J);
-  for (int i = 0; i < 6; i++) {
+  for (int i = 0; i < 6; i++) e_out[i] = e[i];
+  for (int i = 0; i < 36; i++) J_out[i] = J[i];
+}
+MLO_D void prior_add_warp(const IcpProblem& P, const double* T, double* H, SolveScratch& sc) {
+  const uint32_t lane = threadIdx.x & 31u;
+  if (lane == 0) prior_e_and_J(P, T, sc.e, sc.J);
+  __syncwarp();
+  if (lane < 6) {
     double s = 0;
-    for (int m = 0; m < 6; m++) s += P.prior_info[6 * i + m] * e[m];
-    Le[i] = s;
-    for (int j = 0; j < 6; j++) {
-      double t = 0;
-      for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * J[6 * m + j];
-      LJ[6 * i + j] = t;
-    }
+    for (int m = 0; m < 6; m++) s += P.prior_info[6 * lane + m] * sc.e[m];
+    sc.Le[lane] = s;
   }
-  for (int i = 0; i < 6; i++) {
-    for (int m = 0; m < 6; m++) g[i] += J[6 * m + i] * Le[m];
-    for (int j = 0; j < 6; j++)
-      for (int m = 0; m < 6; m++) H[6 * i + j] += J[6 * m + i] * LJ[6 * m + j];
+  for (uint32_t idx = lane; idx < 36; idx += 32) {
+    const uint32_t i = idx / 6, j = idx % 6;
+    double t = 0;
+    for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * sc.J[6 * m + j];
+    sc.LJ[idx] = t;
   }
+  __syncwarp();
+  if (lane < 6) {
+    double gi = sc.g[lane];
+    for (int m = 0; m < 6; m++) gi += sc.J[6 * m + lane] * sc.Le[m];
+    sc.g[lane] = gi;
+  }
+  for (uint32_t idx = lane; idx < 36; idx += 32) {
+    const uint32_t i = idx / 6, j = idx % 6;
+    double h = H[idx];
+    for (int m = 0; m < 6; m++) h += sc.J[6 * m + i] * sc.LJ[6 * m + j];
+    H[idx] = h;
+  }
+  __syncwarp();
 }
 __device__ __noinline__ bool horn_from_sums_ool(const double* a, double n, double* T) { return horn_from_sums(a, n, T); }
 
@@ -828,19 +848,13 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
         const uint32_t i = idx / 6, j = idx % 6, r = i < j ? i : j, c = i < j ? j : i;
         S.H[idx] = sc.tot[r * 6 - (r * (r - 1)) / 2 + (c - r)];
       }
+      if (lane < 6) sc.g[lane] = sc.tot[21 + lane];
       __syncwarp();
+      if (P.has_prior) prior_add_warp(P, sT, S.H, sc);  // (warp-uniform branch)
       if (lane == 0) {
         double g[6];
 #pragma unroll
-        for (int i = 0; i < 6; i++) g[i] = sc.tot[21 + i];
-        if (P.has_prior) {
-          double gs[6];
-#pragma unroll
-          for (int i = 0; i < 6; i++) gs[i] = g[i];
-          prior_add(P, sT, S.H, gs);
-#pragma unroll
-          for (int i = 0; i < 6; i++) g[i] = gs[i];
-        }
+        for (int i = 0; i < 6; i++) g[i] = sc.g[i];
         S.have_H = 1;
         double H[36], mg[6], delta[6];
 #pragma unroll

@@ -1371,6 +1371,34 @@ int32_t mlo_voxel_index(float coord, float voxel_size) { return voxel_index_map(
 void mlo_se3_exp(const double xi[6], double pose[12]) { se3_exp(xi, pose); }
 void mlo_se3_log(const double pose[12], double xi[6]) { se3_log(pose, xi); }
 void mlo_se3_right_jacobian_inv(const double xi[6], double J[36]) { se3_right_jacobian_inv(xi, J); }
+void mlo_cov_tangent_to_ypr(const double T[12], const double cov[36], double out[36]) {
+  // T' = T exp(eps): t' = t + R v, R' = R exp(w^).  Euler rates of R = Rz(yaw) Ry(pitch) Rx(roll) from the body rate w:
+  //   yaw' = (wy sr + wz cr) / cp,  pitch' = wy cr - wz sr,  roll' = wx + (wy sr + wz cr) tp
+  const double pitch = std::atan2(-T[8], std::hypot(T[0], T[4])), roll = std::atan2(T[9], T[10]);
+  const double sr = std::sin(roll), cr = std::cos(roll);
+  double cp = std::cos(pitch);
+  if (std::fabs(cp) < 1e-9) cp = cp < 0 ? -1e-9 : 1e-9;  // gimbal lock: the chart itself is singular there
+  const double tp = std::sin(pitch) / cp;
+  double J[36] = {0};
+  for (int r = 0; r < 3; r++)
+    for (int k = 0; k < 3; k++) J[6 * r + k] = T[4 * r + k];
+  J[6 * 3 + 4] = sr / cp; J[6 * 3 + 5] = cr / cp;
+  J[6 * 4 + 4] = cr;      J[6 * 4 + 5] = -sr;
+  J[6 * 5 + 3] = 1.0;     J[6 * 5 + 4] = sr * tp;  J[6 * 5 + 5] = cr * tp;
+  double JC[36];
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double s = 0;
+      for (int m = 0; m < 6; m++) s += J[6 * i + m] * cov[6 * m + j];
+      JC[6 * i + j] = s;
+    }
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double s = 0;
+      for (int m = 0; m < 6; m++) s += JC[6 * i + m] * J[6 * j + m];
+      out[6 * i + j] = s;
+    }
+}
 
 // ------------------------------------------------------------------ map
 int mlo_map_create(mlo_ctx* c, const mlo_map_params* p, mlo_map** out) {

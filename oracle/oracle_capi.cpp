@@ -213,6 +213,39 @@ void orc_icp_align(void* map, const float* local, uint32_t stride, uint64_t n, c
 // SE(3) helpers exposed for known-answer tests
 void orc_se3_exp(const double* xi, double* pose) { se3_exp(xi).to3x4(pose); }
 void orc_se3_log(const double* pose, double* xi) { se3_log(Pose::from3x4(pose), xi); }
+// Covariance of mp2p_icp::Results::optimal_tf in MRPT's (x y z yaw pitch roll) chart from the tangent-space covariance
+// (consumed at LidarOdometry.cpp:1035-1036): J by central differences of ypr(T exp(eps)), independent of
+// the product's closed form.
+void orc_cov_tangent_to_ypr(const double* pose, const double* cov, double* out) {
+  const Pose T = Pose::from3x4(pose);
+  auto chart = [](const Pose& P, double* v) {
+    v[0] = P.t[0]; v[1] = P.t[1]; v[2] = P.t[2];
+    v[3] = std::atan2(P.R[1][0], P.R[0][0]);
+    v[4] = std::atan2(-P.R[2][0], std::hypot(P.R[0][0], P.R[1][0]));
+    v[5] = std::atan2(P.R[2][1], P.R[2][2]);
+  };
+  double J[36];
+  const double h = 1e-6;
+  for (int k = 0; k < 6; k++) {
+    double e[6] = {0, 0, 0, 0, 0, 0}, a[6], b[6];
+    e[k] = h;
+    chart(compose(T, se3_exp(e)), a);
+    e[k] = -h;
+    chart(compose(T, se3_exp(e)), b);
+    for (int i = 0; i < 6; i++) {
+      double d = a[i] - b[i];
+      if (i >= 3) d = std::remainder(d, 2.0 * M_PI);
+      J[6 * i + k] = d / (2.0 * h);
+    }
+  }
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j < 6; j++) {
+      double s = 0;
+      for (int m = 0; m < 6; m++)
+        for (int n = 0; n < 6; n++) s += J[6 * i + m] * cov[6 * m + n] * J[6 * j + n];
+      out[6 * i + j] = s;
+    }
+}
 void orc_pose_minus(const double* a, const double* b, double* out) {
   minus(Pose::from3x4(a), Pose::from3x4(b)).to3x4(out);
 }

@@ -51,6 +51,7 @@ def lib():
                                     _vp, _u32]
         L.orc_se3_exp.argtypes = [_vp, _vp]
         L.orc_se3_log.argtypes = [_vp, _vp]
+        L.orc_cov_tangent_to_ypr.argtypes = [_vp, _vp, _vp]
         L.orc_pose_minus.argtypes = [_vp, _vp, _vp]
         L.orc_pose_compose.argtypes = [_vp, _vp, _vp]
         L.orc_horn.restype = C.c_int
@@ -82,6 +83,13 @@ def se3_log(pose):
     p = _pose(pose)
     out = np.empty(6)
     lib().orc_se3_log(p.ctypes.data, out.ctypes.data)
+    return out
+
+
+def cov_tangent_to_ypr(pose, cov):
+    p, c = _pose(pose), np.ascontiguousarray(cov, dtype=np.float64).reshape(6, 6)
+    out = np.empty((6, 6))
+    lib().orc_cov_tangent_to_ypr(p.ctypes.data, c.ctypes.data, out.ctypes.data)
     return out
 
 
