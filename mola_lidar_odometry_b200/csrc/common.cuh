@@ -29,9 +29,26 @@ constexpr uint32_t MAP_COUNTERS = 8;  // u32 words of MapDev::counters (map.cuh)
 
 // mola::HashedVoxelPointCloud::coordToGlobalIdx (pipelines/lidar3d-default.yaml:233 voxel_size):
 // static_cast<int32_t>(coord * voxel_size_inv), truncation toward zero.
-MLO_HD int32_t voxel_index_map(float coord, float inv_voxel) { return static_cast<int32_t>(coord * inv_voxel); }
+// [VERIFY] conventions that decide discrete results and could not be checked against upstream's source (SURVEY.md
+// Appendix A) are switchable per context - mlo_set_option("convention_*") - and mirrored by the oracle
+// (oracle/mlo_oracle.hpp conv()): index rounding 0 = truncation toward zero (default), 1 = floor; Geman-McClure weight
+// 0 = c^4/(c^2+e^2)^2 (default), 1 = c^2/(c^2+e^2)^2; cull metric 0 = max-norm in cells (default), 1 = L1 in cells,
+// 2 = Euclidean in cells.  The parity tests run under both settings of each.
+MLO_HD int32_t voxel_index_map(float coord, float inv_voxel, int floor_mode = 0) {
+  const float v = coord * inv_voxel;
+  return floor_mode ? static_cast<int32_t>(floorf(v)) : static_cast<int32_t>(v);
+}
+MLO_HD bool cull_out_of_range(int32_t dx, int32_t dy, int32_t dz, int32_t d, int metric) {
+  const int32_t ax = dx < 0 ? -dx : dx, ay = dy < 0 ? -dy : dy, az = dz < 0 ? -dz : dz;
+  if (metric == 1) return int64_t(ax) + ay + az > d;
+  if (metric == 2) return int64_t(ax) * ax + int64_t(ay) * ay + int64_t(az) * az > int64_t(d) * d;
+  return ax > d || ay > d || az > d;
+}
 // mp2p_icp_filters::FilterDecimateVoxels grid index (default.yaml:289,316): static_cast<int32_t>(coord / resolution)
-MLO_HD int32_t voxel_index_filter(float coord, float resolution) { return static_cast<int32_t>(coord / resolution); }
+MLO_HD int32_t voxel_index_filter(float coord, float resolution, int floor_mode = 0) {
+  const float v = coord / resolution;
+  return floor_mode ? static_cast<int32_t>(floorf(v)) : static_cast<int32_t>(v);
+}
 
 MLO_HD bool key_in_range(int32_t k) { return k > -KEY_BIAS && k < KEY_BIAS - 1; }
 MLO_HD uint64_t pack_key(int32_t kx, int32_t ky, int32_t kz) {

@@ -35,6 +35,7 @@ struct DecimJob {
   uint32_t n_in_static;    // input size when n_in_dev == nullptr
   const uint32_t* n_in_dev;  // input size produced on device by the previous stage
   float resolution;
+  int32_t index_floor;     // [VERIFY] convention: grid index = floor instead of truncation (common.cuh)
   uint32_t min_pts;        // minimum_input_points_to_filter: below it the cloud passes through undecimated
   PointPred pre;           // applied BEFORE the decimation (mlo_voxel_decimate_first with range / bbox)
   PointPred post;          // applied to the decimated points (the 1st-pass pipeline: by-range and bbox sit AFTER the
@@ -127,8 +128,8 @@ __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_claim(const DecimJob* __r
     if (i < n) {
       pred[u] = predicate_keep(j.pre, p[u].x, p[u].y, p[u].z);
       if (pred[u]) {
-        const int32_t kx = voxel_index_filter(p[u].x, j.resolution), ky = voxel_index_filter(p[u].y, j.resolution),
-                      kz = voxel_index_filter(p[u].z, j.resolution);
+        const int32_t kx = voxel_index_filter(p[u].x, j.resolution, j.index_floor), ky = voxel_index_filter(p[u].y, j.resolution, j.index_floor),
+                      kz = voxel_index_filter(p[u].z, j.resolution, j.index_floor);
         if (key_in_range(kx) && key_in_range(ky) && key_in_range(kz)) {
           key[u] = pack_key(kx, ky, kz);
           h[u] = hash_cell(kx, ky, kz) & j.tab_mask;

@@ -74,11 +74,15 @@ MLO_D double table_at(const double* t, uint32_t len, uint32_t it) {
   return t[it < len ? it : len - 1];
 }
 
+// `kernel` carries the [VERIFY] form of the Geman-McClure weight in bit 8 (IcpProblem::robust_kernel, set by the host
+// from mlo_set_option("convention_gm_form")): 0 = c^4/(c^2+e^2)^2, 1 = c^2/(c^2+e^2)^2.
+constexpr int KERNEL_GM_FORM_BIT = 0x100;
 MLO_D double robust_weight(int kernel, double e2, double c) {
-  if (kernel == MLO_KERNEL_GEMAN_MCCLURE) {
+  if ((kernel & 0xFF) == MLO_KERNEL_GEMAN_MCCLURE) {
     const double c2 = c * c, d = e2 + c2;
-    return (c2 * c2) / (d * d);
+    return (kernel & KERNEL_GM_FORM_BIT) ? c2 / (d * d) : (c2 * c2) / (d * d);
   }
+  kernel &= 0xFF;
   if (kernel == MLO_KERNEL_CAUCHY) return 1.0 / (1.0 + e2 / (c * c));
   return 1.0;
 }
@@ -492,9 +496,9 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
     int32_t kq[3] = {0, 0, 0};
     bool active = false;
     if (want) {
-      kq[0] = voxel_index_map(gx, map.inv_voxel);
-      kq[1] = voxel_index_map(gy, map.inv_voxel);
-      kq[2] = voxel_index_map(gz, map.inv_voxel);
+      kq[0] = voxel_index_map(gx, map.inv_voxel, map.index_floor);
+      kq[1] = voxel_index_map(gy, map.inv_voxel, map.index_floor);
+      kq[2] = voxel_index_map(gz, map.inv_voxel, map.index_floor);
       active = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
     }
     // ---- phase 1: probes (thread per query), words -> shared memory
@@ -527,7 +531,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       const unsigned long long b0 = ws.best[lane];
       const float bound = (b0 == ~0ull) ? __int_as_float(0x7f800000) : __uint_as_float(uint32_t(b0 >> 32));
       const float qv[3] = {gx, gy, gz};
-      const AxisGaps gaps = axis_gaps(map.voxel_size, qv, kq);
+      const AxisGaps gaps = axis_gaps(map.voxel_size, qv, kq, map.index_floor);
 #pragma unroll
       for (int e = 0; e < 27; e++) {
         if (e == 13) continue;

@@ -231,9 +231,9 @@ __device__ __noinline__ uint32_t block_match(BlockShared<NT>& sh, const double* 
     if (mine) {
       const float4 l = __ldg(&local[qb + q]);
       compose_point_f(sT, l.x, l.y, l.z, gx, gy, gz);
-      kq[0] = voxel_index_map(gx, map.inv_voxel);
-      kq[1] = voxel_index_map(gy, map.inv_voxel);
-      kq[2] = voxel_index_map(gz, map.inv_voxel);
+      kq[0] = voxel_index_map(gx, map.inv_voxel, map.index_floor);
+      kq[1] = voxel_index_map(gy, map.inv_voxel, map.index_floor);
+      kq[2] = voxel_index_map(gz, map.inv_voxel, map.index_floor);
       active = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
     }
     sh.q[0][tid] = gx;
@@ -271,7 +271,7 @@ __device__ __noinline__ uint32_t block_match(BlockShared<NT>& sh, const double* 
       const unsigned long long b0 = sh.best[tid];
       const float bound = (b0 == ~0ull) ? __int_as_float(0x7f800000) : __uint_as_float(uint32_t(b0 >> 32));
       const float qv[3] = {gx, gy, gz};
-      const AxisGaps gaps = axis_gaps(map.voxel_size, qv, kq);
+      const AxisGaps gaps = axis_gaps(map.voxel_size, qv, kq, map.index_floor);
 #pragma unroll
       for (int e = 0; e < 27; e++) {
         if (e == 13) continue;

@@ -54,6 +54,8 @@ struct MapDev {
   float eig_ratio;
   uint32_t min_pts_plane;
   int32_t kind;
+  int32_t index_floor;  // [VERIFY] convention: voxel index = floor instead of truncation (common.cuh)
+  int32_t cull_metric;  // [VERIFY] convention: metric of remove_voxels_farther_than
 };
 
 // Read-only bucket fetch: two 16-byte loads of one sector (ld.global.nc).
@@ -229,8 +231,8 @@ MLO_D void insert_link_point(const MapDev& m, const float* __restrict__ src, uin
   const float* p = src + size_t(i) * stride;
   float gx, gy, gz;
   compose_point_f(T.m, p[0], p[1], p[2], gx, gy, gz);
-  const int32_t kx = voxel_index_map(gx, m.inv_voxel), ky = voxel_index_map(gy, m.inv_voxel),
-                kz = voxel_index_map(gz, m.inv_voxel);
+  const int32_t kx = voxel_index_map(gx, m.inv_voxel, m.index_floor), ky = voxel_index_map(gy, m.inv_voxel, m.index_floor),
+                kz = voxel_index_map(gz, m.inv_voxel, m.index_floor);
   g_out[i] = make_float4(gx, gy, gz, 0.f);
   if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) {
     atomicOr(&m.counters[2], ERR_KEY_RANGE);
@@ -348,7 +350,7 @@ __global__ void k_rebuild(MapDev src, MapDev dst, uint64_t n_buckets, int32_t sx
     const uint32_t w = b.cell[sub];
     if (w == CELL_ABSENT || w == CELL_PENDING) continue;
     const int32_t kz = kzq * 4 + sub;
-    if (use_filter && (abs(kx - sx) > d || abs(ky - sy) > d || abs(kz - sz) > d)) continue;
+    if (use_filter && cull_out_of_range(kx - sx, ky - sy, kz - sz, d, src.cull_metric)) continue;
     const uint32_t cnt = cell_cnt(w), ov = cell_vid(w);
     const uint64_t c = find_or_insert_cell(dst, kx, ky, kz);
     if (c == ~0ull) continue;
@@ -376,7 +378,7 @@ MLO_D void cull_voxel(const MapDev& m, uint32_t v, int32_t sx, int32_t sy, int32
   if (key == KEY_EMPTY) return;
   int32_t kx, ky, kz;
   unpack_key(key, kx, ky, kz);
-  if (!(abs(kx - sx) > d || abs(ky - sy) > d || abs(kz - sz) > d)) return;
+  if (!cull_out_of_range(kx - sx, ky - sy, kz - sz, d, m.cull_metric)) return;
   const unsigned long long ck = column_key(kx, ky, kz);
   uint64_t h = uint64_t(hash_packed(ck)) & m.mask;
   for (uint64_t probes = 0; probes <= m.mask; probes++) {
@@ -444,21 +446,21 @@ MLO_D BucketRO load_bucket256(const MapDev& m, uint64_t b) {
 struct AxisGaps {
   float g2[3][3];
 };
-MLO_D AxisGaps axis_gaps(float vs, const float qv[3], const int32_t kq[3]) {
+MLO_D AxisGaps axis_gaps(float vs, const float qv[3], const int32_t kq[3], int floor_mode = 0) {
   AxisGaps g;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
     g.g2[a][1] = 0.f;
     {  // dd = +1: lower face of cell kq+1
       const int32_t cc = kq[a] + 1;
-      const float edge = cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs);
+      const float edge = floor_mode ? float(cc) * vs : (cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs));
       float gap = edge - qv[a];
       gap -= 4e-6f * (fabsf(edge) + vs);
       g.g2[a][2] = gap > 0.f ? gap * gap : 0.f;
     }
     {  // dd = -1: upper face of cell kq-1
       const int32_t cc = kq[a] - 1;
-      const float edge = cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs);
+      const float edge = floor_mode ? float(cc + 1) * vs : (cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs));
       float gap = qv[a] - edge;
       gap -= 4e-6f * (fabsf(edge) + vs);
       g.g2[a][0] = gap > 0.f ? gap * gap : 0.f;
@@ -472,7 +474,7 @@ MLO_D AxisGaps axis_gaps(float vs, const float qv[3], const int32_t kq[3]) {
 // point stored in that cell.  Cell boxes follow the truncation-toward-zero index: cell 0 spans (-vs, vs),
 // cell c > 0 spans [c vs, (c+1) vs), cell c < 0 spans ((c-1) vs, c vs]; faces are pulled in by a few ulps
 // so a coordinate that rounds across a face is never excluded.
-MLO_D float cell_lower_bound2(float vs, const float qv[3], const int32_t kq[3], const int32_t dd[3]) {
+MLO_D float cell_lower_bound2(float vs, const float qv[3], const int32_t kq[3], const int32_t dd[3], int floor_mode = 0) {
   float lb2 = 0.f;
 #pragma unroll
   for (int a = 0; a < 3; a++) {
@@ -480,10 +482,10 @@ MLO_D float cell_lower_bound2(float vs, const float qv[3], const int32_t kq[3], 
     const int32_t cc = kq[a] + dd[a];
     float edge, gap;
     if (dd[a] > 0) {  // lower face of cell cc
-      edge = cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs);
+      edge = floor_mode ? float(cc) * vs : (cc > 0 ? float(cc) * vs : (cc == 0 ? -vs : float(cc - 1) * vs));
       gap = edge - qv[a];
     } else {  // upper face of cell cc
-      edge = cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs);
+      edge = floor_mode ? float(cc + 1) * vs : (cc > 0 ? float(cc + 1) * vs : (cc == 0 ? vs : float(cc) * vs));
       gap = qv[a] - edge;
     }
     gap -= 4e-6f * (fabsf(edge) + vs);
@@ -607,7 +609,7 @@ MLO_D NNHit nn_scan_words(const MapDev& m, float qx, float qy, float qz, const i
   // Each lane walks ITS OWN compacted list of candidate cells (bit e of `todo`), so one warp iteration
   // serves every lane's k-th visited cell: the trip count is max-over-lanes of cells visited, not the
   // union of cells any lane visits.
-  const AxisGaps gaps = axis_gaps(m.voxel_size, qv, kq);
+  const AxisGaps gaps = axis_gaps(m.voxel_size, qv, kq, m.index_floor);
   uint32_t todo = 0;
 #pragma unroll
   for (int e = 0; e < 27; e++) {
@@ -626,8 +628,8 @@ MLO_D NNHit nn_scan_words(const MapDev& m, float qx, float qy, float qz, const i
 }
 
 MLO_D NNHit nn_single_thread(const MapDev& m, float qx, float qy, float qz, uint32_t* ws, uint32_t wstride) {
-  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel),
-                         voxel_index_map(qz, m.inv_voxel)};
+  const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel, m.index_floor), voxel_index_map(qy, m.inv_voxel, m.index_floor),
+                         voxel_index_map(qz, m.inv_voxel, m.index_floor)};
   if (!(key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]))) {
     NNHit r;
     r.x = r.y = r.z = 0.f;
@@ -661,8 +663,8 @@ struct WarpProbe {
 MLO_D WarpProbe warp_probe_issue(const MapDev& m, float qx, float qy, float qz) {
   const uint32_t lane = threadIdx.x & 31u;
   WarpProbe p;
-  const int32_t kx = voxel_index_map(qx, m.inv_voxel), ky = voxel_index_map(qy, m.inv_voxel),
-                kz = voxel_index_map(qz, m.inv_voxel);
+  const int32_t kx = voxel_index_map(qx, m.inv_voxel, m.index_floor), ky = voxel_index_map(qy, m.inv_voxel, m.index_floor),
+                kz = voxel_index_map(qz, m.inv_voxel, m.index_floor);
   p.kz = kz;
   p.in_range = key_in_range(kx) && key_in_range(ky) && key_in_range(kz);
   const uint32_t col = lane >> 1, half = lane & 1u;
@@ -742,10 +744,10 @@ MLO_D NNHit warp_nn_finish(const MapDev& m, WarpProbe& p, float qx, float qy, fl
   }
   bool visit = my_cnt > 0 && lane != 13;
   if (visit && bound < __int_as_float(0x7f800000)) {
-    const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel), voxel_index_map(qy, m.inv_voxel), p.kz};
+    const int32_t kq[3] = {voxel_index_map(qx, m.inv_voxel, m.index_floor), voxel_index_map(qy, m.inv_voxel, m.index_floor), p.kz};
     const float qv[3] = {qx, qy, qz};
     const int32_t dd[3] = {int32_t(lane / 9) - 1, int32_t((lane / 3) % 3) - 1, int32_t(lane % 3) - 1};
-    visit = cell_lower_bound2(m.voxel_size, qv, kq, dd) <= bound;  // one cell per lane: the direct form
+    visit = cell_lower_bound2(m.voxel_size, qv, kq, dd, m.index_floor) <= bound;  // one cell per lane: the direct form
   }
   uint32_t occ = __ballot_sync(FULL, visit);
   while (occ) {
@@ -816,8 +818,8 @@ MLO_D PlaneHit nn_plane_thread(const MapDev& m, float qx, float qy, float qz) {
   r.dist = __int_as_float(0x7f800000);
   r.found = 0;
   r.ncand = 0;
-  const int32_t kx = voxel_index_map(qx, m.inv_voxel), ky = voxel_index_map(qy, m.inv_voxel),
-                kz = voxel_index_map(qz, m.inv_voxel);
+  const int32_t kx = voxel_index_map(qx, m.inv_voxel, m.index_floor), ky = voxel_index_map(qy, m.inv_voxel, m.index_floor),
+                kz = voxel_index_map(qz, m.inv_voxel, m.index_floor);
   if (!(key_in_range(kx) && key_in_range(ky) && key_in_range(kz))) return r;
 #pragma unroll 1
   for (int dx = -1; dx <= 1; dx++)

@@ -118,6 +118,7 @@ struct mlo_ctx {
   // profiles/README.md), so the default is "everything in one group".
   int filter_group_mb = 1 << 20;
   int filter_ppt = 4;  // mlo_set_option("filter_ppt"): input points per thread of the decimation kernels (1 / 2 / 4)
+  int conv_index_floor = 0, conv_gm_form = 0, conv_cull_metric = 0;  // [VERIFY] conventions (common.cuh), captured by maps at creation
   int last_align_path = 0, last_stream_groups = 0, last_tail_handover = 0;  // what the last align call did (tests)
   uint64_t large_batch_queries = 0;  // 0 = auto (sm_count * 1024): batches at or above it take the launch sequence
   int tpq_min_queries_per_sm = 512;  // MLO_TPQ_MIN: below this many queries per SM the warp-per-query chunks win
@@ -307,6 +308,8 @@ int alloc_map_buffers(mlo_ctx* c, const mlo_map_params& p, uint64_t table_size, 
   d.eig_ratio = p.max_eigen_ratio_for_planes;
   d.min_pts_plane = p.min_points_for_plane ? p.min_points_for_plane : 5;
   d.kind = p.kind;
+  d.index_floor = c->conv_index_floor;
+  d.cull_metric = c->conv_cull_metric;
   d.mask = table_size - 1;
   CU(c, cudaMallocAsync(&d.buckets, table_size * sizeof(Bucket), c->stream));
   CU(c, cudaMallocAsync(&d.pts, size_t(p.capacity_voxels) * d.row * sizeof(float4), c->stream));
@@ -401,6 +404,8 @@ int map_rebuild(mlo_map* m, bool use_filter, int32_t sx, int32_t sy, int32_t sz,
   if (!m->alt_ready) {
     int rc = alloc_map_buffers(c, m->prm, m->table_size, m->alt);
     if (rc != MLO_OK) return rc;
+    m->alt.index_floor = m->dev.index_floor;  // (a map keeps the conventions it was created with)
+    m->alt.cull_metric = m->dev.cull_metric;
     m->alt_ready = true;
   }
   int rc = clear_map_buffers(c, m->alt, m->table_size);
@@ -434,6 +439,8 @@ int map_ensure_capacity(mlo_map* m, uint64_t n_new_points) {
   }
   MapDev nd{};
   int rc = alloc_map_buffers(c, np, new_table, nd);
+  nd.index_floor = m->dev.index_floor;  // (a map keeps the conventions it was created with)
+  nd.cull_metric = m->dev.cull_metric;
   if (rc == MLO_OK) rc = clear_map_buffers(c, nd, new_table);
   if (rc != MLO_OK) return rc;
   LAUNCH(c, k_rebuild, uint32_t((m->table_size + 255) / 256), 256, m->dev, nd, m->table_size, 0, 0, 0, 0, 0);
@@ -595,6 +602,7 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
       j1.in_t = d_t ? d_t + offsets[b] : nullptr;
       j1.in_stride = stride;
       j1.n_in_static = n;
+      j1.index_floor = j2.index_floor = c->conv_index_floor;
       j1.resolution = fps[b].for_map.voxel_filter_resolution;
       j1.min_pts = fps[b].for_map.minimum_input_points_to_filter;
       j1.npred = cnt + b * CNT_STRIDE + 3;
@@ -905,7 +913,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     P.solver = p.solver;
     P.gn_max_iterations = std::max<uint32_t>(1, p.gn_max_iterations);
     P.gn_min_delta = p.gn_min_delta;
-    P.robust_kernel = p.robust_kernel;
+    P.robust_kernel = p.robust_kernel | (c->conv_gm_form ? KERNEL_GM_FORM_BIT : 0);
     P.matcher_mask = p.matcher_mask;
     any_planes = any_planes || (p.matcher_mask & MLO_MATCHER_PT2PL);
     P.table_len = p.table_len;
@@ -1337,6 +1345,9 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "pers_minb") c->pers_minb = v == 2 ? 2 : (v == 4 ? 4 : 0);
   else if (n == "filter_group_mb") c->filter_group_mb = int(std::max<int64_t>(1, v));
   else if (n == "filter_ppt") c->filter_ppt = int(v);
+  else if (n == "convention_index_floor") c->conv_index_floor = v != 0;
+  else if (n == "convention_gm_form") c->conv_gm_form = v != 0;
+  else if (n == "convention_cull_metric") c->conv_cull_metric = int(std::min<int64_t>(2, std::max<int64_t>(0, v)));
   else return fail(c, MLO_ERR_INVALID_ARG, "unknown option: " + n);
   return MLO_OK;
 }
@@ -1359,6 +1370,9 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   else if (n == "pers_minb") *out = c->pers_minb;
   else if (n == "filter_group_mb") *out = c->filter_group_mb;
   else if (n == "filter_ppt") *out = c->filter_ppt;
+  else if (n == "convention_index_floor") *out = c->conv_index_floor;
+  else if (n == "convention_gm_form") *out = c->conv_gm_form;
+  else if (n == "convention_cull_metric") *out = c->conv_cull_metric;
   else if (n == "last_align_path") *out = c->last_align_path;
   else if (n == "last_stream_groups") *out = c->last_stream_groups;
   else if (n == "last_tail_handover") *out = c->last_tail_handover;
@@ -1488,8 +1502,8 @@ int mlo_map_cull(mlo_map* m, const double sensor[3], float dist) {
   mlo_ctx* c = m->ctx;
   DeviceGuard g(c->device);
   const float inv = m->dev.inv_voxel;
-  const int32_t sx = voxel_index_map(float(sensor[0]), inv), sy = voxel_index_map(float(sensor[1]), inv),
-                sz = voxel_index_map(float(sensor[2]), inv);
+  const int32_t sx = voxel_index_map(float(sensor[0]), inv, m->dev.index_floor), sy = voxel_index_map(float(sensor[1]), inv, m->dev.index_floor),
+                sz = voxel_index_map(float(sensor[2]), inv, m->dev.index_floor);
   const int32_t d = int32_t(std::ceil(dist * inv));
   const size_t e0 = prof_begin(c);
   int rc = map_cull_device(m, sx, sy, sz, d, 0);
@@ -1936,8 +1950,8 @@ int mlo_scan_register(mlo_ctx* c, mlo_map* map, const float* raw, uint32_t strid
     if (cull_farther_than > 0.f) {
       const double s[3] = {out->pose_3x4[3], out->pose_3x4[7], out->pose_3x4[11]};
       const float inv = map->dev.inv_voxel;
-      rc = map_cull_device(map, voxel_index_map(float(s[0]), inv), voxel_index_map(float(s[1]), inv),
-                           voxel_index_map(float(s[2]), inv), int32_t(std::ceil(cull_farther_than * inv)), nmap[0]);
+      rc = map_cull_device(map, voxel_index_map(float(s[0]), inv, map->dev.index_floor), voxel_index_map(float(s[1]), inv, map->dev.index_floor),
+                           voxel_index_map(float(s[2]), inv, map->dev.index_floor), int32_t(std::ceil(cull_farther_than * inv)), nmap[0]);
       if (rc != MLO_OK) return rc;
     }
     prof_end(c, 2, e0);
@@ -2239,9 +2253,9 @@ int mlo_scanset_insert(mlo_scanset* set, uint32_t n_jobs, const mlo_insert_job* 
     d.sx = d.sy = d.sz = 0;
     if (jobs[j].cull_farther_than > 0.f) {
       const float inv = m->dev.inv_voxel;
-      d.sx = voxel_index_map(float(jobs[j].pose_3x4[3]), inv);
-      d.sy = voxel_index_map(float(jobs[j].pose_3x4[7]), inv);
-      d.sz = voxel_index_map(float(jobs[j].pose_3x4[11]), inv);
+      d.sx = voxel_index_map(float(jobs[j].pose_3x4[3]), inv, m->dev.index_floor);
+      d.sy = voxel_index_map(float(jobs[j].pose_3x4[7]), inv, m->dev.index_floor);
+      d.sz = voxel_index_map(float(jobs[j].pose_3x4[11]), inv, m->dev.index_floor);
       d.d = int32_t(std::ceil(jobs[j].cull_farther_than * inv));
       any_cull = true;  // the cull pass only has to visit voxel ids below the high-water mark after this insert
       max_cap = std::max<uint32_t>(max_cap, uint32_t(std::min<uint64_t>(m->dev.capacity_voxels, m->hwm + sl.n_map)));

@@ -40,15 +40,33 @@ namespace orc {
 // ---------------------------------------------------------------- switchable discrete choices
 // mola::HashedVoxelPointCloud::coordToGlobalIdx: static_cast<int32_t>(coord * voxel_size_inv),
 // truncation toward zero (SURVEY.md A.3 [VERIFY trunc vs floor]).
-inline int32_t voxel_index_map(float coord, float inv_voxel) { return static_cast<int32_t>(coord * inv_voxel); }
+// The [VERIFY] choices are switchable at run time (orc_set_conventions) and mirrored by the product
+// (mlo_set_option "convention_*"): whoever checks upstream's source flips a flag on both sides; the parity tests run
+// under both settings of each.  Defaults = the readings recorded in SURVEY.md Appendix A.
+struct Conventions {
+  int index_floor = 0;  // 0: static_cast<int32_t>(x) (truncation toward zero), 1: floor
+  int gm_form = 0;      // 0: c^4/(c^2+e^2)^2, 1: c^2/(c^2+e^2)^2
+  int cull_metric = 0;  // 0: max-norm in cells, 1: L1 in cells, 2: Euclidean in cells
+};
+inline Conventions& conv() {
+  static Conventions c;
+  return c;
+}
+inline int32_t voxel_index_map(float coord, float inv_voxel) {
+  const float v = coord * inv_voxel;
+  return conv().index_floor ? static_cast<int32_t>(std::floor(v)) : static_cast<int32_t>(v);
+}
 // mp2p_icp_filters::PointCloudToVoxelGridSingle: static_cast<int32_t>(coord / resolution)
 // (SURVEY.md A.6 [VERIFY]).
-inline int32_t voxel_index_filter(float coord, float resolution) { return static_cast<int32_t>(coord / resolution); }
+inline int32_t voxel_index_filter(float coord, float resolution) {
+  const float v = coord / resolution;
+  return conv().index_floor ? static_cast<int32_t>(std::floor(v)) : static_cast<int32_t>(v);
+}
 // mp2p_icp robust kernel GemanMcClure: w(e^2) = c^4 / (c^2 + e^2)^2   (SURVEY.md A.4 [VERIFY])
 inline double geman_mcclure_weight(double err_sqr, double c) {
   const double c2 = c * c;
   const double d = err_sqr + c2;
-  return (c2 * c2) / (d * d);
+  return conv().gm_form ? c2 / (d * d) : (c2 * c2) / (d * d);
 }
 inline double cauchy_weight(double err_sqr, double c) { return 1.0 / (1.0 + err_sqr / (c * c)); }
 
@@ -192,7 +210,10 @@ class VoxelMap {
   // insertOpts.remove_voxels_farther_than (default.yaml:238; SURVEY.md A.3 [VERIFY metric]):
   // max-norm in cells against ceil(dist * voxel_size_inv).
   static bool cull_keep(int32_t kx, int32_t ky, int32_t kz, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
-    return std::abs(kx - sx) <= d && std::abs(ky - sy) <= d && std::abs(kz - sz) <= d;
+    const int64_t ax = std::abs(kx - sx), ay = std::abs(ky - sy), az = std::abs(kz - sz);
+    if (conv().cull_metric == 1) return ax + ay + az <= d;
+    if (conv().cull_metric == 2) return ax * ax + ay * ay + az * az <= int64_t(d) * d;
+    return ax <= d && ay <= d && az <= d;
   }
   void cull(const double sensor[3], float dist) {
     if (!(dist > 0.f)) return;

@@ -211,6 +211,11 @@ void orc_icp_align(void* map, const float* local, uint32_t stride, uint64_t n, c
 }
 
 // SE(3) helpers exposed for known-answer tests
+void orc_set_conventions(int index_floor, int gm_form, int cull_metric) {
+  conv().index_floor = index_floor;
+  conv().gm_form = gm_form;
+  conv().cull_metric = cull_metric;
+}
 void orc_se3_exp(const double* xi, double* pose) { se3_exp(xi).to3x4(pose); }
 void orc_se3_log(const double* pose, double* xi) { se3_log(Pose::from3x4(pose), xi); }
 // Covariance of mp2p_icp::Results::optimal_tf in MRPT's (x y z yaw pitch roll) chart from the tangent-space covariance

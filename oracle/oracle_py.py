@@ -86,6 +86,11 @@ def se3_log(pose):
     return out
 
 
+def set_conventions(index_floor=0, gm_form=0, cull_metric=0):
+    """[VERIFY] conventions of the oracle (process-wide): mirror of mlo_set_option('convention_*') on the product side."""
+    lib().orc_set_conventions(int(index_floor), int(gm_form), int(cull_metric))
+
+
 def cov_tangent_to_ypr(pose, cov):
     p, c = _pose(pose), np.ascontiguousarray(cov, dtype=np.float64).reshape(6, 6)
     out = np.empty((6, 6))
