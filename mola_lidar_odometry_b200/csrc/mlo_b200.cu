@@ -741,9 +741,10 @@ int issue_stage_upload(mlo_ctx* c, int slot) {
   st.deferred_src = nullptr;
   const uint64_t total = st.offsets.back();
   const size_t bytes = std::max<size_t>(total * st.stride * sizeof(float), 16);
-  // the slot may still be read by work enqueued earlier on the main stream: order the copy after it
-  CU(c, cudaEventRecord(st.ready, c->stream));
-  CU(c, cudaStreamWaitEvent(c->copy_stream, st.ready, 0));
+  // No ordering against the context stream: the last reader of this slot was the filter of an EARLIER
+  // mlo_scan_register_batch_staged call, and every such call returns only after a stream synchronisation.  (Waiting on
+  // the context stream here would put the copy behind the ICP kernel of the call in progress - the one it is meant to
+  // overlap - on the single-launch align paths.)
   if (st.buf.cap < bytes) {
     CU(c, cudaStreamSynchronize(c->stream));
     CU(c, cudaStreamSynchronize(c->copy_stream));

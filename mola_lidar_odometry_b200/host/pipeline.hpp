@@ -200,10 +200,13 @@ class ICP {
     q.pt2pl_weight = m_pt2pl ? m_pt2pl->weight : 1.0;
     q.threshold_angular_deg = m_pt2pt ? m_pt2pt->thresholdAngularDeg : 0.0;
     // formulas are re-realised per ICP_ITERATION: tabulate them
-    const uint32_t len = std::max<uint32_t>(1, std::min<uint32_t>(p.maxIterations, 64));
-    t1_.assign(len, 0.0);
-    t2_.assign(len, 0.0);
-    t3_.assign(len, 1.0);
+    // (the device reads entry min(it, len - 1): 64 entries cover every formula that has settled by then - the shipped ones
+    // are constant from iteration 20 on; one that still moves at entry 63 is tabulated up to maxIterations)
+    const uint32_t full = std::max<uint32_t>(1, std::min<uint32_t>(p.maxIterations, 300));
+    uint32_t len = std::min<uint32_t>(full, 64);
+    t1_.assign(full, 0.0);
+    t2_.assign(full, 0.0);
+    t3_.assign(full, 1.0);
     if (!source->has("ICP_ITERATION")) source->updateVariable("ICP_ITERATION", 0.0);
     const int it_slot = source->slot("ICP_ITERATION");
     const double saved_it = source->at(it_slot);
@@ -212,7 +215,13 @@ class ICP {
       if (m_pt2pt) t1_[it] = m_pt2pt->threshold.eval(*source);
       if (m_pt2pl) t2_[it] = m_pt2pl->distanceThreshold.eval(*source);
       if (gn) t3_[it] = gn->robustKernelParam.eval(*source);
+      if (it + 1 == len && len < full && len >= 2 &&
+          (t1_[it] != t1_[it - 1] || t2_[it] != t2_[it - 1] || t3_[it] != t3_[it - 1]))
+        len = full;  // still changing: no truncation
     }
+    t1_.resize(len);
+    t2_.resize(len);
+    t3_.resize(len);
     source->set(it_slot, saved_it);
     q.table_len = len;
     q.pt2pt_threshold_by_iter = t1_.data();

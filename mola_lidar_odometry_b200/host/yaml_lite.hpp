@@ -50,7 +50,9 @@ struct YamlNode {
     if (type != Scalar) return d;
     char* e = nullptr;
     const double v = std::strtod(scalar.c_str(), &e);
-    if (e == scalar.c_str()) throw std::runtime_error("yaml: '" + scalar + "' is not a number");
+    while (e && (*e == ' ' || *e == '\t')) e++;
+    // the whole scalar must be the number: '2000*K' or '30 deg' is a formula / a typo, not 2000 or 30
+    if (e == scalar.c_str() || (e && *e != 0)) throw std::runtime_error("yaml: '" + scalar + "' is not a number");
     return v;
   }
   bool boolean(bool d = false) const {
@@ -251,12 +253,12 @@ inline YamlNode parse_block(const std::vector<Line>& L, size_t& i, int indent) {
 }  // namespace detail
 
 inline YamlNode yaml_parse(const std::string& text_in) {
-  const std::string text = detail::expand_env(text_in);
   std::vector<detail::Line> lines;
-  std::istringstream is(text);
+  std::istringstream is(text_in);
   std::string ln;
   while (std::getline(is, ln)) {
-    const std::string s = detail::strip_comment(ln);
+    // comments go first: a ${VAR} mentioned in a comment must not be expanded (nor fail for lack of a default)
+    const std::string s = detail::expand_env(detail::strip_comment(ln));
     const std::string t = detail::trim(s);
     if (t.empty() || t == "---") continue;
     int ind = 0;

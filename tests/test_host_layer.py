@@ -592,3 +592,19 @@ def test_lidar_odometry_gpu_trajectory_with_prior_on_every_scan(ctx, scene, traj
         n_prior += int(a.icp_had_prior)
     assert n_prior == 29
     g.close()
+
+
+def test_yaml_comments_env_and_strict_numbers(built, monkeypatch):
+    """yaml_lite: a ${VAR} without default inside a comment is not expanded; a scalar that only STARTS with a number is
+    refused where a number is required (a formula such as '2000*K' must not be read as 2000)."""
+    from mola_lidar_odometry_b200 import host_api as H
+    from mola_lidar_odometry_b200.api import MloError
+    monkeypatch.delenv("SOME_UNSET_VARIABLE_XYZ", raising=False)
+    y = DEFAULT_YAML.read_text().replace("observations_filter_1st_pass:",
+                                         "# set ${SOME_UNSET_VARIABLE_XYZ} to change this   (comment only)\nobservations_filter_1st_pass:", 1)
+    f = H.filter1(y, 100.0, 100.0)
+    assert f.for_map.voxel_filter_resolution == pytest.approx(max(0.20, 0.55e-2 * 100.0))
+    bad = DEFAULT_YAML.read_text().replace("minimum_input_points_to_filter: 2000", "minimum_input_points_to_filter: 2000*K", 1)
+    assert bad != DEFAULT_YAML.read_text()
+    with pytest.raises(MloError):
+        H.filter1(bad, 100.0, 100.0)
