@@ -245,6 +245,25 @@ int mlo_icp_align_soa(mlo_ctx* ctx, const float* x, const float* y, const float*
                       const mlo_map* global, const double init_pose_3x4[12], const mlo_icp_params* p,
                       mlo_icp_result* out);
 
+/* Per-iteration record of an align call: the content of mp2p_icp's ICP log files (params.generateDebugFiles /
+ * saveIterationDetails, pipelines/lidar3d-default.yaml:177-182; docs/mola_lo_pipelines.rst:239-260) that can be had
+ * without the MRPT serialisation: one record per executed ICP iteration, written by the device as the loop runs.
+ * mlo_icp_log_enable(ctx, n) keeps up to n records per problem for every following align call of the context (0 = off);
+ * mlo_icp_log_read returns those of problem `problem` of the LAST align call, in iteration order. */
+typedef struct mlo_icp_iteration_record {
+  uint32_t iteration;        /* ICP_ITERATION of this record */
+  uint32_t n_pairings;       /* pairings found by the matchers in this iteration */
+  double pose_3x4[12];       /* solution after this iteration's solver step(s) */
+  double threshold_pt2pt;    /* Matcher_Points_DistanceThreshold.threshold realised for this iteration */
+  double threshold_pt2pl;    /* Matcher_Point2Plane.distanceThreshold */
+  double kernel_param;       /* Solver_GaussNewton.robustKernelParam */
+  double step_trans, step_rot; /* the step measure of the stall test (min over prev / prev-prev) */
+  int32_t termination;       /* mlo_term_reason decided after this iteration, MLO_TERM_UNDEFINED = the loop goes on */
+  int32_t pad;
+} mlo_icp_iteration_record;
+int mlo_icp_log_enable(mlo_ctx* ctx, uint32_t max_records_per_problem);
+int mlo_icp_log_read(mlo_ctx* ctx, uint32_t problem, mlo_icp_iteration_record* out, uint32_t max_records, uint32_t* n);
+
 /* B independent aligns against ONE read-only map in one device pass (Monte-Carlo
  * initial poses / independent scans).  Problem b uses local points [offsets[b], offsets[b+1]).
  * `params` has one entry per problem (tables may be shared). */

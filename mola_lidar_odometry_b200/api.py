@@ -80,6 +80,17 @@ class Context:
         self.check(self.lib.mlo_get_option(self.h, name.encode(), C.byref(v)))
         return int(v.value)
 
+    def icp_log_enable(self, max_records: int):
+        """Keep per-iteration records of every following align call (mp2p_icp's ICP log, default.yaml:177-182); 0 = off."""
+        self.check(self.lib.mlo_icp_log_enable(self.h, int(max_records)))
+
+    def icp_log(self, problem: int = 0):
+        n = C.c_uint32()
+        self.check(self.lib.mlo_icp_log_read(self.h, problem, None, 0, C.byref(n)))
+        out = (capi.IcpIterationRecord * max(1, n.value))()
+        self.check(self.lib.mlo_icp_log_read(self.h, problem, out, n.value, C.byref(n)))
+        return list(out)[:n.value]
+
     def profile_enable(self, on: bool = True):
         self.check(self.lib.mlo_profile_enable(self.h, int(on)))
 

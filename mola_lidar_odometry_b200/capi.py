@@ -66,6 +66,16 @@ class IcpResult(C.Structure):
         return np.array(self.cov_6x6[:], dtype=np.float64).reshape(6, 6)
 
 
+class IcpIterationRecord(C.Structure):
+    _fields_ = [("iteration", C.c_uint32), ("n_pairings", C.c_uint32), ("pose_3x4", C.c_double * 12),
+                ("threshold_pt2pt", C.c_double), ("threshold_pt2pl", C.c_double), ("kernel_param", C.c_double),
+                ("step_trans", C.c_double), ("step_rot", C.c_double), ("termination", C.c_int32), ("pad", C.c_int32)]
+
+    @property
+    def pose(self) -> np.ndarray:
+        return np.array(self.pose_3x4[:], dtype=np.float64).reshape(3, 4)
+
+
 class Profile(C.Structure):
     _fields_ = [("filter_1st_ms", C.c_double), ("run_icp_ms", C.c_double), ("update_local_map_ms", C.c_double),
                 ("nn_kernel_ms", C.c_double), ("nn_kernel_launches", C.c_uint64), ("nn_query_iterations", C.c_uint64),
@@ -199,6 +209,8 @@ _SIGNATURES = {
                                            C.POINTER(_u64)]),
     "mlo_deskew": (C.c_int, [_vp, _vp, _u64, _vp, _vp]),
     "mlo_icp_params_default": (None, [C.POINTER(IcpParams)]),
+    "mlo_icp_log_enable": (C.c_int, [_vp, _u32]),
+    "mlo_icp_log_read": (C.c_int, [_vp, _u32, _vp, _u32, C.POINTER(_u32)]),
     "mlo_icp_align": (C.c_int, [_vp, _vp, _u32, _u64, _vp, _vp, C.POINTER(IcpParams), C.POINTER(IcpResult)]),
     "mlo_icp_align_soa": (C.c_int, [_vp, _vp, _vp, _vp, _u64, _vp, _vp, C.POINTER(IcpParams), C.POINTER(IcpResult)]),
     "mlo_icp_align_batch": (C.c_int, [_vp, _u32, _vp, _u32, _vp, _vp, _vp, _vp, _vp]),

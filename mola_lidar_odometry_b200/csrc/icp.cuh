@@ -48,6 +48,9 @@ struct IcpProblem {
   uint32_t n_blocks_acc;  // blocks of k_accumulate (ICP_BLOCK queries each)
   uint32_t n_blocks_pers; // match chunks of the persistent kernel (its own chunk geometry)
   uint32_t map_idx;       // index into the launch's map table (fleet launches: one local map per sequence)
+  mlo_icp_iteration_record* log;  // per-iteration records of this problem (mlo_icp_log_enable), or nullptr
+  uint32_t log_cap;
+  uint32_t log_pad;
 };
 
 // Fleet launches (independent sequences advanced in lock step) give every problem its own local map: the
@@ -915,6 +918,7 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
       S.inner_pending = 0;
       dt = fmin(dt, dt1);
       dr = fmin(dr, dr1);
+      const uint32_t it_now = S.it;
       if (P.hook_enabled && (tH > P.hook_min_trans || wH > P.hook_min_rot)) {
         S.term = MLO_TERM_HOOK_REQUEST;
         S.done = 1;
@@ -929,6 +933,20 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
         }
       }
       next = S.done ? 0 : 2;
+      if (P.log && it_now < P.log_cap) {  // the ICP log (mlo_icp_log_enable)
+        mlo_icp_iteration_record& r = P.log[it_now];
+        r.iteration = it_now;
+        r.n_pairings = uint32_t(S.n_pairs);
+#pragma unroll
+        for (int k = 0; k < 12; k++) r.pose_3x4[k] = sT[k];
+        r.threshold_pt2pt = table_at(P.thr_pt2pt, P.table_len, it_now);
+        r.threshold_pt2pl = table_at(P.thr_pt2pl, P.table_len, it_now);
+        r.kernel_param = table_at(P.kparam, P.table_len, it_now);
+        r.step_trans = dt;
+        r.step_rot = dr;
+        r.termination = S.done ? S.term : MLO_TERM_UNDEFINED;
+        r.pad = 0;
+      }
     }
   }
   __syncwarp();

@@ -49,7 +49,6 @@ __device__ __noinline__ int solve_core_ool(const IcpProblem& P, IcpState& S, Sol
   return solve_core(P, S, sc, after_match);
 }
 
-constexpr uint32_t BLK_LIST_CAP = 8192;  // segments per drain window
 constexpr uint32_t BLK_MAX_CLUSTER = 8;
 
 template <int NT>
@@ -63,245 +62,320 @@ struct BlockShared {
   double T[12];     // this block's copy of the current pose (written by block 0 after every solve)
   int next;         // ... and of the solve's verdict
   uint32_t it;
-  // match scratch
-  uint32_t words[27][NT];  // packed cell words of each thread's 3x3x3 neighbourhood
-  float q[3][NT];
-  unsigned long long best[NT];
-  uint32_t wsum[NT / 32];
-  uint32_t scan_total;
-  uint16_t list[BLK_LIST_CAP];
+  uint32_t owords[NT / 8][28];  // match scratch: the 27 packed cell words of each octet's query (+1 pad: no bank conflicts)
 };
 
-// mola::NDT nearest-plane query from the 27 packed cell words already probed into shared memory: same visiting
-// order and the same strict '<' as nn_plane_thread, but the 27 hash probes are the batched 256-bit loads of
-// probe_words and the per-voxel means are fetched nine at a time instead of one dependent chain per cell.
-MLO_D PlaneHit nn_plane_words(const MapDev& m, float qx, float qy, float qz, const uint32_t* ws, uint32_t wstride) {
-  PlaneHit r;
-  r.cx = r.cy = r.cz = r.nx = r.ny = r.nz = 0.f;
-  r.dist = __int_as_float(0x7f800000);
-  r.found = 0;
-  r.ncand = 0;
-#pragma unroll 1
-  for (int g = 0; g < 3; g++) {
-    float4 mu[9];
-    uint32_t vid[9];
+// ---- octet-per-query match ------------------------------------------------------------------------------------------
+// Eight lanes share one query, a warp runs four queries at once.  Why this shape (measured, profiles/README.md): with
+// one SM per problem a thread-per-query scan is a chain of dependent round trips (57 us per iteration for 653 queries),
+// and a block-wide work list of 8-point segments costs ~50 instructions per candidate slot (ncu: 3.0 M warp
+// instructions per align, the SM's issue slots are the limit).  Here
+//   probe     the 18 column buckets of the 3x3x3 neighbourhood are spread over the 8 lanes (2-3 independent 256-bit
+//             loads per lane, ~50 instructions per lane instead of ~2000 for one thread doing all 27 cells);
+//   own cell  lane s reads slots s, s+8, s+16, s+24 of the query's own voxel together (one round trip), the octet's
+//             best distance is the pruning bound;
+//   cells     every lane tests the box of up to four neighbour cells against the bound (exact pruning, as everywhere);
+//             the surviving cells are read two at a time, lane s again taking slots s, s+8, ...: ~15 instructions per
+//             candidate, up to 8 loads in flight per lane;
+//   result    arg-min over the octet on (d2, canonical order) = the sequential first-minimum rule, bit for bit.
+// Lane 0 of the octet then owns the pairing: threshold test, record, and - fused - its Gauss-Newton / Horn contribution.
+struct OctetHit {
+  float x, y, z, d2;
+  uint32_t found, ncand;
+};
+MLO_D unsigned long long octet_min_u64(unsigned long long k) {
 #pragma unroll
-    for (int u = 0; u < 9; u++) {
-      const uint32_t w = ws[(g * 9 + u) * wstride];
-      vid[u] = CELL_ABSENT;
-      mu[u] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (w != CELL_ABSENT) {
-        vid[u] = cell_vid(w);
-        mu[u] = __ldg(&m.mean[vid[u]]);
-      }
-    }
+  for (int o = 1; o < 8; o <<= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, k, o);
+    k = other < k ? other : k;
+  }
+  return k;
+}
+MLO_D uint32_t octet_sum_u32(uint32_t v) {
 #pragma unroll
-    for (int u = 0; u < 9; u++) {
-      if (vid[u] == CELL_ABSENT) continue;
-      r.ncand += 2;
-      if (mu[u].w == 0.f) continue;
-      const float4 nr = __ldg(&m.normal[vid[u]]);
-      const float ex = qx - mu[u].x, ey = qy - mu[u].y, ez = qz - mu[u].z;
-      const float d = fabsf(nr.x * ex + nr.y * ey + nr.z * ez);
-      if (d < r.dist) {
-        r.dist = d;
-        r.cx = mu[u].x; r.cy = mu[u].y; r.cz = mu[u].z;
-        r.nx = nr.x; r.ny = nr.y; r.nz = nr.z;
-        r.found = 1;
+  for (int o = 1; o < 8; o <<= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+  return v;
+}
+
+// Probe the neighbourhood of cell kq for this octet's query; the 27 packed words land in `ow` (shared, per octet).
+// Returns (on every lane of the octet) the number of points stored in the 27 cells.  Warp-uniform control flow except the
+// per-lane collision loops.
+MLO_D uint32_t octet_probe(const MapDev& m, const int32_t kq[3], bool in_range, uint32_t* ow) {
+  const uint32_t sub = threadIdx.x & 7u;
+  const int32_t kz = kq[2];
+  const int32_t zq0 = (kz - 1) >> 2, zq1 = (kz + 1) >> 2;
+  BucketRO b[3];
+  uint64_t key[3], h[3];
+  bool act[3];
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    const uint32_t idx = sub + 8u * r;  // probe index = column * 2 + half
+    const uint32_t col = idx >> 1, half = idx & 1u;
+    act[r] = in_range && idx < 18u && (half == 0u || zq1 != zq0);
+    key[r] = pack_key(kq[0] + int32_t(col / 3) - 1, kq[1] + int32_t(col % 3) - 1, half ? zq1 : zq0);
+    h[r] = uint64_t(hash_packed(key[r])) & m.mask;
+    b[r].key = KEY_EMPTY;
+    if (act[r]) b[r] = load_bucket256(m, h[r]);
+  }
+#pragma unroll
+  for (int r = 0; r < 3; r++) {
+    if (act[r]) {
+      while (b[r].key != key[r] && b[r].key != KEY_EMPTY) {  // hash collision: linear probing
+        h[r] = (h[r] + 1) & m.mask;
+        b[r] = load_bucket256(m, h[r]);
       }
     }
   }
+  if (!in_range) {
+#pragma unroll
+    for (int r = 0; r < 4; r++)
+      if (sub + 8u * r < 27u) ow[sub + 8u * r] = CELL_ABSENT;
+  } else {
+#pragma unroll
+    for (int r = 0; r < 3; r++) {
+      const uint32_t idx = sub + 8u * r;
+      if (idx >= 18u) continue;
+      const uint32_t col = idx >> 1, half = idx & 1u;
+      const int32_t myzq = half ? zq1 : zq0;
+      if (half && zq1 == zq0) continue;  // (the column's single bucket was taken by the half-0 probe)
+      const bool have = b[r].key == key[r];
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        const int32_t z = kz - 1 + t;
+        if ((z >> 2) != myzq) continue;
+        const uint32_t sidx = uint32_t(z & 3);
+        uint32_t w = sidx == 0 ? b[r].cell[0] : sidx == 1 ? b[r].cell[1] : sidx == 2 ? b[r].cell[2] : b[r].cell[3];
+        if (!have || w == CELL_PENDING) w = CELL_ABSENT;
+        ow[col * 3 + t] = w;
+      }
+    }
+  }
+  __syncwarp();
+  uint32_t n = 0;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t e = sub + 8u * r;
+    if (e < 27u) {
+      const uint32_t w = ow[e];
+      if (w != CELL_ABSENT) n += cell_cnt(w);
+    }
+  }
+  return octet_sum_u32(n);
+}
+
+// lane-local scan of one cell: slots sub, sub+8, sub+16, sub+24; (d2, order) strict first-minimum
+MLO_D void octet_scan_cell(const MapDev& m, uint32_t w, uint32_t e, float qx, float qy, float qz, float& bd2, uint32_t& bord,
+                           float& bx, float& by, float& bz) {
+  const uint32_t sub = threadIdx.x & 7u;
+  const uint32_t c = cell_cnt(w);
+  const float4* row = m.pts + size_t(cell_vid(w)) * m.row;
+  float4 p[4];
+#pragma unroll
+  for (int r = 0; r < 4; r++)
+    if (sub + 8u * r < c) p[r] = __ldg(row + sub + 8u * r);
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    const uint32_t slot = sub + 8u * r;
+    if (slot < c) {
+      const float d2 = sqr_dist(p[r].x, p[r].y, p[r].z, qx, qy, qz);
+      const uint32_t ord = e * 32u + slot;
+      if (d2 < bd2 || (d2 == bd2 && ord < bord)) {
+        bd2 = d2;
+        bord = ord;
+        bx = p[r].x;
+        by = p[r].y;
+        bz = p[r].z;
+      }
+    }
+  }
+}
+
+// NearestNeighborsCapable::nn_single_search for the octet's query (words already probed).  `want` = this octet has a
+// query to search (warp-uniform loops run for the longest octet of the warp).
+MLO_D OctetHit octet_nn(const MapDev& m, float qx, float qy, float qz, const int32_t kq[3], bool want, const uint32_t* ow) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u, sub = lane & 7u, oshift = lane & 24u;  // first lane of this octet in the warp
+  float bd2 = __int_as_float(0x7f800000), bx = 0.f, by = 0.f, bz = 0.f;
+  uint32_t bord = 0xFFFFFFFFu;
+  // own cell first: its best distance is the pruning bound
+  const uint32_t wh = want ? ow[13] : CELL_ABSENT;
+  if (wh != CELL_ABSENT) octet_scan_cell(m, wh, 13u, qx, qy, qz, bd2, bord, bx, by, bz);
+  float bound = bd2;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) bound = fminf(bound, __shfl_xor_sync(FULL, bound, o));
+  // neighbour cells whose box can still hold a point at distance <= bound
+  uint32_t visit = 0;
+  {
+    const float qv[3] = {qx, qy, qz};
+    const AxisGaps gaps = axis_gaps(m.voxel_size, qv, kq, m.index_floor);
+#pragma unroll
+    for (int r = 0; r < 4; r++) {
+      const uint32_t e = sub + 8u * r;
+      bool pass = false;
+      if (want && e < 27u && e != 13u) {
+        const uint32_t we = ow[e];
+        if (we != CELL_ABSENT && cell_cnt(we) != 0) {
+          const float lb = (gaps.g2[0][e / 9] + gaps.g2[1][(e / 3) % 3] + gaps.g2[2][e % 3]) * 0.99999f;
+          pass = lb <= bound;
+        }
+      }
+      const uint32_t bal = __ballot_sync(FULL, pass);
+      visit |= ((bal >> oshift) & 0xFFu) << (8 * r);
+    }
+  }
+  while (__any_sync(FULL, visit != 0u)) {  // two cells per round: up to 8 row loads in flight per lane
+    uint32_t e0 = 0xFFu, e1 = 0xFFu;
+    if (visit) {
+      e0 = __ffs(visit) - 1;
+      visit &= visit - 1;
+    }
+    if (visit) {
+      e1 = __ffs(visit) - 1;
+      visit &= visit - 1;
+    }
+    if (e0 != 0xFFu) octet_scan_cell(m, ow[e0], e0, qx, qy, qz, bd2, bord, bx, by, bz);
+    if (e1 != 0xFFu) octet_scan_cell(m, ow[e1], e1, qx, qy, qz, bd2, bord, bx, by, bz);
+  }
+  // arg-min over the octet on (d2, canonical order)
+  const unsigned long long mykey = bord == 0xFFFFFFFFu ? ~0ull : ((uint64_t(__float_as_uint(bd2)) << 32) | uint64_t(bord));
+  const unsigned long long best = octet_min_u64(mykey);
+  const uint32_t winners = (__ballot_sync(FULL, mykey == best && best != ~0ull) >> oshift) & 0xFFu;
+  const uint32_t src = oshift + (winners ? uint32_t(__ffs(winners) - 1) : 0u);
+  OctetHit r;
+  r.x = __shfl_sync(FULL, bx, src);
+  r.y = __shfl_sync(FULL, by, src);
+  r.z = __shfl_sync(FULL, bz, src);
+  r.d2 = __uint_as_float(uint32_t(best >> 32));
+  r.found = best != ~0ull;
+  r.ncand = 0;
   return r;
 }
 
-// Block-wide exclusive scan of one value per thread (two barriers); `total` is returned on every thread.
-template <int NT>
-MLO_D uint32_t block_exclusive_scan(uint32_t v, BlockShared<NT>& sh, uint32_t& total) {
-  const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
-  uint32_t incl = v;
+// mola::NDT nearest-plane query for the octet's query: lane s takes cells s, s+8, s+16, s+24; the winner is the smallest
+// (|n.(q - mean)|, canonical order) = the first minimum of the sequential (dx, dy, dz) scan.
+MLO_D PlaneHit octet_plane(const MapDev& m, float qx, float qy, float qz, bool want, const uint32_t* ow) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u, sub = lane & 7u, oshift = lane & 24u;
+  float bd = __int_as_float(0x7f800000);
+  uint32_t be = 0xFFFFFFFFu, n = 0;
+  float4 bmu = make_float4(0.f, 0.f, 0.f, 0.f), bn = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 mu[4];
+  uint32_t vid[4];
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, incl, o);
-    if (lane >= uint32_t(o)) incl += y;
-  }
-  if (lane == 31) sh.wsum[warp] = incl;
-  __syncthreads();
-  if (warp == 0) {
-    uint32_t w = lane < NT / 32 ? sh.wsum[lane] : 0u;
-    uint32_t wi = w;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const uint32_t y = __shfl_up_sync(0xFFFFFFFFu, wi, o);
-      if (lane >= uint32_t(o)) wi += y;
+  for (int r = 0; r < 4; r++) {
+    const uint32_t e = sub + 8u * r;
+    vid[r] = CELL_ABSENT;
+    if (want && e < 27u) {
+      const uint32_t w = ow[e];
+      if (w != CELL_ABSENT) {
+        vid[r] = cell_vid(w);
+        mu[r] = __ldg(&m.mean[vid[r]]);
+      }
     }
-    if (lane < NT / 32) sh.wsum[lane] = wi - w;  // exclusive over warps
-    if (lane == 31) sh.scan_total = wi;
   }
-  __syncthreads();
-  total = sh.scan_total;
-  return sh.wsum[warp] + incl - v;
+#pragma unroll
+  for (int r = 0; r < 4; r++) {
+    if (vid[r] == CELL_ABSENT) continue;
+    n += 2;
+    if (mu[r].w == 0.f) continue;
+    const float4 nr = __ldg(&m.normal[vid[r]]);
+    const float ex = qx - mu[r].x, ey = qy - mu[r].y, ez = qz - mu[r].z;
+    const float d = fabsf(nr.x * ex + nr.y * ey + nr.z * ez);
+    if (d < bd) {  // (this lane's cells come in ascending canonical order)
+      bd = d;
+      be = sub + 8u * r;
+      bmu = mu[r];
+      bn = nr;
+    }
+  }
+  const unsigned long long mykey = be == 0xFFFFFFFFu ? ~0ull : ((uint64_t(__float_as_uint(bd)) << 32) | uint64_t(be));
+  const unsigned long long best = octet_min_u64(mykey);
+  const uint32_t winners = (__ballot_sync(FULL, mykey == best && best != ~0ull) >> oshift) & 0xFFu;
+  const uint32_t src = oshift + (winners ? uint32_t(__ffs(winners) - 1) : 0u);
+  PlaneHit r;
+  r.cx = __shfl_sync(FULL, bmu.x, src);
+  r.cy = __shfl_sync(FULL, bmu.y, src);
+  r.cz = __shfl_sync(FULL, bmu.z, src);
+  r.nx = __shfl_sync(FULL, bn.x, src);
+  r.ny = __shfl_sync(FULL, bn.y, src);
+  r.nz = __shfl_sync(FULL, bn.z, src);
+  r.dist = __uint_as_float(uint32_t(best >> 32));
+  r.found = best != ~0ull;
+  r.ncand = octet_sum_u32(n);
+  return r;
 }
 
-// Drain n_items segments of the block's work list: 8 lanes per segment (one coalesced 128-byte read of 8 stored
-// points), NT/8 segments per instruction, four instructions in flight.  Each query's running best is one 64-bit
-// (d2 bits << 32 | canonical order) word updated by a shared-memory atomicMin: exactly the sequential first-minimum rule.
-// item = seg << 14 | e << 9 | q  (q < 512, e < 27, seg < 4)
-template <int NT>
-MLO_D void block_list_drain(const MapDev& map, BlockShared<NT>& sh, uint32_t n_items) {
-  const uint32_t tid = threadIdx.x, grp = tid >> 3, sub = tid & 7u;
-  constexpr uint32_t GROUPS = NT / 8;
-  for (uint32_t base = 0; base < n_items; base += GROUPS * 4) {
-    float4 p[4];
-    uint32_t meta[4];
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      const uint32_t idx = base + u * GROUPS + grp;
-      meta[u] = 0;
-      if (idx < n_items) {
-        const uint32_t it = sh.list[idx];
-        const uint32_t q = it & 511u, e = (it >> 9) & 31u, slot = (it >> 14) * 8u + sub;
-        const uint32_t w = sh.words[e][q];
-        meta[u] = q;
-        if (slot < cell_cnt(w)) {
-          p[u] = __ldg(map.pts + size_t(cell_vid(w)) * map.row + slot);
-          meta[u] = 0x80000000u | ((e * 32u + slot) << 9) | q;
-        }
-      }
-    }
-#pragma unroll
-    for (int u = 0; u < 4; u++) {
-      unsigned long long key = ~0ull;
-      const uint32_t q = meta[u] & 511u;
-      if (meta[u] & 0x80000000u) {
-        const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, sh.q[0][q], sh.q[1][q], sh.q[2][q]);
-        key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 9) & 0x3FFu);
-      }
-#pragma unroll
-      for (int o = 1; o < 8; o <<= 1) {  // segmented min over the 8 lanes of the segment (uniform control flow)
-        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
-        key = other < key ? other : key;
-      }
-      if (sub == 0 && key != ~0ull) atomicMin(&sh.best[q], key);
-    }
-  }
-}
-
-// Publish this thread's segments (cells in `visit`, canonical order) at block-wide offset `off` and drain the list,
-// window by window when the block has more than BLK_LIST_CAP segments.
-template <int NT>
-MLO_D void block_publish_and_drain(const MapDev& map, BlockShared<NT>& sh, uint32_t visit, uint32_t my_items) {
-  uint32_t total;
-  const uint32_t off = block_exclusive_scan<NT>(my_items, sh, total);
-  const uint32_t tid = threadIdx.x;
-  for (uint32_t win = 0; win < total; win += BLK_LIST_CAP) {
-    if (off < win + BLK_LIST_CAP && off + my_items > win) {
-      uint32_t o = off, m = visit;
-      while (m) {
-        const uint32_t e = __ffs(m) - 1;
-        m &= m - 1;
-        const uint32_t np = (cell_cnt(sh.words[e][tid]) + 7u) >> 3;
-        for (uint32_t k = 0; k < np; k++, o++)
-          if (o >= win && o < win + BLK_LIST_CAP) sh.list[o - win] = uint16_t((k << 14) | (e << 9) | tid);
-      }
-    }
-    __syncthreads();
-    block_list_drain<NT>(map, sh, min(BLK_LIST_CAP, total - win));
-    __syncthreads();
-  }
-}
-
-// The match phase of one ICP iteration for the queries of this block: query (pass, thread) = q0 + pass * stride + tid.
-// Out of line so that the probe (18 buckets in flight) and the rest of the kernel each get their own register allocation.
+// The match phase of one ICP iteration for this block's share of the queries, fused with the first linearisation:
+// octet o of block `rank` of a cluster of CL blocks takes queries (o * CL + rank) + k * (NT / 8 * CL).  Lane 0 of the
+// octet adds the pairing's normal-equation terms to a[] (27 sums + pairings count in a[27]); returns the candidate count.
 template <int NT, bool PLANES>
-__device__ __noinline__ uint32_t block_match(BlockShared<NT>& sh, const double* sT, float thr2, float thr_pl, uint32_t q0,
-                                             uint32_t qstride, const float4* __restrict__ local, float4* pairA, float4* pairB) {
+__device__ __noinline__ uint32_t block_match(BlockShared<NT>& sh, const double* sT, float thr2, float thr_pl, double kc,
+                                             uint32_t rank, uint32_t CL, const float4* __restrict__ local, float4* pairA,
+                                             float4* pairB, double* a_out) {
   const IcpProblem& P = sh.P;
+  double a[NACC];  // (registers; handed to the caller once at the end)
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
   const MapDev& map = sh.map;
-  const uint32_t tid = threadIdx.x;
+  const uint32_t tid = threadIdx.x, sub = tid & 7u, oct = tid >> 3;
   const uint64_t qb = P.q_begin;
   const uint32_t nq = P.n_q;
-  uint32_t ncand = 0;
-  for (uint32_t qbase = q0; qbase < nq; qbase += qstride) {  // (block-uniform trip count)
-    const uint32_t q = qbase + tid;
+  uint32_t* ow = sh.owords[oct];
+  uint32_t ncand = 0, npairs = 0;
+  for (uint32_t qbase = 0; qbase < nq; qbase += (NT / 8) * CL) {  // (block-uniform trip count)
+    const uint32_t q = qbase + oct * CL + rank;
     const bool mine = q < nq;
+    float4 l = make_float4(0.f, 0.f, 0.f, 0.f);
     float gx = 0.f, gy = 0.f, gz = 0.f;
-    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f);
     int32_t kq[3] = {0, 0, 0};
-    bool active = false, want = false;
+    bool in_range = false;
     if (mine) {
-      const float4 l = __ldg(&local[qb + q]);
+      l = __ldg(&local[qb + q]);
       compose_point_f(sT, l.x, l.y, l.z, gx, gy, gz);
       kq[0] = voxel_index_map(gx, map.inv_voxel, map.index_floor);
       kq[1] = voxel_index_map(gy, map.inv_voxel, map.index_floor);
       kq[2] = voxel_index_map(gz, map.inv_voxel, map.index_floor);
-      active = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
+      in_range = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
     }
-    sh.q[0][tid] = gx;
-    sh.q[1][tid] = gy;
-    sh.q[2][tid] = gz;
-    sh.best[tid] = ~0ull;
-    // ---- phase 1: probe (thread per query), the 27 packed cell words land in shared memory
-    uint32_t npts = 0;
-    if (active) {
-      npts = probe_words(map, kq, &sh.words[0][tid], NT);
-      bool paired = false;
-      if (PLANES && (P.matcher_mask & MLO_MATCHER_PT2PL)) {
-        const PlaneHit h = nn_plane_words(map, gx, gy, gz, &sh.words[0][tid], NT);
-        ncand += h.ncand;
+    __syncwarp();  // (the previous pass has finished reading this octet's words)
+    const uint32_t npts = octet_probe(map, kq, in_range, ow);
+    float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = make_float4(0.f, 0.f, 0.f, 0.f);
+    bool paired = false;
+    if (PLANES && (P.matcher_mask & MLO_MATCHER_PT2PL)) {  // (block-uniform)
+      const bool wantp = in_range && (P.matcher_mask & MLO_MATCHER_PT2PL);
+      const PlaneHit h = octet_plane(map, gx, gy, gz, wantp, ow);
+      if (wantp) {
+        if (sub == 0) ncand += h.ncand;
         if (h.found && h.dist < thr_pl) {
           paired = true;  // Matcher base rule: the point-to-point matcher skips local points already paired
           pa = make_float4(h.cx, h.cy, h.cz, 2.f);
-          pairB[qb + q] = make_float4(h.nx, h.ny, h.nz, 0.f);
+          pb = make_float4(h.nx, h.ny, h.nz, 0.f);
         }
       }
-      want = (P.matcher_mask & MLO_MATCHER_PT2PT) && !paired;
-      if (want) ncand += npts;
     }
-    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 21);  // probes done (this thread)
-    // ---- phase 2: own cells
-    {
-      const uint32_t wh = want ? sh.words[13][tid] : CELL_ABSENT;
-      const uint32_t np = (wh == CELL_ABSENT) ? 0u : (cell_cnt(wh) + 7u) >> 3;
-      block_publish_and_drain<NT>(map, sh, np ? (1u << 13) : 0u, np);
-    }
-    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 22);  // own cells drained
-    // ---- phase 3: per query, the neighbour cells whose box can still beat the bound from the own cell (exact pruning)
-    uint32_t visit = 0, my_items = 0;
+    const bool want = in_range && (P.matcher_mask & MLO_MATCHER_PT2PT) && !paired;
+    const OctetHit h = octet_nn(map, gx, gy, gz, kq, want, ow);
     if (want) {
-      const unsigned long long b0 = sh.best[tid];
-      const float bound = (b0 == ~0ull) ? __int_as_float(0x7f800000) : __uint_as_float(uint32_t(b0 >> 32));
-      const float qv[3] = {gx, gy, gz};
-      const AxisGaps gaps = axis_gaps(map.voxel_size, qv, kq, map.index_floor);
-#pragma unroll
-      for (int e = 0; e < 27; e++) {
-        if (e == 13) continue;
-        const uint32_t we = sh.words[e][tid];
-        if (we == CELL_ABSENT || cell_cnt(we) == 0) continue;
-        if (MLO_LB2(gaps, e) <= bound) {
-          visit |= 1u << e;
-          my_items += (cell_cnt(we) + 7u) >> 3;
-        }
+      if (sub == 0) ncand += npts;
+      const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
+      if (h.found && h.d2 < lim) pa = make_float4(h.x, h.y, h.z, 1.f);
+    }
+    if (mine && sub == 0) {  // lane 0 of the octet owns the pairing: record + first linearisation
+      pairA[qb + q] = pa;
+      if (pa.w == 1.f) {
+        if (P.solver == MLO_SOLVER_GAUSS_NEWTON) contrib_pt2pt(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
+        else contrib_horn(l.x, l.y, l.z, pa.x, pa.y, pa.z, a);
+        npairs++;
+      } else if (pa.w == 2.f) {
+        pairB[qb + q] = pb;
+        contrib_pt2pl(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, pb.x, pb.y, pb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+        npairs++;
       }
     }
-    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 23);  // neighbour cells selected
-    block_publish_and_drain<NT>(map, sh, visit, my_items);
-    if (blockIdx.x == 0) MLO_TRACE_EVENT(0u, 24);  // neighbour cells drained
-    // ---- result per query
-    if (want) {
-      const unsigned long long b = sh.best[tid];
-      if (b != ~0ull) {
-        const float d2 = __uint_as_float(uint32_t(b >> 32));
-        const uint32_t ord = uint32_t(b & 0xFFFFFFFFu), e = ord >> 5, slot = ord & 31u;
-        const float lim = thr2 + P.ang2 * (gx * gx + gy * gy + gz * gz);
-        if (d2 < lim) {
-          const float4 g = __ldg(map.pts + size_t(cell_vid(sh.words[e][tid])) * map.row + slot);
-          pa = make_float4(g.x, g.y, g.z, 1.f);
-        }
-      }
-    }
-    if (mine) pairA[qb + q] = pa;
-    __syncthreads();  // words / best / q are rewritten by the next pass
   }
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) a_out[k] = a[k];
+  a_out[NACC] = double(npairs);  // (exact: counts are far below 2^53)
   return ncand;
 }
 
@@ -338,7 +412,6 @@ __global__ void __launch_bounds__(NT, 512 / NT)
   const IcpProblem& P = sh.P;
   const uint64_t qb = P.q_begin;
   const uint32_t nq = P.n_q;
-  const uint32_t q0 = rank * NT, qstride = CL * NT;
   BlockShared<NT>* sh0 = CL > 1 ? cluster.map_shared_rank(&sh, 0) : &sh;
   for (;;) {
     const uint32_t it = sh.it;
@@ -349,31 +422,37 @@ __global__ void __launch_bounds__(NT, 512 / NT)
     const float thr2 = float(thr * thr);
     const float thr_pl = float(table_at(P.thr_pt2pl, P.table_len, it));
     const double kc = table_at(P.kparam, P.table_len, it);
-    uint32_t ncand = block_match<NT, PLANES>(sh, sT, thr2, thr_pl, q0, qstride, local, pairA, pairB);
-    if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 12);  // matches done
-    // ---------------- Solver_GaussNewton inner iterations (or the one Horn step) over the stored pairings.
-    // Every thread re-reads the records it wrote itself: no barrier between match and accumulate.
     int next;
     int after_match = 1;
     for (;;) {
       double a[32];
 #pragma unroll
       for (int k = 0; k < 32; k++) a[k] = 0.0;
-      uint32_t npairs = 0;
-      for (uint32_t q = q0 + tid; q < nq; q += qstride) {
-        const float4 pa = pairA[qb + q];
-        if (pa.w == 0.f) continue;
-        const float4 l = __ldg(&local[qb + q]);
-        if (pa.w == 1.f) {
-          if (P.solver == MLO_SOLVER_GAUSS_NEWTON) contrib_pt2pt(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
-          else contrib_horn(l.x, l.y, l.z, pa.x, pa.y, pa.z, a);
-        } else {
-          const float4 nb = pairB[qb + q];
-          contrib_pt2pl(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, nb.x, nb.y, nb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+      uint32_t ncand = 0;
+      if (after_match) {
+        // match fused with the first linearisation (lane 0 of every octet contributes its pairing)
+        ncand = block_match<NT, PLANES>(sh, sT, thr2, thr_pl, kc, rank, CL, local, pairA, pairB, a);
+        if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 12);  // matches done
+      } else {
+        // inner Gauss-Newton iterations >= 1: the lane that recorded a pairing re-reads it (its own write)
+        uint32_t npairs = 0;
+        const uint32_t sub = tid & 7u, oct = tid >> 3;
+        if (sub == 0) {
+          for (uint32_t q = oct * CL + rank; q < nq; q += (NT / 8) * CL) {
+            const float4 pa = pairA[qb + q];
+            if (pa.w == 0.f) continue;
+            const float4 l = __ldg(&local[qb + q]);
+            if (pa.w == 1.f) {
+              contrib_pt2pt(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
+            } else {
+              const float4 nb = pairB[qb + q];
+              contrib_pt2pl(sT, l.x, l.y, l.z, pa.x, pa.y, pa.z, nb.x, nb.y, nb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+            }
+            npairs++;
+          }
         }
-        npairs++;
+        a[NACC] = double(npairs);
       }
-      a[NACC] = double(npairs);  // (exact: counts are far below 2^53)
       a[NACC + 1] = double(ncand);
       const double mine = warp_reduce32_transpose(a);
       sh.wpart[warp][lane] = mine;
@@ -409,7 +488,6 @@ __global__ void __launch_bounds__(NT, 512 / NT)
       if (blockIdx.x == 0) MLO_TRACE_EVENT(prob, 14);  // solved
       next = sh.next;
       after_match = 0;
-      ncand = 0;
       if (next != 1) break;
     }
     if (next == 0) break;

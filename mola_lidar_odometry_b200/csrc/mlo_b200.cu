@@ -119,6 +119,10 @@ struct mlo_ctx {
   int filter_group_mb = 1 << 20;
   int filter_ppt = 4;  // mlo_set_option("filter_ppt"): input points per thread of the decimation kernels (1 / 2 / 4)
   int conv_index_floor = 0, conv_gm_form = 0, conv_cull_metric = 0;  // [VERIFY] conventions (common.cuh), captured by maps at creation
+  uint32_t log_cap = 0;  // mlo_icp_log_enable: records kept per problem (0 = off)
+  DBuf d_log;
+  std::vector<mlo_icp_iteration_record> h_log;
+  uint32_t h_log_problems = 0;
   int last_align_path = 0, last_stream_groups = 0, last_tail_handover = 0;  // what the last align call did (tests)
   uint64_t large_batch_queries = 0;  // 0 = auto (sm_count * 1024): batches at or above it take the launch sequence
   int tpq_min_queries_per_sm = 512;  // MLO_TPQ_MIN: below this many queries per SM the warp-per-query chunks win
@@ -827,10 +831,10 @@ int launch_block(mlo_ctx* c, uint32_t B, uint32_t max_nq, bool planes, const Map
   if (cl != 1 && cl != 2 && cl != 4 && cl != 8) {
     cl = 8;
     while (cl > 1 && B * cl > uint32_t(c->sm_count)) cl >>= 1;
-    while (cl > 1 && max_nq / cl < 64) cl >>= 1;
+    while (cl > 1 && max_nq / cl < 32) cl >>= 1;
   }
   int nt = c->block_threads;
-  if (nt != 256 && nt != 512) nt = (B * cl <= uint32_t(c->sm_count) && max_nq > 128 * cl) ? 512 : 256;
+  if (nt != 256 && nt != 512) nt = (B * cl <= uint32_t(c->sm_count) && max_nq > 32 * cl) ? 512 : 256;  // (8 lanes per query)
   c->last_block_cluster = int(cl);
   c->last_block_threads = nt;
   if (planes) {  // any problem of the batch runs Matcher_Point2Plane
@@ -908,6 +912,8 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     P.q_begin = q_begin[b];
     P.n_q = n_q[b];
     P.map_idx = map_idx[b];
+    P.log = nullptr;
+    P.log_cap = c->log_cap;
     P.max_iterations = p.max_iterations;
     P.min_abs_step_trans = p.min_abs_step_trans;
     P.min_abs_step_rot = p.min_abs_step_rot;
@@ -956,6 +962,11 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     probs[b].kparam = toff[3 * b + 2] == size_t(-1) ? nullptr : base + toff[3 * b + 2];
   }
   const uint64_t total_q = q_end;
+  if (c->log_cap) {
+    CU(c, c->d_log.ensure(size_t(B) * c->log_cap * sizeof(mlo_icp_iteration_record)));
+    CU(c, cudaMemsetAsync(c->d_log.p, 0xFF, size_t(B) * c->log_cap * sizeof(mlo_icp_iteration_record), c->stream));
+    for (uint32_t b = 0; b < B; b++) probs[b].log = c->d_log.as<mlo_icp_iteration_record>() + size_t(b) * c->log_cap;
+  }
   CU(c, c->d_probs.ensure(B * sizeof(IcpProblem)));
   CU(c, c->d_states.ensure(B * sizeof(IcpState)));
   CU(c, c->d_init.ensure(B * 12 * sizeof(double)));
@@ -1183,6 +1194,13 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   }
   prof_end(c, 1, e_icp);
   CU(c, cudaMemcpyAsync(c->h_states.p, dS, B * sizeof(IcpState), cudaMemcpyDeviceToHost, c->stream));
+  c->h_log_problems = 0;
+  if (c->log_cap) {
+    c->h_log.resize(size_t(B) * c->log_cap);
+    CU(c, cudaMemcpyAsync(c->h_log.data(), c->d_log.p, c->h_log.size() * sizeof(mlo_icp_iteration_record), cudaMemcpyDeviceToHost,
+                          c->stream));
+    c->h_log_problems = B;
+  }
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaGetLastError());
   const IcpState* hs = c->h_states.as<IcpState>();
@@ -1293,7 +1311,7 @@ void mlo_destroy(mlo_ctx* c) {
   cudaStreamSynchronize(c->stream);
   for (DBuf* b : {&c->d_in, &c->d_local, &c->d_pairA, &c->d_pairB, &c->d_partials, &c->d_partcnt, &c->d_probs, &c->d_states,
                   &c->d_tables, &c->d_init, &c->d_misc, &c->d_f_tab, &c->d_f_pslot, &c->d_f_flags, &c->d_f_blk, &c->d_f_jobs,
-                  &c->d_f_cnt, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan, &c->d_maps, &c->d_ins_jobs})
+                  &c->d_f_cnt, &c->d_f_map, &c->d_f_icp, &c->d_ins_g, &c->d_ins_slot, &c->d_ins_next, &c->d_queue, &c->d_tchan, &c->d_maps, &c->d_ins_jobs, &c->d_log})
     b->release();
   c->h_misc.release();
   c->h_states.release();
@@ -1773,6 +1791,25 @@ void mlo_icp_params_default(mlo_icp_params* p) {
   p->pt2pt_weight = p->pt2pl_weight = 1.0;
   p->prior_pose_3x4[0] = p->prior_pose_3x4[5] = p->prior_pose_3x4[10] = 1.0;
   p->hook_checkpoint_pose_3x4[0] = p->hook_checkpoint_pose_3x4[5] = p->hook_checkpoint_pose_3x4[10] = 1.0;
+}
+
+int mlo_icp_log_enable(mlo_ctx* c, uint32_t max_records) {
+  if (!c) return MLO_ERR_INVALID_ARG;
+  c->log_cap = std::min<uint32_t>(max_records, 1024u);
+  c->h_log_problems = 0;
+  return MLO_OK;
+}
+int mlo_icp_log_read(mlo_ctx* c, uint32_t problem, mlo_icp_iteration_record* out, uint32_t max_records, uint32_t* n) {
+  if (!c || !n) return MLO_ERR_INVALID_ARG;
+  *n = 0;
+  if (!c->log_cap || problem >= c->h_log_problems) return fail(c, MLO_ERR_INVALID_ARG, "no ICP log for this problem (mlo_icp_log_enable first)");
+  const mlo_icp_iteration_record* r = c->h_log.data() + size_t(problem) * c->log_cap;
+  uint32_t k = 0;
+  while (k < c->log_cap && r[k].iteration == k) k++;  // (unwritten records are all-ones)
+  *n = k;
+  if (out)
+    for (uint32_t i = 0; i < k && i < max_records; i++) out[i] = r[i];
+  return MLO_OK;
 }
 
 int mlo_icp_align_batch(mlo_ctx* c, uint32_t B, const float* local, uint32_t stride, const uint64_t* offsets,

@@ -15,7 +15,7 @@ ctx = Context(0)
 fleet = LidarOdometryFleet(ctx, str(PIPELINES / pipe), S)
 lib = capi.load()
 buf = (C.c_ulonglong * 16384)(); n = C.c_uint()
-names = {11: "iter_start", 12: "match_done", 13: "reduced", 14: "solved", 15: "accumulated", 16: "solve_ret", 21: "probed", 22: "own_drained", 23: "nb_selected", 24: "nb_drained"}
+names = {11: "iter_start", 12: "match_done", 13: "reduced", 14: "solved", 15: "accumulated", 16: "solve_ret", 20: "transformed", 21: "probed", 22: "own_drained", 23: "nb_selected", 24: "nb_drained"}
 for k in range(30):
     outs = fleet.on_lidar([scene.scan(trajs[s][k], scan_seed=(7 + s) * 1000 + k) for s in range(S)], [0.1 * k] * S)
     lib.mlo_debug_trace_read(buf, 16384, C.byref(n))

@@ -36,18 +36,18 @@ def test_struct_sizes_match_header(built, tmp_path):
     import subprocess
     from mola_lidar_odometry_b200 import capi
     src = tmp_path / "sz.c"
-    src.write_text('#include <stdio.h>\n#include "mlo_b200_host.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
+    src.write_text('#include <stdio.h>\n#include "mlo_b200_host.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                    'sizeof(mlo_map_params),sizeof(mlo_decimate_params),sizeof(mlo_filter1_params),'
                    'sizeof(mlo_icp_params),sizeof(mlo_icp_result),sizeof(mlo_profile),'
                    'sizeof(mlo_scan_job),sizeof(mlo_scan_info),sizeof(mlo_align_job),sizeof(mlo_insert_job),'
-                   'sizeof(mlo_map_counts),sizeof(mlo_lo_scan_output));return 0;}\n')
+                   'sizeof(mlo_map_counts),sizeof(mlo_lo_scan_output),sizeof(mlo_icp_iteration_record));return 0;}\n')
     exe = tmp_path / "sz"
     subprocess.run(["gcc", "-I", str(ROOT / "include"), str(src), "-o", str(exe)], check=True)
     got = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     from mola_lidar_odometry_b200 import host_api
     want = [ctypes.sizeof(t) for t in (capi.MapParams, capi.DecimateParams, capi.Filter1Params, capi.IcpParams,
                                        capi.IcpResult, capi.Profile, capi.ScanJob, capi.ScanInfo, capi.AlignJob,
-                                       capi.InsertJob, capi.MapCounts, host_api.ScanOutput)]
+                                       capi.InsertJob, capi.MapCounts, host_api.ScanOutput, capi.IcpIterationRecord)]
     assert host_api.SCAN_OUTPUT_DTYPE.itemsize == ctypes.sizeof(host_api.ScanOutput)
     assert got == want
 

@@ -140,12 +140,18 @@ def test_map_clear_and_empty_inputs(ctx, world):
     assert g.stats() == (0, 0)
 
 
-def test_map_capacity_error(ctx, world):
+def test_map_capacity_is_only_the_initial_size(ctx, world):
+    """A tiny initial capacity is not an error any more (upstream's map is unbounded): the first insert re-hashes the
+    map into larger buffers and the same context keeps working; only sizes above the hard limit are refused."""
     from mola_lidar_odometry_b200.api import LocalMap, MloError
     g = LocalMap(ctx, 1.0, 20, 0.0, 64)
-    with pytest.raises(MloError) as e:
-        g.insert(world["frames"][0]["map_layer"], np.eye(4)[:3])
-    assert e.value.code == -4
+    layer = world["frames"][0]["map_layer"]
+    g.insert(layer, np.eye(4)[:3])
+    o = O.OracleMap(1.0, 20, 0.0)
+    o.insert(layer, np.eye(4)[:3])
+    assert g.stats() == o.stats() and g.stats()[0] > 64
+    with pytest.raises(MloError):
+        LocalMap(ctx, 1.0, 20, 0.0, (1 << 26) + 1)
 
 
 def test_nn_single_bit_exact(ctx, world):

@@ -229,3 +229,31 @@ def test_large_batch_other_paths_agree(ctx, large_case):
             res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
         for gr, orr in zip(res, c["refs"]):
             _check(gr, orr)
+
+
+# ------------------------------------------------------------------ the ICP log (mp2p_icp generateDebugFiles / saveIterationDetails)
+@pytest.mark.parametrize("path", [1, 2, 3])
+def test_icp_iteration_log(ctx, small_case, path):
+    """One record per executed ICP iteration (default.yaml:177-182), written by the device as the loop runs: iteration
+    index, pose after the iteration, realised thresholds, pairings, step measure, termination verdict."""
+    c = small_case
+    ctx.icp_log_enable(64)
+    try:
+        with _Options(ctx, align_path=path):
+            res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        for b, (gr, own) in enumerate(zip(res, c["owners"])):
+            log = ctx.icp_log(b)
+            if gr.termination == 1:      # NoPairings: the loop broke before any solver step
+                assert len(log) == 0
+                continue
+            # Stalled / HookRequest end INSIDE an iteration that nIterations does not count (SURVEY.md A.1)
+            assert len(log) == gr.n_iterations + (1 if gr.termination in (4, 5) else 0)
+            assert [r.iteration for r in log] == list(range(len(log)))
+            assert all(r.termination == 0 for r in log[:-1]) and log[-1].termination == gr.termination
+            assert np.array_equal(log[-1].pose, gr.pose) and log[-1].n_pairings == gr.n_pairings
+            thr = np.ctypeslib.as_array(own.p.pt2pt_threshold_by_iter, shape=(own.p.table_len,))
+            assert all(r.threshold_pt2pt == thr[min(r.iteration, len(thr) - 1)] for r in log)
+            if gr.termination == 4:
+                assert log[-1].step_trans < own.p.min_abs_step_trans and log[-1].step_rot < own.p.min_abs_step_rot
+    finally:
+        ctx.icp_log_enable(0)
