@@ -1007,7 +1007,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   if (path == 0) {
     if (!c->use_persistent) path = 1;
     else if (c->persistent_forced) path = 2;
-    else path = total_queries < large_at ? 3 : 1;
+    else path = total_queries < large_at ? 2 : 1;  // (the block kernel, path 3, measured slower than the queue kernel: profiles/README.md)
   }
   if (path == 2 && !queue_ok) path = 1;
   const bool persistent = path == 2;
@@ -1269,6 +1269,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* tf = getenv("MLO_TABLE_FACTOR")) c->table_factor = std::max(1, atoi(tf));
   if (const char* sg = getenv("MLO_STREAM_GROUPS")) c->stream_groups = std::min(int(mlo_ctx::MAX_GROUPS), std::max(1, atoi(sg)));
   if (const char* ap = getenv("MLO_ALIGN_PATH")) c->align_path = std::min(3, std::max(0, atoi(ap)));
+  if (const char* lb = getenv("MLO_LARGE_BATCH_QUERIES")) c->large_batch_queries = uint64_t(std::max(0ll, atoll(lb)));
   if (const char* tp = getenv("MLO_TAIL_PATH")) c->tail_path = atoi(tp) == 2 ? 2 : 3;
   if (const char* bt = getenv("MLO_BLOCK_THREADS")) c->block_threads = atoi(bt);
   if (const char* bc = getenv("MLO_BLOCK_CLUSTER")) c->block_cluster = atoi(bc);

@@ -15,6 +15,11 @@
 #pragma once
 #include <algorithm>
 #include <array>
+#include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <thread>
 #include <chrono>
 #include <cmath>
 #include <cstring>
@@ -674,6 +679,8 @@ class LidarOdometryT {
     }
     return updateLocalMap;
   }
+  // after_icp() creates the map on the first scan and clears it on a bad first ICP: those calls reach the device
+  bool after_icp_touches_backend() const { return !map_ || trajectory_.size() <= 1; }
   void after_insert(const mlo_map_counts& cnt) {
     map_points_ = cnt.n_points;
     out_.map_updated = true;
@@ -912,6 +919,93 @@ class LidarOdometryT {
 // eval/cli_kitti.sh:23) advanced in lock step on one device: every phase of onLidar() is issued ONCE for all
 // sequences (one filter pass, one align pass over per-sequence local maps, one insert pass), which is what fills
 // a B200 when a single 64-beam scan cannot.  Results are those of the stand-alone instances.
+// A small persistent pool for the per-sequence HOST logic of a fleet step (formula realisation, motion model, gating:
+// pure functions of one sequence's state).  Device passes stay on the caller's thread: one context = one stream = one
+// caller thread (include/mlo_b200.h).  MLO_HOST_THREADS overrides the size (default: min(8, cores / ranks on this node)).
+class HostPool {
+ public:
+  HostPool() {
+    unsigned n = std::max(1u, std::thread::hardware_concurrency());
+    if (const char* lw = std::getenv("LOCAL_WORLD_SIZE")) n = std::max(1u, n / unsigned(std::max(1, std::atoi(lw))));
+    n = std::min(8u, n);
+    if (const char* e = std::getenv("MLO_HOST_THREADS")) n = unsigned(std::max(1, std::atoi(e)));
+    for (unsigned i = 1; i < n; i++) th_.emplace_back([this] { worker(); });
+  }
+  ~HostPool() {
+    {
+      std::lock_guard<std::mutex> l(m_);
+      stop_ = true;
+      gen_++;
+    }
+    cv_.notify_all();
+    for (auto& t : th_) t.join();
+  }
+  // fn(i) for i in [0, count); returns when all are done.  Small counts run inline.
+  void parallel_for(size_t count, const std::function<void(size_t)>& fn) {
+    if (th_.empty() || count < 8) {
+      for (size_t i = 0; i < count; i++) fn(i);
+      return;
+    }
+    {
+      std::lock_guard<std::mutex> l(m_);
+      fn_ = &fn;
+      count_ = count;
+      next_.store(0);
+      pending_ = th_.size();
+      gen_++;
+    }
+    cv_.notify_all();
+    run();
+    std::unique_lock<std::mutex> l(m_);
+    done_.wait(l, [this] { return pending_ == 0; });
+    fn_ = nullptr;
+    if (err_) {
+      auto e = err_;
+      err_ = nullptr;
+      std::rethrow_exception(e);
+    }
+  }
+
+ private:
+  void run() {
+    for (;;) {
+      const size_t i = next_.fetch_add(1);
+      if (i >= count_) return;
+      try {
+        (*fn_)(i);
+      } catch (...) {
+        std::lock_guard<std::mutex> l(m_);
+        if (!err_) err_ = std::current_exception();
+      }
+    }
+  }
+  void worker() {
+    uint64_t seen = 0;
+    for (;;) {
+      {
+        std::unique_lock<std::mutex> l(m_);
+        cv_.wait(l, [&] { return gen_ != seen; });
+        seen = gen_;
+        if (stop_) return;
+      }
+      run();
+      {
+        std::lock_guard<std::mutex> l(m_);
+        if (--pending_ == 0) done_.notify_one();
+      }
+    }
+  }
+  std::vector<std::thread> th_;
+  std::mutex m_;
+  std::condition_variable cv_, done_;
+  const std::function<void(size_t)>* fn_ = nullptr;
+  size_t count_ = 0, pending_ = 0;
+  std::atomic<size_t> next_{0};
+  uint64_t gen_ = 0;
+  bool stop_ = false;
+  std::exception_ptr err_;
+};
+
 template <class Backend>
 class LidarOdometryFleetT {
  public:
@@ -948,15 +1042,20 @@ class LidarOdometryFleetT {
     const uint32_t S = size();
     std::vector<uint32_t> live;  // sequences with an accepted observation this step
     std::vector<mlo_scan_job> fjobs;
-    for (uint32_t i = 0; i < S; i++) {
-      out[i] = ScanOutput{};
-      if (!pts[i] && n[i]) continue;
-      if (!pts[i]) continue;
-      mlo_scan_job j;
-      if (!seq_[i]->begin_scan(pts[i], stride, n[i], stamps[i], t ? t[i] : nullptr, j)) continue;
-      j.slot = i;
-      fjobs.push_back(j);
-      live.push_back(i);
+    {
+      std::vector<mlo_scan_job> all(S);
+      std::vector<uint8_t> ok(S, 0);
+      pool_.parallel_for(S, [&](size_t i) {  // per-sequence host logic: independent states
+        out[i] = ScanOutput{};
+        if (!pts[i]) return;
+        ok[i] = seq_[i]->begin_scan(pts[i], stride, n[i], stamps[i], t ? t[i] : nullptr, all[i]) ? 1 : 0;
+      });
+      for (uint32_t i = 0; i < S; i++)
+        if (ok[i]) {
+          all[i].slot = i;
+          fjobs.push_back(all[i]);
+          live.push_back(i);
+        }
     }
     if (live.empty()) return;
     lap(0);
@@ -968,32 +1067,38 @@ class LidarOdometryFleetT {
     lap(2);
     for (;;) {
       std::vector<uint32_t> who;
-      std::vector<mlo_align_job> ajobs;
       for (uint32_t i : live)
-        if (seq_[i]->icp_pending()) {
-          mlo_align_job a;
-          seq_[i]->make_align_job(a);
-          a.slot = i;
-          ajobs.push_back(a);
-          who.push_back(i);
-        }
+        if (seq_[i]->icp_pending()) who.push_back(i);
       if (who.empty()) break;
+      std::vector<mlo_align_job> ajobs(who.size());
+      pool_.parallel_for(who.size(), [&](size_t k) {  // realises the per-iteration formula tables of each sequence
+        seq_[who[k]]->make_align_job(ajobs[k]);
+        ajobs[k].slot = who[k];
+      });
       std::vector<mlo_icp_result> res(who.size());
       be_.scanset_align(set_, uint32_t(ajobs.size()), ajobs.data(), res.data());
       lap(3);
-      for (size_t k = 0; k < who.size(); k++) seq_[who[k]]->on_align_result(res[k]);
+      pool_.parallel_for(who.size(), [&](size_t k) { seq_[who[k]]->on_align_result(res[k]); });
       run_deskews(who);
       lap(2);
     }
     std::vector<uint32_t> ins;
     std::vector<mlo_insert_job> ijobs;
-    for (uint32_t i : live) {
-      mlo_insert_job j;
-      if (seq_[i]->after_icp(j)) {
-        j.slot = i;
-        ijobs.push_back(j);
-        ins.push_back(i);
-      }
+    {
+      std::vector<mlo_insert_job> all(live.size());
+      std::vector<uint8_t> want(live.size(), 0);
+      bool serial = false;  // (device calls stay on the caller's thread)
+      for (uint32_t i : live) serial = serial || seq_[i]->after_icp_touches_backend();
+      if (serial)
+        for (size_t k = 0; k < live.size(); k++) want[k] = seq_[live[k]]->after_icp(all[k]) ? 1 : 0;
+      else
+        pool_.parallel_for(live.size(), [&](size_t k) { want[k] = seq_[live[k]]->after_icp(all[k]) ? 1 : 0; });
+      for (size_t k = 0; k < live.size(); k++)
+        if (want[k]) {
+          all[k].slot = live[k];
+          ijobs.push_back(all[k]);
+          ins.push_back(live[k]);
+        }
     }
     lap(4);
     if (!ins.empty()) {
@@ -1023,6 +1128,7 @@ class LidarOdometryFleetT {
   Backend& be_;
   std::vector<std::unique_ptr<LidarOdometryT<Backend>>> seq_;
   typename Backend::ScanSet* set_ = nullptr;
+  HostPool pool_;
 };
 
 }  // namespace mlo_host
