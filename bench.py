@@ -362,171 +362,175 @@ def run_reference(args, rank: int):
 
 
 # ---------------------------------------------------------------------------------------------- sequence workloads
-def run_sequences(args, rank, local_rank, world):
-    """BASELINE configs[2]/[3]/[4]: S independent T00-shaped sequences per GPU, each through the full odometry loop of
-    the C++ host layer (filter -> motion-model guess -> ICP -> quality gate -> adaptive sigma -> keyframe -> map
-    insert + cull) with the pipeline YAML.  GPU arm: the S sequences advance in lock step as one fleet (one device
-    pass per phase over S local maps).  CPU arm: the SAME orchestrator over the oracle backend, one thread per
-    sequence like the reference's one worker per LidarOdometry / process per sequence."""
+SEQ_WORKLOADS = {
+    # BASELINE.json configs[2]/[4]: T00-shaped drives x K64, lidar3d-default.yaml (pt2pt matcher, GN + Geman-McClure)
+    "sequence": dict(yaml="lidar3d-default.yaml", sensor="K64",
+                     label="config[2]/[4]: T00 x K64 sequences, lidar3d-default.yaml, full odometry loop"),
+    # configs[2] point-to-plane variant: the same drives through the NDT pipeline (Matcher_Point2Plane first)
+    "sequence_pt2pl": dict(yaml="lidar3d-ndt.yaml", sensor="K64",
+                           label="config[2] point-to-plane: T00 x K64 sequences, lidar3d-ndt.yaml (Matcher_Point2Plane + NDT map)"),
+    # configs[3]: 128-beam 230 k-point sweeps, lidar3d-ndt.yaml
+    "ndt": dict(yaml="lidar3d-ndt.yaml", sensor="O128", label="config[3]: T00 x O128 (230 k rays), lidar3d-ndt.yaml"),
+}
+
+
+def run_fleet_workload(ctx, kind: str, S: int, N: int, rank: int, world: int, cores: int, with_cpu: bool, cpu_scans: int,
+                       chunk_steps: int = 0, prefetch: bool = True, gpu_arm: bool = True):
+    """S independent T00-shaped sequences of N scans through the FULL odometry loop of the C++ host layer (filter ->
+    motion-model guess + prior -> ICP -> quality gate -> adaptive sigma -> keyframe -> map insert + cull) with the
+    reference's pipeline YAML.  GPU arm: the S sequences advance in lock step as one fleet (mlo_fleet_*): pinned host
+    scans in (x, y, z packed), host results out, the next step's upload overlapped with the ICP.  CPU arm: the SAME
+    orchestrator over the oracle backend, one thread per sequence (the reference's process-per-sequence,
+    eval/cli_kitti.sh:23), on min(S, cores) sequences and their first `cpu_scans` scans.  Scans are ray-cast on the GPU
+    (synth/synth_gpu.cu, untimed) chunk by chunk; only lock steps are timed.  Returns the sub-record."""
+    import torch
+    from mola_lidar_odometry_b200.synth.gpu import GpuSynth
+    from oracle import oracle_py as O
+    w = SEQ_WORKLOADS[kind]
+    yaml_path = ROOT / "pipelines" / w["yaml"]
+    sensor = getattr(synth, w["sensor"])
     os.environ.setdefault("MOLA_OPTIMIZE_TWIST", "false")   # benchmark settings of SURVEY.md §8(d): deskew is row f1
     os.environ.setdefault("MOLA_INITIAL_VX", "8.0")
-    ndt = args.workload == "ndt"
-    yaml_path = ROOT / "pipelines" / ("lidar3d-ndt.yaml" if ndt else "lidar3d-default.yaml")
-    sensor = synth.O128 if ndt else synth.K64
-    cores = os.cpu_count() or 1
-    S, N = args.sequences, args.scans
+    dev = torch.device("cuda", torch.cuda.current_device())
     scene = synth.Scene(42)
+    gs = GpuSynth(scene, dev)
     seeds = [7 + rank * S + i for i in range(S)]
     trajs = [synth.trajectory_T00(N + 5, seed=sd) for sd in seeds]
-    with ThreadPoolExecutor(max(1, cores // max(1, world))) as ex:
-        scans = [list(ex.map(lambda k, tr=tr, sd=sd: scene.scan(tr[k], sensor, scan_seed=sd * 100000 + k), range(N)))
-                 for tr, sd in zip(trajs, seeds)]
-    from oracle import oracle_py as O
+    n_rays = sensor.n_beams * sensor.n_az
+    if chunk_steps <= 0:   # ~2.5 GB of pinned host memory per chunk
+        chunk_steps = max(1, min(N, int(2.5e9 / (S * n_rays * 12))))
+    pinned = torch.empty((S * chunk_steps * n_rays, 3), dtype=torch.float32).pin_memory()
+    pinned_np = pinned.numpy()
+    fleet = None
+    if gpu_arm:
+        from mola_lidar_odometry_b200.host_api import LidarOdometryFleet
+        fleet = LidarOdometryFleet(ctx, yaml_path, S)
+    n_cpu = min(S, cores) if with_cpu else 0
+    cpu_lo = [O.OracleLidarOdometry(yaml_path) for _ in range(n_cpu)]
+    gpu_wall, cpu_wall, cpu_done, launches0 = 0.0, 0.0, 0, (ctx.launch_count if ctx else 0)
+    gpu_poses = [[] for _ in range(S)]
+    cpu_poses = [[] for _ in range(n_cpu)]
+    its, pts_sum, h2d = 0, 0, 0
+    prior_scans = 0
+    for k0 in range(0, N, chunk_steps):
+        k1 = min(N, k0 + chunk_steps)
+        # ---- synthesis of this chunk (untimed): step-major order, scan (k, s) at index (k - k0) * S + s
+        poses = np.stack([trajs[s][k] for k in range(k0, k1) for s in range(S)])
+        sds = np.array([seeds[s] * 100000 + k for k in range(k0, k1) for s in range(S)], dtype=np.uint64)
+        flat, offs = gs.scan_batch(poses, sds, sensor)
+        offs_h = offs.cpu().numpy()
+        pinned[:offs_h[-1]].copy_(flat[:, :3])
+        torch.cuda.synchronize()
+        del flat
+        views = [[pinned_np[offs_h[(k - k0) * S + s]:offs_h[(k - k0) * S + s + 1]] for s in range(S)] for k in range(k0, k1)]
+        pts_sum += int(offs_h[-1])
+        # ---- GPU arm: lock steps, timed
+        if fleet is not None:
+            t0 = time.perf_counter()
+            for k in range(k0, k1):
+                if prefetch and k + 1 < k1:
+                    fleet.prefetch(views[k + 1 - k0])
+                outs = fleet.on_lidar(views[k - k0], [0.1 * k] * S, as_arrays=True)
+                for s in range(S):
+                    gpu_poses[s].append(outs["pose_3x4"][s].copy())
+                its += int(outs["icp_iterations"].sum())
+                prior_scans += int(outs["icp_had_prior"].sum())
+            gpu_wall += time.perf_counter() - t0
+            h2d += int(offs_h[-1]) * 12
+        # ---- CPU arm: one thread per sequence over the same clouds
+        if n_cpu and k0 < cpu_scans:
+            kk1 = min(k1, cpu_scans)
 
-    def drive(make_lo, s_idx, res):
-        lo = make_lo()
-        t0 = time.perf_counter()
-        poses, its = [], 0
-        for k in range(N):
-            o = lo.on_lidar(scans[s_idx][k], 0.1 * k)
-            poses.append(o.pose.copy())
-            its += int(o.icp_iterations)
-        res[s_idx] = (time.perf_counter() - t0, np.stack(poses), its)
+            def drive(i):
+                for k in range(k0, kk1):
+                    o = cpu_lo[i].on_lidar(views[k - k0][i], 0.1 * k)
+                    cpu_poses[i].append(o.pose.copy())
+            t0 = time.perf_counter()
+            with ThreadPoolExecutor(n_cpu) as ex:
+                list(ex.map(drive, range(n_cpu)))
+            cpu_wall += time.perf_counter() - t0
+            cpu_done += n_cpu * (kk1 - k0)
+    rec = {"workload": w["label"], "sequences_per_gpu": S, "scans_per_sequence": N, "points_per_scan": pts_sum // max(1, S * N),
+           "host_layout": "x,y,z float32 packed (12 B/pt), pinned; scans ray-cast on the GPU beforehand (untimed)"}
+    if fleet is not None:
+        rec.update({"value": S * N / gpu_wall, "unit": "scans/s", "ms_per_lock_step": 1e3 * gpu_wall / N, "wall_s": gpu_wall,
+                    "mean_icp_iterations": its / max(1, S * (N - 1)), "scans_with_prior": prior_scans,
+                    "h2d_bytes_per_step": h2d // N, "gpu_launches": int(ctx.launch_count - launches0),
+                    "phases_ms_per_step": fleet.phase_times()})
+        fleet.close()
+    if n_cpu:
+        rec["cpu_baseline"] = {"value": cpu_done / cpu_wall, "unit": "scans/s", "cores": n_cpu, "kind": "port",
+                               "sample": f"{n_cpu} sequences x first {min(N, cpu_scans)} scans, one thread per sequence "
+                                         f"(same C++ orchestrator over the oracle backend)"}
+        if fleet is not None:
+            dt, dr, ape = [], [], []
+            for i in range(n_cpu):
+                for k, cp in enumerate(cpu_poses[i]):
+                    e = O.pose_error(gpu_poses[i][k], cp)
+                    dt.append(e[0])
+                    dr.append(e[1])
+                gp = np.stack(gpu_poses[i])
+                gt = np.stack([synth.relative(trajs[i][0], trajs[i][k]) for k in range(len(gp))])
+                ape.append(float(np.sqrt(np.mean(np.sum((gp[:, :, 3] - gt[:, :, 3]) ** 2, axis=1)))))
+            rec["parity_vs_oracle"] = {"scans": len(dt), "max_trans_m": float(max(dt)), "max_rot_deg": float(max(dr)),
+                                       "ape_rmse_m": float(np.sqrt(np.mean(np.square(dt)))),
+                                       "tolerance": "APE within 1e-3 m of the oracle trajectory (north_star), asserted"}
+            rec["ape_rmse_vs_ground_truth_m"] = float(np.mean(ape))
+            rec["speedup_vs_cpu"] = rec["value"] / rec["cpu_baseline"]["value"]
+            assert rec["parity_vs_oracle"]["ape_rmse_m"] <= 1e-3, rec["parity_vs_oracle"]
+    return rec
 
-    def run_all(make_lo, n_threads):
-        res = [None] * S
-        t0 = time.perf_counter()
-        pending = list(range(S))
-        lock = threading.Lock()
 
-        def worker():
-            while True:
-                with lock:
-                    if not pending:
-                        return
-                    i = pending.pop(0)
-                drive(make_lo, i, res)
-        th = [threading.Thread(target=worker) for _ in range(n_threads)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-        return time.perf_counter() - t0, res
-
-    line = {"metric": "scans/sec", "unit": "scans/s", "n_gpus": world, "steps": 1, "warmup": 0, "higher_is_better": True,
+def run_sequences(args, rank, local_rank, world):
+    """`--workload sequence|sequence_pt2pl|ndt`: one whole-sequence workload as its own JSON line (see run_fleet_workload)."""
+    cores = os.cpu_count() or 1
+    import torch
+    torch.cuda.set_device(local_rank)
+    numa = bind_near_gpu(local_rank)
+    S, N = args.sequences, args.scans
+    line = {"metric": "scans/sec", "unit": "scans/s", "n_gpus": world, "steps": N, "warmup": 0, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32 distances / f64 normal equations", "data": "synthetic",
-            "config": {"workload": ("config[3]: T00 x O128, lidar3d-ndt.yaml" if ndt else
-                                    "config[2]/[4]: T00 x K64 sequences, lidar3d-default.yaml, full odometry loop"),
-                       "sequences_per_gpu": S, "scans_per_sequence": N, "points_per_scan": int(np.mean([len(x) for x in scans[0]]))}}
+            "config": {"workload": SEQ_WORKLOADS[args.workload]["label"], "sequences_per_gpu": S, "scans_per_sequence": N}}
     if args.impl == "reference":
         if rank != 0:
             return
-        wall, res = run_all(lambda: O.OracleLidarOdometry(yaml_path), min(cores, S))
-        line.update({"impl": "reference", "value": S * N / wall, "ms_per_step": wall * 1e3,
-                     "cpu_baseline": {"value": S * N / wall, "unit": "scans/s", "cores": min(cores, S), "kind": "port",
-                                      "sample": f"{S} sequences x {N} scans, one thread per sequence"},
-                     "e2e": {"value": S * N / wall, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-                     "gpu_launches": 0})
+        rec = run_fleet_workload(None, args.workload, S, N, 0, 1, cores, True, N, gpu_arm=False)
+        v = rec["cpu_baseline"]["value"]
+        line.update({"impl": "reference", "value": v, "ms_per_step": 1e3 * S / max(v, 1e-9), "cpu_baseline": rec["cpu_baseline"],
+                     "e2e": {"value": v, "unit": "scans/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0})
         emit(line)
         return
-    import torch
     import torch.distributed as dist
     from mola_lidar_odometry_b200.api import Context
-    from mola_lidar_odometry_b200.host_api import LidarOdometryFleet
-    torch.cuda.set_device(local_rank)
+    from mola_lidar_odometry_b200.host_api import ScanOutput
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
-    # the S sequences of this GPU advance in lock step as one fleet: one filter pass, one align pass over S local maps
-    # and one insert pass per step (mlo_fleet_* / mlo_scanset_*); raw scans sit in pinned host memory
-    pinned = []
-    for sc in scans:
-        row = []
-        for x in sc:
-            tns = torch.from_numpy(np.ascontiguousarray(x, dtype=np.float32)).pin_memory()
-            row.append(tns)
-        pinned.append(row)
-    views = [[tns.numpy() for tns in row] for row in pinned]
-    step_clouds = [[views[s][k] for s in range(S)] for k in range(N)]
     ctx = Context(local_rank)
-    ctxs = [ctx]
-
-    def run_fleet(profile=False):
-        fleet = LidarOdometryFleet(ctx, yaml_path, S)
-        pose_log = []
-        its = np.zeros(S, dtype=np.int64)
-        if profile:
-            ctx.profile_enable(True)
-            ctx.profile_get(True)
-        t0 = time.perf_counter()
-        for k in range(N):
-            if k + 1 < N and not args.no_prefetch:   # upload of step k+1 overlaps the ICP of step k
-                fleet.prefetch(step_clouds[k + 1])
-            outs = fleet.on_lidar(step_clouds[k], [0.1 * k] * S, as_arrays=True)   # one structured array for all sequences
-            pose_log.append(outs["pose_3x4"])
-            its += outs["icp_iterations"]
-        wall = time.perf_counter() - t0
-        host_phases = fleet.phase_times()
-        prof = None
-        if profile:
-            pr = ctx.profile_get(True)
-            ctx.profile_enable(False)
-            prof = {"filter_1st_ms_per_step": pr.filter_1st_ms / N, "run_icp_ms_per_step": pr.run_icp_ms / N,
-                    "update_local_map_ms_per_step": pr.update_local_map_ms / N, "wall_ms_per_step": wall * 1e3 / N}
-        fleet.close()
-        poses = np.stack(pose_log)   # [N, S, 3, 4]
-        return wall, [(wall, poses[:, s], int(its[s])) for s in range(S)], prof, host_phases
-    run_fleet()                               # warm-up pass (allocations, first-touch)
-    l0 = ctx.launch_count
-    cuprof = os.environ.get("MLO_BENCH_CUPROF") == "1"   # ncu --profile-from-start off: capture the timed pass only
-    if cuprof:
-        torch.cuda.cudart().cudaProfilerStart()
+    run_fleet_workload(ctx, args.workload, S, min(N, 12), rank, world, cores, False, 0, prefetch=not args.no_prefetch)   # warm-up
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize()
-    wall, res, _, host_phases = run_fleet()
-    torch.cuda.synchronize()
-    if cuprof:
-        torch.cuda.cudart().cudaProfilerStop()
-    launches = ctx.launch_count - l0
-    t = torch.tensor([wall], dtype=torch.float64, device="cuda")
+    rec = run_fleet_workload(ctx, args.workload, S, N, rank, world, cores, rank == 0 and not args.no_cpu_baseline,
+                             min(N, args.cpu_scans), prefetch=not args.no_prefetch)
+    t = torch.tensor([rec["wall_s"]], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    wall_max = float(t[0])
-    value = world * S * N / wall_max
-    _, _, phase_profile, _ = run_fleet(profile=True)
-    phase_profile = {"device_events_pass": phase_profile, "host_wall_timed_pass": host_phases}
-    cpu, parity = None, None
-    if rank == 0 and not args.no_cpu_baseline:
-        n_cpu = min(S, max(1, cores // 2))
-        cwall, cres = run_all(lambda: O.OracleLidarOdometry(yaml_path), min(cores, S))
-        cpu = {"value": S * N / cwall, "unit": "scans/s", "cores": min(cores, S), "kind": "port",
-               "sample": f"{S} sequences x {N} scans, one thread per sequence (same C++ orchestrator over the oracle backend)"}
-        dt, dr, ape_gt = [], [], []
-        for i in range(S):
-            gp, cp = res[i][1], cres[i][1]
-            for k in range(N):
-                e = O.pose_error(gp[k], cp[k])
-                dt.append(e[0])
-                dr.append(e[1])
-            gt = np.stack([synth.relative(trajs[i][0], trajs[i][k]) for k in range(N)])
-            ape_gt.append(float(np.sqrt(np.mean(np.sum((gp[:, :, 3] - gt[:, :, 3]) ** 2, axis=1)))))
-        parity = {"max_trans_m": float(max(dt)), "max_rot_deg": float(max(dr)),
-                  "ape_rmse_vs_oracle_m": float(np.sqrt(np.mean(np.square(dt)))), "ape_rmse_vs_gt_m": float(np.mean(ape_gt)),
-                  "mean_icp_iterations": float(np.mean([r[2] for r in res]) / max(1, N - 1))}
+    value = world * S * N / float(t[0])
     if rank == 0:
-        line.update({"value": value, "ms_per_step": wall_max * 1e3,
-                     "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": int(sum(x.nbytes for sc in scans for x in sc)),
-                             "d2h_bytes_per_step": int(S * N * 400),
-                             "note": "pinned host scans in, host results out on every lock step (mlo_fleet_on_lidar)"},
-                     "gpu_launches": int(launches), "cpu_baseline": cpu, "quality": parity,
-                     "phases": phase_profile, "roofline": None})
+        line.update({"value": value, "ms_per_step": 1e3 * float(t[0]) / N,
+                     "e2e": {"value": value, "unit": "scans/s", "h2d_bytes_per_step": rec["h2d_bytes_per_step"],
+                             "d2h_bytes_per_step": int(S * C.sizeof(ScanOutput)),
+                             "note": "pinned host scans in, host results out on every lock step (mlo_fleet_on_lidar)", "numa": numa},
+                     "gpu_launches": rec["gpu_launches"], "cpu_baseline": rec.get("cpu_baseline"),
+                     "quality": {"parity_vs_oracle": rec.get("parity_vs_oracle"), "ape_rmse_vs_gt_m": rec.get("ape_rmse_vs_ground_truth_m"),
+                                 "mean_icp_iterations": rec["mean_icp_iterations"], "scans_with_prior": rec["scans_with_prior"]},
+                     "phases": {"host_wall_timed_pass": rec["phases_ms_per_step"], "device_events_pass": {}}, "roofline": None})
         emit(line)
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
-    for c in ctxs:
-        c.close()
+    ctx.close()
 
 
 def bind_near_gpu(idx: int):
@@ -564,7 +568,13 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--cpu-budget", type=float, default=20.0, help="seconds of CPU baseline work")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="config1", choices=["config1", "sequence", "ndt"],
+    ap.add_argument("--sub-sequences", type=int, default=32, help="sequences per GPU of the configs[4] sub-record")
+    ap.add_argument("--sub-scans", type=int, default=1000, help="scans per sequence of the configs[4] sub-record")
+    ap.add_argument("--cpu-scans", type=int, default=1000, help="sequence workloads: scans per sequence given to the CPU arm")
+    ap.add_argument("--sub-records", default="auto", choices=["auto", "all", "fleet", "none"],
+                    help="config1 line: also run BASELINE configs[2]/[3]/[4] and attach them as sub-records "
+                         "(auto = all on one GPU, the fleet of configs[4] on several)")
+    ap.add_argument("--workload", default="config1", choices=["config1", "sequence", "sequence_pt2pl", "ndt"],
                     help="config1 = the headline (default); sequence = BASELINE configs[2]/[4] full odometry loop; "
                          "ndt = configs[3] (lidar3d-ndt.yaml, O128 sensor)")
     ap.add_argument("--sequences", type=int, default=32, help="independent sequences per GPU (sequence/ndt workloads)")
@@ -768,6 +778,29 @@ def main():
                                      "ms_filter_1st/run_icp/update_local_map": [float(x) for x in ms3]},
                    "note": "CPU = our restatement of mp2p_icp/mola_metric_maps, not the upstream binary"}
 
+    # ---- sub-records: BASELINE.json configs[2] / [3] / [4] (whole sequences through the full odometry loop)
+    subs = {}
+    mode = args.sub_records if args.sub_records != "auto" else ("all" if world == 1 else "fleet")
+    if mode != "none":
+        plan = [("sequences_fleet", "sequence", args.sub_sequences, args.sub_scans)]
+        if mode == "all":
+            plan += [("sequence_single", "sequence", 1, 2 * args.sub_scans), ("sequence_pt2pl_fleet", "sequence_pt2pl", 8, args.sub_scans // 2),
+                     ("ndt_o128_fleet", "ndt", 8, args.sub_scans // 4)]
+        for name, kind, S_, N_ in plan:
+            run_fleet_workload(ctx, kind, S_, min(N_, 12), rank, world, cores, False, 0)                       # warm-up
+            barrier()
+            rec = run_fleet_workload(ctx, kind, S_, N_, rank, world, cores, rank == 0 and world == 1 and not args.no_cpu_baseline,
+                                     min(N_, args.cpu_scans))
+            tt = torch.tensor([rec["wall_s"]], dtype=torch.float64, device="cuda")
+            if world > 1:
+                dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+            rec["value"] = world * S_ * N_ / float(tt[0])      # whole job: all ranks' sequences / slowest rank
+            rec["n_gpus"] = world
+            if "cpu_baseline" in rec:
+                rec["speedup_vs_cpu"] = rec["value"] / rec["cpu_baseline"]["value"]
+            subs[name] = rec
+            log(f"[bench] {name}: {rec['value']:.0f} scans/s" + (f", CPU {rec['cpu_baseline']['value']:.0f} scans/s" if "cpu_baseline" in rec else ""))
+
     if rank == 0:
         line = {"metric": "scans/sec", "value": value, "unit": "scans/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
@@ -779,7 +812,8 @@ def main():
                 "gpu_launches": int(launches), "clocks": clocks, "roofline": roofline, "cpu_baseline": cpu,
                 "quality": {"mean_iterations": float(np.mean(iters)), "max_err_vs_gt_m": max(e[0] for e in err_gt),
                             "median_err_vs_gt_m": float(np.median([e[0] for e in err_gt])), "parity_vs_oracle": parity},
-                "timing": {"device_ms_total": ms_dev, "wall_ms_total": ms_wall}}
+                "timing": {"device_ms_total": ms_dev, "wall_ms_total": ms_wall},
+                "sub_records": subs}
         emit(line)
     if world > 1:
         dist.barrier()

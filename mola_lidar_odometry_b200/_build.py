@@ -64,6 +64,22 @@ def build_synth(force: bool = False) -> Path:
     return LIB_SYNTH
 
 
+LIB_SYNTH_CUDA = PKG / "synth" / "libmlo_synth_cuda.so"
+
+
+def build_synth_cuda(force: bool = False) -> Path:
+    """synth/synth_gpu.cu: the ray caster as a CUDA kernel (bench.py's sequence workloads; input generator only)."""
+    src = PKG / "synth" / "synth_gpu.cu"
+    if force or _newer(LIB_SYNTH_CUDA, [src]):
+        cmd = [_nvcc(), "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC",
+               "-shared", "-o", str(LIB_SYNTH_CUDA), str(src), "-lcudart"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            print(r.stdout + r.stderr)
+            raise RuntimeError("nvcc failed building libmlo_synth_cuda.so")
+    return LIB_SYNTH_CUDA
+
+
 def build_oracle(force: bool = False) -> Path:
     if force:
         subprocess.run(["make", "-C", str(ROOT / "oracle"), "clean"], check=True, capture_output=True)
@@ -86,6 +102,7 @@ def build_cli(force: bool = False) -> Path:
 
 def build_all(force: bool = False, verbose: bool = False) -> None:
     build_synth(force)
+    build_synth_cuda(force)
     build_cuda(force, verbose)
     build_oracle(force)
     build_cli(force)

@@ -456,12 +456,119 @@ MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
   __syncwarp();
 }
 
+// ---- bulk-async variant of the drain (A/B, MLO_WL_VARIANT=4): the 8-point row segments of a round are fetched by
+// cp.async.bulk (the TMA unit, SASS UBLKCP) into a per-warp shared-memory stage, completion on an mbarrier, and the next
+// round's copies are in flight while the current round is reduced - the software pipeline of PIPE without its register
+// cost (rows never sit in registers while in flight).  16 segments of <= 128 bytes per round and warp.
+struct WarpStage {
+  float4 pts[2][16][8];
+  unsigned long long bar[2];
+};
+MLO_D uint32_t smem_u32(const void* p) { return uint32_t(__cvta_generic_to_shared(p)); }
+MLO_D void mbar_init(unsigned long long* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+MLO_D void mbar_expect_tx(unsigned long long* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+MLO_D bool mbar_try_wait(unsigned long long* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+MLO_D void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, unsigned long long* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+MLO_D void wl_bulk_issue(const MapDev& map, const WarpScratch& ws, WarpStage& st, uint32_t n, uint32_t base, int s) {
+  const uint32_t lane = threadIdx.x & 31u;
+  uint32_t bytes = 0;
+  const float4* src = nullptr;
+  if (lane < 16 && base + lane < n) {
+    const uint32_t it = ws.list[base + lane];
+    const uint32_t q = it & 31u, e = (it >> 5) & 31u, k = it >> 10;
+    const uint32_t w = ws.words[e][q];
+    const uint32_t c = cell_cnt(w);
+    const uint32_t npts = c > k * 8u ? min(8u, c - k * 8u) : 0u;
+    bytes = npts * 16u;
+    src = map.pts + size_t(cell_vid(w)) * map.row + k * 8u;
+  }
+  uint32_t total = bytes;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xFFFFFFFFu, total, o);
+  if (lane == 0) mbar_expect_tx(&st.bar[s], total);  // (one arrival per phase; the copies complete its byte count)
+  __syncwarp();
+  if (bytes) bulk_g2s(&st.pts[s][lane][0], src, bytes, &st.bar[s]);
+}
+MLO_D void wl_bulk_consume(WarpScratch& ws, WarpStage& st, uint32_t n, uint32_t base, int s, uint32_t parity) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  uint32_t spins = 0;
+  while (!mbar_try_wait(&st.bar[s], parity)) {
+    if (++spins > (1u << 22)) break;  // safety net: never hang the device
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const uint32_t j = u * 4 + grp, idx = base + j;
+    unsigned long long key = ~0ull;
+    uint32_t q = 0;
+    if (idx < n) {
+      const uint32_t it = ws.list[idx];
+      q = it & 31u;
+      const uint32_t e = (it >> 5) & 31u, slot = (it >> 10) * 8u + sub;
+      if (slot < cell_cnt(ws.words[e][q])) {
+        const float4 p = st.pts[s][j][sub];
+        const float d2 = sqr_dist(p.x, p.y, p.z, ws.q[0][q], ws.q[1][q], ws.q[2][q]);
+        key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t(e * 32u + slot);
+      }
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+      key = other < key ? other : key;
+    }
+    if (sub == 0 && key != ~0ull) atomicMin(&ws.best[q], key);
+  }
+}
+// `par` = the phase parities of the two stage barriers of this warp (bit s), carried across calls
+MLO_D void wl_process_bulk(const MapDev& map, WarpScratch& ws, WarpStage& st, uint32_t n, uint32_t& par) {
+  if (n) wl_bulk_issue(map, ws, st, n, 0, 0);
+  int s = 0;
+  for (uint32_t base = 0; base < n; base += 16, s ^= 1) {
+    if (base + 16 < n) {
+      // the other stage was read (generic proxy) two rounds ago: order those reads before the async-proxy writes
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      __syncwarp();
+      wl_bulk_issue(map, ws, st, n, base + 16, s ^ 1);
+    }
+    wl_bulk_consume(ws, st, n, base, s, (par >> s) & 1u);
+    par ^= 1u << s;
+    __syncwarp();
+  }
+  // an odd number of rounds leaves the next call starting on stage 0 again: parities are per stage, so nothing to fix up
+  __syncwarp();
+}
+
 constexpr uint32_t WL_BLOCK = 32;  // the work-list kernel runs one warp per block: a chunk is 32 queries
-template <int NWARPS, bool PIPE = false>
+template <int NWARPS, bool PIPE = false, bool BULK = false>
 MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
   __shared__ WarpScratch s_ws[NWARPS];
+  __shared__ __align__(128) WarpStage s_stage[BULK ? NWARPS : 1];
+  uint32_t bulk_par = 0;
+  if constexpr (BULK) {
+    if ((threadIdx.x & 31u) == 0) {
+      mbar_init(&s_stage[threadIdx.x >> 5].bar[0], 1);
+      mbar_init(&s_stage[threadIdx.x >> 5].bar[1], 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncwarp();
+  }
   const uint32_t FULL = 0xFFFFFFFFu;
   const double thr = table_at(P.thr_pt2pt, P.table_len, it);
   const float thr2 = float(thr * thr);
@@ -526,7 +633,8 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       uint32_t off = incl - np;
       for (uint32_t k = 0; k < np; k++) ws.list[off + k] = uint16_t((k << 10) | (13u << 5) | lane);
       __syncwarp();
-      wl_process<PIPE>(map, ws, total);
+      if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
+      else wl_process<PIPE>(map, ws, total);
     }
     // ---- phase 3: per query, the neighbour cells that can still beat the bound from the own cell
     uint32_t visit = 0, my_items = 0;
@@ -569,7 +677,8 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
         }
       }
       __syncwarp();
-      wl_process<PIPE>(map, ws, total);
+      if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
+      else wl_process<PIPE>(map, ws, total);
       start = end;
     }
     // ---- result per query
@@ -1087,7 +1196,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
 }
 
 // four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
-template <bool MULTI, bool PIPE = false, int MINB = 8>
+template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false>
 __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_match_accumulate_wl4(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
                            const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,
@@ -1101,8 +1210,8 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
   if (MULTI) stage_map(sMap, maps, P.map_idx);
   __syncthreads();
-  if constexpr (MULTI) chunk_match_wl<4, PIPE>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
-  else chunk_match_wl<4, PIPE>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  if constexpr (MULTI) chunk_match_wl<4, PIPE, BULK>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  else chunk_match_wl<4, PIPE, BULK>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
 template <int MIN_BLOCKS>

@@ -400,6 +400,10 @@ MLO_D void cull_voxel(const MapDev& m, uint32_t v, int32_t sx, int32_t sy, int32
 __global__ void k_cull_inplace(MapDev m, int32_t sx, int32_t sy, int32_t sz, int32_t d) {
   cull_voxel(m, blockIdx.x * blockDim.x + threadIdx.x, sx, sy, sz, d);
 }
+// the counters of every job's map into ONE contiguous buffer (a fleet step then needs one device-to-host copy, not one per map)
+__global__ void k_gather_counters(const InsertJobDev* __restrict__ jobs, uint32_t* __restrict__ out) {
+  if (threadIdx.x < MAP_COUNTERS) out[blockIdx.x * MAP_COUNTERS + threadIdx.x] = jobs[blockIdx.x].m.counters[threadIdx.x];
+}
 __global__ void k_cull_inplace_batch(const InsertJobDev* __restrict__ jobs) {
   const InsertJobDev& j = jobs[blockIdx.y];
   if (j.d < 0) return;

@@ -1106,6 +1106,9 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
 #define MLO_WL_LAUNCH(MB)                                                                                              \
   LAUNCH_ON(c, sg, k_match_accumulate_wl<MB>, grid_g, WL_BLOCK, map->dev, gP, gS, d_local, c->d_pairA.as<float4>(),   \
             c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
+#define MLO_WL4_BULK_LAUNCH(MB)                                                                                             \
+  LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, true>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,    \
+            c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
 #define MLO_WL4_LAUNCH(PIPE, MB)                                                                                            \
   LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, PIPE, MB>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,           \
             c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
@@ -1114,6 +1117,8 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
             case 1: MLO_WL4_LAUNCH(true, 8); break;
             case 2: MLO_WL4_LAUNCH(true, 6); break;
             case 3: MLO_WL4_LAUNCH(false, 6); break;
+            case 4: MLO_WL4_BULK_LAUNCH(5); break;  // cp.async.bulk staging of the row segments (A/B)
+            case 5: MLO_WL4_BULK_LAUNCH(4); break;
             default: MLO_WL4_LAUNCH(false, 8); break;
           }
         }
@@ -2312,9 +2317,10 @@ int mlo_scanset_insert(mlo_scanset* set, uint32_t n_jobs, const mlo_insert_job* 
   }
   if (any_cull) LAUNCH(c, k_cull_inplace_batch, dim3((max_cap + 255) / 256, n_jobs), 256, ddj);
   CU(c, cudaGetLastError());
-  for (uint32_t j = 0; j < n_jobs; j++)
-    CU(c, cudaMemcpyAsync(h + size_t(j) * MAP_COUNTERS, jobs[j].map->dev.counters, MAP_COUNTERS * sizeof(uint32_t),
-                          cudaMemcpyDeviceToHost, c->stream));
+  // (one gather kernel + ONE device-to-host copy: a copy per map cost ~10 us each, 1.3 ms of a 128-sequence lock step)
+  CU(c, c->d_misc.ensure(std::max<size_t>(256, size_t(n_jobs) * MAP_COUNTERS * sizeof(uint32_t))));
+  LAUNCH(c, k_gather_counters, n_jobs, 32, ddj, c->d_misc.as<uint32_t>());
+  CU(c, cudaMemcpyAsync(h, c->d_misc.p, size_t(n_jobs) * MAP_COUNTERS * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
   prof_end(c, 2, e0);
   CU(c, cudaStreamSynchronize(c->stream));
   CU(c, cudaGetLastError());

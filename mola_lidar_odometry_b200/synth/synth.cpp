@@ -160,6 +160,16 @@ void* synth_scene_create(uint64_t seed, float extent_m, int n_poles, int n_cars)
   return make_scene(seed, extent_m, n_poles, n_cars);
 }
 void synth_scene_destroy(void* s) { delete static_cast<Scene*>(s); }
+// flat copies of the primitives (for the CUDA ray caster, synth_gpu.cu): boxes 6 floats, cylinders 5, spheres 4 each
+void synth_scene_export(void* s, int* n_boxes, float* boxes, int* n_cyls, float* cyls, int* n_sphs, float* sphs) {
+  const Scene& S = *static_cast<Scene*>(s);
+  *n_boxes = int(S.boxes.size());
+  *n_cyls = int(S.cyls.size());
+  *n_sphs = int(S.sphs.size());
+  if (boxes) std::memcpy(boxes, S.boxes.data(), S.boxes.size() * sizeof(Box));
+  if (cyls) std::memcpy(cyls, S.cyls.data(), S.cyls.size() * sizeof(Cyl));
+  if (sphs) std::memcpy(sphs, S.sphs.data(), S.sphs.size() * sizeof(Sph));
+}
 void synth_scene_counts(void* s, int* n_boxes, int* n_cyls) {
   *n_boxes = int(static_cast<Scene*>(s)->boxes.size());
   *n_cyls = int(static_cast<Scene*>(s)->cyls.size());
