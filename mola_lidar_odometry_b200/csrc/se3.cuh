@@ -149,11 +149,14 @@ MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
   mat3_mul(F, F, FF);
   // A = I - F/2 + k FF,  k = 1/t^2 - (1 + cos t) / (2 t sin t)
   double k, c1, c2, c3;
-  if (t2 < 1e-8) {
-    k = (1.0 / 12.0) + t2 * (1.0 / 720.0);
-    c1 = (1.0 / 6.0) - t2 * (1.0 / 120.0);
-    c2 = (1.0 / 24.0) - t2 * (1.0 / 720.0);
-    c3 = (1.0 / 120.0) - t2 * (1.0 / 2520.0);
+  if (t2 < 2.5e-3) {
+    // Taylor series for |phi| < 0.05 rad (truncation < 1e-16).  The closed forms below cancel catastrophically for small
+    // angles: c2's numerator t^2 + 2 cos t - 2 ~ t^4 / 12 is pure round-off below t ~ 1e-2 (found against the BCH series,
+    // tests/test_oracle_independent.py::test_se3_small_angle_accuracy_against_series).
+    k = (1.0 / 12.0) + t2 * ((1.0 / 720.0) + t2 * ((1.0 / 30240.0) + t2 * (1.0 / 1209600.0)));
+    c1 = (1.0 / 6.0) - t2 * ((1.0 / 120.0) - t2 * ((1.0 / 5040.0) - t2 * (1.0 / 362880.0)));
+    c2 = (1.0 / 24.0) - t2 * ((1.0 / 720.0) - t2 * ((1.0 / 40320.0) - t2 * (1.0 / 3628800.0)));
+    c3 = (1.0 / 120.0) - t2 * ((1.0 / 2520.0) - t2 * ((1.0 / 120960.0) - t2 * (1.0 / 9979200.0)));
   } else {
     const double t = sqrt(t2), s = sin(t), c = cos(t);
     k = 1.0 / t2 - (1.0 + c) / (2.0 * t * s);

@@ -62,9 +62,9 @@ inline void so3_exp(const double w[3], double R[3][3]) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const double th = std::sqrt(th2);
   double A, B;  // A = sin(th)/th, B = (1-cos(th))/th^2
-  if (th < 1e-8) {
-    A = 1.0 - th2 / 6.0;
-    B = 0.5 - th2 / 24.0;
+  if (th < 0.05) {  // series (see se3_exp): (1 - cos th) / th^2 cancels catastrophically for small th
+    A = 1.0 - th2 / 6.0 + th2 * th2 / 120.0 - th2 * th2 * th2 / 5040.0 + th2 * th2 * th2 * th2 / 362880.0;
+    B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0 - th2 * th2 * th2 / 40320.0 + th2 * th2 * th2 * th2 / 3628800.0;
   } else {
     A = std::sin(th) / th;
     B = (1.0 - std::cos(th)) / th2;
@@ -133,9 +133,11 @@ inline Pose se3_exp(const double xi[6]) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const double th = std::sqrt(th2);
   double B, C;  // B=(1-cos)/th^2, C=(th-sin)/th^3
-  if (th < 1e-8) {
-    B = 0.5 - th2 / 24.0;
-    C = 1.0 / 6.0 - th2 / 120.0;
+  if (th < 0.05) {
+    // Taylor series: below ~0.05 rad the closed forms cancel catastrophically ((1 - cos th) carries an absolute error
+    // of 1e-16 against a value of th^2 / 2), which a finite-difference Jacobian of log(D exp(e)) then amplifies by 1/h
+    B = 0.5 - th2 / 24.0 + th2 * th2 / 720.0 - th2 * th2 * th2 / 40320.0 + th2 * th2 * th2 * th2 / 3628800.0;
+    C = 1.0 / 6.0 - th2 / 120.0 + th2 * th2 / 5040.0 - th2 * th2 * th2 / 362880.0 + th2 * th2 * th2 * th2 / 39916800.0;
   } else {
     B = (1.0 - std::cos(th)) / th2;
     C = (th - std::sin(th)) / (th2 * th);
@@ -155,8 +157,8 @@ inline void se3_log(const Pose& p, double xi[6]) {
   const double th2 = w[0] * w[0] + w[1] * w[1] + w[2] * w[2];
   const double th = std::sqrt(th2);
   double D;  // V^-1 = I - 1/2 [w]x + D [w]x^2
-  if (th < 1e-6)
-    D = 1.0 / 12.0 + th2 / 720.0;
+  if (th < 0.05)  // series of (1 - (th/2) cot(th/2)) / th^2: the closed form below loses all digits for small th
+    D = 1.0 / 12.0 + th2 / 720.0 + th2 * th2 / 30240.0 + th2 * th2 * th2 / 1209600.0 + th2 * th2 * th2 * th2 / 47900160.0;
   else
     D = (1.0 - (th * std::sin(th)) / (2.0 * (1.0 - std::cos(th)))) / th2;
   const double* t = p.t;
