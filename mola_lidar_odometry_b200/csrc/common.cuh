@@ -24,7 +24,7 @@ namespace mlo {
 constexpr uint64_t KEY_EMPTY = 0xFFFFFFFFFFFFFFFFull;
 constexpr int32_t KEY_BIAS = 1 << 20;  // 21 bits per axis
 constexpr uint32_t HARD_LIMIT_PTS = 32; // upstream HARDLIMIT_MAX_POINTS_PER_VOXEL
-enum : uint32_t { ERR_CAPACITY = 1u, ERR_KEY_RANGE = 2u };  // device-side error bits
+enum : uint32_t { ERR_CAPACITY = 1u, ERR_KEY_RANGE = 2u, ERR_CTA_FALLBACK = 4u };  // device-side error bits (the last: filter.cuh k_decim_cta)
 constexpr uint32_t MAP_COUNTERS = 8;  // u32 words of MapDev::counters (map.cuh)
 
 // mola::HashedVoxelPointCloud::coordToGlobalIdx (pipelines/lidar3d-default.yaml:233 voxel_size):

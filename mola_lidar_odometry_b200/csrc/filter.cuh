@@ -340,6 +340,192 @@ __global__ void __launch_bounds__(DECIM_BLOCK) k_decim_finalize(const DecimJob* 
   }
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// FirstPoint decimation of one cloud by ONE thread block, scratch in SHARED memory (large batches: one block per SM,
+// a cloud per block, the hardware block scheduler hands the next cloud to whichever SM finishes first).
+//
+//   table   one 64-bit word per voxel: (packed voxel key << 32) | smallest input index.  Equal keys share the high
+//           word, so atomicMin on the whole word IS "smallest index of that voxel"; an entry never changes its key once
+//           claimed (CAS from EMPTY), so a plain read that shows the voxel with a smaller index already settles a point
+//           without any atomic - the common case, since a block walks its cloud in ascending index order.
+//   key     11 + 11 + 10 bits around grid index 0 (sensor-frame clouds: +-1024 cells in x / y, +-512 in z).  A point
+//           outside that box, or a table that runs full, raises ERR_CTA_FALLBACK and the host repeats the batch with
+//           k_decim_claim / k_decim_finalize (global tables, 3 x 21-bit keys): exact whenever it succeeds.
+//   bitmap  one bit per input point; winners that pass `post` set theirs, then a block-wide prefix sum over the bitmap
+//           words gives every winner its rank: the output is in input order, as FirstPoint over a sequential walk.
+//
+// The raw cloud is read once (coalesced, PPT loads in flight per thread); the few thousand winners are fetched again by
+// index.  No global scratch, no memset, no candidate buffers, no inter-block look-back: DRAM sees N_in * 16 bytes in and
+// N_out * 16 bytes out, which is SURVEY.md §8(d)'s figure for this operator.
+constexpr uint32_t CTA_DECIM_THREADS = 1024;
+constexpr unsigned long long CTA_EMPTY = ~0ull;
+constexpr uint32_t CTA_MAX_PROBES = 256;
+
+MLO_D bool pack_key32(int32_t kx, int32_t ky, int32_t kz, uint32_t& pk) {
+  const uint32_t ux = uint32_t(kx + 1024), uy = uint32_t(ky + 1024), uz = uint32_t(kz + 512);
+  pk = (ux << 21) | (uy << 10) | uz;
+  return ux < 2048u && uy < 2048u && uz < 1024u;
+}
+
+// false = no room within CTA_MAX_PROBES slots
+MLO_D bool cta_table_put(unsigned long long* tab, uint32_t T, uint32_t pk, uint32_t i) {
+  const unsigned long long want = (uint64_t(pk) << 32) | i;
+  uint32_t slot = __umulhi(hash_mix(pk * HASH_PX), T);
+  for (uint32_t probes = 0; probes < CTA_MAX_PROBES; probes++) {
+    unsigned long long cur = *reinterpret_cast<volatile unsigned long long*>(&tab[slot]);
+    if (cur == CTA_EMPTY) {
+      cur = atomicCAS(&tab[slot], CTA_EMPTY, want);
+      if (cur == CTA_EMPTY) return true;
+    }
+    if (uint32_t(cur >> 32) == pk) {
+      if (cur > want) atomicMin(&tab[slot], want);
+      return true;
+    }
+    slot = slot + 1 == T ? 0u : slot + 1;
+  }
+  return false;
+}
+
+template <int PPT>
+__global__ void __launch_bounds__(CTA_DECIM_THREADS, 1) k_decim_cta(const DecimJob* __restrict__ jobs, uint32_t tab_cap, uint32_t bitmap_cap_words) {
+  extern __shared__ __align__(16) unsigned char cta_smem[];
+  unsigned long long* tab = reinterpret_cast<unsigned long long*>(cta_smem);
+  uint32_t* bitmap = reinterpret_cast<uint32_t*>(tab + tab_cap);
+  __shared__ uint32_t s_wsum[CTA_DECIM_THREADS / 32];
+  __shared__ uint32_t s_npred, s_fail;
+  const DecimJob& j = jobs[blockIdx.x];
+  const uint32_t n = job_n(j);
+  if (n == 0) return;  // (n_out / npred were cleared by the host)
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+  const uint32_t words = (n + 31u) >> 5;
+  if (words > bitmap_cap_words) {  // (the host sizes the bitmap for the largest cloud of the batch)
+    if (tid == 0) atomicOr(j.err, ERR_CTA_FALLBACK);
+    return;
+  }
+  const uint32_t T = min(tab_cap, max(2048u, n * 4u));
+  const bool has_pre = j.pre.use_range || j.pre.use_bbox;
+  const bool has_post = j.post.use_range || j.post.use_bbox;
+  const bool pass_static = n < j.min_pts;  // fewer inputs than minimum_input_points_to_filter: certain pass-through
+  if (!pass_static)
+    for (uint32_t s = tid; s < T; s += CTA_DECIM_THREADS) tab[s] = CTA_EMPTY;
+  for (uint32_t s = tid; s < words; s += CTA_DECIM_THREADS) bitmap[s] = 0u;
+  if (tid == 0) {
+    s_npred = 0;
+    s_fail = 0;
+  }
+  __syncthreads();
+
+  // ---- pass A: the cloud, once
+  uint32_t my_pred = 0;
+  bool fail = false;
+  for (uint32_t base = 0; base < n; base += CTA_DECIM_THREADS * PPT) {
+    float4 p[PPT];
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      const uint32_t i = base + u * CTA_DECIM_THREADS + tid;
+      p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (i < n) p[u] = load_point(j.in, j.in_stride, i);
+    }
+#pragma unroll
+    for (int u = 0; u < PPT; u++) {
+      const uint32_t i = base + u * CTA_DECIM_THREADS + tid;
+      if (i >= n) continue;
+      if (!predicate_keep(j.pre, p[u].x, p[u].y, p[u].z)) continue;
+      const int32_t kx = voxel_index_filter(p[u].x, j.resolution, j.index_floor), ky = voxel_index_filter(p[u].y, j.resolution, j.index_floor),
+                    kz = voxel_index_filter(p[u].z, j.resolution, j.index_floor);
+      uint32_t pk;
+      if (!pack_key32(kx, ky, kz, pk)) {
+        fail = true;
+        continue;
+      }
+      my_pred++;
+      if (pass_static) {
+        if (!has_post || predicate_keep(j.post, p[u].x, p[u].y, p[u].z)) atomicOr(&bitmap[i >> 5], 1u << (i & 31u));
+      } else if (!cta_table_put(tab, T, pk, i)) {
+        fail = true;
+      }
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) my_pred += __shfl_xor_sync(FULL, my_pred, o);
+  if (lane == 0 && my_pred) atomicAdd(&s_npred, my_pred);
+  if (fail) atomicOr(&s_fail, 1u);
+  __syncthreads();
+  if (s_fail) {
+    if (tid == 0) atomicOr(j.err, ERR_CTA_FALLBACK);
+    return;
+  }
+  const uint32_t npred = s_npred;
+  if (!pass_static) {
+    if (has_pre && npred < j.min_pts) {
+      // pass-through decided by the number of survivors of `pre` (known only now): every survivor that passes `post`
+      for (uint32_t i = tid; i < n; i += CTA_DECIM_THREADS) {
+        const float4 q = load_point(j.in, j.in_stride, i);
+        if (!predicate_keep(j.pre, q.x, q.y, q.z)) continue;
+        if (!has_post || predicate_keep(j.post, q.x, q.y, q.z)) atomicOr(&bitmap[i >> 5], 1u << (i & 31u));
+      }
+    } else {
+      // ---- pass B: winners = the table's entries
+      for (uint32_t s = tid; s < T; s += CTA_DECIM_THREADS) {
+        const unsigned long long e = tab[s];
+        if (e == CTA_EMPTY) continue;
+        const uint32_t i = uint32_t(e);
+        bool keep = true;
+        if (has_post) {
+          const float4 q = load_point(j.in, j.in_stride, i);
+          keep = predicate_keep(j.post, q.x, q.y, q.z);
+        }
+        if (keep) atomicOr(&bitmap[i >> 5], 1u << (i & 31u));
+      }
+    }
+  }
+  __syncthreads();
+
+  // ---- pass C: ranks from the bitmap (thread t owns words [t * wpt, (t + 1) * wpt)), winners out in input order
+  const uint32_t wpt = (words + CTA_DECIM_THREADS - 1) / CTA_DECIM_THREADS;
+  const uint32_t w0 = min(words, tid * wpt), w1 = min(words, w0 + wpt);
+  uint32_t cnt = 0;
+  for (uint32_t w = w0; w < w1; w++) cnt += __popc(bitmap[w]);
+  uint32_t incl = cnt;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const uint32_t y = __shfl_up_sync(FULL, incl, o);
+    if (lane >= uint32_t(o)) incl += y;
+  }
+  if (lane == 31) s_wsum[warp] = incl;
+  __syncthreads();
+  if (warp == 0) {
+    const uint32_t v = s_wsum[lane];
+    uint32_t wi = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t y = __shfl_up_sync(FULL, wi, o);
+      if (lane >= uint32_t(o)) wi += y;
+    }
+    s_wsum[lane] = wi - v;
+    if (lane == 31) {
+      *j.n_out = wi;
+      *j.npred = npred;
+    }
+  }
+  __syncthreads();
+  uint32_t rank = s_wsum[warp] + incl - cnt;
+  for (uint32_t w = w0; w < w1; w++) {
+    uint32_t bits = bitmap[w];
+    while (bits) {
+      const uint32_t i = (w << 5) + uint32_t(__ffs(bits) - 1);
+      bits &= bits - 1;
+      float4 q = load_point(j.in, j.in_stride, i);
+      if (j.in_t) q.w = __ldg(j.in_t + i);
+      else if (!j.keep_w) q.w = 0.f;
+      j.out[rank] = q;
+      if (j.out_idx) j.out_idx[rank] = i;
+      rank++;
+    }
+  }
+}
+
 // mp2p_icp_filters::FilterDeskew (pipelines/lidar3d-default.yaml:328-350): p' = exp_SO3(w t) p + v t, t = in.w.
 // Same operation order and the same small-angle series as the CPU statement (bit-exact for |w t| < 0.05 rad).
 MLO_D void deskew_coeffs(double th2, double& A, double& B) {

@@ -456,6 +456,75 @@ MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
   __syncwarp();
 }
 
+// ---- contiguous-range drain (MLO_WL_VARIANT 6-8): each group of 8 lanes owns a CONTIGUOUS quarter of the list, so
+// consecutive items of a group mostly belong to the same query: the running best of that query stays in a register of
+// each lane (one 64-bit compare per candidate point) and the 8 lanes are merged (3 shuffle steps + one shared-memory
+// atomicMin) only when a group moves on to the next query - not after every segment as in wl_consume.  The merge runs
+// under a warp-uniform vote, i.e. for all four groups whenever any of them crosses a query boundary.  Same keys, same
+// minimum: bit-identical pairings.  DEPTH = row loads in flight per lane.
+MLO_D void wl_oct_flush(WarpScratch& ws, uint32_t sub, bool flush, uint32_t cur_q, unsigned long long& best) {
+  unsigned long long key = best;
+#pragma unroll
+  for (int o = 1; o < 8; o <<= 1) {
+    const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+    key = other < key ? other : key;
+  }
+  if (flush) {
+    if (sub == 0 && key != ~0ull) atomicMin(&ws.best[cur_q], key);
+    best = ~0ull;
+  }
+}
+template <int DEPTH>
+MLO_D void wl_process_oct(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  const uint32_t per = (n + 3u) >> 2;  // items per group
+  const uint32_t g0 = grp * per, g1 = min(n, g0 + per);
+  uint32_t cur_q = 32u;  // none yet
+  float qx = 0.f, qy = 0.f, qz = 0.f;
+  unsigned long long best = ~0ull;
+  for (uint32_t r = 0; r < per; r += DEPTH) {
+    float4 p[DEPTH];
+    uint32_t meta[DEPTH];  // (item valid << 31) | (point valid << 30) | (order << 5) | q
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++) {
+      const uint32_t idx = g0 + r + u;
+      meta[u] = 0;
+      if (idx < g1) {
+        const uint32_t it = ws.list[idx];
+        const uint32_t q = it & 31u, e = (it >> 5) & 31u, slot = (it >> 10) * 8u + sub;
+        const uint32_t w = ws.words[e][q];
+        meta[u] = 0x80000000u | q;
+        if (slot < cell_cnt(w)) {
+          p[u] = __ldg(map.pts + size_t(cell_vid(w)) * map.row + slot);
+          meta[u] = 0xC0000000u | ((e * 32u + slot) << 5) | q;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < DEPTH; u++) {
+      const uint32_t q = meta[u] & 31u;
+      const bool moved = (meta[u] & 0x80000000u) && q != cur_q;
+      if (__any_sync(FULL, moved)) {  // (warp-uniform)
+        wl_oct_flush(ws, sub, moved && cur_q < 32u, cur_q, best);
+        if (moved) {
+          cur_q = q;
+          qx = ws.q[0][q];
+          qy = ws.q[1][q];
+          qz = ws.q[2][q];
+        }
+      }
+      if (meta[u] & 0x40000000u) {
+        const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, qx, qy, qz);
+        const unsigned long long key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu);
+        best = key < best ? key : best;
+      }
+    }
+  }
+  wl_oct_flush(ws, sub, cur_q < 32u, cur_q, best);
+  __syncwarp();
+}
+
 // ---- bulk-async variant of the drain (A/B, MLO_WL_VARIANT=4): the 8-point row segments of a round are fetched by
 // cp.async.bulk (the TMA unit, SASS UBLKCP) into a per-warp shared-memory stage, completion on an mbarrier, and the next
 // round's copies are in flight while the current round is reduced - the software pipeline of PIPE without its register
@@ -554,7 +623,7 @@ MLO_D void wl_process_bulk(const MapDev& map, WarpScratch& ws, WarpStage& st, ui
 }
 
 constexpr uint32_t WL_BLOCK = 32;  // the work-list kernel runs one warp per block: a chunk is 32 queries
-template <int NWARPS, bool PIPE = false, bool BULK = false>
+template <int NWARPS, bool PIPE = false, bool BULK = false, int OCT = 0, bool WPART = false>
 MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
@@ -634,6 +703,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       for (uint32_t k = 0; k < np; k++) ws.list[off + k] = uint16_t((k << 10) | (13u << 5) | lane);
       __syncwarp();
       if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
+      else if constexpr (OCT > 0) wl_process_oct<OCT>(map, ws, total);
       else wl_process<PIPE>(map, ws, total);
     }
     // ---- phase 3: per query, the neighbour cells that can still beat the bound from the own cell
@@ -678,6 +748,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       }
       __syncwarp();
       if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
+      else if constexpr (OCT > 0) wl_process_oct<OCT>(map, ws, total);
       else wl_process<PIPE>(map, ws, total);
       start = end;
     }
@@ -713,6 +784,16 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       pairB[P.q_begin + q] = pb;
     }
     pairA[P.q_begin + q] = pa;
+  }
+  if constexpr (WPART && NWARPS > 1) {
+    // every warp of the block publishes its own partial (P.n_blocks counts 32-query chunks): no block barrier, a warp
+    // that finishes its work list early retires without waiting for its neighbours
+    const uint32_t wchunk = chunk * NWARPS + warp;
+    if (wchunk < P.n_blocks) {
+      const uint32_t pbi = P.part_begin + wchunk;
+      warp_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+    }
+    return;
   }
   const uint32_t pbi = P.part_begin + chunk;
   if (NWARPS == 1)
@@ -1196,13 +1277,13 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
 }
 
 // four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
-template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false>
+template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false, int OCT = 0, bool WPART = false>
 __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_match_accumulate_wl4(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
                            const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,
                            float4* __restrict__ pairB, double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
   const IcpProblem& P = probs[blockIdx.y];
-  if (blockIdx.x >= P.n_blocks) return;
+  if (blockIdx.x * (WPART ? 4u : 1u) >= P.n_blocks) return;
   const IcpState& S = states[blockIdx.y];
   if (S.done) return;
   __shared__ double sT[12];
@@ -1210,8 +1291,8 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
   if (MULTI) stage_map(sMap, maps, P.map_idx);
   __syncthreads();
-  if constexpr (MULTI) chunk_match_wl<4, PIPE, BULK>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
-  else chunk_match_wl<4, PIPE, BULK>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  if constexpr (MULTI) chunk_match_wl<4, PIPE, BULK, OCT, WPART>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  else chunk_match_wl<4, PIPE, BULK, OCT, WPART>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
 template <int MIN_BLOCKS>
@@ -1468,6 +1549,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
       sum_partials_block(P, partials, part_cnt, phase == 0 ? P.n_blocks_pers : P.n_blocks_acc, s_solve);
       MLO_TRACE_EVENT(prob, 5);  // partials summed
     }
+    int nx = 0;  // (block-uniform: read behind a barrier / returned behind a barrier)
     if (s_last) {
       if (threadIdx.x < 32) {
         const int n = solve_step(P, S, s_solve, phase == 0);
@@ -1475,14 +1557,12 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
       }
       __syncthreads();
       MLO_TRACE_EVENT(prob, 6);  // first solve done
-      int nx = s_nx;
+      nx = s_nx;
       if (fuse && P.n_q <= FUSE_MAX_Q) nx = fused_inner_iterations(P, S, s_solve, nx, s_it, local, pairA, pairB);
-      if (threadIdx.x == 0) s_nx = nx;
-      __syncthreads();
       MLO_TRACE_EVENT(prob, 7);  // fused inner iterations done
     }
     if (s_last && threadIdx.x < 32) {
-      const int next = s_nx;
+      const int next = nx;
       if (threadIdx.x == 0) __threadfence();  // state of the problem visible before its next items
       __syncwarp();
       if (next == 1) {

@@ -118,6 +118,14 @@ struct mlo_ctx {
   // profiles/README.md), so the default is "everything in one group".
   int filter_group_mb = 1 << 20;
   int filter_ppt = 4;  // mlo_set_option("filter_ppt"): input points per thread of the decimation kernels (1 / 2 / 4)
+  // mlo_set_option("filter_kernel"): 0 = by batch size (default), 1 = k_decim_claim / k_decim_finalize (global scratch
+  // tables, blocks of a cloud spread over the device), 2 = k_decim_cta (one thread block per cloud, scratch in shared
+  // memory; falls back to 1 for a batch whose clouds do not fit its 32-bit keys / its table).
+  int filter_kernel = 0;
+  int filter_cta_min_clouds = 16;  // mlo_set_option("filter_cta_min_clouds"): smallest batch that takes k_decim_cta under 0
+  int filter_cta_backoff = 0;      // batches left before k_decim_cta is tried again after a fallback
+  int last_filter_kernel = 0;      // what the last filter batch ran (tests)
+  bool cta_attr_set = false;
   int conv_index_floor = 0, conv_gm_form = 0, conv_cull_metric = 0;  // [VERIFY] conventions (common.cuh), captured by maps at creation
   uint32_t log_cap = 0;  // mlo_icp_log_enable: records kept per problem (0 = off)
   DBuf d_log;
@@ -243,6 +251,11 @@ int fail(mlo_ctx* c, int code, const std::string& msg) {
   do {                                                 \
     kern<<<grid, block, 0, (ctx)->stream>>>(__VA_ARGS__); \
     (ctx)->launches++;                                 \
+  } while (0)
+#define LAUNCH_SMEM(ctx, kern, grid, block, smem, ...)          \
+  do {                                                          \
+    kern<<<grid, block, smem, (ctx)->stream>>>(__VA_ARGS__);    \
+    (ctx)->launches++;                                          \
   } while (0)
 #define LAUNCH_ON(ctx, strm, kern, grid, block, ...) \
   do {                                               \
@@ -499,12 +512,50 @@ struct FilterBatch {
   bool single = false;
   uint32_t* d_idx_out = nullptr;
   const float* d_t = nullptr;
+  bool used_cta = false;  // the batch ran k_decim_cta (a raised ERR_CTA_FALLBACK repeats it with the global-table kernels)
 };
 constexpr uint32_t CNT_STRIDE = 8;
+constexpr size_t CTA_DECIM_SMEM = 220 * 1024;  // dynamic shared memory of k_decim_cta: table + bitmap
+
+// The parts of a cloud's two decimation jobs that do not depend on the scratch layout (inputs, predicates, outputs).
+// j1 / j2 must be zero-initialised by the caller or carry only scratch pointers.
+void fill_decim_jobs(mlo_ctx* c, DecimJob& j1, DecimJob& j2, uint32_t b, const float* d_raw, uint32_t stride, const uint64_t* offsets,
+                     const mlo_filter1_params* fps, bool single_decimate_idx, uint32_t* d_idx_out, const float* d_t, DBuf& b_map,
+                     DBuf& b_icp, uint32_t* cnt) {
+  const uint32_t n = uint32_t(offsets[b + 1] - offsets[b]);
+  j1.err = j2.err = cnt + b * CNT_STRIDE + 5;
+  j1.in = d_raw + offsets[b] * stride;
+  j1.in_t = d_t ? d_t + offsets[b] : nullptr;
+  j1.in_stride = stride;
+  j1.n_in_static = n;
+  j1.index_floor = j2.index_floor = c->conv_index_floor;
+  j1.resolution = fps[b].for_map.voxel_filter_resolution;
+  j1.min_pts = fps[b].for_map.minimum_input_points_to_filter;
+  j1.npred = cnt + b * CNT_STRIDE + 3;
+  if (single_decimate_idx) {  // mlo_voxel_decimate_first: predicates in front of ONE decimation, indices out
+    fill_pred(j1.pre, fps[b].for_map, true);
+    j1.out = b_map.as<float4>() + offsets[b];
+    j1.n_out = cnt + b * CNT_STRIDE + 0;
+    j1.out_idx = d_idx_out + offsets[b];
+  } else {
+    fill_pred(j1.post, fps[b].for_icp, true);
+    j1.out = b_map.as<float4>() + offsets[b];
+    j1.n_out = cnt + b * CNT_STRIDE + 1;
+    j2.in = reinterpret_cast<const float*>(b_map.as<float4>() + offsets[b]);
+    j2.in_stride = 4;
+    j2.keep_w = d_t ? 1 : 0;
+    j2.n_in_dev = cnt + b * CNT_STRIDE + 1;
+    j2.resolution = fps[b].for_icp.voxel_filter_resolution;
+    j2.min_pts = fps[b].for_icp.minimum_input_points_to_filter;
+    j2.npred = cnt + b * CNT_STRIDE + 4;
+    j2.out = b_icp.as<float4>() + offsets[b];
+    j2.n_out = cnt + b * CNT_STRIDE + 2;
+  }
+}
 
 int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n_clouds, const uint64_t* offsets,
                      const mlo_filter1_params* fps, bool single_decimate_idx, uint32_t* d_idx_out, FilterBatch& fb,
-                     const float* d_t = nullptr, bool conservative = false) {
+                     const float* d_t = nullptr, bool conservative = false, bool force_global = false) {
   fb.n_clouds = n_clouds;
   fb.out_off.assign(offsets, offsets + n_clouds + 1);
   fb.d_raw = d_raw;
@@ -524,6 +575,41 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
   uint32_t* cnt = b_cnt.as<uint32_t>();
   CU(c, cudaMemsetAsync(cnt, 0, std::max<size_t>(size_t(n_clouds), 1) * CNT_STRIDE * sizeof(uint32_t), c->stream));
   if (total == 0 || max_n == 0) return MLO_OK;
+  // ---- which kernels: one block per cloud with shared-memory scratch (large batches), or global scratch tables
+  const size_t bitmap_words = (size_t(max_n) + 31) / 32;
+  const bool cta_fits = bitmap_words * 4 + 4096 * 8 <= CTA_DECIM_SMEM;
+  bool use_cta = false;
+  if (!force_global && !conservative && cta_fits) {
+    if (c->filter_kernel == 2) use_cta = true;
+    else if (c->filter_kernel == 0 && int(n_clouds) >= c->filter_cta_min_clouds) {
+      if (c->filter_cta_backoff > 0) c->filter_cta_backoff--;
+      else use_cta = true;
+    }
+  }
+  fb.used_cta = use_cta;
+  c->last_filter_kernel = use_cta ? 2 : 1;
+  if (use_cta) {
+    const uint32_t tab_cap = uint32_t((CTA_DECIM_SMEM - bitmap_words * 4) / 8);
+    if (!c->cta_attr_set) {
+      CU(c, cudaFuncSetAttribute(k_decim_cta<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, int(CTA_DECIM_SMEM)));
+      c->cta_attr_set = true;
+    }
+    CU(c, b_map.ensure(total * sizeof(float4)));
+    CU(c, b_icp.ensure(total * sizeof(float4)));
+    CU(c, c->d_f_jobs.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
+    CU(c, c->h_stage.ensure(2 * size_t(n_clouds) * sizeof(DecimJob)));
+    DecimJob* hj = c->h_stage.as<DecimJob>();
+    std::memset(hj, 0, 2 * size_t(n_clouds) * sizeof(DecimJob));
+    for (uint32_t b = 0; b < n_clouds; b++)
+      fill_decim_jobs(c, hj[b], hj[n_clouds + b], b, d_raw, stride, offsets, fps, single_decimate_idx, d_idx_out, d_t, b_map, b_icp, cnt);
+    CU(c, cudaMemcpyAsync(c->d_f_jobs.p, hj, 2 * size_t(n_clouds) * sizeof(DecimJob), cudaMemcpyHostToDevice, c->stream));
+    const DecimJob* dj1 = c->d_f_jobs.as<DecimJob>();
+    for (int stage = 0; stage < (single_decimate_idx ? 1 : 2); stage++)
+      LAUNCH_SMEM(c, k_decim_cta<4>, n_clouds, CTA_DECIM_THREADS, CTA_DECIM_SMEM, dj1 + size_t(stage) * n_clouds, tab_cap,
+                  uint32_t(bitmap_words));
+    CU(c, cudaGetLastError());
+    return MLO_OK;
+  }
   // ---- per-cloud scratch geometry and the groups
   // stage-1 table: half an entry per input point (a 0.5 m grid keeps a third of a 64-beam sweep at most: load factor
   // <= 0.6); stage-2 table: an eighth (its input is the map layer, its output a few thousand points).  A cloud that
@@ -601,34 +687,7 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
       j1.tab_mask = uint32_t(geo[b].tab1 - 1);
       j2.tab = tab + t_off + geo[b].tab1;
       j2.tab_mask = geo[b].tab2 ? uint32_t(geo[b].tab2 - 1) : 0u;
-      j1.err = j2.err = cnt + b * CNT_STRIDE + 5;
-      j1.in = d_raw + offsets[b] * stride;
-      j1.in_t = d_t ? d_t + offsets[b] : nullptr;
-      j1.in_stride = stride;
-      j1.n_in_static = n;
-      j1.index_floor = j2.index_floor = c->conv_index_floor;
-      j1.resolution = fps[b].for_map.voxel_filter_resolution;
-      j1.min_pts = fps[b].for_map.minimum_input_points_to_filter;
-      j1.npred = cnt + b * CNT_STRIDE + 3;
-      if (single_decimate_idx) {  // mlo_voxel_decimate_first: predicates in front of ONE decimation, indices out
-        fill_pred(j1.pre, fps[b].for_map, true);
-        j1.out = b_map.as<float4>() + offsets[b];
-        j1.n_out = cnt + b * CNT_STRIDE + 0;
-        j1.out_idx = d_idx_out + offsets[b];
-      } else {
-        fill_pred(j1.post, fps[b].for_icp, true);
-        j1.out = b_map.as<float4>() + offsets[b];
-        j1.n_out = cnt + b * CNT_STRIDE + 1;
-        j2.in = reinterpret_cast<const float*>(b_map.as<float4>() + offsets[b]);
-        j2.in_stride = 4;
-        j2.keep_w = d_t ? 1 : 0;
-        j2.n_in_dev = cnt + b * CNT_STRIDE + 1;
-        j2.resolution = fps[b].for_icp.voxel_filter_resolution;
-        j2.min_pts = fps[b].for_icp.minimum_input_points_to_filter;
-        j2.npred = cnt + b * CNT_STRIDE + 4;
-        j2.out = b_icp.as<float4>() + offsets[b];
-        j2.n_out = cnt + b * CNT_STRIDE + 2;
-      }
+      fill_decim_jobs(c, j1, j2, b, d_raw, stride, offsets, fps, single_decimate_idx, d_idx_out, d_t, b_map, b_icp, cnt);
       t_off += geo[b].tab1 + geo[b].tab2;
       p_off += geo[b].pts;
       k_off += geo[b].nblk;
@@ -668,21 +727,30 @@ int run_filter_batch(mlo_ctx* c, const float* d_raw, uint32_t stride, uint32_t n
 int filter_counts(mlo_ctx* c, FilterBatch& fb, std::vector<uint32_t>& h) {
   const DBuf& b_cnt = fb.out_cnt ? *fb.out_cnt : c->d_f_cnt;
   h.assign(std::max<size_t>(fb.n_clouds, 1) * CNT_STRIDE, 0u);
-  for (int attempt = 0; attempt < 2; attempt++) {
+  bool conservative = false;
+  for (int attempt = 0; attempt < 3; attempt++) {
     CU(c, cudaMemcpyAsync(h.data(), b_cnt.p, h.size() * sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
     CU(c, cudaStreamSynchronize(c->stream));
-    bool full = false;
+    bool full = false, fallback = false;
     for (uint32_t b = 0; b < fb.n_clouds; b++) {
       if (h[b * CNT_STRIDE + 5] & ERR_KEY_RANGE) return fail(c, MLO_ERR_KEY_RANGE, "voxel index outside the packed 21-bit range");
       full = full || (h[b * CNT_STRIDE + 5] & ERR_CAPACITY);
+      fallback = fallback || (h[b * CNT_STRIDE + 5] & ERR_CTA_FALLBACK);
     }
-    if (!full) return MLO_OK;
-    if (attempt == 1) return fail(c, MLO_ERR_CAPACITY, "decimation scratch table exhausted");
+    if (!full && !fallback) return MLO_OK;
+    if (fallback && fb.used_cta) {
+      // a cloud outside k_decim_cta's 32-bit key box, or more voxels than its shared-memory table holds: the global-table
+      // kernels take the batch, and the next batches of this context go to them directly for a while
+      c->filter_cta_backoff = 64;
+    } else {
+      if (conservative) return fail(c, MLO_ERR_CAPACITY, "decimation scratch table exhausted");
+      conservative = true;
+    }
     std::vector<uint64_t> offs = fb.out_off;
-    int rc = run_filter_batch(c, fb.d_raw, fb.stride, fb.n_clouds, offs.data(), fb.fps, fb.single, fb.d_idx_out, fb, fb.d_t, true);
+    int rc = run_filter_batch(c, fb.d_raw, fb.stride, fb.n_clouds, offs.data(), fb.fps, fb.single, fb.d_idx_out, fb, fb.d_t, conservative, true);
     if (rc != MLO_OK) return rc;
   }
-  return MLO_OK;
+  return fail(c, MLO_ERR_CAPACITY, "decimation scratch table exhausted");
 }
 
 __global__ void k_to_float4(const float* __restrict__ src, uint32_t stride, uint64_t n, float4* __restrict__ dst) {
@@ -940,7 +1008,10 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     std::memcpy(P.hook_checkpoint, p.hook_checkpoint_pose_3x4, sizeof(P.hook_checkpoint));
     const bool use_wl = use_tpq && (multi || c->force_kernel != 1);
     const uint32_t qpb_pers = use_tpq ? ICP_BLOCK : (ICP_BLOCK / 32) * qpw;  // persistent kernel: tpq or warp chunks
-    const uint32_t qpb = use_wl ? ((multi || c->wl_warps == 4) ? ICP_BLOCK : WL_BLOCK) : qpb_pers;  // launch sequence: work-list chunks
+    // launch sequence: work-list chunks of 128 queries (one partial per block) or of 32 (one partial per warp: one-warp
+    // blocks, or four-warp blocks without the closing block barrier - wl_variant 10 / 11)
+    const bool warp_partials = !multi && (c->wl_warps != 4 || c->wl_variant == 10 || c->wl_variant == 11);
+    const uint32_t qpb = use_wl ? (warp_partials ? WL_BLOCK : ICP_BLOCK) : qpb_pers;
     P.n_blocks = (P.n_q + qpb - 1) / qpb;
     P.n_blocks_pers = (P.n_q + qpb_pers - 1) / qpb_pers;
     P.n_blocks_acc = (P.n_q + ICP_BLOCK - 1) / ICP_BLOCK;
@@ -1112,8 +1183,21 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
 #define MLO_WL4_LAUNCH(PIPE, MB)                                                                                            \
   LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, PIPE, MB>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS, d_local,           \
             c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
+#define MLO_WL4_OCT_LAUNCH(DEPTH, MB)                                                                                       \
+  LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, false, DEPTH>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS,   \
+            d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
+#define MLO_WL4_WPART_LAUNCH(MB)                                                                                            \
+  LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, false, 0, true>), dim3((grid_g.x + 3) / 4, grid_g.y), ICP_BLOCK,  \
+            map->dev, d_maps, gP, gS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), \
+            c->d_partcnt.as<uint32_t>())
         if (c->wl_warps == 4) {
           switch (c->wl_variant) {  // MLO_WL_VARIANT: A/B of the drain loop (profiles/README.md)
+            case 6: MLO_WL4_OCT_LAUNCH(4, 6); break;  // contiguous-range drain, register-resident running best
+            case 7: MLO_WL4_OCT_LAUNCH(4, 8); break;
+            case 8: MLO_WL4_OCT_LAUNCH(8, 6); break;
+            case 9: MLO_WL4_OCT_LAUNCH(8, 5); break;
+            case 10: MLO_WL4_WPART_LAUNCH(6); break;  // one partial per warp, no block barrier
+            case 11: MLO_WL4_WPART_LAUNCH(8); break;
             case 1: MLO_WL4_LAUNCH(true, 8); break;
             case 2: MLO_WL4_LAUNCH(true, 6); break;
             case 3: MLO_WL4_LAUNCH(false, 6); break;
@@ -1280,6 +1364,8 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* bc = getenv("MLO_BLOCK_CLUSTER")) c->block_cluster = atoi(bc);
   if (const char* fg = getenv("MLO_FILTER_GROUP_MB")) c->filter_group_mb = std::max(1, atoi(fg));
   if (const char* fp = getenv("MLO_FILTER_PPT")) c->filter_ppt = atoi(fp);
+  if (const char* fk = getenv("MLO_FILTER_KERNEL")) c->filter_kernel = atoi(fk);
+  if (const char* fm = getenv("MLO_FILTER_CTA_MIN_CLOUDS")) c->filter_cta_min_clouds = std::max(1, atoi(fm));
   if (const char* pk = getenv("MLO_PERSISTENT")) {
     c->use_persistent = atoi(pk) != 0;
     c->persistent_forced = atoi(pk) == 2;  // 2 = always, regardless of batch size (experiments)
@@ -1370,6 +1456,8 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "pers_minb") c->pers_minb = v == 2 ? 2 : (v == 4 ? 4 : 0);
   else if (n == "filter_group_mb") c->filter_group_mb = int(std::max<int64_t>(1, v));
   else if (n == "filter_ppt") c->filter_ppt = int(v);
+  else if (n == "filter_kernel") c->filter_kernel = int(v);
+  else if (n == "filter_cta_min_clouds") c->filter_cta_min_clouds = int(std::max<int64_t>(1, v));
   else if (n == "convention_index_floor") c->conv_index_floor = v != 0;
   else if (n == "convention_gm_form") c->conv_gm_form = v != 0;
   else if (n == "convention_cull_metric") c->conv_cull_metric = int(std::min<int64_t>(2, std::max<int64_t>(0, v)));
@@ -1395,6 +1483,9 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   else if (n == "pers_minb") *out = c->pers_minb;
   else if (n == "filter_group_mb") *out = c->filter_group_mb;
   else if (n == "filter_ppt") *out = c->filter_ppt;
+  else if (n == "filter_kernel") *out = c->filter_kernel;
+  else if (n == "filter_cta_min_clouds") *out = c->filter_cta_min_clouds;
+  else if (n == "last_filter_kernel") *out = c->last_filter_kernel;
   else if (n == "convention_index_floor") *out = c->conv_index_floor;
   else if (n == "convention_gm_form") *out = c->conv_gm_form;
   else if (n == "convention_cull_metric") *out = c->conv_cull_metric;

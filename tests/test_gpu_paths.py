@@ -221,6 +221,24 @@ def test_large_batch_launch_sequence_matches_the_oracle(ctx, large_case, groups,
     print(f"large batch ({c['total_q']} queries): worst GPU-vs-oracle pose delta {worst}")
 
 
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+def test_large_batch_drain_variants_are_identical(ctx, large_case, variant):
+    """The drain loop of the work-list kernel exists in several forms (include/mlo_b200.h "wl_variant": segment-wise
+    merge, software-pipelined, cp.async.bulk staging, contiguous ranges with a register-resident best).  All of them take
+    the minimum of the same 64-bit (distance bits, visiting order) keys, so poses, iteration counts and pairing counts
+    must be IDENTICAL between variants, not merely within tolerance."""
+    c = large_case
+    with _Options(ctx, wl_variant=3):
+        base = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+    with _Options(ctx, wl_variant=variant):
+        res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        assert ctx.get_option("last_align_path") == 1
+    for a, b, orr in zip(res, base, c["refs"]):
+        assert np.array_equal(np.asarray(a.pose), np.asarray(b.pose))
+        assert int(a.n_iterations) == int(b.n_iterations) and int(a.n_pairings) == int(b.n_pairings)
+        _check(a, orr)
+
+
 def test_large_batch_other_paths_agree(ctx, large_case):
     """The same 128 problems through the queue-driven kernel and the block kernel (two blocks per SM at this size)."""
     c = large_case
