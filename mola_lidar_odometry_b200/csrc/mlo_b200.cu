@@ -122,7 +122,10 @@ struct mlo_ctx {
   // tables, blocks of a cloud spread over the device), 2 = k_decim_cta (one thread block per cloud, scratch in shared
   // memory; falls back to 1 for a batch whose clouds do not fit its 32-bit keys / its table).
   int filter_kernel = 0;
-  int filter_cta_min_clouds = 16;  // mlo_set_option("filter_cta_min_clouds"): smallest batch that takes k_decim_cta under 0
+  // mlo_set_option("filter_cta_min_clouds"): smallest batch that takes k_decim_cta under 0.  Filter wall per lock step of
+  // a fleet, global tables vs block per cloud: 1 cloud 0.098 / 0.195 ms, 8: 0.157 / 0.233, 32: 0.297 / 0.298,
+  // 512 (config[1]): 2.5 / 0.65 ms (profiles/README.md)
+  int filter_cta_min_clouds = 32;
   int filter_cta_backoff = 0;      // batches left before k_decim_cta is tried again after a fallback
   int last_filter_kernel = 0;      // what the last filter batch ran (tests)
   bool cta_attr_set = false;

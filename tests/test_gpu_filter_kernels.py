@@ -37,10 +37,12 @@ class _Options:
 def test_decimate_first_both_kernels(ctx, world, kernel, res, min_pts):
     raw = world["frames"][3]["raw"]
     p = capi.decimate_params(res, min_pts)
+    oi = O.decimate_first(raw, p)
     with _Options(ctx, filter_kernel=kernel):
         gi = ctx.voxel_decimate_first(raw, p)
-        assert ctx.get_option("last_filter_kernel") == kernel
-    assert np.array_equal(gi, O.decimate_first(raw, p))
+        # (a 0.2 m grid keeps more voxels of a 130 k-point sweep than the shared-memory table holds: form 2 hands over to form 1)
+        assert ctx.get_option("last_filter_kernel") == (1 if len(oi) > 20_000 and min_pts <= len(raw) else kernel)
+    assert np.array_equal(gi, oi)
 
 
 @pytest.mark.parametrize("kernel", [1, 2])
@@ -80,25 +82,26 @@ def test_filter_chain_both_kernels(ctx, world, kernel):
 
 
 def test_ragged_batch_and_policy(ctx, world):
-    """24 clouds of different sizes (one empty, one tiny) in one filter pass: by default a batch of this size takes the
+    """40 clouds of different sizes (one empty, one tiny) in one filter pass: by default a batch of this size takes the
     block-per-cloud kernel; layers bit-exact either way."""
     from mola_lidar_odometry_b200.api import ScanSet
     frames, fp = world["frames"], world["fp"]
     rng = np.random.default_rng(3)
+    NB = 40
     clouds = []
-    for s in range(24):
+    for s in range(NB):
         raw = frames[s % len(frames)]["raw"]
         n = int(rng.integers(3000, len(raw)))
         clouds.append(np.ascontiguousarray(raw[:n]))
     clouds[5] = np.zeros((0, clouds[0].shape[1]), np.float32)
     clouds[9] = np.ascontiguousarray(clouds[9][:37])
     want = [O.filter_1st_pass(c, fp) if len(c) else (np.zeros((0, 3), np.float32),) * 2 for c in clouds]
-    sset = ScanSet(ctx, 24)
+    sset = ScanSet(ctx, NB)
     for kernel, expect in ((0, 2), (1, 1), (2, 2)):
         with _Options(ctx, filter_kernel=kernel):
-            info = sset.filter(list(range(24)), clouds, [fp] * 24)
+            info = sset.filter(list(range(NB)), clouds, [fp] * NB)
             assert ctx.get_option("last_filter_kernel") == expect
-        for s in range(24):
+        for s in range(NB):
             assert (info[s].n_map, info[s].n_icp) == (len(want[s][0]), len(want[s][1])), (kernel, s)
             if len(clouds[s]):
                 assert np.array_equal(sset.download(s, 0), want[s][0])
