@@ -416,9 +416,13 @@ __global__ void __launch_bounds__(CTA_DECIM_THREADS, 1) k_decim_cta(const DecimJ
   }
   __syncthreads();
 
-  // ---- pass A: the cloud, once
+  // ---- pass A: the cloud, once.  Straight-line per point (flags, no early exits) and a __syncwarp after every table
+  // insert: the lanes of a warp walk the PPT points of a round together instead of drifting apart after the first
+  // divergent probe (measured: 585 M vs 346 M warp instructions for the same work with `continue`-style exits).
   uint32_t my_pred = 0;
   bool fail = false;
+  const float res = j.resolution;
+  const int fmode = j.index_floor;
   for (uint32_t base = 0; base < n; base += CTA_DECIM_THREADS * PPT) {
     float4 p[PPT];
 #pragma unroll
@@ -427,23 +431,31 @@ __global__ void __launch_bounds__(CTA_DECIM_THREADS, 1) k_decim_cta(const DecimJ
       p[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       if (i < n) p[u] = load_point(j.in, j.in_stride, i);
     }
+    uint32_t pk[PPT];
+    bool valid[PPT];
 #pragma unroll
     for (int u = 0; u < PPT; u++) {
       const uint32_t i = base + u * CTA_DECIM_THREADS + tid;
-      if (i >= n) continue;
-      if (!predicate_keep(j.pre, p[u].x, p[u].y, p[u].z)) continue;
-      const int32_t kx = voxel_index_filter(p[u].x, j.resolution, j.index_floor), ky = voxel_index_filter(p[u].y, j.resolution, j.index_floor),
-                    kz = voxel_index_filter(p[u].z, j.resolution, j.index_floor);
-      uint32_t pk;
-      if (!pack_key32(kx, ky, kz, pk)) {
-        fail = true;
-        continue;
+      const bool pre = (i < n) && (!has_pre || predicate_keep(j.pre, p[u].x, p[u].y, p[u].z));
+      const int32_t kx = voxel_index_filter(p[u].x, res, fmode), ky = voxel_index_filter(p[u].y, res, fmode),
+                    kz = voxel_index_filter(p[u].z, res, fmode);
+      const bool packs = pack_key32(kx, ky, kz, pk[u]);
+      fail = fail || (pre && !packs);
+      valid[u] = pre && packs;
+      my_pred += valid[u] ? 1u : 0u;
+    }
+    if (pass_static) {
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const uint32_t i = base + u * CTA_DECIM_THREADS + tid;
+        if (valid[u] && (!has_post || predicate_keep(j.post, p[u].x, p[u].y, p[u].z))) atomicOr(&bitmap[i >> 5], 1u << (i & 31u));
       }
-      my_pred++;
-      if (pass_static) {
-        if (!has_post || predicate_keep(j.post, p[u].x, p[u].y, p[u].z)) atomicOr(&bitmap[i >> 5], 1u << (i & 31u));
-      } else if (!cta_table_put(tab, T, pk, i)) {
-        fail = true;
+    } else {
+#pragma unroll
+      for (int u = 0; u < PPT; u++) {
+        const uint32_t i = base + u * CTA_DECIM_THREADS + tid;
+        if (valid[u] && !cta_table_put(tab, T, pk[u], i)) fail = true;
+        __syncwarp();
       }
     }
   }

@@ -887,6 +887,26 @@ MLO_D bool horn_from_sums(const double* a, double n, double* T) {
   return true;
 }
 
+#ifdef MLO_TRACE
+// Timeline of problem 0 inside the persistent kernel (scratch builds only: scratch/trace_persistent.py).
+__device__ unsigned long long g_trace[16384];
+__device__ unsigned int g_trace_n;
+MLO_D void trace_event(uint32_t prob, uint32_t code) {
+  if (prob != 0) return;
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  const unsigned int i = atomicAdd(&g_trace_n, 1u);
+  if (i < 16384) g_trace[i] = (t << 8) | code;
+}
+#define MLO_TRACE_EVENT(prob, code) do { if (threadIdx.x == 0) trace_event(prob, code); } while (0)
+#define MLO_TRACE_SOLVE(code) do { if ((threadIdx.x & 31u) == 0) trace_event(0u, code); } while (0)
+MLO_D void trace_event_any(uint32_t code) { trace_event(0u, code); }
+#else
+MLO_D void trace_event_any(uint32_t) {}
+#define MLO_TRACE_EVENT(prob, code) do { } while (0)
+#define MLO_TRACE_SOLVE(code) do { } while (0)
+#endif
+
 // End-of-iteration bookkeeping of mp2p_icp::ICP::align — step measure against prev and prev-prev,
 // hook-as-data, stall test, iteration counter, MaxIterations — lives in solve_core below.
 
@@ -1047,7 +1067,9 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
       }
       if (lane < 6) sc.g[lane] = sc.tot[21 + lane];
       __syncwarp();
+      MLO_TRACE_SOLVE(40);  // system laid out
       if (P.has_prior) prior_add_warp(P, sT, S.H, sc);  // (warp-uniform branch)
+      MLO_TRACE_SOLVE(41);  // prior term added
       if (lane == 0) {
         double g[6];
 #pragma unroll
@@ -1059,6 +1081,7 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
 #pragma unroll
         for (int i = 0; i < 6; i++) mg[i] = -g[i];
         const bool ok = ldlt6(H, mg, delta);
+        MLO_TRACE_SOLVE(42);  // 6x6 solved
         if (!ok) {
           S.term = MLO_TERM_SOLVER_ERROR;
           S.done = 1;
@@ -1068,6 +1091,7 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
           pose_mul(sT, E, Tn);
 #pragma unroll
           for (int i = 0; i < 12; i++) sT[i] = Tn[i];
+          MLO_TRACE_SOLVE(43);  // retraction done
           double dn = 0;
 #pragma unroll
           for (int i = 0; i < 6; i++) dn += delta[i] * delta[i];
@@ -1093,6 +1117,7 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
       const double* ref = lane == 0 ? S.prev : (lane == 1 ? S.prev2 : P.hook_checkpoint);
       pose_measures(sT, ref, dt, dr, tD, wD);
     }
+    MLO_TRACE_SOLVE(44);  // step measures done
     const double dt1 = __shfl_sync(FULL, dt, 1), dr1 = __shfl_sync(FULL, dr, 1);
     const double tH = __shfl_sync(FULL, tD, 2), wH = __shfl_sync(FULL, wD, 2);
     __syncwarp();  // lane 1 has read prev2 before lane 0 overwrites it below
@@ -1143,30 +1168,41 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
   return __shfl_sync(FULL, next, 0);
 }
 
-// solve_core for callers whose problem and state live in GLOBAL memory (launch sequence, queue-driven kernel):
-// stage both in shared memory (two coalesced reads, one coalesced write-back by the whole warp instead of ~150 serial,
-// mostly dependent global accesses by lane 0).
-__device__ __noinline__ int solve_step(const IcpProblem& Pg, IcpState& Sg, SolveScratch& sc, int after_match) {
+// solve_core for callers whose problem and state live in GLOBAL memory (launch sequence, queue-driven kernel): the
+// solving block stages both in shared memory ONCE per solve phase (two coalesced reads by a whole warp instead of ~150
+// serial, mostly dependent global accesses by lane 0); the first solve and every fused inner iteration that follows work
+// on the staged copy (the re-linearisation reads the new pose from there), and the state goes back to global memory in
+// one coalesced write when the phase is over.
+struct SolveStage {
+  IcpProblem P;
+  IcpState S;
+};
+static_assert(sizeof(IcpProblem) % 4 == 0 && sizeof(IcpState) % 4 == 0, "copied word by word");
+// (one warp)
+MLO_D void solve_stage_in(const IcpProblem& Pg, const IcpState& Sg, SolveStage& st) {
   const uint32_t lane = threadIdx.x & 31u;
-  __shared__ IcpProblem sP;
-  __shared__ IcpState sS;
-  static_assert(sizeof(IcpProblem) % 4 == 0 && sizeof(IcpState) % 4 == 0, "copied word by word");
-  {
-    const uint32_t* gp = reinterpret_cast<const uint32_t*>(&Pg);
-    const uint32_t* gs = reinterpret_cast<const uint32_t*>(&Sg);
-    uint32_t* dp = reinterpret_cast<uint32_t*>(&sP);
-    uint32_t* ds = reinterpret_cast<uint32_t*>(&sS);
-    for (uint32_t i = lane; i < sizeof(IcpProblem) / 4; i += 32) dp[i] = __ldg(gp + i);
-    for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) ds[i] = __ldcg(gs + i);
-  }
+  const uint32_t* gp = reinterpret_cast<const uint32_t*>(&Pg);
+  const uint32_t* gs = reinterpret_cast<const uint32_t*>(&Sg);
+  uint32_t* dp = reinterpret_cast<uint32_t*>(&st.P);
+  uint32_t* ds = reinterpret_cast<uint32_t*>(&st.S);
+  for (uint32_t i = lane; i < sizeof(IcpProblem) / 4; i += 32) dp[i] = __ldg(gp + i);
+  for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) ds[i] = __ldcg(gs + i);
   __syncwarp();
-  const int next = solve_core(sP, sS, sc, after_match);
+}
+// (one warp) the state back to global memory, fenced: whoever is told about this problem next sees it
+MLO_D void solve_stage_out(IcpState& Sg, const SolveStage& st) {
+  const uint32_t lane = threadIdx.x & 31u;
   __syncwarp();
-  {
-    uint32_t* gs = reinterpret_cast<uint32_t*>(&Sg);
-    const uint32_t* ds = reinterpret_cast<const uint32_t*>(&sS);
-    for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) gs[i] = ds[i];
-  }
+  uint32_t* gs = reinterpret_cast<uint32_t*>(&Sg);
+  const uint32_t* ds = reinterpret_cast<const uint32_t*>(&st.S);
+  for (uint32_t i = lane; i < sizeof(IcpState) / 4; i += 32) gs[i] = ds[i];
+  __threadfence();
+  __syncwarp();
+}
+__device__ __noinline__ int solve_core_staged(SolveStage& st, SolveScratch& sc, int after_match) {
+  MLO_TRACE_SOLVE(45);  // problem + state staged
+  const int next = solve_core(st.P, st.S, sc, after_match);
+  MLO_TRACE_SOLVE(46);  // solve_core returned
   return next;
 }
 
@@ -1202,18 +1238,14 @@ MLO_D void block_reduce_to(double* a, uint32_t npairs, SolveScratch& sc) {
   }
   __syncthreads();
 }
-// every thread of the (ICP_BLOCK-wide) block calls this with the block-uniform `next` of the preceding solve
-MLO_D int fused_inner_iterations(const IcpProblem& P, IcpState& S, SolveScratch& sc, int next, uint32_t it, const float4* __restrict__ local,
+// every thread of the (ICP_BLOCK-wide) block calls this with the block-uniform `next` of the preceding solve, whose
+// problem and state sit in `st` (written by the block's first warp; the caller's barrier made them visible)
+MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uint32_t it, const float4* __restrict__ local,
                                  const float4* pairA, const float4* pairB) {
-  __shared__ double f_T[12];
   __shared__ int f_next;
+  const IcpProblem& P = st.P;
   while (next == 1) {
-    // the pose was written to the problem state by this block's first warp (solve_step): fence + barrier, then read it
-    // back through L2
-    if (threadIdx.x < 32) __threadfence();
-    __syncthreads();
-    if (threadIdx.x < 12) f_T[threadIdx.x] = __ldcg(&S.T[threadIdx.x]);
-    __syncthreads();
+    const double* f_T = st.S.T;  // the pose the first warp just retracted
     const double kc = table_at(P.kparam, P.table_len, it);
     double a[NACC];
 #pragma unroll
@@ -1231,15 +1263,34 @@ MLO_D int fused_inner_iterations(const IcpProblem& P, IcpState& S, SolveScratch&
       }
       npairs++;
     }
-    block_reduce_to(a, npairs, sc);
+    block_reduce_to(a, npairs, sc);  // (its barrier: every thread has read the pose before the first warp moves it)
     if (threadIdx.x < 32) {
-      const int n = solve_step(P, S, sc, 0);
+      const int n = solve_core_staged(st, sc, 0);
       if (threadIdx.x == 0) f_next = n;
     }
     __syncthreads();
     next = f_next;
     __syncthreads();
   }
+  return next;
+}
+
+// One solve phase of a problem by the block that owns it at this moment (ICP_BLOCK threads, all of them call this; the
+// sums of the current linearisation sit in sc.tot / sc.cnt): first solve, fused inner iterations if allowed, state back
+// to global memory.  Returns the block-uniform verdict (0 finished, 1 inner iteration pending, 2 next ICP iteration).
+MLO_D int solve_phase(const IcpProblem& Pg, IcpState& Sg, SolveStage& st, SolveScratch& sc, int after_match, int fuse, uint32_t it,
+                      const float4* __restrict__ local, const float4* pairA, const float4* pairB) {
+  __shared__ int p_next;
+  if (threadIdx.x < 32) {
+    solve_stage_in(Pg, Sg, st);
+    const int n = solve_core_staged(st, sc, after_match);
+    if (threadIdx.x == 0) p_next = n;
+  }
+  __syncthreads();
+  int next = p_next;
+  if (fuse && st.P.n_q <= FUSE_MAX_Q) next = fused_inner_iterations(st, sc, next, it, local, pairA, pairB);
+  if (threadIdx.x < 32) solve_stage_out(Sg, st);
+  __syncthreads();
   return next;
 }
 
@@ -1335,16 +1386,10 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   if (S.done) return;
   if (!after_match && !S.inner_pending) return;
   __shared__ SolveScratch sc;
-  __shared__ int s_next;
+  __shared__ SolveStage st;
   const uint32_t it = S.it;  // (the match phase of this iteration used the same index; read before the solve bumps it)
   sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc);
-  if (threadIdx.x < 32) {
-    const int n = solve_step(P, S, sc, after_match);
-    if (threadIdx.x == 0) s_next = n;
-  }
-  __syncthreads();
-  int next = s_next;
-  if (fuse && P.n_q <= FUSE_MAX_Q) next = fused_inner_iterations(P, S, sc, next, it, local, pairA, pairB);
+  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -1378,23 +1423,6 @@ __global__ void k_init_states(const IcpProblem* __restrict__ probs, IcpState* __
   }
 }
 
-#ifdef MLO_TRACE
-// Timeline of problem 0 inside the persistent kernel (scratch builds only: scratch/trace_persistent.py).
-__device__ unsigned long long g_trace[16384];
-__device__ unsigned int g_trace_n;
-MLO_D void trace_event(uint32_t prob, uint32_t code) {
-  if (prob != 0) return;
-  unsigned long long t;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-  const unsigned int i = atomicAdd(&g_trace_n, 1u);
-  if (i < 16384) g_trace[i] = (t << 8) | code;
-}
-#define MLO_TRACE_EVENT(prob, code) do { if (threadIdx.x == 0) trace_event(prob, code); } while (0)
-MLO_D void trace_event_any(uint32_t code) { trace_event(0u, code); }
-#else
-MLO_D void trace_event_any(uint32_t) {}
-#define MLO_TRACE_EVENT(prob, code) do { } while (0)
-#endif
 
 // ------------------------------------------------------------------ persistent, queue-driven align
 // One launch runs the whole ICP::align loop of a batch.  Work items = (problem, phase, chunk); a bounded
@@ -1486,7 +1514,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
                      IcpQueue q, uint32_t qpw, int fuse) {
   __shared__ MapDev sMap;
   __shared__ SolveScratch s_solve;
-  __shared__ int s_nx;
+  __shared__ SolveStage s_stage;
   __shared__ uint32_t s_item;
   __shared__ int s_last;
   __shared__ double sT[12];
@@ -1549,22 +1577,13 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
       sum_partials_block(P, partials, part_cnt, phase == 0 ? P.n_blocks_pers : P.n_blocks_acc, s_solve);
       MLO_TRACE_EVENT(prob, 5);  // partials summed
     }
-    int nx = 0;  // (block-uniform: read behind a barrier / returned behind a barrier)
+    int nx = 0;  // (block-uniform)
     if (s_last) {
-      if (threadIdx.x < 32) {
-        const int n = solve_step(P, S, s_solve, phase == 0);
-        if (threadIdx.x == 0) s_nx = n;
-      }
-      __syncthreads();
-      MLO_TRACE_EVENT(prob, 6);  // first solve done
-      nx = s_nx;
-      if (fuse && P.n_q <= FUSE_MAX_Q) nx = fused_inner_iterations(P, S, s_solve, nx, s_it, local, pairA, pairB);
-      MLO_TRACE_EVENT(prob, 7);  // fused inner iterations done
+      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB);
+      MLO_TRACE_EVENT(prob, 7);  // solve phase (with its fused inner iterations) done, state written back
     }
     if (s_last && threadIdx.x < 32) {
       const int next = nx;
-      if (threadIdx.x == 0) __threadfence();  // state of the problem visible before its next items
-      __syncwarp();
       if (next == 1) {
         queue_push(q, prob, 1u, P.n_blocks_acc);
       } else if (next == 2) {

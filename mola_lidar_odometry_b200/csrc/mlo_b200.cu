@@ -744,7 +744,7 @@ int filter_counts(mlo_ctx* c, FilterBatch& fb, std::vector<uint32_t>& h) {
     if (fallback && fb.used_cta) {
       // a cloud outside k_decim_cta's 32-bit key box, or more voxels than its shared-memory table holds: the global-table
       // kernels take the batch, and the next batches of this context go to them directly for a while
-      c->filter_cta_backoff = 64;
+      if (c->filter_kernel == 0) c->filter_cta_backoff = 64;
     } else {
       if (conservative) return fail(c, MLO_ERR_CAPACITY, "decimation scratch table exhausted");
       conservative = true;
@@ -1459,7 +1459,10 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "pers_minb") c->pers_minb = v == 2 ? 2 : (v == 4 ? 4 : 0);
   else if (n == "filter_group_mb") c->filter_group_mb = int(std::max<int64_t>(1, v));
   else if (n == "filter_ppt") c->filter_ppt = int(v);
-  else if (n == "filter_kernel") c->filter_kernel = int(v);
+  else if (n == "filter_kernel") {
+    c->filter_kernel = int(v);
+    c->filter_cta_backoff = 0;
+  }
   else if (n == "filter_cta_min_clouds") c->filter_cta_min_clouds = int(std::max<int64_t>(1, v));
   else if (n == "convention_index_floor") c->conv_index_floor = v != 0;
   else if (n == "convention_gm_form") c->conv_gm_form = v != 0;
