@@ -922,10 +922,32 @@ struct SolveScratch {
   uint32_t pcnt[SOLVE_WARPS][2];
   // prior term, spread over the warp (prior_add_warp)
   double g[6], e[6], Le[6], J[36], LJ[36];
+  double m[10][9];  // 3x3 intermediates of the warp-parallel right-Jacobian inverse (jr_inv_warp)
 };
+// The solving block's shared-memory copy of a problem and its state (solve_phase below).
+struct SolveStage {
+  IcpProblem P;
+  IcpState S;
+};
+static_assert(sizeof(IcpProblem) % 4 == 0 && sizeof(IcpState) % 4 == 0, "copied word by word");
+constexpr uint32_t STAGE_P_WORDS = sizeof(IcpProblem) / 4, STAGE_S_WORDS = sizeof(IcpState) / 4;
+constexpr uint32_t STAGE_P_REGS = (STAGE_P_WORDS + 31) / 32, STAGE_S_REGS = (STAGE_S_WORDS + 31) / 32;
+
+// `st` != nullptr: the last warp also stages the problem and its state for the solve that follows - its loads are issued
+// BEFORE the partial loads and stored after them, so the two round trips to L2 overlap instead of following each other.
 MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const uint32_t* part_cnt, uint32_t nblk,
-                              SolveScratch& sc) {
+                              SolveScratch& sc, const IcpState* Sg = nullptr, SolveStage* st = nullptr) {
   const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+  const bool stager = st != nullptr && warp == SOLVE_WARPS - 1;
+  uint32_t rp[STAGE_P_REGS], rs[STAGE_S_REGS];
+  if (stager) {
+    const uint32_t* gp = reinterpret_cast<const uint32_t*>(&P);
+    const uint32_t* gs = reinterpret_cast<const uint32_t*>(Sg);
+#pragma unroll
+    for (uint32_t u = 0; u < STAGE_P_REGS; u++) rp[u] = lane + 32 * u < STAGE_P_WORDS ? __ldg(gp + lane + 32 * u) : 0u;
+#pragma unroll
+    for (uint32_t u = 0; u < STAGE_S_REGS; u++) rs[u] = lane + 32 * u < STAGE_S_WORDS ? __ldcg(gs + lane + 32 * u) : 0u;
+  }
   if (warp < SOLVE_WARPS) {
     if (lane < NACC) {
       double acc = 0.0;
@@ -945,6 +967,16 @@ MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const
       for (uint32_t b = warp; b < nblk; b += SOLVE_WARPS) cnt += __ldcg(&part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)]);
       sc.pcnt[warp][lane - NACC] = cnt;
     }
+  }
+  if (stager) {
+    uint32_t* dp = reinterpret_cast<uint32_t*>(&st->P);
+    uint32_t* ds = reinterpret_cast<uint32_t*>(&st->S);
+#pragma unroll
+    for (uint32_t u = 0; u < STAGE_P_REGS; u++)
+      if (lane + 32 * u < STAGE_P_WORDS) dp[lane + 32 * u] = rp[u];
+#pragma unroll
+    for (uint32_t u = 0; u < STAGE_S_REGS; u++)
+      if (lane + 32 * u < STAGE_S_WORDS) ds[lane + 32 * u] = rs[u];
   }
   __syncthreads();
   if (threadIdx.x < NACC) {
@@ -966,18 +998,85 @@ MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const
 // g += J^T L e ; H += J^T L J.  Lane 0 evaluates e and J (out of line: loop-heavy, keeps the common path's arrays in
 // registers); the 6x6 products are spread over the warp, one output entry per lane, each entry summed in the same order
 // (m = 0..5 onto the running value) as a single-thread loop would: same bits, a third of the time.
-__device__ __noinline__ void prior_e_and_J(const IcpProblem& P, const double* T, double* e_out, double* J_out) {
-  double D[12], e[6], J[36];
+__device__ __noinline__ void prior_e(const IcpProblem& P, const double* T, double* e_out) {
+  double D[12], e[6];
   pose_minus(T, P.prior_pose, D);
   se3_log(D, e);
-  se3_right_jacobian_inv(e, J);
   for (int i = 0; i < 6; i++) e_out[i] = e[i];
-  for (int i = 0; i < 36; i++) J_out[i] = J[i];
+}
+// se3_right_jacobian_inv (se3.cuh) by nine lanes of a warp, one 3x3 entry each: the ten 3x3 products of the closed form
+// are five dependent levels of 3-term dot products instead of ~550 serial double operations on one lane.  Every entry is
+// evaluated by the SAME expression, in the same order, as in the single-thread function: identical bits.
+// xi and J live in shared memory; the whole warp must call this.
+MLO_D double m3e(const double* A, const double* B, uint32_t i, uint32_t j) {
+  return A[3 * i] * B[j] + A[3 * i + 1] * B[3 + j] + A[3 * i + 2] * B[6 + j];
+}
+MLO_D double hat_entry(const double* w, uint32_t idx) {
+  switch (idx) {
+    case 1: return -w[2];
+    case 2: return w[1];
+    case 3: return w[2];
+    case 5: return -w[0];
+    case 6: return -w[1];
+    case 7: return w[0];
+    default: return 0.0;
+  }
+}
+__device__ __noinline__ void jr_inv_warp(const double* xi, double* J, double (*m)[9]) {
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool on = lane < 9;
+  const uint32_t idx = on ? lane : 0u, i = idx / 3, j = idx % 3;
+  const double rho[3] = {-xi[0], -xi[1], -xi[2]};
+  const double phi[3] = {-xi[3], -xi[4], -xi[5]};
+  const double t2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  double k, c1, c2, c3;
+  jr_inv_coeffs(t2, k, c1, c2, c3);
+  double* Pm = m[0]; double* F = m[1]; double* FP = m[2]; double* PF = m[3]; double* FPF = m[4];
+  double* A = m[5]; double* Q = m[6]; double* AQ = m[7];
+  // level 0: P = hat(rho), F = hat(phi)
+  const double p_e = hat_entry(rho, idx), f_e = hat_entry(phi, idx);
+  if (on) {
+    Pm[idx] = p_e;
+    F[idx] = f_e;
+  }
+  __syncwarp();
+  // level 1: FF, FP, PF
+  const double ff_e = m3e(F, F, i, j), fp_e = m3e(F, Pm, i, j), pf_e = m3e(Pm, F, i, j);
+  const double a_e = ((idx % 4 == 0) ? 1.0 : 0.0) - 0.5 * f_e + k * ff_e;
+  if (on) {
+    FP[idx] = fp_e;
+    PF[idx] = pf_e;
+    A[idx] = a_e;
+  }
+  __syncwarp();
+  // level 2: FPF, FFP, PFF
+  const double fpf_e = m3e(FP, F, i, j), ffp_e = m3e(F, FP, i, j), pff_e = m3e(PF, F, i, j);
+  if (on) FPF[idx] = fpf_e;
+  __syncwarp();
+  // level 3: FPFF, FFPF, then Q
+  const double fpff_e = m3e(FPF, F, i, j), ffpf_e = m3e(F, FPF, i, j);
+  const double q_e = 0.5 * p_e + c1 * (fp_e + pf_e + fpf_e) + c2 * (ffp_e + pff_e - 3.0 * fpf_e) + c3 * (fpff_e + ffpf_e);
+  if (on) Q[idx] = q_e;
+  __syncwarp();
+  // level 4: AQ
+  const double aq_e = m3e(A, Q, i, j);
+  if (on) AQ[idx] = aq_e;
+  __syncwarp();
+  // level 5: AQA and the 6x6 blocks
+  const double aqa_e = m3e(AQ, A, i, j);
+  if (on) {
+    J[6 * i + j] = a_e;
+    J[6 * i + 3 + j] = -aqa_e;
+    J[6 * (i + 3) + j] = 0.0;
+    J[6 * (i + 3) + 3 + j] = a_e;
+  }
+  __syncwarp();
 }
 MLO_D void prior_add_warp(const IcpProblem& P, const double* T, double* H, SolveScratch& sc) {
   const uint32_t lane = threadIdx.x & 31u;
-  if (lane == 0) prior_e_and_J(P, T, sc.e, sc.J);
+  if (lane == 0) prior_e(P, T, sc.e);
   __syncwarp();
+  jr_inv_warp(sc.e, sc.J, sc.m);
   if (lane < 6) {
     double s = 0;
     for (int m = 0; m < 6; m++) s += P.prior_info[6 * lane + m] * sc.e[m];
@@ -1173,11 +1272,6 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
 // serial, mostly dependent global accesses by lane 0); the first solve and every fused inner iteration that follows work
 // on the staged copy (the re-linearisation reads the new pose from there), and the state goes back to global memory in
 // one coalesced write when the phase is over.
-struct SolveStage {
-  IcpProblem P;
-  IcpState S;
-};
-static_assert(sizeof(IcpProblem) % 4 == 0 && sizeof(IcpState) % 4 == 0, "copied word by word");
 // (one warp)
 MLO_D void solve_stage_in(const IcpProblem& Pg, const IcpState& Sg, SolveStage& st) {
   const uint32_t lane = threadIdx.x & 31u;
@@ -1279,10 +1373,10 @@ MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uin
 // sums of the current linearisation sit in sc.tot / sc.cnt): first solve, fused inner iterations if allowed, state back
 // to global memory.  Returns the block-uniform verdict (0 finished, 1 inner iteration pending, 2 next ICP iteration).
 MLO_D int solve_phase(const IcpProblem& Pg, IcpState& Sg, SolveStage& st, SolveScratch& sc, int after_match, int fuse, uint32_t it,
-                      const float4* __restrict__ local, const float4* pairA, const float4* pairB) {
+                      const float4* __restrict__ local, const float4* pairA, const float4* pairB, bool staged = false) {
   __shared__ int p_next;
   if (threadIdx.x < 32) {
-    solve_stage_in(Pg, Sg, st);
+    if (!staged) solve_stage_in(Pg, Sg, st);  // (staged = sum_partials_block already brought them in)
     const int n = solve_core_staged(st, sc, after_match);
     if (threadIdx.x == 0) p_next = n;
   }
@@ -1388,8 +1482,8 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   __shared__ SolveScratch sc;
   __shared__ SolveStage st;
   const uint32_t it = S.it;  // (the match phase of this iteration used the same index; read before the solve bumps it)
-  sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc);
-  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB);
+  sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc, &S, &st);
+  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB, true);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -1574,12 +1668,12 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     if (s_last) {
       MLO_TRACE_EVENT(prob, 4);  // last chunk of the phase finished
       __threadfence();  // acquire: the other blocks' partials (read through L2) and the problem state
-      sum_partials_block(P, partials, part_cnt, phase == 0 ? P.n_blocks_pers : P.n_blocks_acc, s_solve);
+      sum_partials_block(P, partials, part_cnt, phase == 0 ? P.n_blocks_pers : P.n_blocks_acc, s_solve, &S, &s_stage);
       MLO_TRACE_EVENT(prob, 5);  // partials summed
     }
     int nx = 0;  // (block-uniform)
     if (s_last) {
-      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB);
+      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB, true);
       MLO_TRACE_EVENT(prob, 7);  // solve phase (with its fused inner iterations) done, state written back
     }
     if (s_last && threadIdx.x < 32) {

@@ -138,17 +138,8 @@ MLO_HD void se3_log(const double* T, double* xi) {
 // Closed-form d log(D exp(eps)) / d eps at eps = 0, i.e. the inverse right Jacobian of SE(3) at
 // xi = log(D) (the e2 half of MRPT's jacob_dDinvP1invP2_de1e2 used for the prior term,
 // LidarOdometry.cpp:854-877 -> Solver_GaussNewton prior).  J is 6x6 row-major.
-MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
-  // Jr^-1(xi) = Jl^-1(-xi); with Jl^-1 = [[A, -A Q A], [0, A]], A = Jl_so3^-1(phi)
-  const double rho[3] = {-xi[0], -xi[1], -xi[2]};
-  const double phi[3] = {-xi[3], -xi[4], -xi[5]};
-  const double t2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
-  double P[9], F[9], FF[9];
-  hat(rho, P);
-  hat(phi, F);
-  mat3_mul(F, F, FF);
-  // A = I - F/2 + k FF,  k = 1/t^2 - (1 + cos t) / (2 t sin t)
-  double k, c1, c2, c3;
+// Scalar coefficients of Jl_so3^-1 and of the Q block (se3_right_jacobian_inv below; csrc/icp.cuh jr_inv_warp)
+MLO_HD void jr_inv_coeffs(double t2, double& k, double& c1, double& c2, double& c3) {
   if (t2 < 2.5e-3) {
     // Taylor series for |phi| < 0.05 rad (truncation < 1e-16).  The closed forms below cancel catastrophically for small
     // angles: c2's numerator t^2 + 2 cos t - 2 ~ t^4 / 12 is pure round-off below t ~ 1e-2 (found against the BCH series,
@@ -164,6 +155,20 @@ MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
     c2 = (t2 + 2.0 * c - 2.0) / (2.0 * t2 * t2);
     c3 = (2.0 * t - 3.0 * s + t * c) / (2.0 * t2 * t2 * t);
   }
+}
+
+MLO_HD void se3_right_jacobian_inv(const double* xi, double* J) {
+  // Jr^-1(xi) = Jl^-1(-xi); with Jl^-1 = [[A, -A Q A], [0, A]], A = Jl_so3^-1(phi)
+  const double rho[3] = {-xi[0], -xi[1], -xi[2]};
+  const double phi[3] = {-xi[3], -xi[4], -xi[5]};
+  const double t2 = phi[0] * phi[0] + phi[1] * phi[1] + phi[2] * phi[2];
+  double P[9], F[9], FF[9];
+  hat(rho, P);
+  hat(phi, F);
+  mat3_mul(F, F, FF);
+  // A = I - F/2 + k FF,  k = 1/t^2 - (1 + cos t) / (2 t sin t)
+  double k, c1, c2, c3;
+  jr_inv_coeffs(t2, k, c1, c2, c3);
   double A[9];
   #pragma unroll
   for (int i = 0; i < 9; i++) A[i] = ((i % 4 == 0) ? 1.0 : 0.0) - 0.5 * F[i] + k * FF[i];
