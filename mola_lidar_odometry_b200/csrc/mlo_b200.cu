@@ -151,6 +151,9 @@ struct mlo_ctx {
   int qpw_floor = 4;         // MLO_QPW_FLOOR: fewest queries a warp handles per chunk in the warp-per-query kernels
   bool fuse_inner = true;    // MLO_FUSE_INNER=0: inner GN iterations as separate accumulate + solve launches (A/B)
   bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
+  int tail_queries_per_sm = 512;  // mlo_set_option("tail_queries_per_sm"): the hand-over happens once the still-active problems
+                                  // hold fewer queries than this per SM
+  int check_every = 4;            // mlo_set_option("check_every"): ICP iterations between two looks at the active-problem counter
   int consuming_slot = -1;  // staging slot read by the compute call in progress
   // transfers registered by a prefetch call and enqueued from inside the next compute call, right after that call's
   // own small parameter uploads (the H2D copy engine serves transfers in submission order)
@@ -1072,7 +1075,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
   const size_t e_icp = prof_begin(c);
   const dim3 grid(std::max(max_blocks, 1u), B);
   const dim3 grid_acc(std::max(max_blocks_acc, 1u), B);
-  const uint32_t check_every = 4;
+  const uint32_t check_every = uint32_t(std::max(1, c->check_every));
   // the queue-driven kernel wins while a launch sequence would be latency/launch-bound (small batches);
   // for large batches one kernel per phase streams better (profiles/README.md)
   const uint64_t large_at = c->large_batch_queries ? c->large_batch_queries : uint64_t(c->sm_count) * 1024;
@@ -1244,7 +1247,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
       // Tail hand-over: once few problems remain, a launch sequence is latency-bound (each iteration still costs
       // four launches); the queue-driven kernel finishes the stragglers in one launch.
       const uint64_t avg_q = total_queries / std::max<uint32_t>(B, 1);
-      if (c->tail_handover && c->tail_path == 3 && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * 512) {
+      if (c->tail_handover && c->tail_path == 3 && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * uint64_t(std::max(1, c->tail_queries_per_sm))) {
         const size_t e_nn = prof_begin(c);
         int rc = launch_block(c, B, max_nq, any_planes, d_maps, dP, dS, d_local);  // (finished problems leave at once)
         c->last_tail_handover = 3;
@@ -1252,7 +1255,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
         if (rc != MLO_OK) return rc;
         break;
       }
-      if (c->use_persistent && c->tail_handover && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * 512 &&
+      if (c->use_persistent && c->tail_handover && it + 1 < max_it && uint64_t(*h_active) * avg_q < uint64_t(c->sm_count) * uint64_t(std::max(1, c->tail_queries_per_sm)) &&
           queue_ok) {
         const uint32_t qcap = uint32_t(next_pow2(std::max<uint64_t>(2ull * part_total, 1024)));
         CU(c, c->d_queue.ensure((2ull * qcap + 8 + B) * sizeof(uint32_t)));
@@ -1351,6 +1354,8 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   c->dev_name = prop.name;
   if (const char* fk = getenv("MLO_FORCE_KERNEL")) c->force_kernel = atoi(fk);
   if (const char* th = getenv("MLO_TAIL_HANDOVER")) c->tail_handover = atoi(th) != 0;
+  if (const char* tq = getenv("MLO_TAIL_QUERIES_PER_SM")) c->tail_queries_per_sm = std::max(1, atoi(tq));
+  if (const char* ce = getenv("MLO_CHECK_EVERY")) c->check_every = std::max(1, atoi(ce));
   if (const char* fi = getenv("MLO_FUSE_INNER")) c->fuse_inner = atoi(fi) != 0;
   if (const char* pm = getenv("MLO_PERS_MINB")) c->pers_minb = atoi(pm) == 2 ? 2 : (atoi(pm) == 4 ? 4 : 0);
   if (const char* qf = getenv("MLO_QPW_FLOOR")) c->qpw_floor = std::min(32, std::max(1, atoi(qf)));
@@ -1448,6 +1453,8 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   if (n == "align_path") c->align_path = int(std::min<int64_t>(3, std::max<int64_t>(0, v)));
   else if (n == "tail_path") c->tail_path = v == 2 ? 2 : 3;
   else if (n == "tail_handover") c->tail_handover = v != 0;
+  else if (n == "tail_queries_per_sm") c->tail_queries_per_sm = int(std::max<int64_t>(1, v));
+  else if (n == "check_every") c->check_every = int(std::max<int64_t>(1, v));
   else if (n == "block_threads") c->block_threads = int(v);
   else if (n == "block_cluster") c->block_cluster = int(v);
   else if (n == "stream_groups") c->stream_groups = int(std::min<int64_t>(mlo_ctx::MAX_GROUPS, std::max<int64_t>(1, v)));
@@ -1476,6 +1483,8 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   if (n == "align_path") *out = c->align_path;
   else if (n == "tail_path") *out = c->tail_path;
   else if (n == "tail_handover") *out = c->tail_handover;
+  else if (n == "tail_queries_per_sm") *out = c->tail_queries_per_sm;
+  else if (n == "check_every") *out = c->check_every;
   else if (n == "block_threads") *out = c->block_threads;
   else if (n == "block_cluster") *out = c->block_cluster;
   else if (n == "last_block_cluster") *out = c->last_block_cluster;
