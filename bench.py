@@ -744,7 +744,8 @@ def main():
     achieved = (alg_bytes / 1e9) / (nn_ms * 1e-3) if nn_ms > 0 else 0.0
     traffic, traffic_note = None, None
     try:
-        tj = json.loads((ROOT / "profiles" / "r01_traffic.json").read_text())
+        tfile = ROOT / "profiles" / "r02_traffic.json"
+        tj = json.loads((tfile if tfile.exists() else ROOT / "profiles" / "r01_traffic.json").read_text())
         traffic = tj["dram_bytes_per_launch"]
         traffic_note = (f"ncu --set full capture of one full-activity launch at B=512 ({tj['capture'].split(' ')[0]}); "
                         f"algorithmic bytes of that launch: {tj['algorithmic_bytes_same_launch']:.3g}")

@@ -10,7 +10,8 @@ S = int(sys.argv[1]) if len(sys.argv) > 1 else 1
 scene = synth.Scene(42)
 trajs = [synth.trajectory_T00(40, seed=7 + s) for s in range(S)]
 ctx = Context(0)
-fleet = LidarOdometryFleet(ctx, "/root/repo/pipelines/lidar3d-default.yaml", S)
+YAML = sys.argv[2] if len(sys.argv) > 2 else "lidar3d-default.yaml"
+fleet = LidarOdometryFleet(ctx, "/root/repo/pipelines/" + YAML, S)
 lib = capi.load()
 buf = (C.c_ulonglong * 16384)(); n = C.c_uint()
 names = {1: "pop_match0", 2: "pop_acc0", 3: "chunk0_done", 4: "last_chunk_done", 5: "partials_summed", 6: "solve1_done", 7: "fused_done", 8: "next_published", 40: "sys_laid_out", 41: "prior_added", 42: "ldlt_done", 43: "retracted", 44: "measured", 45: "staged", 46: "core_ret"}
