@@ -385,6 +385,7 @@ struct WarpScratch {
   float q[3][32];
   unsigned long long best[32];
   uint16_t list[WL_CAP];
+  uint32_t bd2[32], bord[32];  // the split form of `best` used by wl_process_a32: distance bits / visiting order
 };
 
 // one batch of the drain: 4 segments per lane group (16 per warp); issue the loads of [base, base + 16)
@@ -453,6 +454,66 @@ MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
       }
     }
   }
+  __syncwarp();
+}
+
+// ---- split-key drain (MLO_WL_VARIANT 12 / 13): the running best of a query is kept as TWO 32-bit words, distance bits
+// and visiting order, so that every update is a native 32-bit shared-memory atomicMin (ATOMS.MIN) instead of the CAS
+// loop a 64-bit shared atomicMin compiles to (ATOMS.CAST.SPIN: ~20 instructions, 15 % of the kernel's instruction
+// stream), and the minimum over the 8 lanes of a segment is taken on the 32-bit distance alone (lowest lane among equal
+// distances = lowest slot = lowest order within a segment).  Exactly the 64-bit rule:
+//   1  d2 goes to bd2[q] by atomicMin, which returns the previous value;
+//   2  after a __syncwarp, a candidate whose d2 equals bd2[q] is a current minimum; if it strictly lowered the word it is
+//      the FIRST to reach that value and resets bord[q] (orders recorded for a larger distance are obsolete);
+//   3  after another __syncwarp every current minimum offers its order to bord[q] by atomicMin.
+// Candidates that tie on the distance - in the same round or rounds apart - therefore end with the smallest order.
+MLO_D void wl_consume_a32(WarpScratch& ws, uint32_t grp, uint32_t sub, const float4 (&p)[4], const uint32_t (&meta)[4]) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  uint32_t d2b[4], old[4];
+  bool win[4];
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const uint32_t q = meta[u] & 31u;
+    const bool valid = (meta[u] & 0x80000000u) != 0;
+    d2b[u] = 0xFFFFFFFFu;
+    if (valid) d2b[u] = __float_as_uint(sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]));
+    uint32_t m = d2b[u];
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
+    const bool is_min = valid && d2b[u] == m;
+    const uint32_t b = (__ballot_sync(FULL, is_min) >> (8u * grp)) & 0xFFu;
+    win[u] = is_min && sub == uint32_t(__ffs(b) - 1);
+  }
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    old[u] = 0;
+    if (win[u]) old[u] = atomicMin(&ws.bd2[meta[u] & 31u], d2b[u]);
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    if (win[u]) {
+      const uint32_t q = meta[u] & 31u;
+      win[u] = ws.bd2[q] == d2b[u];
+      if (win[u] && old[u] > d2b[u]) ws.bord[q] = 0xFFFFFFFFu;
+    }
+  }
+  __syncwarp();
+#pragma unroll
+  for (int u = 0; u < 4; u++)
+    if (win[u]) atomicMin(&ws.bord[meta[u] & 31u], (meta[u] >> 5) & 0x3FFu);
+}
+MLO_D void wl_process_a32(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  for (uint32_t base = 0; base < n; base += 16) {
+    float4 p[4];
+    uint32_t meta[4];
+    wl_issue(map, ws, n, base, grp, sub, p, meta);
+    wl_consume_a32(ws, grp, sub, p, meta);
+  }
+  __syncwarp();
+  // fold the split words back into the 64-bit form the rest of the chunk reads
+  ws.best[lane] = ws.bd2[lane] == 0xFFFFFFFFu ? ~0ull : ((uint64_t(ws.bd2[lane]) << 32) | uint64_t(ws.bord[lane]));
   __syncwarp();
 }
 
@@ -623,7 +684,7 @@ MLO_D void wl_process_bulk(const MapDev& map, WarpScratch& ws, WarpStage& st, ui
 }
 
 constexpr uint32_t WL_BLOCK = 32;  // the work-list kernel runs one warp per block: a chunk is 32 queries
-template <int NWARPS, bool PIPE = false, bool BULK = false, int OCT = 0, bool WPART = false>
+template <int NWARPS, bool PIPE = false, bool BULK = false, int OCT = 0, bool WPART = false, bool A32 = false>
 MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
@@ -672,6 +733,10 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
     ws.q[1][lane] = gy;
     ws.q[2][lane] = gz;
     ws.best[lane] = ~0ull;
+    if constexpr (A32) {
+      ws.bd2[lane] = 0xFFFFFFFFu;
+      ws.bord[lane] = 0xFFFFFFFFu;
+    }
     int32_t kq[3] = {0, 0, 0};
     bool active = false;
     if (want) {
@@ -704,6 +769,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       __syncwarp();
       if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
       else if constexpr (OCT > 0) wl_process_oct<OCT>(map, ws, total);
+      else if constexpr (A32) wl_process_a32(map, ws, total);
       else wl_process<PIPE>(map, ws, total);
     }
     // ---- phase 3: per query, the neighbour cells that can still beat the bound from the own cell
@@ -749,6 +815,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       __syncwarp();
       if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
       else if constexpr (OCT > 0) wl_process_oct<OCT>(map, ws, total);
+      else if constexpr (A32) wl_process_a32(map, ws, total);
       else wl_process<PIPE>(map, ws, total);
       start = end;
     }
@@ -1422,7 +1489,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
 }
 
 // four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
-template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false, int OCT = 0, bool WPART = false>
+template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false, int OCT = 0, bool WPART = false, bool A32 = false>
 __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_match_accumulate_wl4(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
                            const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,
@@ -1436,8 +1503,8 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
   if (threadIdx.x < 12) sT[threadIdx.x] = S.T[threadIdx.x];
   if (MULTI) stage_map(sMap, maps, P.map_idx);
   __syncthreads();
-  if constexpr (MULTI) chunk_match_wl<4, PIPE, BULK, OCT, WPART>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
-  else chunk_match_wl<4, PIPE, BULK, OCT, WPART>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  if constexpr (MULTI) chunk_match_wl<4, PIPE, BULK, OCT, WPART, A32>(sMap, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
+  else chunk_match_wl<4, PIPE, BULK, OCT, WPART, A32>(map, P, sT, S.it, blockIdx.x, local, pairA, pairB, partials, part_cnt);
 }
 
 template <int MIN_BLOCKS>

@@ -221,7 +221,7 @@ def test_large_batch_launch_sequence_matches_the_oracle(ctx, large_case, groups,
     print(f"large batch ({c['total_q']} queries): worst GPU-vs-oracle pose delta {worst}")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
 def test_large_batch_drain_variants_are_identical(ctx, large_case, variant):
     """The drain loop of the work-list kernel exists in several forms (include/mlo_b200.h "wl_variant": segment-wise
     merge, software-pipelined, cp.async.bulk staging, contiguous ranges with a register-resident best).  All of them take
@@ -234,8 +234,12 @@ def test_large_batch_drain_variants_are_identical(ctx, large_case, variant):
         res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
         assert ctx.get_option("last_align_path") == 1
     for a, b, orr in zip(res, base, c["refs"]):
-        assert np.array_equal(np.asarray(a.pose), np.asarray(b.pose))
+        if variant in (10, 11):   # one partial per warp: the same pairings, summed in a different grouping
+            assert np.allclose(np.asarray(a.pose), np.asarray(b.pose), rtol=0, atol=1e-9)
+        else:
+            assert np.array_equal(np.asarray(a.pose), np.asarray(b.pose))
         assert int(a.n_iterations) == int(b.n_iterations) and int(a.n_pairings) == int(b.n_pairings)
+        assert int(a.n_candidate_points) == int(b.n_candidate_points)
         _check(a, orr)
 
 
