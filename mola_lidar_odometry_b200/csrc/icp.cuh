@@ -14,6 +14,7 @@
 // A launch covers a batch of independent problems (blockIdx.y), all against one read-only map.
 #pragma once
 #include "map.cuh"
+#include "octet.cuh"
 #include "se3.cuh"
 
 namespace mlo {
@@ -248,13 +249,43 @@ MLO_D void chunk_match_warp(const MapDev& map, const IcpProblem& P, const double
   float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t ncand = 0;
   bool paired = false;
-  if ((P.matcher_mask & MLO_MATCHER_PT2PL) && mine) {
-    const PlaneHit h = nn_plane_thread(map, gx, gy, gz);
-    ncand += h.ncand;
-    if (h.found && h.dist < thr_pl) {
-      paired = true;
-      pa = make_float4(h.cx, h.cy, h.cz, 2.f);
-      pb = make_float4(h.nx, h.ny, h.nz, 0.f);
+  if (P.matcher_mask & MLO_MATCHER_PT2PL) {  // (warp-uniform)
+    // mola::NDT nearest-plane search, four queries of the warp at a time, eight lanes per query (octet.cuh): the 18
+    // column buckets of a neighbourhood are probed by the eight lanes together, then each lane reads the mean / normal
+    // of up to four cells - three round trips for four queries, where one thread walking the 27 cells of its query
+    // (nn_plane_thread) is a chain of ~80 dependent loads with four lanes of the warp active.
+    __shared__ uint32_t s_ow[ICP_BLOCK / 8][28];
+    const uint32_t og = lane >> 3;
+    uint32_t* ow = s_ow[threadIdx.x >> 3];
+    for (uint32_t base = 0; base < nq_warp; base += 4) {  // (nq_warp is warp-uniform)
+      const uint32_t src = base + og;  // the query this octet serves
+      const bool have = src < nq_warp;
+      const float ox = __shfl_sync(FULL, gx, src & 31u), oy = __shfl_sync(FULL, gy, src & 31u), oz = __shfl_sync(FULL, gz, src & 31u);
+      int32_t kq[3] = {0, 0, 0};
+      bool in_range = false;
+      if (have) {
+        kq[0] = voxel_index_map(ox, map.inv_voxel, map.index_floor);
+        kq[1] = voxel_index_map(oy, map.inv_voxel, map.index_floor);
+        kq[2] = voxel_index_map(oz, map.inv_voxel, map.index_floor);
+        in_range = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
+      }
+      octet_probe(map, kq, in_range, ow);
+      const PlaneHit h = octet_plane(map, ox, oy, oz, in_range, ow);
+      __syncwarp();
+      // hand each result to the lane that owns the query: lane base + j takes it from lane 8 j
+      const uint32_t from = lane >= base && lane < base + 4 ? 8u * (lane - base) : 0u;
+      const float hcx = __shfl_sync(FULL, h.cx, from), hcy = __shfl_sync(FULL, h.cy, from), hcz = __shfl_sync(FULL, h.cz, from);
+      const float hnx = __shfl_sync(FULL, h.nx, from), hny = __shfl_sync(FULL, h.ny, from), hnz = __shfl_sync(FULL, h.nz, from);
+      const float hd = __shfl_sync(FULL, h.dist, from);
+      const uint32_t hf = __shfl_sync(FULL, h.found, from), hn = __shfl_sync(FULL, h.ncand, from);
+      if (mine && lane >= base && lane < base + 4) {
+        ncand += hn;
+        if (hf && hd < thr_pl) {
+          paired = true;
+          pa = make_float4(hcx, hcy, hcz, 2.f);
+          pb = make_float4(hnx, hny, hnz, 0.f);
+        }
+      }
     }
   }
   if (P.matcher_mask & MLO_MATCHER_PT2PT) {
