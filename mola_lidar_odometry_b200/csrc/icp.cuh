@@ -223,9 +223,64 @@ MLO_D void warp_reduce_store(double* a, uint32_t npairs, uint32_t ncand, double*
 // 4 warps x qpw queries (warp-per-query form).  The chunk functions below are shared by the
 // one-kernel-per-phase launch sequence and by the persistent queue-driven kernel.
 
+// mola::NDT nearest-plane search for the (up to 32) queries a warp holds one per lane, four queries at a time, eight
+// lanes per query (octet.cuh): the 18 column buckets of a neighbourhood are probed by the eight lanes together, then each
+// lane reads the mean / normal of up to four cells - three round trips for four queries, where one thread walking the
+// 27 cells of its query (nn_plane_thread) is a chain of ~80 dependent loads with four lanes of the warp active.
+// Compiled only into the PLANES instantiations of the callers: the point-to-point-only pipelines must not pay for this
+// code in the registers of their hot path (present but not executed, it cost the 32-sequence fleet of the default
+// pipeline 8 %; as a __noinline__ function it crashes ptxas 12.9).
+struct PlanePairing {
+  float4 a, b;
+  uint32_t ncand;
+  bool paired;
+};
+MLO_D void warp_plane_match(const MapDev& map, float gx, float gy, float gz, uint32_t nq_warp, float thr_pl, uint32_t* ow,
+                                              PlanePairing& out) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u;
+  const bool mine = lane < nq_warp;
+  out.a = make_float4(0.f, 0.f, 0.f, 0.f);
+  out.b = make_float4(0.f, 0.f, 0.f, 0.f);
+  out.ncand = 0;
+  out.paired = false;
+  const uint32_t og = lane >> 3;
+  for (uint32_t base = 0; base < nq_warp; base += 4) {  // (nq_warp is warp-uniform)
+    const uint32_t src = base + og;  // the query this octet serves
+    const bool have = src < nq_warp;
+    const float ox = __shfl_sync(FULL, gx, src & 31u), oy = __shfl_sync(FULL, gy, src & 31u), oz = __shfl_sync(FULL, gz, src & 31u);
+    int32_t kq[3] = {0, 0, 0};
+    bool in_range = false;
+    if (have) {
+      kq[0] = voxel_index_map(ox, map.inv_voxel, map.index_floor);
+      kq[1] = voxel_index_map(oy, map.inv_voxel, map.index_floor);
+      kq[2] = voxel_index_map(oz, map.inv_voxel, map.index_floor);
+      in_range = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
+    }
+    octet_probe(map, kq, in_range, ow);
+    const PlaneHit h = octet_plane(map, ox, oy, oz, in_range, ow);
+    __syncwarp();
+    // hand each result to the lane that owns the query: lane base + j takes it from lane 8 j
+    const uint32_t from = lane >= base && lane < base + 4 ? 8u * (lane - base) : 0u;
+    const float hcx = __shfl_sync(FULL, h.cx, from), hcy = __shfl_sync(FULL, h.cy, from), hcz = __shfl_sync(FULL, h.cz, from);
+    const float hnx = __shfl_sync(FULL, h.nx, from), hny = __shfl_sync(FULL, h.ny, from), hnz = __shfl_sync(FULL, h.nz, from);
+    const float hd = __shfl_sync(FULL, h.dist, from);
+    const uint32_t hf = __shfl_sync(FULL, h.found, from), hn = __shfl_sync(FULL, h.ncand, from);
+    if (mine && lane >= base && lane < base + 4) {
+      out.ncand += hn;
+      if (hf && hd < thr_pl) {
+        out.paired = true;
+        out.a = make_float4(hcx, hcy, hcz, 2.f);
+        out.b = make_float4(hnx, hny, hnz, 0.f);
+      }
+    }
+  }
+}
+
 // Warp-per-query chunk: a warp owns `qpw` consecutive queries.  Lane t holds query t: its local point, its
 // transformed point and, after the warp-cooperative NN of that query (map.cuh: probe prefetched one query
 // ahead), its pairing.  The normal-equation terms are computed once per query by the owning lane.
+template <bool PLANES = true>
 MLO_D void chunk_match_warp(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                             const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                             double* __restrict__ partials, uint32_t* __restrict__ part_cnt, uint32_t qpw) {
@@ -249,43 +304,15 @@ MLO_D void chunk_match_warp(const MapDev& map, const IcpProblem& P, const double
   float4 pb = make_float4(0.f, 0.f, 0.f, 0.f);
   uint32_t ncand = 0;
   bool paired = false;
-  if (P.matcher_mask & MLO_MATCHER_PT2PL) {  // (warp-uniform)
-    // mola::NDT nearest-plane search, four queries of the warp at a time, eight lanes per query (octet.cuh): the 18
-    // column buckets of a neighbourhood are probed by the eight lanes together, then each lane reads the mean / normal
-    // of up to four cells - three round trips for four queries, where one thread walking the 27 cells of its query
-    // (nn_plane_thread) is a chain of ~80 dependent loads with four lanes of the warp active.
-    __shared__ uint32_t s_ow[ICP_BLOCK / 8][28];
-    const uint32_t og = lane >> 3;
-    uint32_t* ow = s_ow[threadIdx.x >> 3];
-    for (uint32_t base = 0; base < nq_warp; base += 4) {  // (nq_warp is warp-uniform)
-      const uint32_t src = base + og;  // the query this octet serves
-      const bool have = src < nq_warp;
-      const float ox = __shfl_sync(FULL, gx, src & 31u), oy = __shfl_sync(FULL, gy, src & 31u), oz = __shfl_sync(FULL, gz, src & 31u);
-      int32_t kq[3] = {0, 0, 0};
-      bool in_range = false;
-      if (have) {
-        kq[0] = voxel_index_map(ox, map.inv_voxel, map.index_floor);
-        kq[1] = voxel_index_map(oy, map.inv_voxel, map.index_floor);
-        kq[2] = voxel_index_map(oz, map.inv_voxel, map.index_floor);
-        in_range = key_in_range(kq[0]) && key_in_range(kq[1]) && key_in_range(kq[2]);
-      }
-      octet_probe(map, kq, in_range, ow);
-      const PlaneHit h = octet_plane(map, ox, oy, oz, in_range, ow);
-      __syncwarp();
-      // hand each result to the lane that owns the query: lane base + j takes it from lane 8 j
-      const uint32_t from = lane >= base && lane < base + 4 ? 8u * (lane - base) : 0u;
-      const float hcx = __shfl_sync(FULL, h.cx, from), hcy = __shfl_sync(FULL, h.cy, from), hcz = __shfl_sync(FULL, h.cz, from);
-      const float hnx = __shfl_sync(FULL, h.nx, from), hny = __shfl_sync(FULL, h.ny, from), hnz = __shfl_sync(FULL, h.nz, from);
-      const float hd = __shfl_sync(FULL, h.dist, from);
-      const uint32_t hf = __shfl_sync(FULL, h.found, from), hn = __shfl_sync(FULL, h.ncand, from);
-      if (mine && lane >= base && lane < base + 4) {
-        ncand += hn;
-        if (hf && hd < thr_pl) {
-          paired = true;
-          pa = make_float4(hcx, hcy, hcz, 2.f);
-          pb = make_float4(hnx, hny, hnz, 0.f);
-        }
-      }
+  if (PLANES && (P.matcher_mask & MLO_MATCHER_PT2PL)) {  // (warp-uniform)
+    __shared__ uint32_t s_ow[ICP_BLOCK / 8][28];  // the 27 cell words of each octet's query
+    PlanePairing pp;
+    warp_plane_match(map, gx, gy, gz, nq_warp, thr_pl, s_ow[threadIdx.x >> 3], pp);
+    ncand += pp.ncand;
+    if (mine && pp.paired) {
+      paired = true;
+      pa = pp.a;
+      pb = pp.b;
     }
   }
   if (P.matcher_mask & MLO_MATCHER_PT2PT) {
@@ -1664,11 +1691,11 @@ __device__ __noinline__ void chunk_match_tpq_ool(const MapDev& map, const IcpPro
                                                  double* partials, uint32_t* part_cnt) {
   chunk_match_tpq(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt);
 }
-template <int TAG>
+template <int TAG, bool PLANES>
 __device__ __noinline__ void chunk_match_warp_ool(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it,
                                                   uint32_t chunk, const float4* local, float4* pairA, float4* pairB,
                                                   double* partials, uint32_t* part_cnt, uint32_t qpw) {
-  chunk_match_warp(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+  chunk_match_warp<PLANES>(map, P, sT, it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
 }
 template <int TAG>
 __device__ __noinline__ void chunk_accumulate_ool(const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
@@ -1699,7 +1726,7 @@ __global__ void k_queue_build(const IcpProblem* __restrict__ probs, const IcpSta
   atomicAdd(&q.ctrl[2], 1u);
 }
 
-template <bool TPQ, bool MULTI, int MINB = 4>
+template <bool TPQ, bool MULTI, int MINB = 4, bool PLANES = true>
 __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_icp_persistent(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs, IcpState* states,
                      const float4* __restrict__ local, float4* pairA, float4* pairB, double* partials, uint32_t* part_cnt,
@@ -1745,13 +1772,13 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     if (MULTI && phase == 0) stage_map(sMap, maps, P.map_idx);
     __syncthreads();
     if (phase == 0) {
-      constexpr int TAG = (TPQ ? 2 : 0) + (MULTI ? 1 : 0) + (MINB == 4 ? 0 : 4);  // one out-of-line copy per kernel instance
+      constexpr int TAG = (TPQ ? 2 : 0) + (MULTI ? 1 : 0) + (MINB == 4 ? 0 : 4) + (PLANES ? 0 : 8);  // one out-of-line copy per kernel instance
       if constexpr (TPQ && MULTI) chunk_match_tpq_ool<TAG>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
       else if constexpr (TPQ) chunk_match_tpq_ool<TAG>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
-      else if constexpr (MULTI) chunk_match_warp_ool<TAG>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
-      else chunk_match_warp_ool<TAG>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+      else if constexpr (MULTI) chunk_match_warp_ool<TAG, PLANES>(sMap, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
+      else chunk_match_warp_ool<TAG, PLANES>(map, P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt, qpw);
     } else {
-      chunk_accumulate_ool<(TPQ ? 2 : 0) + (MULTI ? 1 : 0) + (MINB == 4 ? 0 : 4)>(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
+      chunk_accumulate_ool<(TPQ ? 2 : 0) + (MULTI ? 1 : 0) + (MINB == 4 ? 0 : 4) + (PLANES ? 0 : 8)>(P, sT, s_it, chunk, local, pairA, pairB, partials, part_cnt);
     }
     __syncthreads();
     if (threadIdx.x == 0) {

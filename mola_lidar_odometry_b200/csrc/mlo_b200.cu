@@ -851,22 +851,26 @@ int issue_deferred_uploads(mlo_ctx* c, int except_slot) {
 }
 
 void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const MapDev& map, const MapDev* d_maps,
-                       const IcpProblem* dP, IcpState* dS, const float4* d_local, const IcpQueue& q, uint32_t qpw) {
-#define MLO_PERS(T, M, QPW)                                                                                              \
+                       const IcpProblem* dP, IcpState* dS, const float4* d_local, const IcpQueue& q, uint32_t qpw, bool planes = true) {
+#define MLO_PERS(T, M, PL, QPW)                                                                                          \
   do {                                                                                                                   \
     if (c->pers_minb_now == 2)                                                                                           \
-      LAUNCH(c, (k_icp_persistent<T, M, 2>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),     \
+      LAUNCH(c, (k_icp_persistent<T, M, 2, PL>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(), \
              c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW,                   \
              c->fuse_inner ? 1 : 0);                                                                                     \
     else                                                                                                                 \
-      LAUNCH(c, (k_icp_persistent<T, M, 4>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(),     \
+      LAUNCH(c, (k_icp_persistent<T, M, 4, PL>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(), \
              c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW,                   \
              c->fuse_inner ? 1 : 0);                                                                                     \
   } while (0)
-  if (tpq && multi) MLO_PERS(true, true, 0u);
-  else if (tpq) MLO_PERS(true, false, 0u);
-  else if (multi) MLO_PERS(false, true, qpw);
-  else MLO_PERS(false, false, qpw);
+  // (the warp-per-query form exists with and without the point-to-plane matcher's code: point-to-point pipelines run
+  // the lean instantiation)
+  if (tpq && multi) MLO_PERS(true, true, true, 0u);
+  else if (tpq) MLO_PERS(true, false, true, 0u);
+  else if (multi && planes) MLO_PERS(false, true, true, qpw);
+  else if (multi) MLO_PERS(false, true, false, qpw);
+  else if (planes) MLO_PERS(false, false, true, qpw);
+  else MLO_PERS(false, false, false, qpw);
 #undef MLO_PERS
 }
 
@@ -1139,7 +1143,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
       const uint32_t resident = c->pers_minb_now == 2 ? uint32_t(2 * c->sm_count) : uint32_t(c->persistent_blocks);
       const uint32_t nblk = std::min<uint32_t>(resident, std::max<uint32_t>(part_total, 1u));
       const size_t e_nn = prof_begin(c);
-      launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
+      launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw, any_planes);
       prof_end(c, 3, e_nn);
       {
         int rc = issue_deferred_once();
@@ -1283,7 +1287,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
         const uint32_t resident = c->pers_minb_now == 2 ? uint32_t(2 * c->sm_count) : uint32_t(c->persistent_blocks);
         const uint32_t nblk = std::min<uint32_t>(resident, std::max<uint32_t>(part_total, 1u));
         const size_t e_nn = prof_begin(c);
-        launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw);
+        launch_persistent(c, use_tpq, multi, nblk, map->dev, d_maps, dP, dS, d_local, q, qpw, any_planes);
         prof_end(c, 3, e_nn);
         CU(c, cudaMemcpyAsync(h_active, q.ctrl + 4, sizeof(uint32_t), cudaMemcpyDeviceToHost, c->stream));
         CU(c, cudaStreamSynchronize(c->stream));
