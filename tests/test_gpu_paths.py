@@ -243,6 +243,18 @@ def test_large_batch_drain_variants_are_identical(ctx, large_case, variant):
         _check(a, orr)
 
 
+@pytest.mark.parametrize("per_sm,every", [(2048, 2), (64, 8), (512, 1)])
+def test_large_batch_hand_over_point_does_not_change_results(ctx, large_case, per_sm, every):
+    """Where the launch sequence hands its stragglers to the queue-driven kernel (mlo_set_option "tail_queries_per_sm",
+    "check_every") is a scheduling decision: every problem still matches the oracle."""
+    c = large_case
+    with _Options(ctx, tail_queries_per_sm=per_sm, check_every=every):
+        res = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in c["owners"]])
+        assert ctx.get_option("last_align_path") == 1
+    for gr, orr in zip(res, c["refs"]):
+        _check(gr, orr)
+
+
 def test_large_batch_other_paths_agree(ctx, large_case):
     """The same 128 problems through the queue-driven kernel and the block kernel (two blocks per SM at this size)."""
     c = large_case
