@@ -94,7 +94,7 @@ uint64_t mlo_launch_count(const mlo_ctx* ctx);
  * device, 2 one thread block per cloud with its scratch in shared memory), "filter_cta_min_clouds" (batch size at which 0
  * picks 2), "force_kernel", "wl_variant" (drain loop of the work-list kernel: 0-3 segment-wise merge at 8 / 6 blocks per
  * SM, plain or software-pipelined; 4-5 cp.async.bulk staging; 6-9 contiguous ranges per lane group; 10-11 one partial per
- * warp; 12-13 split 32-bit keys), "wl_warps", "pers_minb"; read-only "last_align_path", "last_stream_groups", "last_tail_handover",
+ * warp; 12-13 split 32-bit keys; 14-15 ballot winner; 16-17 eight segments per round; 18-19 run merging), "wl_warps", "pers_minb"; read-only "last_align_path", "last_stream_groups", "last_tail_handover",
  * "last_block_cluster", "last_block_threads" describe the last align call, "last_filter_kernel" the last filter batch.
  * Unknown name: MLO_ERR_INVALID_ARG. */
 int mlo_set_option(mlo_ctx* ctx, const char* name, int64_t value);

@@ -515,6 +515,124 @@ MLO_D void wl_process(const MapDev& map, WarpScratch& ws, uint32_t n) {
   __syncwarp();
 }
 
+// ---- run-merging drain (MLO_WL_VARIANT 18 / 19): consecutive work-list items mostly belong to the SAME query (a query
+// brings ~13 row segments), so the four lane groups of one instruction usually update the same 64-bit best and their
+// shared-memory atomicMin CAS loops collide.  Here the groups first merge their segment minima along the run of equal
+// queries (two conditional shuffle steps towards the run's first group) and only that group touches shared memory.
+MLO_D void wl_consume_runs(WarpScratch& ws, uint32_t lane, const float4 (&p)[4], const uint32_t (&meta)[4]) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t sub = lane & 7u, grp = lane >> 3;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    unsigned long long key = ~0ull;
+    const uint32_t q = meta[u] & 31u;
+    if (meta[u] & 0x80000000u) {
+      const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]);
+      key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu);
+    }
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) {
+      const unsigned long long other = __shfl_xor_sync(FULL, key, o);
+      key = other < key ? other : key;
+    }
+    // merge along the run of groups that hold the same query (items are sorted by query: runs are contiguous)
+    const uint32_t q_prev = __shfl_up_sync(FULL, q, 8);
+#pragma unroll
+    for (int o = 8; o <= 16; o <<= 1) {
+      const unsigned long long kd = __shfl_down_sync(FULL, key, o);
+      const uint32_t qd = __shfl_down_sync(FULL, q, o);
+      if (qd == q && kd < key) key = kd;  // (beyond the warp's edge a lane reads itself: a no-op)
+    }
+    const bool first_of_run = grp == 0 || q_prev != q;
+    if (sub == 0 && first_of_run && key != ~0ull) atomicMin(&ws.best[q], key);
+  }
+}
+MLO_D void wl_process_runs(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  for (uint32_t base = 0; base < n; base += 16) {
+    float4 p[4];
+    uint32_t meta[4];
+    wl_issue(map, ws, n, base, grp, sub, p, meta);
+    wl_consume_runs(ws, lane, p, meta);
+  }
+  __syncwarp();
+}
+
+// ---- deep drain (MLO_WL_VARIANT 16 / 17): the default's issue / consume pair with EIGHT row segments per lane group and
+// round (32 per warp) instead of four: half as many dependent rounds per work list, twice the row loads in flight, at
+// the price of 16 more registers (96 at 5 blocks/SM, or 80 with spills at 6).
+MLO_D void wl_process_deep(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  for (uint32_t base = 0; base < n; base += 32) {
+    float4 p[8];
+    uint32_t meta[8];
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const uint32_t idx = base + u * 4 + grp;
+      meta[u] = 0;
+      if (idx < n) {
+        const uint32_t it = ws.list[idx];
+        const uint32_t q = it & 31u, e = (it >> 5) & 31u, slot = (it >> 10) * 8u + sub;
+        const uint32_t w = ws.words[e][q];
+        meta[u] = q;
+        if (slot < cell_cnt(w)) {
+          p[u] = __ldg(map.pts + size_t(cell_vid(w)) * map.row + slot);
+          meta[u] = 0x80000000u | ((e * 32u + slot) << 5) | q;
+        }
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      unsigned long long key = ~0ull;
+      const uint32_t q = meta[u] & 31u;
+      if (meta[u] & 0x80000000u) {
+        const float d2 = sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]);
+        key = (uint64_t(__float_as_uint(d2)) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu);
+      }
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        const unsigned long long other = __shfl_xor_sync(0xFFFFFFFFu, key, o);
+        key = other < key ? other : key;
+      }
+      if (sub == 0 && key != ~0ull) atomicMin(&ws.best[q], key);
+    }
+  }
+  __syncwarp();
+}
+
+// ---- ballot drain (MLO_WL_VARIANT 14 / 15): as wl_consume, but the minimum over the 8 lanes of a segment is taken on the
+// 32-bit distance alone (3 x SHFL + min instead of 3 x (2 SHFL + 64-bit compare + 2 selects)) and the lane that holds it -
+// the lowest such lane: lowest slot = lowest order within a segment - is found by a ballot and updates the query's 64-bit
+// best itself; no key travels between lanes.  Each segment is still consumed as soon as its own load has arrived.
+MLO_D void wl_consume_ballot(WarpScratch& ws, uint32_t lane, const float4 (&p)[4], const uint32_t (&meta)[4]) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t sub = lane & 7u, oshift = lane & 24u;
+#pragma unroll
+  for (int u = 0; u < 4; u++) {
+    const uint32_t q = meta[u] & 31u;
+    const bool valid = (meta[u] & 0x80000000u) != 0;
+    uint32_t d2b = 0xFFFFFFFFu;
+    if (valid) d2b = __float_as_uint(sqr_dist(p[u].x, p[u].y, p[u].z, ws.q[0][q], ws.q[1][q], ws.q[2][q]));
+    uint32_t m = d2b;
+#pragma unroll
+    for (int o = 1; o < 8; o <<= 1) m = min(m, __shfl_xor_sync(FULL, m, o));
+    const bool is_min = valid && d2b == m;
+    const uint32_t b = (__ballot_sync(FULL, is_min) >> oshift) & 0xFFu;
+    if (is_min && sub == uint32_t(__ffs(b) - 1))
+      atomicMin(&ws.best[q], (uint64_t(d2b) << 32) | uint64_t((meta[u] >> 5) & 0x3FFu));
+  }
+}
+MLO_D void wl_process_ballot(const MapDev& map, WarpScratch& ws, uint32_t n) {
+  const uint32_t lane = threadIdx.x & 31u, grp = lane >> 3, sub = lane & 7u;
+  for (uint32_t base = 0; base < n; base += 16) {
+    float4 p[4];
+    uint32_t meta[4];
+    wl_issue(map, ws, n, base, grp, sub, p, meta);
+    wl_consume_ballot(ws, lane, p, meta);
+  }
+  __syncwarp();
+}
+
 // ---- split-key drain (MLO_WL_VARIANT 12 / 13): the running best of a query is kept as TWO 32-bit words, distance bits
 // and visiting order, so that every update is a native 32-bit shared-memory atomicMin (ATOMS.MIN) instead of the CAS
 // loop a 64-bit shared atomicMin compiles to (ATOMS.CAST.SPIN: ~20 instructions, 15 % of the kernel's instruction
@@ -742,7 +860,7 @@ MLO_D void wl_process_bulk(const MapDev& map, WarpScratch& ws, WarpStage& st, ui
 }
 
 constexpr uint32_t WL_BLOCK = 32;  // the work-list kernel runs one warp per block: a chunk is 32 queries
-template <int NWARPS, bool PIPE = false, bool BULK = false, int OCT = 0, bool WPART = false, bool A32 = false>
+template <int NWARPS, bool PIPE = false, bool BULK = false, int OCT = 0, bool WPART = false, int A32 = 0>
 MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* sT, uint32_t it, uint32_t chunk,
                           const float4* __restrict__ local, float4* __restrict__ pairA, float4* __restrict__ pairB,
                           double* __restrict__ partials, uint32_t* __restrict__ part_cnt) {
@@ -791,7 +909,7 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
     ws.q[1][lane] = gy;
     ws.q[2][lane] = gz;
     ws.best[lane] = ~0ull;
-    if constexpr (A32) {
+    if constexpr (A32 == 1) {
       ws.bd2[lane] = 0xFFFFFFFFu;
       ws.bord[lane] = 0xFFFFFFFFu;
     }
@@ -827,7 +945,10 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       __syncwarp();
       if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
       else if constexpr (OCT > 0) wl_process_oct<OCT>(map, ws, total);
-      else if constexpr (A32) wl_process_a32(map, ws, total);
+      else if constexpr (A32 == 1) wl_process_a32(map, ws, total);
+      else if constexpr (A32 == 2) wl_process_ballot(map, ws, total);
+      else if constexpr (A32 == 3) wl_process_deep(map, ws, total);
+      else if constexpr (A32 == 4) wl_process_runs(map, ws, total);
       else wl_process<PIPE>(map, ws, total);
     }
     // ---- phase 3: per query, the neighbour cells that can still beat the bound from the own cell
@@ -873,7 +994,10 @@ MLO_D void chunk_match_wl(const MapDev& map, const IcpProblem& P, const double* 
       __syncwarp();
       if constexpr (BULK) wl_process_bulk(map, ws, s_stage[warp], total, bulk_par);
       else if constexpr (OCT > 0) wl_process_oct<OCT>(map, ws, total);
-      else if constexpr (A32) wl_process_a32(map, ws, total);
+      else if constexpr (A32 == 1) wl_process_a32(map, ws, total);
+      else if constexpr (A32 == 2) wl_process_ballot(map, ws, total);
+      else if constexpr (A32 == 3) wl_process_deep(map, ws, total);
+      else if constexpr (A32 == 4) wl_process_runs(map, ws, total);
       else wl_process<PIPE>(map, ws, total);
       start = end;
     }
@@ -1547,7 +1671,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, 4)
 }
 
 // four-warp variant of the work-list kernel (chunk = ICP_BLOCK queries), kept for A/B runs
-template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false, int OCT = 0, bool WPART = false, bool A32 = false>
+template <bool MULTI, bool PIPE = false, int MINB = 8, bool BULK = false, int OCT = 0, bool WPART = false, int A32 = 0>
 __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     k_match_accumulate_wl4(MapDev map, const MapDev* __restrict__ maps, const IcpProblem* __restrict__ probs,
                            const IcpState* __restrict__ states, const float4* __restrict__ local, float4* __restrict__ pairA,

@@ -1196,8 +1196,8 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
 #define MLO_WL4_OCT_LAUNCH(DEPTH, MB)                                                                                       \
   LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, false, DEPTH>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, gS,   \
             d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
-#define MLO_WL4_A32_LAUNCH(MB)                                                                                              \
-  LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, false, 0, false, true>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, \
+#define MLO_WL4_A32_LAUNCH(MB, MODE)                                                                                        \
+  LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, false, 0, false, MODE>), grid_g, ICP_BLOCK, map->dev, d_maps, gP, \
             gS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>())
 #define MLO_WL4_WPART_LAUNCH(MB)                                                                                            \
   LAUNCH_ON(c, sg, (k_match_accumulate_wl4<false, false, MB, false, 0, true>), dim3((grid_g.x + 3) / 4, grid_g.y), ICP_BLOCK,  \
@@ -1209,8 +1209,14 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
             case 7: MLO_WL4_OCT_LAUNCH(4, 8); break;
             case 8: MLO_WL4_OCT_LAUNCH(8, 6); break;
             case 9: MLO_WL4_OCT_LAUNCH(8, 5); break;
-            case 12: MLO_WL4_A32_LAUNCH(6); break;  // split 32-bit keys: native shared-memory atomics
-            case 13: MLO_WL4_A32_LAUNCH(8); break;
+            case 12: MLO_WL4_A32_LAUNCH(6, 1); break;  // split 32-bit keys: native shared-memory atomics
+            case 13: MLO_WL4_A32_LAUNCH(8, 1); break;
+            case 14: MLO_WL4_A32_LAUNCH(6, 2); break;  // 32-bit segment minimum + ballot, 64-bit best
+            case 15: MLO_WL4_A32_LAUNCH(8, 2); break;
+            case 16: MLO_WL4_A32_LAUNCH(5, 3); break;  // eight segments per lane group and round
+            case 17: MLO_WL4_A32_LAUNCH(6, 3); break;
+            case 18: MLO_WL4_A32_LAUNCH(6, 4); break;  // segment minima merged along runs of equal queries before the atomic
+            case 19: MLO_WL4_A32_LAUNCH(8, 4); break;
             case 10: MLO_WL4_WPART_LAUNCH(6); break;  // one partial per warp, no block barrier
             case 11: MLO_WL4_WPART_LAUNCH(8); break;
             case 1: MLO_WL4_LAUNCH(true, 8); break;

@@ -221,7 +221,7 @@ def test_large_batch_launch_sequence_matches_the_oracle(ctx, large_case, groups,
     print(f"large batch ({c['total_q']} queries): worst GPU-vs-oracle pose delta {worst}")
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19])
 def test_large_batch_drain_variants_are_identical(ctx, large_case, variant):
     """The drain loop of the work-list kernel exists in several forms (include/mlo_b200.h "wl_variant": segment-wise
     merge, software-pipelined, cp.async.bulk staging, contiguous ranges with a register-resident best).  All of them take
