@@ -156,6 +156,49 @@ MLO_D void contrib_horn(float lx, float ly, float lz, float gx, float gy, float 
   }
 }
 
+// Transposing warp reduction: on return lane k holds the warp-wide sum of v[k] (k = 0..31).
+// Step h halves the live entries: lanes with bit h set keep the upper half and hand the lower half to their
+// partner, so the whole reduction costs 16+8+4+2+1 = 31 double shuffles.  Fixed order: reproducible.
+MLO_D double warp_reduce32_transpose(double (&v)[32]) {
+  const uint32_t lane = threadIdx.x & 31u;
+#pragma unroll
+  for (int h = 16; h >= 1; h >>= 1) {
+    const bool up = (lane & uint32_t(h)) != 0;
+#pragma unroll
+    for (int k = 0; k < h; k++) {
+      const double send = up ? v[k] : v[k + h];
+      const double keep = up ? v[k + h] : v[k];
+      v[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h);
+    }
+  }
+  return v[0];
+}
+
+// The same block reduction with the transposing warp step (31 double shuffles instead of 27 x 5): for the latency-bound
+// callers (warp-per-query chunks, re-linearisation chunks of the queue-driven kernel).  Lane 27 / 28 of the array carry
+// the pairing / candidate counts (exact in double).  The summation order differs from block_reduce_store's butterfly,
+// so a caller must stay with one of the two.
+MLO_D void block_reduce_store_t(const double* a, uint32_t npairs, uint32_t ncand, double* part, uint32_t* part_cnt) {
+  __shared__ double sm[ICP_BLOCK / 32][32];
+  const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[32];
+#pragma unroll
+  for (int k = 0; k < int(NACC); k++) v[k] = a[k];
+  v[NACC] = double(npairs);
+  v[NACC + 1] = double(ncand);
+#pragma unroll
+  for (int k = int(NACC) + 2; k < 32; k++) v[k] = 0.0;
+  sm[warp][lane] = warp_reduce32_transpose(v);
+  __syncthreads();
+  if (threadIdx.x < NACC + 2) {
+    double t = 0.0;
+#pragma unroll
+    for (int w = 0; w < int(ICP_BLOCK / 32); w++) t += sm[w][threadIdx.x];
+    if (threadIdx.x < NACC) part[threadIdx.x] = t;
+    else part_cnt[threadIdx.x - NACC] = uint32_t(t);
+  }
+}
+
 // warp butterfly + ordered cross-warp sum in shared memory; thread k < NACC of the block ends with element k.
 MLO_D void block_reduce_store(double* a, uint32_t npairs, uint32_t ncand, double* part, uint32_t* part_cnt) {
   __shared__ double sm[ICP_BLOCK / 32][NACC];
@@ -376,7 +419,7 @@ MLO_D void chunk_match_warp(const MapDev& map, const IcpProblem& P, const double
     pairA[P.q_begin + qbase + lane] = pa;
   }
   const uint32_t pbi = P.part_begin + chunk;
-  block_reduce_store(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+  block_reduce_store_t(a, npairs, ncand, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
 // Thread-per-query chunk for large batches: one query per thread, map.cuh nn_single_thread (pruned,
@@ -1076,7 +1119,7 @@ MLO_D void chunk_accumulate(const IcpProblem& P, const double* sT, uint32_t it, 
     }
   }
   const uint32_t pbi = P.part_begin + chunk;
-  block_reduce_store(a, npairs, 0u, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
+  block_reduce_store_t(a, npairs, 0u, partials + size_t(pbi) * NACC, part_cnt + 2 * size_t(pbi));
 }
 
 // Horn's closed form from the reduced sums (Solver_Horn): dominant eigenvector of the 4x4 N matrix.
@@ -1556,16 +1599,15 @@ __device__ __noinline__ int solve_core_staged(SolveStage& st, SolveScratch& sc, 
 constexpr uint32_t FUSE_MAX_Q = 16384;  // <= 128 pairings per thread
 MLO_D void block_reduce_to(double* a, uint32_t npairs, SolveScratch& sc) {
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  double v[32];
 #pragma unroll
-  for (int k = 0; k < int(NACC); k++) {
-    double v = a[k];
+  for (int k = 0; k < int(NACC); k++) v[k] = a[k];
+  v[NACC] = double(npairs);
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-    if (lane == 0) sc.part[warp][k] = v;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) npairs += __shfl_xor_sync(0xFFFFFFFFu, npairs, o);
-  if (lane == 0) sc.pcnt[warp][0] = npairs;
+  for (int k = int(NACC) + 1; k < 32; k++) v[k] = 0.0;
+  const double mine = warp_reduce32_transpose(v);  // lane k: the warp's sum of element k
+  if (lane < NACC) sc.part[warp][lane] = mine;
+  else if (lane == NACC) sc.pcnt[warp][0] = uint32_t(mine);
   __syncthreads();
   if (threadIdx.x < NACC) {
     double t = sc.part[0][threadIdx.x];
@@ -1581,10 +1623,20 @@ MLO_D void block_reduce_to(double* a, uint32_t npairs, SolveScratch& sc) {
   }
   __syncthreads();
 }
+// Pairings of the problem being solved, copied into shared memory by the three warps that would otherwise idle while
+// the first warp solves (solve_phase): the re-linearisation of a fused inner iteration then reads them from there instead
+// of waiting on two dependent global loads per pairing.  Point-to-point pairings only (no normals); problems with more
+// than PAIR_STAGE_MAX queries read the rest from global memory.
+constexpr uint32_t PAIR_STAGE_MAX = 768;
+struct PairStage {
+  float4 pa[PAIR_STAGE_MAX];
+  float4 l[PAIR_STAGE_MAX];
+};
+
 // every thread of the (ICP_BLOCK-wide) block calls this with the block-uniform `next` of the preceding solve, whose
 // problem and state sit in `st` (written by the block's first warp; the caller's barrier made them visible)
 MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uint32_t it, const float4* __restrict__ local,
-                                 const float4* pairA, const float4* pairB) {
+                                 const float4* pairA, const float4* pairB, const PairStage* ps) {
   __shared__ int f_next;
   const IcpProblem& P = st.P;
   while (next == 1) {
@@ -1595,9 +1647,10 @@ MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uin
     for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
     uint32_t npairs = 0;
     for (uint32_t q = threadIdx.x; q < P.n_q; q += ICP_BLOCK) {
-      const float4 pa = __ldcg(&pairA[P.q_begin + q]);
+      const bool staged = ps != nullptr && q < PAIR_STAGE_MAX;  // (block-uniform pointer)
+      const float4 pa = staged ? ps->pa[q] : __ldcg(&pairA[P.q_begin + q]);
       if (pa.w == 0.f) continue;
-      const float4 l = __ldg(&local[P.q_begin + q]);
+      const float4 l = staged ? ps->l[q] : __ldg(&local[P.q_begin + q]);
       if (pa.w == 1.f) {
         contrib_pt2pt(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
       } else {
@@ -1622,16 +1675,26 @@ MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uin
 // sums of the current linearisation sit in sc.tot / sc.cnt): first solve, fused inner iterations if allowed, state back
 // to global memory.  Returns the block-uniform verdict (0 finished, 1 inner iteration pending, 2 next ICP iteration).
 MLO_D int solve_phase(const IcpProblem& Pg, IcpState& Sg, SolveStage& st, SolveScratch& sc, int after_match, int fuse, uint32_t it,
-                      const float4* __restrict__ local, const float4* pairA, const float4* pairB, bool staged = false) {
+                      const float4* __restrict__ local, const float4* pairA, const float4* pairB, bool staged = false,
+                      PairStage* ps = nullptr) {
   __shared__ int p_next;
+  // (the staged problem is visible to every warp only when sum_partials_block brought it in behind its barrier)
+  const bool prefetch = ps != nullptr && staged && fuse && st.P.n_q <= FUSE_MAX_Q && st.P.solver == MLO_SOLVER_GAUSS_NEWTON &&
+                        st.P.gn_max_iterations > 1;
   if (threadIdx.x < 32) {
     if (!staged) solve_stage_in(Pg, Sg, st);  // (staged = sum_partials_block already brought them in)
     const int n = solve_core_staged(st, sc, after_match);
     if (threadIdx.x == 0) p_next = n;
+  } else if (prefetch) {
+    const uint32_t nq = min(st.P.n_q, PAIR_STAGE_MAX), qb = st.P.q_begin;
+    for (uint32_t q = threadIdx.x - 32; q < nq; q += ICP_BLOCK - 32) {
+      ps->pa[q] = __ldcg(&pairA[qb + q]);
+      ps->l[q] = __ldg(&local[qb + q]);
+    }
   }
   __syncthreads();
   int next = p_next;
-  if (fuse && st.P.n_q <= FUSE_MAX_Q) next = fused_inner_iterations(st, sc, next, it, local, pairA, pairB);
+  if (fuse && st.P.n_q <= FUSE_MAX_Q) next = fused_inner_iterations(st, sc, next, it, local, pairA, pairB, prefetch ? ps : nullptr);
   if (threadIdx.x < 32) solve_stage_out(Sg, st);
   __syncthreads();
   return next;
@@ -1732,7 +1795,8 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   __shared__ SolveStage st;
   const uint32_t it = S.it;  // (the match phase of this iteration used the same index; read before the solve bumps it)
   sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc, &S, &st);
-  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB, true);
+  __shared__ PairStage ps;
+  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB, true, &ps);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -1858,6 +1922,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
   __shared__ MapDev sMap;
   __shared__ SolveScratch s_solve;
   __shared__ SolveStage s_stage;
+  __shared__ PairStage s_pairs;
   __shared__ uint32_t s_item;
   __shared__ int s_last;
   __shared__ double sT[12];
@@ -1922,7 +1987,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     }
     int nx = 0;  // (block-uniform)
     if (s_last) {
-      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB, true);
+      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB, true, &s_pairs);
       MLO_TRACE_EVENT(prob, 7);  // solve phase (with its fused inner iterations) done, state written back
     }
     if (s_last && threadIdx.x < 32) {

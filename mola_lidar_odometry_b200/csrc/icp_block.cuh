@@ -27,24 +27,6 @@
 namespace mlo {
 namespace cg = cooperative_groups;
 
-// Transposing warp reduction: on return lane k holds the warp-wide sum of v[k] (k = 0..31).
-// Step h halves the live entries: lanes with bit h set keep the upper half and hand the lower half to their
-// partner, so the whole reduction costs 16+8+4+2+1 = 31 double shuffles.  Fixed order: reproducible.
-MLO_D double warp_reduce32_transpose(double (&v)[32]) {
-  const uint32_t lane = threadIdx.x & 31u;
-#pragma unroll
-  for (int h = 16; h >= 1; h >>= 1) {
-    const bool up = (lane & uint32_t(h)) != 0;
-#pragma unroll
-    for (int k = 0; k < h; k++) {
-      const double send = up ? v[k] : v[k + h];
-      const double keep = up ? v[k + h] : v[k];
-      v[k] = keep + __shfl_xor_sync(0xFFFFFFFFu, send, h);
-    }
-  }
-  return v[0];
-}
-
 __device__ __noinline__ int solve_core_ool(const IcpProblem& P, IcpState& S, SolveScratch& sc, int after_match) {
   return solve_core(P, S, sc, after_match);
 }
