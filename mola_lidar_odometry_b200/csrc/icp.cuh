@@ -1368,7 +1368,9 @@ MLO_D void prior_add_warp(const IcpProblem& P, const double* T, double* H, Solve
   const uint32_t lane = threadIdx.x & 31u;
   if (lane == 0) prior_e(P, T, sc.e);
   __syncwarp();
+  MLO_TRACE_SOLVE(47);  // prior: error vector done
   jr_inv_warp(sc.e, sc.J, sc.m);
+  MLO_TRACE_SOLVE(48);  // prior: Jacobian done
   if (lane < 6) {
     double s = 0;
     for (int m = 0; m < 6; m++) s += P.prior_info[6 * lane + m] * sc.e[m];

@@ -14,7 +14,7 @@ YAML = sys.argv[2] if len(sys.argv) > 2 else "lidar3d-default.yaml"
 fleet = LidarOdometryFleet(ctx, "/root/repo/pipelines/" + YAML, S)
 lib = capi.load()
 buf = (C.c_ulonglong * 16384)(); n = C.c_uint()
-names = {1: "pop_match0", 2: "pop_acc0", 3: "chunk0_done", 4: "last_chunk_done", 5: "partials_summed", 6: "solve1_done", 7: "fused_done", 8: "next_published", 40: "sys_laid_out", 41: "prior_added", 42: "ldlt_done", 43: "retracted", 44: "measured", 45: "staged", 46: "core_ret"}
+names = {1: "pop_match0", 2: "pop_acc0", 3: "chunk0_done", 4: "last_chunk_done", 5: "partials_summed", 6: "solve1_done", 7: "fused_done", 8: "next_published", 40: "sys_laid_out", 41: "prior_added", 42: "ldlt_done", 43: "retracted", 44: "measured", 45: "staged", 46: "core_ret", 47: "prior_e", 48: "prior_J"}
 for k in range(30):
     outs = fleet.on_lidar([scene.scan(trajs[s][k], scan_seed=(7 + s) * 1000 + k) for s in range(S)], [0.1 * k] * S)
     lib.mlo_debug_trace_read(buf, 16384, C.byref(n))
