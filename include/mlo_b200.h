@@ -89,7 +89,8 @@ uint64_t mlo_launch_count(const mlo_ctx* ctx);
  * exercise one specific device path).  Names: "align_path" (0 auto, 1 one kernel per phase = the large-batch launch
  * sequence, 2 queue-driven persistent kernel, 3 one thread block per problem), "large_batch_queries" (total queries at
  * which auto picks the launch sequence; 0 = SM count x 1024), "tail_handover", "tail_path", "stream_groups",
- * "fuse_inner", "block_threads" (256 / 512), "block_cluster" (thread blocks per problem: 1 / 2 / 4 / 8), "filter_group_mb",
+ * "fuse_inner", "prior_ahead" (a second warp linearises the prior term for the next solve while the first finishes the
+ * current one), "tail_queries_per_sm", "check_every", "block_threads" (256 / 512), "block_cluster" (thread blocks per problem: 1 / 2 / 4 / 8), "filter_group_mb",
  * "filter_ppt", "filter_kernel" (0 by batch size, 1 global scratch tables with the blocks of a cloud spread over the
  * device, 2 one thread block per cloud with its scratch in shared memory), "filter_cta_min_clouds" (batch size at which 0
  * picks 2), "force_kernel", "wl_variant" (drain loop of the work-list kernel: 0-3 segment-wise merge at 8 / 6 blocks per

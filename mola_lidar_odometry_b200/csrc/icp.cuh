@@ -71,6 +71,11 @@ struct IcpState {
   int32_t inner_pending;  // 1: another inner GN iteration must run for the current ICP iteration
   uint32_t inner;         // index of the next inner iteration
   uint64_t n_pairs, n_potential, n_query_it, n_cand;
+  // linearisation of the prior term at the CURRENT pose T, prepared ahead of the solve that will use it (solve_phase:
+  // a second warp computes it while the first finishes the previous solve): error, right-Jacobian inverse, L e, L J.
+  // prior_valid = 0 whenever T has moved since.
+  double pe[6], pJ[36], pLe[6], pLJ[36];
+  int32_t prior_valid, pad_;
 };
 
 MLO_D double table_at(const double* t, uint32_t len, uint32_t it) {
@@ -1364,36 +1369,55 @@ __device__ __noinline__ void jr_inv_warp(const double* xi, double* J, double (*m
   }
   __syncwarp();
 }
-MLO_D void prior_add_warp(const IcpProblem& P, const double* T, double* H, SolveScratch& sc) {
+// (one warp) linearisation of the prior term at pose T: e, J, L e, L J into the given arrays; m = 3x3 scratch
+MLO_D void prior_compute_warp(const IcpProblem& P, const double* T, double* e, double* J, double* Le, double* LJ, double (*m)[9]) {
   const uint32_t lane = threadIdx.x & 31u;
-  if (lane == 0) prior_e(P, T, sc.e);
+  if (lane == 0) prior_e(P, T, e);
   __syncwarp();
   MLO_TRACE_SOLVE(47);  // prior: error vector done
-  jr_inv_warp(sc.e, sc.J, sc.m);
+  jr_inv_warp(e, J, m);
   MLO_TRACE_SOLVE(48);  // prior: Jacobian done
   if (lane < 6) {
     double s = 0;
-    for (int m = 0; m < 6; m++) s += P.prior_info[6 * lane + m] * sc.e[m];
-    sc.Le[lane] = s;
+    for (int k = 0; k < 6; k++) s += P.prior_info[6 * lane + k] * e[k];
+    Le[lane] = s;
   }
   for (uint32_t idx = lane; idx < 36; idx += 32) {
     const uint32_t i = idx / 6, j = idx % 6;
     double t = 0;
-    for (int m = 0; m < 6; m++) t += P.prior_info[6 * i + m] * sc.J[6 * m + j];
-    sc.LJ[idx] = t;
+    for (int k = 0; k < 6; k++) t += P.prior_info[6 * i + k] * J[6 * k + j];
+    LJ[idx] = t;
   }
   __syncwarp();
+}
+// (one warp) g += J^T L e ; H += J^T L J, each entry summed term by term onto the running value
+MLO_D void prior_accumulate_warp(const double* J, const double* Le, const double* LJ, double* g, double* H) {
+  const uint32_t lane = threadIdx.x & 31u;
   if (lane < 6) {
-    double gi = sc.g[lane];
-    for (int m = 0; m < 6; m++) gi += sc.J[6 * m + lane] * sc.Le[m];
-    sc.g[lane] = gi;
+    double gi = g[lane];
+    for (int k = 0; k < 6; k++) gi += J[6 * k + lane] * Le[k];
+    g[lane] = gi;
   }
   for (uint32_t idx = lane; idx < 36; idx += 32) {
     const uint32_t i = idx / 6, j = idx % 6;
     double h = H[idx];
-    for (int m = 0; m < 6; m++) h += sc.J[6 * m + i] * sc.LJ[6 * m + j];
+    for (int k = 0; k < 6; k++) h += J[6 * k + i] * LJ[6 * k + j];
     H[idx] = h;
   }
+  __syncwarp();
+}
+MLO_D void prior_add_warp(const IcpProblem& P, IcpState& S, SolveScratch& sc) {
+  if (S.prior_valid) {  // prepared ahead by another warp for exactly this pose (solve_phase)
+    prior_accumulate_warp(S.pJ, S.pLe, S.pLJ, sc.g, S.H);
+  } else {
+    prior_compute_warp(P, S.T, sc.e, sc.J, sc.Le, sc.LJ, sc.m);
+    prior_accumulate_warp(sc.J, sc.Le, sc.LJ, sc.g, S.H);
+  }
+}
+// (one warp, while the others are busy elsewhere) prepare the prior's linearisation at the pose the next solve starts from
+MLO_D void prior_precompute_warp(const IcpProblem& P, IcpState& S, SolveScratch& sc) {
+  prior_compute_warp(P, S.T, S.pe, S.pJ, S.pLe, S.pLJ, sc.m);
+  if ((threadIdx.x & 31u) == 0) S.prior_valid = 1;
   __syncwarp();
 }
 __device__ __noinline__ bool horn_from_sums_ool(const double* a, double n, double* T) { return horn_from_sums(a, n, T); }
@@ -1413,10 +1437,9 @@ MLO_D void pose_measures(const double* T, const double* ref, double& dt, double&
   wD = dr;  // se3_log's rotation half IS so3_log_of_pose(D)
 }
 
-// Executed by ONE warp once the 27 sums (+ counts) of the current linearisation sit in sc.tot / sc.cnt.
-// P and S live in shared memory.  Returns (on every lane) 0 = problem finished, 1 = another inner GN iteration is
-// pending, 2 = next ICP iteration.
-MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int after_match) {
+// Part A (sums -> system -> prior -> LDL^T -> retraction) returns 0 = finished, 1 = inner iteration pending, 3 = the last
+// inner iteration retracted: part B (step measures, termination, log) follows and returns 0 or 2.
+MLO_D int solve_part_a(const IcpProblem& P, IcpState& S, SolveScratch& sc, int after_match) {
   const uint32_t FULL = 0xFFFFFFFFu;
   const uint32_t lane = threadIdx.x & 31u;
   const uint32_t npairs = sc.cnt[0];
@@ -1461,7 +1484,7 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
       if (lane < 6) sc.g[lane] = sc.tot[21 + lane];
       __syncwarp();
       MLO_TRACE_SOLVE(40);  // system laid out
-      if (P.has_prior) prior_add_warp(P, sT, S.H, sc);  // (warp-uniform branch)
+      if (P.has_prior) prior_add_warp(P, S, sc);  // (warp-uniform branch)
       MLO_TRACE_SOLVE(41);  // prior term added
       if (lane == 0) {
         double g[6];
@@ -1484,6 +1507,7 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
           pose_mul(sT, E, Tn);
 #pragma unroll
           for (int i = 0; i < 12; i++) sT[i] = Tn[i];
+          S.prior_valid = 0;  // (a prepared prior linearisation belongs to the pose just left)
           MLO_TRACE_SOLVE(43);  // retraction done
           double dn = 0;
 #pragma unroll
@@ -1500,8 +1524,15 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
       }
     }
   }
-  next = __shfl_sync(FULL, next, 0);
-  if (next == 3) {
+  __syncwarp();
+  return __shfl_sync(FULL, next, 0);
+}
+MLO_D int solve_part_b(const IcpProblem& P, IcpState& S) {
+  const uint32_t FULL = 0xFFFFFFFFu;
+  const uint32_t lane = threadIdx.x & 31u;
+  double* const sT = S.T;
+  int next = 0;
+  {
     __syncwarp();  // the new pose (written by lane 0) is visible to lanes 1 and 2
     const int has2 = S.has_prev2;
     double dt = 1e300, dr = 1e300, tD = 0.0, wD = 0.0;
@@ -1560,6 +1591,13 @@ MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int aft
   __syncwarp();
   return __shfl_sync(FULL, next, 0);
 }
+// Executed by ONE warp once the 27 sums (+ counts) of the current linearisation sit in sc.tot / sc.cnt.
+// P and S live in shared memory.  Returns (on every lane) 0 = problem finished, 1 = another inner GN iteration is
+// pending, 2 = next ICP iteration.
+MLO_D int solve_core(const IcpProblem& P, IcpState& S, SolveScratch& sc, int after_match) {
+  const int a = solve_part_a(P, S, sc, after_match);
+  return a == 3 ? solve_part_b(P, S) : a;
+}
 
 // solve_core for callers whose problem and state live in GLOBAL memory (launch sequence, queue-driven kernel): the
 // solving block stages both in shared memory ONCE per solve phase (two coalesced reads by a whole warp instead of ~150
@@ -1587,11 +1625,42 @@ MLO_D void solve_stage_out(IcpState& Sg, const SolveStage& st) {
   __threadfence();
   __syncwarp();
 }
-__device__ __noinline__ int solve_core_staged(SolveStage& st, SolveScratch& sc, int after_match) {
+__device__ __noinline__ int solve_part_a_staged(SolveStage& st, SolveScratch& sc, int after_match) {
   MLO_TRACE_SOLVE(45);  // problem + state staged
-  const int next = solve_core(st.P, st.S, sc, after_match);
-  MLO_TRACE_SOLVE(46);  // solve_core returned
-  return next;
+  const int code = solve_part_a(st.P, st.S, sc, after_match);
+  MLO_TRACE_SOLVE(46);  // part A returned
+  return code;
+}
+__device__ __noinline__ int solve_part_b_staged(SolveStage& st) { return solve_part_b(st.P, st.S); }
+__device__ __noinline__ void prior_precompute_staged(SolveStage& st, SolveScratch& sc) { prior_precompute_warp(st.P, st.S, sc); }
+
+// One solve by a block of ICP_BLOCK threads on the staged copy, every thread calls it: the first warp runs part A; once
+// the new pose stands, the first warp finishes the iteration's bookkeeping (part B: three SE(3) logs, termination, log
+// record) WHILE the second warp prepares the prior's linearisation at that pose for the next solve of the problem -
+// ~2 us of serial double-precision work taken off the next solve's critical path.  Returns the block-uniform verdict
+// (0 finished, 1 inner iteration pending, 2 next ICP iteration).
+MLO_D int block_solve(SolveStage& st, SolveScratch& sc, int after_match, bool prior_ahead) {
+  // (two words: a thread still reading part A's verdict never races with part B's; between two calls of a block there
+  // is always a barrier - the fused loop's reduction, solve_phase's closing one)
+  __shared__ int b_code_a, b_code_b;
+  const uint32_t warp = threadIdx.x >> 5;
+  if (warp == 0) {
+    const int code = solve_part_a_staged(st, sc, after_match);
+    if (threadIdx.x == 0) b_code_a = code;
+  }
+  __syncthreads();  // the new pose is visible to every warp
+  int code = b_code_a;
+  if (code == 3) {  // (block-uniform)
+    if (warp == 0) {
+      const int n = solve_part_b_staged(st);
+      if (threadIdx.x == 0) b_code_b = n;
+    } else if (warp == 1 && prior_ahead) {
+      prior_precompute_staged(st, sc);
+    }
+    __syncthreads();
+    code = b_code_b;
+  }
+  return code;
 }
 
 // Inner Gauss-Newton iterations >= 1 inside the block that just solved (small problems): the block re-linearises ALL
@@ -1638,9 +1707,12 @@ struct PairStage {
 // every thread of the (ICP_BLOCK-wide) block calls this with the block-uniform `next` of the preceding solve, whose
 // problem and state sit in `st` (written by the block's first warp; the caller's barrier made them visible)
 MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uint32_t it, const float4* __restrict__ local,
-                                 const float4* pairA, const float4* pairB, const PairStage* ps) {
-  __shared__ int f_next;
+                                 const float4* pairA, const float4* pairB, const PairStage* ps, bool prior_ahead) {
   const IcpProblem& P = st.P;
+  const uint32_t warp = threadIdx.x >> 5;
+  // with a prior to prepare, the second warp does that while the other three re-linearise (thread rank 0..95)
+  const uint32_t rank = prior_ahead ? (warp == 0 ? threadIdx.x : threadIdx.x - 32u) : threadIdx.x;
+  const uint32_t nthr = prior_ahead ? ICP_BLOCK - 32u : ICP_BLOCK;
   while (next == 1) {
     const double* f_T = st.S.T;  // the pose the first warp just retracted
     const double kc = table_at(P.kparam, P.table_len, it);
@@ -1648,27 +1720,25 @@ MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uin
 #pragma unroll
     for (int k = 0; k < int(NACC); k++) a[k] = 0.0;
     uint32_t npairs = 0;
-    for (uint32_t q = threadIdx.x; q < P.n_q; q += ICP_BLOCK) {
-      const bool staged = ps != nullptr && q < PAIR_STAGE_MAX;  // (block-uniform pointer)
-      const float4 pa = staged ? ps->pa[q] : __ldcg(&pairA[P.q_begin + q]);
-      if (pa.w == 0.f) continue;
-      const float4 l = staged ? ps->l[q] : __ldg(&local[P.q_begin + q]);
-      if (pa.w == 1.f) {
-        contrib_pt2pt(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
-      } else {
-        const float4 nb = __ldcg(&pairB[P.q_begin + q]);
-        contrib_pt2pl(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, nb.x, nb.y, nb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+    if (prior_ahead && warp == 1) {
+      prior_precompute_staged(st, sc);
+    } else {
+      for (uint32_t q = rank; q < P.n_q; q += nthr) {
+        const bool staged = ps != nullptr && q < PAIR_STAGE_MAX;  // (block-uniform pointer)
+        const float4 pa = staged ? ps->pa[q] : __ldcg(&pairA[P.q_begin + q]);
+        if (pa.w == 0.f) continue;
+        const float4 l = staged ? ps->l[q] : __ldg(&local[P.q_begin + q]);
+        if (pa.w == 1.f) {
+          contrib_pt2pt(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, P.w_pt2pt, P.robust_kernel, kc, a);
+        } else {
+          const float4 nb = __ldcg(&pairB[P.q_begin + q]);
+          contrib_pt2pl(f_T, l.x, l.y, l.z, pa.x, pa.y, pa.z, nb.x, nb.y, nb.z, P.w_pt2pl, P.robust_kernel, kc, a);
+        }
+        npairs++;
       }
-      npairs++;
     }
-    block_reduce_to(a, npairs, sc);  // (its barrier: every thread has read the pose before the first warp moves it)
-    if (threadIdx.x < 32) {
-      const int n = solve_core_staged(st, sc, 0);
-      if (threadIdx.x == 0) f_next = n;
-    }
-    __syncthreads();
-    next = f_next;
-    __syncthreads();
+    block_reduce_to(a, npairs, sc);  // (its barriers: every thread has read the pose; the prepared prior is visible)
+    next = block_solve(st, sc, 0, prior_ahead);
   }
   return next;
 }
@@ -1677,26 +1747,23 @@ MLO_D int fused_inner_iterations(SolveStage& st, SolveScratch& sc, int next, uin
 // sums of the current linearisation sit in sc.tot / sc.cnt): first solve, fused inner iterations if allowed, state back
 // to global memory.  Returns the block-uniform verdict (0 finished, 1 inner iteration pending, 2 next ICP iteration).
 MLO_D int solve_phase(const IcpProblem& Pg, IcpState& Sg, SolveStage& st, SolveScratch& sc, int after_match, int fuse, uint32_t it,
-                      const float4* __restrict__ local, const float4* pairA, const float4* pairB, bool staged = false,
-                      PairStage* ps = nullptr) {
-  __shared__ int p_next;
-  // (the staged problem is visible to every warp only when sum_partials_block brought it in behind its barrier)
-  const bool prefetch = ps != nullptr && staged && fuse && st.P.n_q <= FUSE_MAX_Q && st.P.solver == MLO_SOLVER_GAUSS_NEWTON &&
-                        st.P.gn_max_iterations > 1;
-  if (threadIdx.x < 32) {
-    if (!staged) solve_stage_in(Pg, Sg, st);  // (staged = sum_partials_block already brought them in)
-    const int n = solve_core_staged(st, sc, after_match);
-    if (threadIdx.x == 0) p_next = n;
-  } else if (prefetch) {
+                      const float4* __restrict__ local, const float4* pairA, const float4* pairB, PairStage* ps) {
+  // (the staged problem is visible to every warp: sum_partials_block brought it in behind its barrier)
+  const bool gn = st.P.solver == MLO_SOLVER_GAUSS_NEWTON;
+  // `fuse`: bit 0 = run the inner iterations inside this block, bit 1 = prepare the prior's linearisation ahead (host options
+  // "fuse_inner", "prior_ahead")
+  const bool fused = (fuse & 1) && st.P.n_q <= FUSE_MAX_Q;
+  const bool prefetch = fused && gn && st.P.gn_max_iterations > 1;
+  const bool prior_ahead = (fuse & 2) && gn && st.P.has_prior;
+  if (threadIdx.x >= 32 && prefetch) {
     const uint32_t nq = min(st.P.n_q, PAIR_STAGE_MAX), qb = st.P.q_begin;
     for (uint32_t q = threadIdx.x - 32; q < nq; q += ICP_BLOCK - 32) {
       ps->pa[q] = __ldcg(&pairA[qb + q]);
       ps->l[q] = __ldg(&local[qb + q]);
     }
   }
-  __syncthreads();
-  int next = p_next;
-  if (fuse && st.P.n_q <= FUSE_MAX_Q) next = fused_inner_iterations(st, sc, next, it, local, pairA, pairB, prefetch ? ps : nullptr);
+  int next = block_solve(st, sc, after_match, prior_ahead);  // (its first barrier also publishes the prefetched pairings)
+  if (fused) next = fused_inner_iterations(st, sc, next, it, local, pairA, pairB, prefetch ? ps : nullptr, prior_ahead);
   if (threadIdx.x < 32) solve_stage_out(Sg, st);
   __syncthreads();
   return next;
@@ -1798,7 +1865,7 @@ __global__ void __launch_bounds__(ICP_BLOCK)
   const uint32_t it = S.it;  // (the match phase of this iteration used the same index; read before the solve bumps it)
   sum_partials_block(P, partials, part_cnt, after_match ? P.n_blocks : P.n_blocks_acc, sc, &S, &st);
   __shared__ PairStage ps;
-  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB, true, &ps);
+  const int next = solve_phase(P, S, st, sc, after_match, fuse, it, local, pairA, pairB, &ps);
   if (next == 0 && threadIdx.x == 0) atomicSub(n_active, 1u);
 }
 
@@ -1814,6 +1881,7 @@ __global__ void k_init_states(const IcpProblem* __restrict__ probs, IcpState* __
   }
   for (int k = 0; k < 36; k++) S.H[k] = 0.0;
   S.has_prev2 = 0;
+  S.prior_valid = 0;
   S.have_H = 0;
   S.it = 0;
   S.inner_pending = 0;
@@ -1989,7 +2057,7 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
     }
     int nx = 0;  // (block-uniform)
     if (s_last) {
-      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB, true, &s_pairs);
+      nx = solve_phase(P, S, s_stage, s_solve, phase == 0, fuse, s_it, local, pairA, pairB, &s_pairs);
       MLO_TRACE_EVENT(prob, 7);  // solve phase (with its fused inner iterations) done, state written back
     }
     if (s_last && threadIdx.x < 32) {

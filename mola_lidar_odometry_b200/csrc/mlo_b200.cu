@@ -150,6 +150,8 @@ struct mlo_ctx {
   int pers_minb_now = 4;     // the choice for the align call in progress
   int qpw_floor = 4;         // MLO_QPW_FLOOR: fewest queries a warp handles per chunk in the warp-per-query kernels
   bool fuse_inner = true;    // MLO_FUSE_INNER=0: inner GN iterations as separate accumulate + solve launches (A/B)
+  bool prior_ahead = true;   // mlo_set_option("prior_ahead"): a second warp prepares the prior's linearisation for the next solve
+                             // while the first finishes the current one (icp.cuh block_solve)
   bool tail_handover = true;  // MLO_TAIL_HANDOVER=0 disables the launch-sequence -> persistent hand-over
   int tail_queries_per_sm = 512;  // mlo_set_option("tail_queries_per_sm"): the hand-over happens once the still-active problems
                                   // hold fewer queries than this per SM
@@ -857,11 +859,11 @@ void launch_persistent(mlo_ctx* c, bool tpq, bool multi, uint32_t nblk, const Ma
     if (c->pers_minb_now == 2)                                                                                           \
       LAUNCH(c, (k_icp_persistent<T, M, 2, PL>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(), \
              c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW,                   \
-             c->fuse_inner ? 1 : 0);                                                                                     \
+             (c->fuse_inner ? 1 : 0) | (c->prior_ahead ? 2 : 0));                                                                                     \
     else                                                                                                                 \
       LAUNCH(c, (k_icp_persistent<T, M, 4, PL>), nblk, ICP_BLOCK, map, d_maps, dP, dS, d_local, c->d_pairA.as<float4>(), \
              c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), q, QPW,                   \
-             c->fuse_inner ? 1 : 0);                                                                                     \
+             (c->fuse_inner ? 1 : 0) | (c->prior_ahead ? 2 : 0));                                                                                     \
   } while (0)
   // (the warp-per-query form exists with and without the point-to-plane matcher's code: point-to-point pipelines run
   // the lean instantiation)
@@ -1240,7 +1242,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
                   c->d_pairA.as<float4>(), c->d_pairB.as<float4>(), c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), qpw);
       if (g == 0) prof_end(c, 3, e_nn);
       // problems up to FUSE_MAX_Q queries run their inner Gauss-Newton iterations inside the solve block
-      const int fuse = (c->fuse_inner && max_nq <= FUSE_MAX_Q) ? 1 : 0;
+      const int fuse = ((c->fuse_inner && max_nq <= FUSE_MAX_Q) ? 1 : 0) | (c->prior_ahead ? 2 : 0);
       LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active, fuse,
                 d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
       for (uint32_t inner = 1; inner < max_inner && !fuse; inner++) {
@@ -1372,6 +1374,7 @@ int mlo_create(int cuda_device, mlo_ctx** out) {
   if (const char* tq = getenv("MLO_TAIL_QUERIES_PER_SM")) c->tail_queries_per_sm = std::max(1, atoi(tq));
   if (const char* ce = getenv("MLO_CHECK_EVERY")) c->check_every = std::max(1, atoi(ce));
   if (const char* fi = getenv("MLO_FUSE_INNER")) c->fuse_inner = atoi(fi) != 0;
+  if (const char* pa = getenv("MLO_PRIOR_AHEAD")) c->prior_ahead = atoi(pa) != 0;
   if (const char* pm = getenv("MLO_PERS_MINB")) c->pers_minb = atoi(pm) == 2 ? 2 : (atoi(pm) == 4 ? 4 : 0);
   if (const char* qf = getenv("MLO_QPW_FLOOR")) c->qpw_floor = std::min(32, std::max(1, atoi(qf)));
   if (const char* wb = getenv("MLO_WL_MIN_BLOCKS")) c->wl_min_blocks = atoi(wb);
@@ -1474,6 +1477,7 @@ int mlo_set_option(mlo_ctx* c, const char* name, int64_t v) {
   else if (n == "block_cluster") c->block_cluster = int(v);
   else if (n == "stream_groups") c->stream_groups = int(std::min<int64_t>(mlo_ctx::MAX_GROUPS, std::max<int64_t>(1, v)));
   else if (n == "fuse_inner") c->fuse_inner = v != 0;
+  else if (n == "prior_ahead") c->prior_ahead = v != 0;
   else if (n == "force_kernel") c->force_kernel = int(v);
   else if (n == "wl_variant") c->wl_variant = int(v);
   else if (n == "wl_warps") c->wl_warps = int(v);
@@ -1506,6 +1510,7 @@ int mlo_get_option(const mlo_ctx* c, const char* name, int64_t* out) {
   else if (n == "last_block_threads") *out = c->last_block_threads;
   else if (n == "stream_groups") *out = c->stream_groups;
   else if (n == "fuse_inner") *out = c->fuse_inner;
+  else if (n == "prior_ahead") *out = c->prior_ahead;
   else if (n == "force_kernel") *out = c->force_kernel;
   else if (n == "wl_variant") *out = c->wl_variant;
   else if (n == "wl_warps") *out = c->wl_warps;

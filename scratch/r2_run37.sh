@@ -1,0 +1,19 @@
+#!/bin/bash
+cd "$(dirname "$0")/.."
+O=gpurun_out
+run() { # S env args
+  echo "== S=$1 $2 $3"
+  env $2 timeout 300 python bench.py --sequences $1 $3 2> $O/r2K_last.err | python -c "
+import json,sys
+d=json.loads(sys.stdin.read()); print(round(d['value'],1),'scans/s', {k:round(v,3) for k,v in d['phases']['host_wall_timed_pass'].items()})" || tail -5 $O/r2K_last.err
+}
+{
+run 128 MLO_PRIOR_AHEAD=1 "--workload sequence --scans 40 --no-cpu-baseline"
+run 128 MLO_PRIOR_AHEAD=0 "--workload sequence --scans 40 --no-cpu-baseline"
+run 32 MLO_PRIOR_AHEAD=1 "--workload sequence --scans 200 --no-cpu-baseline"
+run 32 MLO_PRIOR_AHEAD=0 "--workload sequence --scans 200 --no-cpu-baseline"
+run 64 MLO_PRIOR_AHEAD=1 "--workload sequence --scans 60 --no-cpu-baseline"
+run 1 MLO_PRIOR_AHEAD=1 "--workload sequence --scans 300 --no-cpu-baseline"
+run 1 MLO_PRIOR_AHEAD=0 "--workload sequence --scans 300 --no-cpu-baseline"
+} > $O/r2K_ab.log 2>&1
+cut -c1-330 $O/r2K_ab.log

@@ -106,6 +106,29 @@ def test_every_align_path_matches_the_oracle(ctx, small_case, path, fuse):
     assert {1, 3, 4, 5} <= terms   # NoPairings, MaxIterations, Stalled, HookRequest all occur in this batch
 
 
+@pytest.mark.parametrize("path", [1, 2])
+def test_prior_prepared_ahead_is_bit_identical(ctx, small_case, path):
+    """mlo_set_option "prior_ahead": a second warp linearises the prior term for the next solve while the first finishes
+    the current one.  Same code, same inputs: poses, iteration counts and covariances must not move by a bit - with the
+    prior on EVERY problem of the batch here."""
+    c = small_case
+    owners = []
+    for j, init in enumerate(c["inits"]):
+        ip = capi.IcpParamsOwner(sigma=2.0 if j % 2 == 0 else 1.0)
+        info = np.diag([50.0, 50.0, 50.0, 2000.0, 2000.0, 2000.0]) * (1.0 + 0.1 * j)
+        info[0, 4] = info[4, 0] = 3.0
+        ip.set_prior(init, info)
+        owners.append(ip)
+    res = {}
+    for ahead in (0, 1):
+        with _Options(ctx, align_path=path, prior_ahead=ahead):
+            res[ahead] = ctx.icp_align_batch(c["locals"], c["g"], c["inits"], [o.p for o in owners])
+    for a, b in zip(res[0], res[1]):
+        assert np.array_equal(np.asarray(a.pose), np.asarray(b.pose))
+        assert np.array_equal(a.cov, b.cov)
+        assert int(a.n_iterations) == int(b.n_iterations) and int(a.termination) == int(b.termination)
+
+
 @pytest.mark.parametrize("threads", [256, 512])
 @pytest.mark.parametrize("cluster", [1, 2, 4, 8])
 def test_block_kernel_geometries(ctx, small_case, threads, cluster):
