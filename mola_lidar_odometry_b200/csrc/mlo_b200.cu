@@ -1245,10 +1245,10 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
       const int fuse = ((c->fuse_inner && max_nq <= FUSE_MAX_Q) ? 1 : 0) | (c->prior_ahead ? 2 : 0);
       LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 1, d_active, fuse,
                 d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
-      for (uint32_t inner = 1; inner < max_inner && !fuse; inner++) {
+      for (uint32_t inner = 1; inner < max_inner && !(fuse & 1); inner++) {
         LAUNCH_ON(c, sg, k_accumulate, grid_acc_g, ICP_BLOCK, gP, gS, d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>(),
                   c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>());
-        LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active, 0,
+        LAUNCH_ON(c, sg, k_solve, Bg, ICP_BLOCK, gP, gS, c->d_partials.as<double>(), c->d_partcnt.as<uint32_t>(), 0, d_active, fuse & 2,
                   d_local, c->d_pairA.as<float4>(), c->d_pairB.as<float4>());
       }
     }
