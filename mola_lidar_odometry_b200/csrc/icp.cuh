@@ -1257,11 +1257,32 @@ MLO_D void sum_partials_block(const IcpProblem& P, const double* partials, const
 #pragma unroll
         for (int u = 0; u < 8; u++) acc += v[u];
       }
-      for (; b < nblk; b += SOLVE_WARPS) acc += __ldcg(base + size_t(b) * NACC);
+      if (b < nblk) {
+        // the last (up to eight) partials of this warp: again all loads in flight before the first add - a plain
+        // `acc += load` loop is one L2 round trip per partial (41 chunks: three of them in a row on warp 0).  Added in
+        // the same ascending order; the absent ones contribute +0.0.
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const uint32_t bb = b + u * SOLVE_WARPS;
+          v[u] = bb < nblk ? __ldcg(base + size_t(bb) * NACC) : 0.0;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) acc += v[u];
+      }
       sc.part[warp][lane] = acc;
     } else if (lane < NACC + 2) {
       uint32_t cnt = 0;
-      for (uint32_t b = warp; b < nblk; b += SOLVE_WARPS) cnt += __ldcg(&part_cnt[2 * size_t(P.part_begin + b) + (lane - NACC)]);
+      for (uint32_t b0 = warp; b0 < nblk; b0 += 8 * SOLVE_WARPS) {  // (eight loads in flight, as above)
+        uint32_t v[8];
+#pragma unroll
+        for (int u = 0; u < 8; u++) {
+          const uint32_t bb = b0 + u * SOLVE_WARPS;
+          v[u] = bb < nblk ? __ldcg(&part_cnt[2 * size_t(P.part_begin + bb) + (lane - NACC)]) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < 8; u++) cnt += v[u];
+      }
       sc.pcnt[warp][lane - NACC] = cnt;
     }
   }
