@@ -1929,8 +1929,10 @@ __global__ void k_init_states(const IcpProblem* __restrict__ probs, IcpState* __
 // next phase (inner GN re-linearisation, or the match phase of the next ICP iteration), so problems advance
 // independently: no grid-wide barrier, no host round trip, no idle tail while other problems still iterate.
 struct IcpQueue {
-  uint32_t* items;
-  uint32_t* seq;
+  // one 64-bit word per slot: (sequence number << 32) | item.  Sequence = ticket of the producer that may fill the slot
+  // (free), ticket + 1 once filled: a consumer polls ONE word and has the item with it (it used to be a sequence array and
+  // an item array: one more dependent L2 round trip per pop, one more fence per push).
+  unsigned long long* slots;
   uint32_t mask;       // ring capacity - 1
   uint32_t* ctrl;      // [0] head, [1] tail, [2] problems active, [3] all done, [4] error/timeout
   uint32_t* phase_cnt; // per problem: chunks of the current phase completed
@@ -1939,6 +1941,9 @@ constexpr uint32_t ITEM_EXIT = 0xFFFFFFFFu;
 MLO_HD uint32_t item_make(uint32_t prob, uint32_t chunk, uint32_t phase) { return (prob << 16) | (chunk << 1) | phase; }
 
 MLO_D uint32_t ld_volatile_u32(const uint32_t* p) { return *reinterpret_cast<const volatile uint32_t*>(p); }
+MLO_D unsigned long long ld_volatile_u64(const unsigned long long* p) { return *reinterpret_cast<const volatile unsigned long long*>(p); }
+MLO_D void st_volatile_u64(unsigned long long* p, unsigned long long v) { *reinterpret_cast<volatile unsigned long long*>(p) = v; }
+MLO_HD unsigned long long slot_word(uint32_t seq, uint32_t item) { return (static_cast<unsigned long long>(seq) << 32) | item; }
 
 // lanes of one warp publish n consecutive items (prob, phase, chunk 0..n-1)
 MLO_D void queue_push(const IcpQueue& q, uint32_t prob, uint32_t phase, uint32_t n) {
@@ -1949,7 +1954,7 @@ MLO_D void queue_push(const IcpQueue& q, uint32_t prob, uint32_t phase, uint32_t
   for (uint32_t i = lane; i < n; i += 32) {
     const uint32_t t = pos + i, slot = t & q.mask;
     uint32_t spins = 0;
-    while (ld_volatile_u32(&q.seq[slot]) != t) {  // slot still holds an unconsumed older item (ring full): rare
+    while (uint32_t(ld_volatile_u64(&q.slots[slot]) >> 32) != t) {  // slot still holds an unconsumed older item (ring full): rare
       __nanosleep(64);
       if (++spins > (1u << 24)) {
         atomicExch(&q.ctrl[4], 1u);
@@ -1957,9 +1962,7 @@ MLO_D void queue_push(const IcpQueue& q, uint32_t prob, uint32_t phase, uint32_t
         break;
       }
     }
-    *reinterpret_cast<volatile uint32_t*>(&q.items[slot]) = item_make(prob, i, phase);
-    __threadfence();
-    *reinterpret_cast<volatile uint32_t*>(&q.seq[slot]) = t + 1;
+    st_volatile_u64(&q.slots[slot], slot_word(t + 1, item_make(prob, i, phase)));  // (item and sequence in one store)
   }
 }
 
@@ -1988,7 +1991,7 @@ __device__ __noinline__ void chunk_accumulate_ool(const IcpProblem& P, const dou
 // each active problem appends the chunks of its next match phase.
 __global__ void k_queue_reset(IcpQueue q, uint32_t n_problems) {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i <= q.mask) q.seq[i] = i;
+  if (i <= q.mask) q.slots[i] = slot_word(i, 0u);
   if (i < n_problems) q.phase_cnt[i] = 0;
   if (i < 8) q.ctrl[i] = 0;
 }
@@ -1999,8 +2002,7 @@ __global__ void k_queue_build(const IcpProblem* __restrict__ probs, const IcpSta
   const uint32_t n = probs[b].n_blocks_pers;
   const uint32_t pos = atomicAdd(&q.ctrl[1], n);
   for (uint32_t i = 0; i < n; i++) {
-    q.items[(pos + i) & q.mask] = item_make(b, i, 0u);
-    q.seq[(pos + i) & q.mask] = pos + i + 1;
+    q.slots[(pos + i) & q.mask] = slot_word(pos + i + 1, item_make(b, i, 0u));
   }
   atomicAdd(&q.ctrl[2], 1u);
 }
@@ -2024,10 +2026,11 @@ __global__ void __launch_bounds__(ICP_BLOCK, MINB)
       const uint32_t slot = t & q.mask;
       uint32_t item = ITEM_EXIT, spins = 0;
       for (;;) {
-        if (ld_volatile_u32(&q.seq[slot]) == t + 1) {
-          __threadfence();
-          item = ld_volatile_u32(&q.items[slot]);
-          *reinterpret_cast<volatile uint32_t*>(&q.seq[slot]) = t + q.mask + 1;  // free the slot for ticket t + capacity
+        const unsigned long long v = ld_volatile_u64(&q.slots[slot]);
+        if (uint32_t(v >> 32) == t + 1) {
+          item = uint32_t(v);
+          st_volatile_u64(&q.slots[slot], slot_word(t + q.mask + 1, 0u));  // free the slot for ticket t + capacity
+          __threadfence();  // acquire: what the producer wrote before publishing (problem state) is visible below
           break;
         }
         if (ld_volatile_u32(&q.ctrl[3])) break;  // every problem finished

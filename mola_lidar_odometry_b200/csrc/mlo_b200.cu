@@ -133,6 +133,7 @@ struct mlo_ctx {
   uint32_t log_cap = 0;  // mlo_icp_log_enable: records kept per problem (0 = off)
   DBuf d_log;
   std::vector<mlo_icp_iteration_record> h_log;
+  std::vector<unsigned long long> h_queue;  // host image of the work queue's slot words
   uint32_t h_log_problems = 0;
   int last_align_path = 0, last_stream_groups = 0, last_tail_handover = 0;  // what the last align call did (tests)
   uint64_t large_batch_queries = 0;  // 0 = auto (sm_count * 1024): batches at or above it take the launch sequence
@@ -1117,23 +1118,18 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
     }
     if (n_act) {
       const uint32_t qcap = uint32_t(next_pow2(std::max<uint64_t>(2ull * part_total, 1024)));
-      std::vector<uint32_t> seq(qcap);
-      for (uint32_t i = 0; i < qcap; i++) seq[i] = i < items.size() ? i + 1 : i;
-      items.resize(qcap, 0u);
+      const uint32_t n_items = uint32_t(std::min<size_t>(items.size(), qcap));
+      c->h_queue.resize(qcap);  // (a member: the asynchronous upload below must not outlive a local)
+      for (uint32_t i = 0; i < qcap; i++) c->h_queue[i] = i < n_items ? slot_word(i + 1, items[i]) : slot_word(i, 0u);
       CU(c, c->d_queue.ensure((2ull * qcap + 8 + B) * sizeof(uint32_t)));
       uint32_t* dq = c->d_queue.as<uint32_t>();
       IcpQueue q;
-      q.items = dq;
-      q.seq = dq + qcap;
+      q.slots = reinterpret_cast<unsigned long long*>(dq);
       q.ctrl = dq + 2ull * qcap;
       q.phase_cnt = dq + 2ull * qcap + 8;
       q.mask = qcap - 1;
-      uint32_t n_items = 0;
-      for (uint32_t i = 0; i < qcap; i++)
-        if (seq[i] == i + 1) n_items++;
       const uint32_t h_ctrl[8] = {0u, n_items, n_act, 0u, 0u, 0u, 0u, 0u};
-      CU(c, cudaMemcpyAsync(q.items, items.data(), qcap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
-      CU(c, cudaMemcpyAsync(q.seq, seq.data(), qcap * sizeof(uint32_t), cudaMemcpyHostToDevice, c->stream));
+      CU(c, cudaMemcpyAsync(q.slots, c->h_queue.data(), qcap * sizeof(unsigned long long), cudaMemcpyHostToDevice, c->stream));
       CU(c, cudaMemcpyAsync(q.ctrl, h_ctrl, sizeof(h_ctrl), cudaMemcpyHostToDevice, c->stream));
       CU(c, cudaMemsetAsync(q.phase_cnt, 0, B * sizeof(uint32_t), c->stream));
       if (c->persistent_blocks == 0) {
@@ -1278,8 +1274,7 @@ int align_batch_core(mlo_ctx* c, uint32_t B, const float4* d_local, const uint64
         CU(c, c->d_queue.ensure((2ull * qcap + 8 + B) * sizeof(uint32_t)));
         uint32_t* dq = c->d_queue.as<uint32_t>();
         IcpQueue q;
-        q.items = dq;
-        q.seq = dq + qcap;
+        q.slots = reinterpret_cast<unsigned long long*>(dq);
         q.ctrl = dq + 2ull * qcap;
         q.phase_cnt = dq + 2ull * qcap + 8;
         q.mask = qcap - 1;
